@@ -14,6 +14,12 @@
  * pinned against (i) the reference's Householder GMRES (gmres.hpp:449-631) and (ii) the reference pipelined
  * host path with the documented one-line fix (oracle/_ref/libvcl_ref_gmresfix.so).
  *
+ * ARITHMETIC: this file is compiled with -ffp-contract=off; wherever the reference, built by oracle/Makefile's recipe
+ * (g++ -O3 -march=x86-64-v3, generic tuning), fuses a multiply-add, fma() is written out explicitly, and where it does not
+ * (the in-row CSR chain `dot += a[i]*x[col[i]]`: GCC avoids FMA in reduction chains under generic tuning) it is not.
+ * tests/test_oracle.py checks the SpMV forms BIT-FOR-BIT against that reference build; the CUDA kernels use the same
+ * explicit operations (__dmul_rn/__dadd_rn vs fma).
+ *
  * All citations are relative to /root/reference.
  */
 #include "vcl_oracle.h"
@@ -123,7 +129,7 @@ void vclo_csr_spmv(int rows, const u32 *rp, const u32 *ci, const double *v,
       dot += v[i] * x[(size_t)ci[i] * (size_t)incx + (size_t)offx];
     size_t idx = (size_t)row * (size_t)incy + (size_t)offy;
     if (beta < 0 || beta > 0)
-      y[idx] = alpha * dot + beta * y[idx];
+      y[idx] = fma(beta, y[idx], alpha * dot);   /* the reference build fuses this one */
     else
       y[idx] = alpha * dot;
   }
@@ -198,10 +204,10 @@ void vclo_sell_spmv(int rows, int C, const u32 *cols_per_block, const u32 *block
       {
         size_t idx = (size_t)block_start[b] + (size_t)j * (size_t)C + (size_t)rib;
         double val = elements[idx];
-        acc += (val > 0 || val < 0) ? x[(size_t)col_idx[idx] * (size_t)incx + (size_t)offx] * val : 0;
+        if (val > 0 || val < 0) acc = fma(x[(size_t)col_idx[idx] * (size_t)incx + (size_t)offx], val, acc);   /* fused in the reference build */
       }
       size_t yi = (size_t)row * (size_t)incy + (size_t)offy;
-      if (beta < 0 || beta > 0) y[yi] = alpha * acc + beta * y[yi];
+      if (beta < 0 || beta > 0) y[yi] = fma(beta, y[yi], alpha * acc);
       else                      y[yi] = alpha * acc;
     }
   }

@@ -1,0 +1,253 @@
+// backend.cu -- backend handle + device memory runtime of libvcl_b200.so.
+// Replaces viennacl/backend/cuda.hpp:103-200 and the handle plumbing of backend/mem_handle.hpp:89-245 /
+// backend/memory.hpp:54-367 for the CUDA domain (the C++ facade keeps mem_handle and calls these).
+#include "common.cuh"
+#include "solver_state.cuh"
+
+ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, const char *file, int line)
+{
+  if (b)
+  {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s (%s:%d)", what, file, line);
+    b->last_error = buf;
+  }
+  return st;
+}
+
+ViennaCLStatus vcl_cuda_fail(ViennaCLBackend b, cudaError_t e, const char *what, const char *file, int line)
+{
+  if (b)
+  {
+    char buf[768];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s (%s:%d)", (int)e, cudaGetErrorString(e), what, file, line);
+    b->last_error = buf;
+  }
+  if (e == cudaErrorMemoryAllocation) return ViennaCLB200OutOfMemory;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return ViennaCLB200NoDevice;
+  return ViennaCLB200CudaError;
+}
+
+ViennaCLStatus vcl_ws_reserve(ViennaCLBackend b, size_t bytes)
+{
+  if (b->ws_bytes >= bytes) return ViennaCLSuccess;
+  if (b->ws) { VCL_CUDA(b, cudaStreamSynchronize(b->stream)); VCL_CUDA(b, cudaFree(b->ws)); b->ws = nullptr; b->ws_bytes = 0; }
+  VCL_CUDA(b, cudaMalloc(&b->ws, bytes));
+  b->ws_bytes = bytes;
+  return ViennaCLSuccess;
+}
+
+static ViennaCLStatus backend_init(ViennaCLBackend b, int device, void *stream)
+{
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return vcl_fail(b, ViennaCLB200NoDevice, "no CUDA device available: libvcl_b200 has no CPU fallback", __FILE__, __LINE__);
+  if (device < 0) { VCL_CUDA(b, cudaGetDevice(&device)); }
+  VCL_REQUIRE(b, device < count, "device index out of range");
+  VCL_CUDA(b, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VCL_CUDA(b, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return vcl_fail(b, ViennaCLB200NoDevice, "libvcl_b200 is built for sm_100a (B200) only", __FILE__, __LINE__);
+  b->device = device;
+  b->sm_count = prop.multiProcessorCount;
+  b->l2_bytes = (size_t)prop.l2CacheSize;
+  if (stream) { b->stream = (cudaStream_t)stream; b->owns_stream = false; }
+  else { VCL_CUDA(b, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->owns_stream = true; }
+  VCL_CUDA(b, cudaStreamCreateWithFlags(&b->comm_stream, cudaStreamNonBlocking));
+  VCL_CUDA(b, cudaEventCreateWithFlags(&b->ev_a, cudaEventDisableTiming));
+  VCL_CUDA(b, cudaEventCreateWithFlags(&b->ev_b, cudaEventDisableTiming));
+  VCL_CUDA(b, cudaEventCreate(&b->tm_begin));
+  VCL_CUDA(b, cudaEventCreate(&b->tm_end));
+  VCL_CUDA(b, cudaMalloc(&b->partials, sizeof(double) * VCL_MAX_QUANT * VCL_MAX_BLOCKS));
+  VCL_CUDA(b, cudaMalloc(&b->tickets, sizeof(unsigned int) * 16));
+  VCL_CUDA(b, cudaMemset(b->tickets, 0, sizeof(unsigned int) * 16));
+  VCL_CUDA(b, cudaMalloc(&b->dscal, sizeof(double) * 64));
+  VCL_CUDA(b, cudaMemset(b->dscal, 0, sizeof(double) * 64));
+  VCL_CUDA(b, cudaMallocHost(&b->hscal, sizeof(double) * 64));
+  VCL_CUDA(b, cudaMalloc(&b->dstate, sizeof(SolverState)));
+  VCL_CUDA(b, cudaMemset(b->dstate, 0, sizeof(SolverState)));
+  VCL_CUDA(b, cudaMallocHost(&b->hstate, sizeof(SolverState)));
+  VCL_CUDA(b, cudaDeviceSynchronize());
+  return ViennaCLSuccess;
+}
+
+extern "C" {
+
+const char *ViennaCLB200Version(void) { return "vcl_b200 0.1 (sm_100a)"; }
+
+ViennaCLStatus ViennaCLBackendCreate(ViennaCLBackend *backend)
+{
+  return ViennaCLBackendCreateOnDevice(backend, -1, nullptr);
+}
+
+ViennaCLStatus ViennaCLBackendCreateOnDevice(ViennaCLBackend *backend, ViennaCLInt device, void *cuda_stream)
+{
+  if (!backend) return ViennaCLB200InvalidArgument;
+  ViennaCLBackend b = new ViennaCLBackend_impl();
+  ViennaCLStatus st = backend_init(b, device, cuda_stream);
+  if (st != ViennaCLSuccess)
+  {
+    fprintf(stderr, "libvcl_b200: backend creation failed: %s\n", b->last_error.c_str());
+    delete b;
+    *backend = nullptr;
+    return st;
+  }
+  *backend = b;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendDestroy(ViennaCLBackend *backend)
+{
+  if (!backend || !*backend) return ViennaCLSuccess;
+  ViennaCLBackend b = *backend;
+  cudaSetDevice(b->device);
+  cudaStreamSynchronize(b->stream);
+  ViennaCLBackendCommDestroy(b);
+  if (b->ws) cudaFree(b->ws);
+  if (b->flush_buf) cudaFree(b->flush_buf);
+  cudaFree(b->partials); cudaFree(b->tickets); cudaFree(b->dscal); cudaFreeHost(b->hscal);
+  cudaFree(b->dstate); cudaFreeHost(b->hstate);
+  cudaEventDestroy(b->ev_a); cudaEventDestroy(b->ev_b); cudaEventDestroy(b->tm_begin); cudaEventDestroy(b->tm_end);
+  cudaStreamDestroy(b->comm_stream);
+  if (b->owns_stream) cudaStreamDestroy(b->stream);
+  delete b;
+  *backend = nullptr;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendSynchronize(ViennaCLBackend b)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendGetStream(ViennaCLBackend b, void **s)
+{
+  VCL_CHECK_BACKEND(b);
+  *s = (void*)b->stream;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendGetDevice(ViennaCLBackend b, ViennaCLInt *device, ViennaCLInt *sm_count)
+{
+  VCL_CHECK_BACKEND(b);
+  if (device) *device = b->device;
+  if (sm_count) *sm_count = b->sm_count;
+  return ViennaCLSuccess;
+}
+
+const char *ViennaCLBackendLastError(ViennaCLBackend b) { return b ? b->last_error.c_str() : "backend not initialised"; }
+
+ViennaCLStatus ViennaCLBackendTimerBegin(ViennaCLBackend b)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_CUDA(b, cudaEventRecord(b->tm_begin, b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendTimerEnd(ViennaCLBackend b, double *ms)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_CUDA(b, cudaEventRecord(b->tm_end, b->stream));
+  VCL_CUDA(b, cudaEventSynchronize(b->tm_end));
+  float f = 0;
+  VCL_CUDA(b, cudaEventElapsedTime(&f, b->tm_begin, b->tm_end));
+  if (ms) *ms = (double)f;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendFlushL2(ViennaCLBackend b)
+{
+  VCL_CHECK_BACKEND(b);
+  if (!b->flush_buf)
+  {
+    b->flush_bytes = (b->l2_bytes ? b->l2_bytes : (size_t)128 << 20) * 2;
+    VCL_CUDA(b, cudaMalloc(&b->flush_buf, b->flush_bytes));
+  }
+  VCL_CUDA(b, cudaMemsetAsync(b->flush_buf, 0, b->flush_bytes, b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend b, long long *launches)
+{
+  VCL_CHECK_BACKEND(b);
+  *launches = b->launches;
+  return ViennaCLSuccess;
+}
+
+// ---------------------------------------------------------------- memory ----------------------------------------------------------------
+ViennaCLStatus ViennaCLCUDAMemAlloc(ViennaCLBackend b, void **ptr, size_t bytes)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, ptr != nullptr, "null out pointer");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+  *ptr = nullptr;
+  if (bytes == 0) return ViennaCLSuccess;
+  VCL_CUDA(b, cudaMalloc(ptr, bytes));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDAMemFree(ViennaCLBackend b, void *ptr)
+{
+  VCL_CHECK_BACKEND(b);
+  if (!ptr) return ViennaCLSuccess;
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  VCL_CUDA(b, cudaFree(ptr));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDAMemWrite(ViennaCLBackend b, void *dst, size_t off, const void *src, size_t bytes, ViennaCLInt async)
+{
+  VCL_CHECK_BACKEND(b);
+  if (bytes == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, dst && src, "null pointer");
+  VCL_CUDA(b, cudaMemcpyAsync((char*)dst + off, src, bytes, cudaMemcpyHostToDevice, b->stream));
+  if (!async) VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDAMemRead(ViennaCLBackend b, const void *src, size_t off, void *dst, size_t bytes, ViennaCLInt async)
+{
+  VCL_CHECK_BACKEND(b);
+  if (bytes == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, dst && src, "null pointer");
+  VCL_CUDA(b, cudaMemcpyAsync(dst, (const char*)src + off, bytes, cudaMemcpyDeviceToHost, b->stream));
+  if (!async) VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDAMemCopy(ViennaCLBackend b, const void *src, size_t soff, void *dst, size_t doff, size_t bytes)
+{
+  VCL_CHECK_BACKEND(b);
+  if (bytes == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, dst && src, "null pointer");
+  VCL_CUDA(b, cudaMemcpyAsync((char*)dst + doff, (const char*)src + soff, bytes, cudaMemcpyDeviceToDevice, b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDAMemSet(ViennaCLBackend b, void *dst, ViennaCLInt value, size_t bytes)
+{
+  VCL_CHECK_BACKEND(b);
+  if (bytes == 0) return ViennaCLSuccess;
+  VCL_CUDA(b, cudaMemsetAsync(dst, value, bytes, b->stream));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLHostAllocPinned(ViennaCLBackend b, void **ptr, size_t bytes)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_CUDA(b, cudaMallocHost(ptr, bytes ? bytes : 1));
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLHostFreePinned(ViennaCLBackend b, void *ptr)
+{
+  VCL_CHECK_BACKEND(b);
+  if (ptr) VCL_CUDA(b, cudaFreeHost(ptr));
+  return ViennaCLSuccess;
+}
+
+} // extern "C"

@@ -1,0 +1,144 @@
+// common.cuh -- shared internals of libvcl_b200.so (backend handle, error plumbing, deterministic reductions).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "vcl_b200.h"
+
+typedef unsigned int u32;
+
+// ------------------------------------------------------------------------------------------------
+// Backend handle (the "stream and/or device descriptors" libviennacl left as a TODO,
+// libviennacl/src/viennacl_private.hpp:38-41).  A handle is single-threaded; handles are independent.
+// ------------------------------------------------------------------------------------------------
+struct SolverState;   // solvers.cu
+
+struct ViennaCLBackend_impl
+{
+  int device = 0;
+  int sm_count = 148;
+  size_t l2_bytes = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  cudaStream_t comm_stream = nullptr;          // halo traffic (multi-GPU)
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;  // generic fork/join events
+  cudaEvent_t tm_begin = nullptr, tm_end = nullptr;
+  std::string last_error;
+  long long launches = 0;
+
+  // reduction scratch shared by all kernels launched through this handle (kernels on one stream never overlap)
+  double *partials = nullptr;                  // [VCL_MAX_QUANT][VCL_MAX_BLOCKS]
+  unsigned int *tickets = nullptr;             // [16], zero between kernels
+  double *dscal = nullptr;                     // 64 device doubles: results of stand-alone reductions etc.
+  double *hscal = nullptr;                     // pinned mirror of dscal
+  SolverState *dstate = nullptr;               // device solver state
+  SolverState *hstate = nullptr;               // pinned mirror
+  void *flush_buf = nullptr; size_t flush_bytes = 0;
+
+  // workspace pool for solver temporaries (grown on demand, freed at destroy)
+  void *ws = nullptr; size_t ws_bytes = 0;
+
+  // NCCL (dlopen'ed lazily, dist.cu)
+  void *nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+#define VCL_MAX_BLOCKS 2048     // upper bound on the grid of any reducing kernel
+#define VCL_MAX_QUANT  64       // quantities reduced at once (GMRES stage 1 reduces up to VCL_GMRES_MAX_KRYLOV dots)
+
+ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, const char *file, int line);
+ViennaCLStatus vcl_cuda_fail(ViennaCLBackend b, cudaError_t e, const char *what, const char *file, int line);
+ViennaCLStatus vcl_ws_reserve(ViennaCLBackend b, size_t bytes);   // ensures b->ws holds >= bytes
+
+#define VCL_CHECK_BACKEND(b) do { if (!(b)) return ViennaCLB200NotInitialized; } while (0)
+#define VCL_REQUIRE(b, cond, msg) do { if (!(cond)) return vcl_fail((b), ViennaCLB200InvalidArgument, msg, __FILE__, __LINE__); } while (0)
+#define VCL_CUDA(b, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return vcl_cuda_fail((b), e__, #expr, __FILE__, __LINE__); } while (0)
+#define VCL_TRY(expr) do { ViennaCLStatus s__ = (expr); if (s__ != ViennaCLSuccess) return s__; } while (0)
+// after every launch (cf. VIENNACL_CUDA_LAST_ERROR_CHECK, linalg/cuda/common.hpp:30,165-175)
+#define VCL_LAUNCHED(b, name) do { (b)->launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return vcl_cuda_fail((b), e__, name, __FILE__, __LINE__); } while (0)
+
+static inline int vcl_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+  // XOR butterfly: every lane ends with the same, order-deterministic value.
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// Sum of NQ per-thread values over the block; result valid in thread 0.  smem: NQ * 32 doubles.
+template<int NQ>
+__device__ __forceinline__ void block_sum(double (&v)[NQ], double *smem)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) v[q] = warp_sum(v[q]);
+  __syncthreads();               // smem may still be in use by the caller
+  if (lane == 0)
+  {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) smem[q * 32 + wid] = v[q];
+  }
+  __syncthreads();
+  if (wid == 0)
+  {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+    {
+      double t = (lane < nw) ? smem[q * 32 + lane] : 0.0;
+      v[q] = warp_sum(t);
+    }
+  }
+}
+
+// Grid-wide deterministic reduction, second stage done by whichever block finishes last (fixed summation order, so the
+// result does not depend on which block that is).  Every block calls this with its NQ block-local sums (valid in thread 0
+// after block_sum).  Returns true in ALL threads of the last block, with totals[] valid in thread 0 of that block.
+// partials: [NQ][VCL_MAX_BLOCKS]; ticket: one counter, left at zero on exit.
+template<int NQ>
+__device__ __forceinline__ bool grid_sum_last_block(double (&v)[NQ], double *partials, unsigned int *ticket, double *smem)
+{
+  __shared__ bool s_last;
+  block_sum<NQ>(v, smem);
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) partials[q * VCL_MAX_BLOCKS + blockIdx.x] = v[q];
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  double acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+  {
+    acc[q] = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+      acc[q] += __ldcg(partials + q * VCL_MAX_BLOCKS + i);
+  }
+  block_sum<NQ>(acc, smem);
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = acc[q];
+    *ticket = 0u;
+  }
+  return true;
+}
+
+#endif // __CUDACC__

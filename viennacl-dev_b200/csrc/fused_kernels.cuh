@@ -1,0 +1,370 @@
+// fused_kernels.cuh -- fused vector-update + inner-product kernels of the pipelined Krylov solvers and the
+// fused SpMV epilogues.  Replaces cuda/iterative_operations.hpp:43-103 (K5), :733-886 (K9, K10), :1597-1894 (K14-K17)
+// and the reduction halves of K6-K8 / K11-K13.
+//
+// Common design: persistent grid (a few CTAs per SM), 16-byte vector loads, per-CTA partial sums reduced in a fixed order
+// by whichever CTA finishes last (grid_sum_last_block) -> results are run-to-run deterministic; the last CTA also advances
+// the solver's scalar recurrences in device memory (SolverState), which removes the per-iteration blocking D2H copy of the
+// reference drivers (cg.hpp:168, bicgstab.hpp:180).
+#pragma once
+#include "common.cuh"
+#include "solver_state.cuh"
+
+#define VEC_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// Scalar recurrences (run by one thread)
+// ------------------------------------------------------------------------------------------------
+// cg.hpp:170-180.  sums[0] = <r,r>, sums[1] = <Ap,Ap>, sums[2] = <p,Ap>
+__device__ __forceinline__ void cg_advance(SolverState *st)
+{
+  const double rr = st->sums[0], ApAp = st->sums[1], pAp = st->sums[2];
+  st->iters += 1;
+  st->est = sqrt(fabs(rr / st->norm_rhs_sq));
+  if (fabs(rr / st->norm_rhs_sq) < st->tol * st->tol || fabs(rr) < st->abs_tol * st->abs_tol) { st->done = VCL_CONVERGED; return; }
+  if (st->iters >= st->maxit) { st->done = VCL_MAXIT; return; }
+  const double alpha = rr / pAp;
+  st->alpha = alpha;
+  st->beta = (alpha * alpha * ApAp - rr) / rr;
+}
+
+// bicgstab.hpp:184-199.  chunks: 0 <r,r0*>, 1 <As,As>, 2 <As,s>, 3 <Ap,r0*>, 4 <As,r0*>, 5 <s,s>
+__device__ __forceinline__ void bicgstab_advance(SolverState *st)
+{
+  const double r_r0 = st->sums[0], As_As = st->sums[1], As_s = st->sums[2], Ap_r0 = st->sums[3], As_r0 = st->sums[4], s_s = st->sums[5];
+  st->iters += 1;
+  st->alpha = r_r0 / Ap_r0;
+  st->beta = -As_r0 / Ap_r0;
+  const double omega = As_s / As_As;
+  st->omega = omega;
+  const double res = sqrt(s_s - 2.0 * omega * As_s + omega * omega * As_As);
+  st->residual_norm = res;
+  st->est = fabs(res / st->norm_rhs);
+  if (fabs(res / st->norm_rhs) < st->tol || res < st->abs_tol) st->done = VCL_CONVERGED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused SpMV epilogue:  Ap[r] = dot (optionally / diag[r]);  <Ap,Ap>, <p,Ap>, <Ap,r0*>
+// host_based/iterative_operations.hpp:58-103.  STEP selects what the last CTA does after the reduction.
+// ------------------------------------------------------------------------------------------------
+enum { STEP_NONE = 0, STEP_CG = 1, STEP_BICGSTAB = 2, STEP_PBICG_ALPHA = 3, STEP_PBICG_OMEGA = 4 };
+
+template<int STEP, bool USE_R0, bool JACOBI>
+struct EpiFused
+{
+  double *Ap; const double *p; const double *r0; const double *diag;
+  double *partials; unsigned int *ticket;
+  SolverState *st;                 // NULL in per-op API mode
+  double *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
+  double acc[3];
+  static constexpr int NQ = 3;
+
+  __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
+  __device__ __forceinline__ void row(u32 r, double dot)
+  {
+    if (JACOBI) dot = dot / diag[r];
+    Ap[r] = dot;
+    acc[0] = fma(dot, dot, acc[0]);
+    acc[1] = fma(p[r], dot, acc[1]);
+    if (USE_R0) acc[2] = fma(dot, r0[r], acc[2]);
+  }
+  __device__ __forceinline__ void finish(double *smem)
+  {
+    if (grid_sum_last_block<3>(acc, partials, ticket, smem) && threadIdx.x == 0)
+    {
+      if (out0) *out0 = acc[0];
+      if (out1) *out1 = acc[1];
+      if (USE_R0 && out2) *out2 = acc[2];
+      if (STEP == STEP_CG) cg_advance(st);
+      if (STEP == STEP_BICGSTAB) bicgstab_advance(st);
+      if (STEP == STEP_PBICG_ALPHA) st->alpha = st->ip_rr0 / acc[2];                       // bicgstab.hpp:449
+      if (STEP == STEP_PBICG_OMEGA) { const double nt = sqrt(acc[0]); st->omega = acc[1] / (nt * nt); }  // bicgstab.hpp:455-456
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Helpers for streaming vector kernels: every thread handles pairs (16-byte accesses); a scalar tail covers odd n.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double *p, long long i) { return *reinterpret_cast<const double2*>(p + i); }
+__device__ __forceinline__ void st2(double *p, long long i, double2 v) { *reinterpret_cast<double2*>(p + i) = v; }
+
+// ------------------------------------------------------------------------------------------------
+// CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap, double alpha_v, double beta_v,
+                 SolverState *st, double *partials, unsigned int *ticket, double *out_rr)
+{
+  __shared__ double s_red[32];
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  const double alpha = st ? st->alpha : alpha_v;
+  const double beta  = st ? st->beta  : beta_v;
+  double acc[1] = {0.0};
+  const long long npairs = n >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = i * 2;
+    double2 vx = ld2(x, k), vp = ld2(p, k), vr = ld2(r, k); const double2 va = ld2(Ap, k);
+    vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
+    vr.x = fma(-alpha, va.x, vr.x);      vr.y = fma(-alpha, va.y, vr.y);
+    vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
+    acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
+    st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const long long k = n - 1;
+    double vp = p[k], vr = r[k];
+    x[k] = fma(alpha, vp, x[k]);
+    vr = fma(-alpha, Ap[k], vr);
+    vp = fma(beta, vp, vr);
+    acc[0] = fma(vr, vr, acc[0]);
+    p[k] = vp; r[k] = vr;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_rr = acc[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// BiCGStab: s = r - alpha Ap with alpha = <r,r0*>/<Ap,r0*> taken from device memory; <s,s>
+// (host_based/iterative_operations.hpp:518-563; cuda K9 :733-788 recomputes alpha in every CTA, here it is two loads)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *Ap,
+                         const double *in_r_r0, const double *in_Ap_r0,
+                         SolverState *st, double *partials, unsigned int *ticket, double *out_ss)
+{
+  __shared__ double s_red[32];
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  const double alpha = (*in_r_r0) / (*in_Ap_r0);
+  double acc[1] = {0.0};
+  const long long npairs = n >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = i * 2;
+    const double2 vr = ld2(r, k), va = ld2(Ap, k);
+    double2 vs;
+    vs.x = fma(-alpha, va.x, vr.x); vs.y = fma(-alpha, va.y, vr.y);
+    acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
+    st2(s, k, vs);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const long long k = n - 1;
+    const double vs = fma(-alpha, Ap[k], r[k]);
+    acc[0] = fma(vs, vs, acc[0]);
+    s[k] = vs;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_ss = acc[0];
+}
+
+// x += alpha p + omega s;  r = s - omega As;  p = r + beta (p - omega Ap);  <r,r0*>     (host_based/iterative_operations.hpp:572-621)
+__global__ void __launch_bounds__(VEC_THREADS)
+bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double omega_v, const double *s,
+                       double *r, const double *As, double beta_v, const double *Ap, const double *r0,
+                       SolverState *st, double *partials, unsigned int *ticket, double *out_r_r0)
+{
+  __shared__ double s_red[32];
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  const double alpha = st ? st->alpha : alpha_v;
+  const double beta  = st ? st->beta  : beta_v;
+  const double omega = st ? st->omega : omega_v;
+  double acc[1] = {0.0};
+  const long long npairs = n >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = i * 2;
+    double2 vx = ld2(x, k), vp = ld2(p, k); const double2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
+    double2 vr;
+    vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
+    vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
+    vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
+    acc[0] = fma(vr.x, v0.x, acc[0]);                acc[0] = fma(vr.y, v0.y, acc[0]);
+    st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const long long k = n - 1;
+    double vp = p[k]; const double vs = s[k];
+    x[k] += alpha * vp + omega * vs;
+    const double vr = fma(-omega, As[k], vs);
+    vp = fma(beta, fma(-omega, Ap[k], vp), vr);
+    acc[0] = fma(vr, r0[k], acc[0]);
+    r[k] = vr; p[k] = vp;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0)
+  {
+    *out_r_r0 = acc[0];
+    if (st != nullptr && st->iters >= st->maxit) st->done = VCL_MAXIT;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Left-preconditioned BiCGStab (bicgstab.hpp:398-489), device-resident scalars
+// ------------------------------------------------------------------------------------------------
+// s = r - alpha t0                                            (bicgstab.hpp:451)
+__global__ void __launch_bounds__(VEC_THREADS)
+pbicg_s_kernel(long long n, double *s, const double *r, const double *t0, const SolverState *st)
+{
+  if (st->done != VCL_RUNNING || st->need_restart) return;
+  const double alpha = st->alpha;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s[i] = fma(-alpha, t0[i], r[i]);
+}
+
+// x += alpha p + omega s; r = s - omega t1; ||r||^2, <r,r0*>; then beta / restart bookkeeping   (bicgstab.hpp:458-474)
+__global__ void __launch_bounds__(VEC_THREADS)
+pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double *r, const double *t1, const double *r0,
+                SolverState *st, double *partials, unsigned int *ticket)
+{
+  __shared__ double s_red[64];
+  if (st->done != VCL_RUNNING || st->need_restart) return;
+  const double alpha = st->alpha, omega = st->omega;
+  double acc[2] = {0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    const double vs = s[i];
+    x[i] += alpha * p[i] + omega * vs;
+    const double vr = fma(-omega, t1[i], vs);
+    r[i] = vr;
+    acc[0] = fma(vr, vr, acc[0]);
+    acc[1] = fma(vr, r0[i], acc[1]);
+  }
+  if (grid_sum_last_block<2>(acc, partials, ticket, s_red) && threadIdx.x == 0)
+  {
+    const int i = st->iters;            // index of the iteration just finished
+    st->iters = i + 1;
+    const double res = sqrt(acc[0]);
+    st->residual_norm = res;
+    st->est = fabs(res / st->norm_rhs);
+    if (res / st->norm_rhs < st->tol || res < st->abs_tol) { st->done = VCL_CONVERGED; return; }
+    const double new_ip = acc[1];
+    st->beta = new_ip / st->ip_rr0 * alpha / omega;
+    st->ip_rr0 = new_ip;
+    if (new_ip == 0.0 || omega == 0.0 || i - st->last_restart > st->restart_every) st->need_restart = 1;
+    if (st->iters >= st->maxit) st->done = VCL_MAXIT;
+  }
+}
+
+// p -= omega t0; p = r + beta p                               (bicgstab.hpp:479-480)
+__global__ void __launch_bounds__(VEC_THREADS)
+pbicg_p_kernel(long long n, double *p, const double *r, const double *t0, const SolverState *st)
+{
+  if (st->done != VCL_RUNNING || st->need_restart) return;
+  const double beta = st->beta, omega = st->omega;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = fma(beta, fma(-omega, t0[i], p[i]), r[i]);
+}
+
+// restart: r = (b - r) [/ diag]; p = r; r0 = r; ip_rr0 = ||r||^2     (bicgstab.hpp:430-442; r holds A*x on entry)
+template<bool JACOBI>
+__global__ void __launch_bounds__(VEC_THREADS)
+pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double *r0, const double *diag,
+                     SolverState *st, double *partials, unsigned int *ticket)
+{
+  __shared__ double s_red[32];
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    double v = b[i] - r[i];
+    if (JACOBI) v = v / diag[i];
+    r[i] = v; p[i] = v; r0[i] = v;
+    acc[0] = fma(v, v, acc[0]);
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0)
+  {
+    const double nrm = sqrt(acc[0]);
+    st->ip_rr0 = nrm * nrm;
+    st->need_restart = 0;
+    st->last_restart = st->iters;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMRES (classical Gram-Schmidt, gmres.hpp:241-284)
+// ------------------------------------------------------------------------------------------------
+// stage 1: h_j = <v_j, v_k>, j < k, ALL k vectors in one pass (the reference sweeps 7 at a time and re-reads v_k,
+// cuda/iterative_operations.hpp:1690-1735).  KMAX = compile-time bound on k.
+template<int KMAX>
+__global__ void __launch_bounds__(VEC_THREADS)
+gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double *out_h, int out_stride,
+                 double *partials, unsigned int *ticket)
+{
+  __shared__ double s_red[KMAX * 32];
+  const double *vk = basis + (size_t)k * isz;
+  double acc[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) acc[j] = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    const double v = vk[i];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) acc[j] = fma(basis[(size_t)j * isz + i], v, acc[j]);
+  }
+  if (grid_sum_last_block<KMAX>(acc, partials, ticket, s_red) && threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < k) out_h[(size_t)j * out_stride] = acc[j];
+  }
+}
+
+// stage 2: v_k -= sum_j h_j v_j; R[j + k*m] = h_j; ||v_k||^2       (host_based/iterative_operations.hpp:852-893)
+__global__ void __launch_bounds__(VEC_THREADS)
+gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double *h, int h_stride,
+                 double *R, int krylov_dim, double *out_norm_sq, double *partials, unsigned int *ticket)
+{
+  __shared__ double s_red[32];
+  __shared__ double s_h[VCL_GMRES_MAX_KRYLOV];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) s_h[j] = h[(size_t)j * h_stride];
+  __syncthreads();
+  double *vk = basis + (size_t)k * isz;
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    double v = vk[i];
+    for (int j = 0; j < k; ++j) v = fma(-s_h[j], basis[(size_t)j * isz + i], v);
+    acc[0] = fma(v, v, acc[0]);
+    vk[i] = v;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
+  {
+    for (int j = threadIdx.x; j < k; j += blockDim.x) R[(size_t)j + (size_t)k * krylov_dim] = s_h[j];
+    if (threadIdx.x == 0) *out_norm_sq = acc[0];
+  }
+}
+
+// normalize: R[off] = ||v_k||; v_k /= ||v_k||; xi_k = <r, v_k>      (host_based/iterative_operations.hpp:733-778)
+__global__ void __launch_bounds__(VEC_THREADS)
+gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, int offset_in_R, const double *in_norm_sq,
+                       double *out_r_dot_vk, double *partials, unsigned int *ticket)
+{
+  __shared__ double s_red[32];
+  const double nrm = sqrt(*in_norm_sq);
+  if (blockIdx.x == 0 && threadIdx.x == 0) R[offset_in_R] = nrm;
+  double acc[1] = {0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    const double v = vk[i] / nrm;
+    acc[0] = fma(res[i], v, acc[0]);
+    vk[i] = v;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_r_dot_vk = acc[0];
+}
+
+// x += c_0 r + sum_{j=1}^{k-1} c_j v_{j-1}                         (host_based/iterative_operations.hpp:895-922)
+__global__ void __launch_bounds__(VEC_THREADS)
+gmres_update_kernel(long long n, double *x, const double *res, const double *basis, long long isz, const double *coef, int k)
+{
+  __shared__ double s_c[VCL_GMRES_MAX_KRYLOV];
+  for (int j = threadIdx.x; j < max(k, 1); j += blockDim.x) s_c[j] = coef[j];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  {
+    double v = x[i];
+    v = fma(s_c[0], res[i], v);
+    for (int j = 1; j < k; ++j) v = fma(s_c[j], basis[(size_t)(j - 1) * isz + i], v);
+    x[i] = v;
+  }
+}

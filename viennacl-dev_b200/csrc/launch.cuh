@@ -1,0 +1,54 @@
+// launch.cuh -- grid sizing + launch of the SpMV kernel templates (shared by spmv.cu and solvers.cu).
+#pragma once
+#include <algorithm>
+#include "spmv_kernels.cuh"
+
+// Resident CTAs per SM for a kernel, queried once per instantiation (all B200s of a box are identical).
+template<class K>
+static int vcl_occupancy(K kernel, int threads)
+{
+  static int cached = 0;
+  if (cached == 0)
+  {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n <= 0) n = 1;
+    cached = n;
+  }
+  return cached;
+}
+
+static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Grids are persistent: (resident CTAs per SM) x (SM count) CTAs loop over the row blocks, so the number of per-CTA
+// reduction partials stays small and block b's partial is a deterministic function of the matrix alone.
+template<class Epi>
+static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &A, XVec xv, Epi epi)
+{
+  CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.num_blocks};
+  if (A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx))
+  {
+    const int occ = vcl_occupancy(csr_stream_kernel<Epi>, CSR_BLOCK_THREADS);
+    int grid = std::min(A.num_blocks, std::min(b->sm_count * occ, VCL_MAX_BLOCKS));
+    csr_stream_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+    VCL_LAUNCHED(b, "csr_stream_kernel");
+  }
+  else
+  {
+    const int occ = vcl_occupancy(csr_scalar_kernel<Epi>, 256);
+    int grid = std::max(1, std::min(vcl_div_up(A.rows, 256), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+    csr_scalar_kernel<Epi><<<grid, 256, 0, b->stream>>>(d, xv, epi);
+    VCL_LAUNCHED(b, "csr_scalar_kernel");
+  }
+  return ViennaCLSuccess;
+}
+
+template<class Epi>
+static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
+{
+  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values};
+  const int occ = vcl_occupancy(sell_kernel<Epi>, 256);
+  int grid = std::max(1, std::min(vcl_div_up(A.rows, 256), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+  sell_kernel<Epi><<<grid, 256, 0, b->stream>>>(d, xv, epi);
+  VCL_LAUNCHED(b, "sell_kernel");
+  return ViennaCLSuccess;
+}

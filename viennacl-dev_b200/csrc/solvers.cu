@@ -1,0 +1,602 @@
+// solvers.cu -- solver drivers (CG / BiCGStab / GMRES) and the per-step C-ABI entry points.
+// Drivers restate linalg/cg.hpp:128-187, bicgstab.hpp:97-215 and :398-489, gmres.hpp:181-367 with the iteration loop kept
+// next to the kernels: scalars live in device memory (SolverState), iterations are enqueued in batches, and the host looks
+// at the state once per batch (with a monitor callback installed: once per iteration, as the reference's contract demands).
+#include "fused_kernels.cuh"
+#include "launch.cuh"
+#include "blas1.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+struct MatOp
+{
+  int fmt;                 // 0 CSR, 1 SELL
+  ViennaCLCUDADcsr csr;
+  ViennaCLCUDADsell sell;
+  int rows() const { return fmt == 0 ? csr.rows : sell.rows; }
+  int cols() const { return fmt == 0 ? csr.cols : sell.cols; }
+};
+
+template<class Epi>
+ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const double *x, Epi epi)
+{
+  XVec xv = {x, 0, 1};
+  if (A.fmt == 0) return vcl_launch_csr(b, A.csr, xv, epi);
+  return vcl_launch_sell(b, A.sell, xv, epi);
+}
+
+ViennaCLStatus plain_prod(ViennaCLBackend b, const MatOp &A, const double *x, double *y)
+{
+  EpiAxpby epi = {y, 0, 1, 1.0, 0.0};
+  return launch_prod(b, A, x, epi);
+}
+
+int vec_grid(ViennaCLBackend b, long long n)
+{
+  long long want = (n / 2 + VEC_THREADS - 1) / VEC_THREADS;
+  return (int)std::max(1LL, std::min(want, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+}
+
+ViennaCLStatus check_matrix(ViennaCLBackend b, const MatOp &A)
+{
+  VCL_REQUIRE(b, A.rows() >= 0 && A.rows() == A.cols(), "solvers need a square matrix");
+  if (A.fmt == 0) VCL_REQUIRE(b, A.rows() == 0 || (A.csr.row_ptr && (A.csr.nnz == 0 || (A.csr.col_idx && A.csr.values))), "null CSR array");
+  else VCL_REQUIRE(b, A.rows() == 0 || (A.sell.columns_per_block && A.sell.block_start && A.sell.rows_per_block > 0), "bad SELL matrix");
+  return ViennaCLSuccess;
+}
+
+// carve 256-byte aligned sub-buffers out of the backend workspace
+struct Carver
+{
+  char *base; size_t off;
+  explicit Carver(void *p) : base((char*)p), off(0) {}
+  double *take(size_t n) { double *p = (double*)(base + off); off += ((n * sizeof(double) + 255) / 256) * 256; return p; }
+  static size_t need(size_t n) { return ((n * sizeof(double) + 255) / 256) * 256; }
+};
+
+ViennaCLStatus push_state(ViennaCLBackend b)
+{
+  VCL_CUDA(b, cudaMemcpyAsync(b->dstate, b->hstate, sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));   // hstate is reused as the read-back mirror
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus pull_state(ViennaCLBackend b)
+{
+  VCL_CUDA(b, cudaMemcpyAsync(b->hstate, b->dstate, sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  return ViennaCLSuccess;
+}
+
+const int kBatch = 32;   // iterations enqueued between two looks at the device state
+
+// ------------------------------------------------------------------------------------------------
+// CG  (cg.hpp:128-187)
+// ------------------------------------------------------------------------------------------------
+ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, tag != nullptr, "null tag");
+  VCL_TRY(check_matrix(b, A));
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: only the unpreconditioned pipelined path is provided (DESIGN.md, next rows)");
+  const long long n = A.rows();
+  tag->iters = 0; tag->error = 0.0;
+  if (n == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, rhs && x, "null vector");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+  VCL_TRY(vcl_ws_reserve(b, 3 * Carver::need(n)));
+  Carver cv(b->ws);
+  double *r = cv.take(n), *p = cv.take(n), *Ap = cv.take(n);
+
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_TRY(plain_prod(b, A, p, Ap));
+  VCL_TRY(vcl_dot_async(b, n, r, 0, 1, r, 0, 1, b->dscal + 0));
+  VCL_TRY(vcl_dot_async(b, n, p, 0, 1, Ap, 0, 1, b->dscal + 1));
+  VCL_TRY(vcl_dot_async(b, n, Ap, 0, 1, Ap, 0, 1, b->dscal + 2));
+  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 3 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+
+  double norm_rhs_squared = std::sqrt(b->hscal[0]); norm_rhs_squared *= norm_rhs_squared;          // cg.hpp:147
+  if (norm_rhs_squared <= tag->abs_tolerance * tag->abs_tolerance) return ViennaCLSuccess;         // cg.hpp:149-150
+  const double rr = norm_rhs_squared;
+  const double alpha = rr / b->hscal[1];
+  double beta = std::sqrt(b->hscal[2]); beta = (alpha * alpha * beta * beta - rr) / rr;            // cg.hpp:153-154
+
+  SolverState *h = b->hstate;
+  std::memset(h, 0, sizeof(SolverState));
+  h->alpha = alpha; h->beta = beta; h->norm_rhs_sq = norm_rhs_squared; h->norm_rhs = std::sqrt(norm_rhs_squared);
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = rr;
+  VCL_TRY(push_state(b));
+  SolverState *st = b->dstate;
+
+  const int grid = vec_grid(b, n);
+  const int batch = tag->monitor ? 1 : kBatch;
+  int launched = 0;
+  while (launched < tag->max_iterations)
+  {
+    const int nb = std::min(batch, tag->max_iterations - launched);
+    for (int k = 0; k < nb; ++k)
+    {
+      cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, &st->sums[0]);
+      VCL_LAUNCHED(b, "cg_update_kernel");
+      EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, p, epi));
+    }
+    launched += nb;
+    VCL_TRY(pull_state(b));
+    if (tag->monitor && tag->monitor(x, h->est, tag->monitor_user)) break;          // cg.hpp:174 (monitor first, then the test)
+    if (h->done != VCL_RUNNING) break;
+  }
+  tag->iters = h->iters;
+  tag->error = std::sqrt(std::fabs(h->sums[0]) / norm_rhs_squared);                 // cg.hpp:184
+  return ViennaCLSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined BiCGStab  (bicgstab.hpp:97-215)
+// ------------------------------------------------------------------------------------------------
+ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  const long long n = A.rows();
+  VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
+  Carver cv(b->ws);
+  double *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *Ap = cv.take(n), *s = cv.take(n), *As = cv.take(n);
+
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r0, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  double ss = 0.0;
+  VCL_TRY(vcl_dot_host(b, n, r, 0, 1, r, 0, 1, &ss));
+  const double norm_rhs = std::sqrt(ss);
+  if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                       // bicgstab.hpp:140-141
+
+  SolverState *h = b->hstate;
+  std::memset(h, 0, sizeof(SolverState));
+  h->norm_rhs = norm_rhs; h->norm_rhs_sq = norm_rhs * norm_rhs; h->residual_norm = norm_rhs;
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations;
+  h->sums[0] = norm_rhs * norm_rhs;                                                 // bicgstab.hpp:131
+  VCL_TRY(push_state(b));
+  SolverState *st = b->dstate;
+
+  const int grid = vec_grid(b, n);
+  const int batch = tag->monitor ? 1 : kBatch;
+  int launched = 0;
+  bool stopped = false;
+  while (launched < tag->max_iterations && !stopped)
+  {
+    const int nb = std::min(batch, tag->max_iterations - launched);
+    for (int k = 0; k < nb; ++k)
+    {
+      EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, p, e1));
+      bicgstab_update_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, &st->sums[0], &st->sums[3], st, b->partials, b->tickets, &st->sums[5]);
+      VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
+      EpiFused<STEP_BICGSTAB, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[4], {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, s, e2));
+      if (tag->monitor)
+      {
+        // the reference shows the monitor the iterate BEFORE this step's vector update (bicgstab.hpp:196-206)
+        VCL_TRY(pull_state(b));
+        if (tag->monitor(x, h->est, tag->monitor_user)) { stopped = true; break; }
+        if (h->done != VCL_RUNNING) break;
+      }
+      bicgstab_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, 0.0, p, 0.0, s, r, As, 0.0, Ap, r0, st, b->partials, b->tickets, &st->sums[0]);
+      VCL_LAUNCHED(b, "bicgstab_update_kernel");
+    }
+    launched += nb;
+    VCL_TRY(pull_state(b));
+    if (h->done != VCL_RUNNING) break;
+  }
+  tag->iters = h->iters;
+  tag->error = h->residual_norm / norm_rhs;                                          // bicgstab.hpp:212
+  return ViennaCLSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Left-preconditioned BiCGStab with Jacobi  (bicgstab.hpp:398-489, jacobi_precond.hpp:103-130)
+// Five kernels per iteration instead of the reference's 2 SpMV + 2 element_div + ~12 BLAS-1 launches + ~6 blocking
+// scalar read-backs; the divide by diag(A) is folded into the SpMV epilogue.
+// ------------------------------------------------------------------------------------------------
+ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
+  const long long n = A.rows();
+  VCL_TRY(vcl_ws_reserve(b, 7 * Carver::need(n)));
+  Carver cv(b->ws);
+  double *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *t0 = cv.take(n), *t1 = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
+
+  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  double ss = 0.0;
+  VCL_TRY(vcl_dot_host(b, n, rhs, 0, 1, rhs, 0, 1, &ss));
+  const double norm_rhs = std::sqrt(ss);
+  if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                       // bicgstab.hpp:424-425
+
+  SolverState *h = b->hstate;
+  std::memset(h, 0, sizeof(SolverState));
+  h->norm_rhs = norm_rhs; h->norm_rhs_sq = norm_rhs * norm_rhs; h->residual_norm = norm_rhs;
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations;
+  h->restart_every = tag->max_iterations_before_restart;
+  h->need_restart = 1;
+  VCL_TRY(push_state(b));
+  SolverState *st = b->dstate;
+
+  const int grid = vec_grid(b, n);
+  const int batch = tag->monitor ? 1 : kBatch;
+  while (true)
+  {
+    if (h->need_restart)
+    {
+      VCL_TRY(plain_prod(b, A, x, r));                                               // residual = A*x
+      pbicg_restart_kernel<true><<<grid, VEC_THREADS, 0, b->stream>>>(n, rhs, r, p, r0, diag, st, b->partials, b->tickets);
+      VCL_LAUNCHED(b, "pbicg_restart_kernel");
+      h->need_restart = 0;
+    }
+    const int remaining = tag->max_iterations - h->iters;
+    if (remaining <= 0) break;
+    const int nb = std::min(batch, remaining);
+    for (int k = 0; k < nb; ++k)
+    {
+      EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, p, e1));
+      pbicg_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, t0, st);
+      VCL_LAUNCHED(b, "pbicg_s_kernel");
+      EpiFused<STEP_PBICG_OMEGA, false, true> e2 = {t1, s, nullptr, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, s, e2));
+      pbicg_xr_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, s, r, t1, r0, st, b->partials, b->tickets);
+      VCL_LAUNCHED(b, "pbicg_xr_kernel");
+      pbicg_p_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, p, r, t0, st);
+      VCL_LAUNCHED(b, "pbicg_p_kernel");
+    }
+    VCL_TRY(pull_state(b));
+    if (tag->monitor && tag->monitor(x, h->est, tag->monitor_user)) break;
+    if (h->done != VCL_RUNNING) break;
+  }
+  tag->iters = h->iters;
+  tag->error = h->residual_norm / norm_rhs;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, tag != nullptr, "null tag");
+  VCL_TRY(check_matrix(b, A));
+  tag->iters = 0; tag->error = 0.0;
+  if (A.rows() == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, rhs && x, "null vector");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+  if (tag->precond == ViennaCLB200PrecondJacobi) return bicgstab_jacobi(b, A, rhs, x, tag);
+  return bicgstab_pipelined(b, A, rhs, x, tag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMRES(m), pipelined simpler-GMRES with classical Gram-Schmidt  (gmres.hpp:181-367)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VEC_THREADS)
+scale_residual_kernel(long long n, double *res, double rho0)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    res[i] = res[i] / rho0;
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+residual_kernel(long long n, double *res, const double *rhs)     // res = rhs - res
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    res[i] = rhs[i] - res[i];
+}
+
+ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const double *basis, long long n, long long isz, int k, double *out_h, int stride)
+{
+  if (k <= 8)       gmres_gs1_kernel<8><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  else if (k <= 16) gmres_gs1_kernel<16><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  else if (k <= 32) gmres_gs1_kernel<32><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  else              gmres_gs1_kernel<64><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  VCL_LAUNCHED(b, "gmres_gs1_kernel");
+  return ViennaCLSuccess;
+}
+
+int scalar_grid(ViennaCLBackend b, long long n)
+{
+  return (int)std::max(1LL, std::min((n + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+}
+
+ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, tag != nullptr, "null tag");
+  VCL_TRY(check_matrix(b, A));
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "GMRES: only the unpreconditioned pipelined path is provided (DESIGN.md, next rows)");
+  VCL_REQUIRE(b, tag->krylov_dim >= 1 && tag->krylov_dim <= VCL_GMRES_MAX_KRYLOV, "krylov_dim must be in [1, 64]");
+  const long long n = A.rows();
+  tag->iters = 0; tag->error = 0.0;
+  if (n == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, rhs && x, "null vector");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+
+  const int m = tag->krylov_dim;
+  const long long isz = (n + 127) / 128 * 128;                      // internal_size(): padded to 128 (forwards.h:385, gmres.hpp:192)
+  const size_t small = Carver::need((size_t)m * m) + 4 * Carver::need(m);
+  VCL_TRY(vcl_ws_reserve(b, Carver::need(n) + Carver::need((size_t)isz * m) + small));
+  Carver cv(b->ws);
+  double *res = cv.take(n), *V = cv.take((size_t)isz * m), *R = cv.take((size_t)m * m);
+  double *d_xi = cv.take(m), *d_h = cv.take(m), *d_coef = cv.take(m);
+  double *d_nsq = b->dscal + 8, *d_junk = b->dscal + 9;
+
+  std::vector<double> hR((size_t)m * m), xi(m), eta(m), coef(m, 0.0);
+
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(res, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(R, 0, sizeof(double) * m * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_xi, 0, sizeof(double) * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_coef, 0, sizeof(double) * m, b->stream));
+  double ss = 0.0;
+  VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
+  const double norm_rhs = std::sqrt(ss);
+  double rho_0 = norm_rhs, rho = 1.0;
+
+  unsigned max_restarts = (unsigned)tag->max_iterations / (unsigned)m;         // gmres.hpp:74-80
+  if (max_restarts > 0 && max_restarts * (unsigned)m == (unsigned)tag->max_iterations) max_restarts -= 1;
+
+  const int grid = scalar_grid(b, n);
+  for (unsigned restart = 0; restart <= max_restarts; ++restart)
+  {
+    if (restart > 0)
+    {
+      VCL_TRY(plain_prod(b, A, x, res));
+      residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rhs);
+      VCL_LAUNCHED(b, "residual_kernel");
+      VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
+      rho_0 = std::sqrt(ss);
+    }
+    if (rho_0 <= tag->abs_tolerance) break;                                     // gmres.hpp:227-228
+    scale_residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rho_0);
+    VCL_LAUNCHED(b, "scale_residual_kernel");
+    rho = 1.0;
+    if (rho_0 / norm_rhs < tag->tolerance || rho_0 < tag->abs_tolerance) break; // gmres.hpp:234-235
+
+    int k;
+    for (k = 0; k < m; ++k)
+    {
+      double *vk = V + (size_t)k * isz;
+      const double *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
+      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, b->partials, b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}};
+      VCL_TRY(launch_prod(b, A, src, e));
+      if (k > 0)
+      {
+        VCL_TRY(launch_gs1(b, grid, V, n, isz, k, d_h, 1));
+        gmres_gs2_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(V, n, isz, k, d_h, 1, R, m, d_nsq, b->partials, b->tickets);
+        VCL_LAUNCHED(b, "gmres_gs2_kernel");
+      }
+      gmres_normalize_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, vk, res, R, k * m + k, d_nsq, d_xi + k, b->partials, b->tickets);
+      VCL_LAUNCHED(b, "gmres_normalize_kernel");
+    }
+
+    VCL_CUDA(b, cudaMemcpyAsync(xi.data(), d_xi, sizeof(double) * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(hR.data(), R, sizeof(double) * m * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+
+    size_t kk = (size_t)k;
+    const size_t full = kk;                                                      // gmres.hpp:306-314
+    for (size_t i = 0; i < kk; ++i)
+      if (std::fabs(hR[i + i * kk]) < tag->tolerance * hR[0]) { kk = i; break; }
+
+    for (size_t i = 0; i < kk; ++i)                                              // gmres.hpp:318-331
+    {
+      tag->iters += 1;
+      if (xi[i] >= rho || xi[i] <= -rho) { kk = i; break; }
+      rho *= std::sin(std::acos(xi[i] / rho));
+    }
+
+    eta = xi;                                                                    // gmres.hpp:336-345
+    for (long i2 = (long)kk - 1; i2 > -1; --i2)
+    {
+      const size_t i = (size_t)i2;
+      for (size_t j = i + 1; j < kk; ++j) eta[i] -= hR[i + j * full] * eta[j];
+      eta[i] /= hR[i + i * full];
+    }
+    for (size_t i = 0; i < kk; ++i) coef[i] = rho_0 * eta[i];                    // gmres.hpp:351-352
+
+    VCL_CUDA(b, cudaMemcpyAsync(d_coef, coef.data(), sizeof(double) * m, cudaMemcpyHostToDevice, b->stream));
+    gmres_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, res, V, isz, d_coef, (int)kk);
+    VCL_LAUNCHED(b, "gmres_update_kernel");
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));                               // coef (pageable) must outlive the copy
+
+    tag->error = std::fabs(rho * rho_0 / norm_rhs);                              // gmres.hpp:360
+    if (tag->monitor && tag->monitor(x, std::fabs(rho * rho_0 / norm_rhs), tag->monitor_user)) break;
+  }
+  return ViennaCLSuccess;
+}
+
+// sums `chunk` entries starting at in[0] into out[0] (per-op API: tolerate producers that spread partials over a chunk)
+__global__ void chunk_sum_kernel(const double *in, int chunk, double *out)
+{
+  __shared__ double s_red[32];
+  double acc[1] = {0.0};
+  for (int i = threadIdx.x; i < chunk; i += blockDim.x) acc[0] += in[i];
+  block_sum<1>(acc, s_red);
+  if (threadIdx.x == 0) out[0] = acc[0];
+}
+
+MatOp from_csr(const ViennaCLCUDADcsr *A) { MatOp m; m.fmt = 0; m.csr = *A; m.sell = ViennaCLCUDADsell(); return m; }
+MatOp from_sell(const ViennaCLCUDADsell *A) { MatOp m; m.fmt = 1; m.sell = *A; m.csr = ViennaCLCUDADcsr(); return m; }
+
+ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p, double *Ap, const double *r0,
+                              double *out_ApAp, double *out_pAp, double *out_Apr0)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_TRY(check_matrix(b, A));
+  if (A.rows() == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, p && Ap && p != Ap, "bad vectors");
+  if (r0)
+  {
+    EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}};
+    return launch_prod(b, A, p, e);
+  }
+  EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, nullptr, {0.0, 0.0, 0.0}};
+  return launch_prod(b, A, p, e);
+}
+
+} // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+ViennaCLStatus ViennaCLCUDADcsr_cg(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return cg_solve(b, from_csr(A), rhs, x, tag); }
+ViennaCLStatus ViennaCLCUDADsell_cg(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return cg_solve(b, from_sell(A), rhs, x, tag); }
+ViennaCLStatus ViennaCLCUDADcsr_bicgstab(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return bicgstab_solve(b, from_csr(A), rhs, x, tag); }
+ViennaCLStatus ViennaCLCUDADsell_bicgstab(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return bicgstab_solve(b, from_sell(A), rhs, x, tag); }
+ViennaCLStatus ViennaCLCUDADcsr_gmres(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_csr(A), rhs, x, tag); }
+ViennaCLStatus ViennaCLCUDADsell_gmres(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_sell(A), rhs, x, tag); }
+
+// ---- per-step entry points (linalg/iterative_operations.hpp) ----
+ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend b, ViennaCLInt n, double *result, double alpha,
+                                                       double *p, double *r, const double *Ap, double beta,
+                                                       double *buf, ViennaCLInt buf_size)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && buf && buf_size >= 3, "bad arguments");
+  if (n == 0) return ViennaCLSuccess;
+  cg_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, p, r, Ap, alpha, beta, nullptr, b->partials, b->tickets, buf);
+  VCL_LAUNCHED(b, "cg_update_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
+                                                  double *buf, ViennaCLInt buf_size)
+{
+  VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
+  const int chunk = buf_size / 3;
+  return fused_prod_api(b, from_csr(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
+                                                   double *buf, ViennaCLInt buf_size)
+{
+  VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
+  const int chunk = buf_size / 3;
+  return fused_prod_api(b, from_sell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_update_s(ViennaCLBackend b, ViennaCLInt n, double *s, const double *r, const double *Ap,
+                                                        double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && buf && chunk >= 1, "bad arguments");
+  if (n == 0) return ViennaCLSuccess;
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf, chunk, b->dscal + 16);
+  VCL_LAUNCHED(b, "chunk_sum_kernel");
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + 3 * (size_t)chunk, chunk, b->dscal + 17);
+  VCL_LAUNCHED(b, "chunk_sum_kernel");
+  bicgstab_update_s_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, b->dscal + 16, b->dscal + 17, nullptr,
+                                                                        b->partials, b->tickets, buf + chunk_offset);
+  VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_vector_update(ViennaCLBackend b, ViennaCLInt n, double *result, double alpha, double *p,
+                                                             double omega, const double *s, double *residual, const double *As,
+                                                             double beta, const double *Ap, const double *r0star,
+                                                             double *buf, ViennaCLInt chunk)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && buf, "bad arguments");
+  (void)chunk;
+  if (n == 0) return ViennaCLSuccess;
+  bicgstab_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, alpha, p, omega, s, residual, As, beta, Ap, r0star,
+                                                                      nullptr, b->partials, b->tickets, buf);
+  VCL_LAUNCHED(b, "bicgstab_update_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
+                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{
+  VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
+  return fused_prod_api(b, from_csr(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
+                                                         const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{
+  VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
+  return fused_prod_api(b, from_sell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_normalize_vk(ViennaCLBackend b, ViennaCLInt n, double *v_k, const double *residual,
+                                                         double *R, ViennaCLInt offset_in_R, const double *buf,
+                                                         double *r_dot_vk, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && v_k && residual && R && buf && r_dot_vk && chunk >= 1, "bad arguments");
+  if (n == 0) return ViennaCLSuccess;
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + chunk, chunk, b->dscal + 16);      // ||v_k||^2 lives in chunk 1
+  VCL_LAUNCHED(b, "chunk_sum_kernel");
+  gmres_normalize_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, v_k, residual, R, offset_in_R, b->dscal + 16,
+                                                                         r_dot_vk + chunk_offset, b->partials, b->tickets);
+  VCL_LAUNCHED(b, "gmres_normalize_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage1(ViennaCLBackend b, const double *basis, ViennaCLInt n,
+                                                                ViennaCLInt internal_n, ViennaCLInt k, double *vi_in_vk, ViennaCLInt chunk)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && basis && vi_in_vk && k >= 0 && k < VCL_GMRES_MAX_KRYLOV && chunk >= 1, "bad arguments");
+  if (n == 0 || k == 0) return ViennaCLSuccess;
+  return launch_gs1(b, scalar_grid(b, n), basis, n, internal_n, k, vi_in_vk, chunk);
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend b, double *basis, ViennaCLInt n,
+                                                                ViennaCLInt internal_n, ViennaCLInt k, const double *vi_in_vk,
+                                                                double *R, ViennaCLInt krylov_dim, double *buf, ViennaCLInt chunk)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && basis && vi_in_vk && R && buf && k >= 0 && k < VCL_GMRES_MAX_KRYLOV && chunk >= 1, "bad arguments");
+  if (n == 0) return ViennaCLSuccess;
+  // second reduction stage of <v_i, v_k>: fold each chunk into its first element (no-op for our own stage 1)
+  for (int j = 0; j < k; ++j)
+  {
+    chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, b->dscal + 16 + j);
+    VCL_LAUNCHED(b, "chunk_sum_kernel");
+  }
+  gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, b->dscal + 16, 1, R, krylov_dim,
+                                                                   buf + chunk, b->partials, b->tickets);
+  VCL_LAUNCHED(b, "gmres_gs2_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_update_result(ViennaCLBackend b, ViennaCLInt n, double *result, const double *residual,
+                                                          const double *basis, ViennaCLInt internal_n, const double *coefficients, ViennaCLInt k)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, n >= 0 && result && residual && coefficients && k >= 0 && k <= VCL_GMRES_MAX_KRYLOV, "bad arguments");
+  if (n == 0) return ViennaCLSuccess;
+  gmres_update_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, residual, basis, internal_n, coefficients, k);
+  VCL_LAUNCHED(b, "gmres_update_kernel");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
+                                                     double *buf, ViennaCLInt buf_size)
+{ return ViennaCLCUDADpipelined_cg_prod_csr(b, A, p, Ap, buf, buf_size); }
+
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
+                                                      double *buf, ViennaCLInt buf_size)
+{ return ViennaCLCUDADpipelined_cg_prod_sell(b, A, p, Ap, buf, buf_size); }
+
+} // extern "C"

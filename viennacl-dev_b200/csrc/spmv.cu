@@ -1,0 +1,194 @@
+// spmv.cu -- C-ABI entry points for CSR / SELL SpMV, row blocks, row_info and CSR->SELL conversion.
+#include "spmv_kernels.cuh"
+#include "launch.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Row blocks (compressed_matrix.hpp:1152-1188 analogue).  Greedy over whole rows: a block closes when the next row would
+// exceed VCL_B200_CSR_BLOCK_NNZ staged entries or VCL_B200_CSR_BLOCK_ROWS rows; a longer row gets a block of its own.
+// Like the reference this runs on the host after a D2H copy of row_ptr (set-up path, outside every timed region).
+// ------------------------------------------------------------------------------------------------
+static void build_row_blocks(const u32 *rp, int rows, std::vector<u32> &blk)
+{
+  blk.clear();
+  blk.push_back(0);
+  int r = 0;
+  while (r < rows)
+  {
+    const u32 start = rp[r];
+    // staged range begins at the 4-aligned entry below `start`
+    const u32 slack = start & 3u;
+    int e = r;
+    while (e < rows && e - r < VCL_B200_CSR_BLOCK_ROWS && (rp[e + 1] - start) + slack <= VCL_B200_CSR_BLOCK_NNZ) ++e;
+    if (e == r) e = r + 1;          // single long row
+    blk.push_back((u32)e);
+    r = e;
+  }
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCLInt rows, const unsigned int *row_ptr,
+                                                     unsigned int *row_blocks, ViennaCLInt *num_blocks)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && num_blocks, "bad arguments");
+  if (rows == 0) { *num_blocks = 0; return ViennaCLSuccess; }
+  VCL_REQUIRE(b, row_ptr, "null row_ptr");
+  std::vector<u32> rp((size_t)rows + 1), blk;
+  VCL_CUDA(b, cudaMemcpyAsync(rp.data(), row_ptr, sizeof(u32) * ((size_t)rows + 1), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  build_row_blocks(rp.data(), rows, blk);
+  const int nb = (int)blk.size() - 1;
+  if (row_blocks)
+  {
+    VCL_REQUIRE(b, *num_blocks >= nb, "row_blocks buffer too small");
+    VCL_CUDA(b, cudaMemcpyAsync(row_blocks, blk.data(), sizeof(u32) * blk.size(), cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  }
+  *num_blocks = nb;
+  return ViennaCLSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prod_impl
+// ------------------------------------------------------------------------------------------------
+extern "C" ViennaCLStatus ViennaCLCUDADcsrmv(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
+                                             const unsigned int *row_ptr, const unsigned int *col_idx, const double *values,
+                                             const unsigned int *row_blocks, ViennaCLInt num_blocks,
+                                             const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                             double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && cols >= 0 && nnz >= 0, "negative size");
+  if (rows == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, row_ptr && x && y && (nnz == 0 || (col_idx && values)), "null pointer");
+  VCL_REQUIRE(b, incx != 0 && incy != 0, "zero stride");
+  VCL_REQUIRE(b, x != y, "x and y alias: the facade resolves x = A*x through a temporary (compressed_matrix.hpp:1237-1242)");
+  ViennaCLCUDADcsr A = {rows, cols, nnz, row_ptr, col_idx, values, row_blocks, num_blocks};
+  EpiAxpby epi = {y, offy, incy, alpha, beta};
+  XVec xv = {x, offx, incx};
+  return vcl_launch_csr(b, A, xv, epi);
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADsellmv(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt rows_per_block,
+                                              const unsigned int *columns_per_block, const unsigned int *col_idx,
+                                              const unsigned int *block_start, const double *values,
+                                              const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                              double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && cols >= 0 && rows_per_block > 0, "bad size");
+  if (rows == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, columns_per_block && block_start && x && y, "null pointer");
+  VCL_REQUIRE(b, incx != 0 && incy != 0, "zero stride");
+  VCL_REQUIRE(b, x != y, "x and y alias");
+  ViennaCLCUDADsell A = {rows, cols, rows_per_block, columns_per_block, col_idx, block_start, values};
+  EpiAxpby epi = {y, offy, incy, alpha, beta};
+  XVec xv = {x, offx, incx};
+  return vcl_launch_sell(b, A, xv, epi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row_info (cuda/sparse_matrix_operations.hpp:53-119): inf-/1-/2-norm or diagonal of every row
+// ------------------------------------------------------------------------------------------------
+__global__ void csr_row_info_kernel(int rows, const u32 * __restrict__ rp, const u32 * __restrict__ ci,
+                                    const double * __restrict__ va, double *out, int option)
+{
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    double value = 0.0;
+    const u32 e = rp[r + 1];
+    switch (option)
+    {
+    case 0: for (u32 k = rp[r]; k < e; ++k) value = fmax(value, fabs(va[k])); break;
+    case 1: for (u32 k = rp[r]; k < e; ++k) value += fabs(va[k]); break;
+    case 2: for (u32 k = rp[r]; k < e; ++k) value += va[k] * va[k]; value = sqrt(value); break;
+    default:
+      for (u32 k = rp[r]; k < e; ++k)
+        if (ci[k] == (u32)r) { value = va[k]; break; }
+      break;
+    }
+    out[r] = value;
+  }
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADcsr_row_info(ViennaCLBackend b, ViennaCLInt rows,
+                                                    const unsigned int *row_ptr, const unsigned int *col_idx, const double *values,
+                                                    double *result, ViennaCLInt option)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && option >= 0 && option <= 3, "bad arguments");
+  if (rows == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, row_ptr && result, "null pointer");
+  int grid = std::min(vcl_div_up(rows, 256), b->sm_count * 8);
+  csr_row_info_kernel<<<grid, 256, 0, b->stream>>>(rows, row_ptr, col_idx, values, result, option);
+  VCL_LAUNCHED(b, "csr_row_info_kernel");
+  return ViennaCLSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR -> SELL-C (sliced_ell_matrix.hpp:140-214 layout): widths on device, slice offsets scanned on the host (set-up path),
+// entries scattered on device.
+// ------------------------------------------------------------------------------------------------
+__global__ void sell_width_kernel(int rows, int C, const u32 * __restrict__ rp, u32 *cpb)
+{
+  const int nslices = (rows - 1) / C + 1;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += (long long)gridDim.x * blockDim.x)
+  {
+    u32 w = 0;
+    const long long r_end = min((long long)rows, (s + 1) * C);
+    for (long long r = s * C; r < r_end; ++r) w = max(w, rp[r + 1] - rp[r]);
+    cpb[s] = w;
+  }
+}
+
+__global__ void sell_fill_kernel(int rows, int C, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const double * __restrict__ cva,
+                                 const u32 * __restrict__ cpb, const u32 * __restrict__ bs, u32 *ci, double *va)
+{
+  // one thread per (row of the padded slice): writes its real entries, then zero/col-0 padding up to the slice width
+  const long long padded_rows = ((long long)(rows - 1) / C + 1) * C;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < padded_rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    const u32 s = (u32)(r / C);
+    const u32 w = cpb[s];
+    size_t idx = (size_t)bs[s] + (size_t)(r - (long long)s * C);
+    u32 j = 0;
+    if (r < rows)
+    {
+      const u32 e = rp[r + 1];
+      for (u32 k = rp[r]; k < e; ++k, ++j, idx += C) { ci[idx] = cci[k]; va[idx] = cva[k]; }
+    }
+    for (; j < w; ++j, idx += C) { ci[idx] = 0u; va[idx] = 0.0; }
+  }
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt C,
+                                                const unsigned int *row_ptr, const unsigned int *csr_col, const double *csr_val,
+                                                unsigned int *columns_per_block, unsigned int *block_start, long long *padded_nnz,
+                                                unsigned int *col_idx, double *values)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && C > 0 && padded_nnz, "bad arguments");
+  if (rows == 0) { *padded_nnz = 0; return ViennaCLSuccess; }
+  VCL_REQUIRE(b, row_ptr && columns_per_block && block_start, "null pointer");
+  const int nslices = (rows - 1) / C + 1;
+  if (!col_idx || !values)
+  {
+    int grid = std::min(vcl_div_up(nslices, 256), b->sm_count * 8);
+    sell_width_kernel<<<grid, 256, 0, b->stream>>>(rows, C, row_ptr, columns_per_block);
+    VCL_LAUNCHED(b, "sell_width_kernel");
+    std::vector<u32> w((size_t)nslices), start((size_t)nslices);
+    VCL_CUDA(b, cudaMemcpyAsync(w.data(), columns_per_block, sizeof(u32) * nslices, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    unsigned long long off = 0;
+    for (int s = 0; s < nslices; ++s) { start[s] = (u32)off; off += (unsigned long long)w[s] * (unsigned long long)C; }
+    VCL_REQUIRE(b, off <= 0xFFFFFFFFull, "SELL storage exceeds 32-bit offsets (sliced_ell_matrix.hpp:134-137 uses unsigned int)");
+    VCL_CUDA(b, cudaMemcpyAsync(block_start, start.data(), sizeof(u32) * nslices, cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    *padded_nnz = (long long)off;
+    return ViennaCLSuccess;
+  }
+  const long long padded_rows = (long long)nslices * C;
+  int grid = std::min(vcl_div_up(padded_rows, 256), b->sm_count * 8);
+  sell_fill_kernel<<<grid, 256, 0, b->stream>>>(rows, C, row_ptr, csr_col, csr_val, columns_per_block, block_start, col_idx, values);
+  VCL_LAUNCHED(b, "sell_fill_kernel");
+  return ViennaCLSuccess;
+}

@@ -1,0 +1,209 @@
+// spmv_kernels.cuh -- sm_100a SpMV kernels for CSR (row-block streaming) and SELL-C-sigma, parameterised by an
+// epilogue functor so that the same streaming code serves  y = alpha*A*x + beta*y  (prod_impl) and the fused
+// "SpMV + inner products" steps of the pipelined solvers.
+//
+// Replaces cuda/sparse_matrix_operations.hpp:137-249 (K1/K2), :2196-2237 (K4) and the SpMV halves of
+// cuda/iterative_operations.hpp:113-274, :543-607, :895-1074, :1381-1453 (K6-K8, K11-K13).
+//
+// Data path (CSR): each CTA owns whole rows [blk[b], blk[b+1]) (<= 256 rows, <= 2048 nnz).  The contiguous value and
+// column-index ranges of those rows are streamed global->shared with 16-byte cp.async (no register staging, L1 bypass),
+// then one thread per row walks its entries in shared memory IN STORAGE ORDER with a single fma chain -- the same
+// operation order as the reference host backend (host_based/sparse_matrix_operations.hpp:167-184), so results agree
+// bit-for-bit with an FMA-contracted build of it.  x is gathered through L1/L2 (adjacent rows of a stencil matrix
+// gather adjacent x entries, so the gathers of a warp coalesce).
+#pragma once
+#include "common.cuh"
+#include "solver_state.cuh"
+
+#define CSR_BLOCK_THREADS 256
+#define CSR_CAP (VCL_B200_CSR_BLOCK_NNZ)          // staged non-zeros per row block
+#define CSR_STAGE (CSR_CAP + 4)                   // + alignment slack
+
+struct CsrDev
+{
+  int rows; u32 nnz;
+  const u32 *rp, *ci; const double *va;
+  const u32 *blk; int nblk;
+};
+
+struct SellDev
+{
+  int rows; int C;
+  const u32 *cpb, *ci, *bs; const double *va;
+};
+
+struct XVec { const double *x; int off, inc; };
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues
+// ------------------------------------------------------------------------------------------------
+// y[off + r*inc] = alpha*dot + beta*y   (spmv_alpha_beta semantics, cuda/sparse_matrix_operations.hpp:130: beta == 0 -> y not read)
+struct EpiAxpby
+{
+  double *y; int off, inc; double alpha, beta;
+  static constexpr int NQ = 0;
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ void row(u32 r, double dot)
+  {
+    size_t idx = (size_t)r * (size_t)inc + (size_t)off;
+    if (beta != 0.0) y[idx] = alpha * dot + beta * y[idx];
+    else             y[idx] = alpha * dot;
+  }
+  __device__ __forceinline__ void finish(double *) {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// CSR, row-block streaming
+// ------------------------------------------------------------------------------------------------
+template<class Epi>
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS)
+csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
+{
+  __shared__ __align__(16) double s_val[CSR_STAGE];
+  __shared__ __align__(16) u32    s_col[CSR_STAGE];
+  __shared__ u32 s_rp[CSR_BLOCK_THREADS + 1];
+  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+
+  if (epi.skip()) return;
+  const int tid = threadIdx.x;
+  const double * __restrict__ x = xv.x;
+
+  for (int b = blockIdx.x; b < A.nblk; b += gridDim.x)
+  {
+    const u32 r0 = A.blk[b], r1 = A.blk[b + 1];
+    const u32 nrows = r1 - r0;
+    const u32 n0 = A.rp[r0], n1 = A.rp[r1];
+
+    if (n1 - n0 > CSR_CAP)
+    {
+      // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
+      double part[1] = {0.0};
+      for (u32 k = n0 + tid; k < n1; k += CSR_BLOCK_THREADS)
+        part[0] = fma(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], part[0]);
+      __shared__ double s_long[32];
+      block_sum<1>(part, s_long);
+      if (tid == 0) epi.row(r0, part[0]);
+      __syncthreads();
+      continue;
+    }
+
+    // ---- stage values / column indices: 16-byte cp.async from the enclosing 16-byte aligned range ----
+    const u32 a0 = n0 & ~3u;
+    const u32 cnt = n1 - a0;
+    for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2)
+    {
+      if (a0 + i + 2 <= A.nnz) cp_async16(&s_val[i], A.va + a0 + i);
+      else if (a0 + i < A.nnz) s_val[i] = A.va[a0 + i];
+    }
+    for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4)
+    {
+      if (a0 + i + 4 <= A.nnz) cp_async16(&s_col[i], A.ci + a0 + i);
+      else { for (u32 k = 0; k < 4 && a0 + i + k < A.nnz; ++k) s_col[i + k] = A.ci[a0 + i + k]; }
+    }
+    cp_async_commit();
+    if ((u32)tid <= nrows) s_rp[tid] = A.rp[r0 + tid];
+    if (tid == 0 && nrows == CSR_BLOCK_THREADS) s_rp[CSR_BLOCK_THREADS] = n1;
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- one thread per row, sequential fma chain in storage order ----
+    if ((u32)tid < nrows)
+    {
+      u32 j = s_rp[tid] - a0;
+      const u32 e = s_rp[tid + 1] - a0;
+      double dot = 0.0;
+      for (; j + 4 <= e; j += 4)
+      {
+        const u32 c0 = s_col[j], c1 = s_col[j + 1], c2 = s_col[j + 2], c3 = s_col[j + 3];
+        const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
+        const double x2 = x[(size_t)c2 * xv.inc + xv.off], x3 = x[(size_t)c3 * xv.inc + xv.off];
+        dot = fma(s_val[j], x0, dot); dot = fma(s_val[j + 1], x1, dot);
+        dot = fma(s_val[j + 2], x2, dot); dot = fma(s_val[j + 3], x3, dot);
+      }
+      if (j + 2 <= e)
+      {
+        const u32 c0 = s_col[j], c1 = s_col[j + 1];
+        const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
+        dot = fma(s_val[j], x0, dot); dot = fma(s_val[j + 1], x1, dot);
+        j += 2;
+      }
+      if (j < e) dot = fma(s_val[j], x[(size_t)s_col[j] * xv.inc + xv.off], dot);
+      epi.row(r0 + tid, dot);
+    }
+    __syncthreads();
+  }
+  epi.finish(s_red);
+}
+
+// Plan-free CSR kernel: one thread per row, sequential order (used when no row blocks are supplied or the
+// arrays are not 16-byte aligned, e.g. oddly offset user-wrapped buffers).
+template<class Epi>
+__global__ void __launch_bounds__(256)
+csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
+{
+  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  if (epi.skip()) return;
+  const double * __restrict__ x = xv.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    double dot = 0.0;
+    const u32 e = A.rp[r + 1];
+    for (u32 k = A.rp[r]; k < e; ++k)
+      dot = fma(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], dot);
+    epi.row((u32)r, dot);
+  }
+  epi.finish(s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SELL-C-sigma (sigma = 1): one thread per row, slice-column-major storage gives fully coalesced 8-/4-byte loads per
+// warp for C a multiple of 32.  Entry loads are issued four slice-columns ahead of the fma chain.
+// Zero-valued (padding) slots never touch x: cuda/sparse_matrix_operations.hpp:2231, host :1833.
+// ------------------------------------------------------------------------------------------------
+template<class Epi>
+__global__ void __launch_bounds__(256)
+sell_kernel(SellDev A, XVec xv, Epi epi)
+{
+  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  if (epi.skip()) return;
+  const double * __restrict__ x = xv.x;
+  const double * __restrict__ va = A.va;
+  const u32 * __restrict__ ci = A.ci;
+  const size_t C = (size_t)A.C;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    const u32 slice = (u32)(r / A.C);
+    const u32 w = A.cpb[slice];
+    size_t idx = (size_t)A.bs[slice] + (size_t)(r - (long long)slice * A.C);
+    double acc = 0.0;
+    u32 j = 0;
+    for (; j + 4 <= w; j += 4, idx += 4 * C)
+    {
+      const double v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * C], v3 = va[idx + 3 * C];
+      const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * C], c3 = ci[idx + 3 * C];
+      const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
+      const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
+      const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
+      const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
+      if (v0 != 0.0) acc = fma(x0, v0, acc);
+      if (v1 != 0.0) acc = fma(x1, v1, acc);
+      if (v2 != 0.0) acc = fma(x2, v2, acc);
+      if (v3 != 0.0) acc = fma(x3, v3, acc);
+    }
+    for (; j < w; ++j, idx += C)
+    {
+      const double v0 = va[idx];
+      if (v0 != 0.0) acc = fma(x[(size_t)ci[idx] * xv.inc + xv.off], v0, acc);
+    }
+    epi.row((u32)r, acc);
+  }
+  epi.finish(s_red);
+}
