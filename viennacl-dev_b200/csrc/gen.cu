@@ -24,7 +24,7 @@ __device__ __forceinline__ unsigned long long stencil_offset(const StencilGeom &
   {
     per_row = 7;
     missing += (l > 0 ? nxy : rem);                                          // rows with l' == 0
-    missing += (l == g.nz - 1 ? rem : 0);                                    // rows with l' == nz-1
+    missing += (l > g.nz - 1 ? nxy : (l == g.nz - 1 ? rem : 0));             // rows with l' == nz-1 (l == nz only for r == rows)
   }
   return (unsigned long long)(per_row * r - missing);
 }
@@ -58,7 +58,7 @@ static unsigned long long host_offset(const StencilGeom &g, long long r)
   const long long L = j + (long long)g.ny * l;
   long long missing = (L + (i > 0 ? 1 : 0)) + L + (l * g.nx + (j > 0 ? g.nx : i)) + (l * g.nx + (j == g.ny - 1 ? i : 0));
   long long per_row = 5;
-  if (g.nz > 1) { per_row = 7; missing += (l > 0 ? nxy : rem); missing += (l == g.nz - 1 ? rem : 0); }
+  if (g.nz > 1) { per_row = 7; missing += (l > 0 ? nxy : rem); missing += (l > g.nz - 1 ? nxy : (l == g.nz - 1 ? rem : 0)); }
   return (unsigned long long)(per_row * r - missing);
 }
 

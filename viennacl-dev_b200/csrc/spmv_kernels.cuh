@@ -7,9 +7,9 @@
 //
 // Data path (CSR): each CTA owns whole rows [blk[b], blk[b+1]) (<= 256 rows, <= 2048 nnz).  The contiguous value and
 // column-index ranges of those rows are streamed global->shared with 16-byte cp.async (no register staging, L1 bypass),
-// then one thread per row walks its entries in shared memory IN STORAGE ORDER with a single fma chain -- the same
-// operation order as the reference host backend (host_based/sparse_matrix_operations.hpp:167-184), so results agree
-// bit-for-bit with an FMA-contracted build of it.  x is gathered through L1/L2 (adjacent rows of a stencil matrix
+// then one thread per row walks its entries in shared memory IN STORAGE ORDER with a single accumulation chain -- the same
+// operation order and roundings as the reference host backend (host_based/sparse_matrix_operations.hpp:167-184), so
+// results agree bit-for-bit with it (see madd()).  x is gathered through L1/L2 (adjacent rows of a stencil matrix
 // gather adjacent x entries, so the gathers of a warp coalesce).
 #pragma once
 #include "common.cuh"
@@ -34,6 +34,11 @@ struct SellDev
 
 struct XVec { const double *x; int off, inc; };
 
+// In-row CSR accumulation step.  The reference host backend (host_based/sparse_matrix_operations.hpp:167-184), built with
+// g++ -O3 for x86-64-v3, evaluates `dot += a*x` as a rounded multiply followed by a rounded add (GCC does not form FMA
+// chains in reductions under generic tuning); the same two roundings are used here so that CSR results match it bit for bit.
+__device__ __forceinline__ double madd(double a, double x, double acc) { return __dadd_rn(acc, __dmul_rn(a, x)); }
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -54,8 +59,9 @@ struct EpiAxpby
   __device__ __forceinline__ void row(u32 r, double dot)
   {
     size_t idx = (size_t)r * (size_t)inc + (size_t)off;
-    if (beta != 0.0) y[idx] = alpha * dot + beta * y[idx];
-    else             y[idx] = alpha * dot;
+    // same operations as the reference host build: t = alpha*dot (rounded), then one fused beta*y + t
+    if (beta != 0.0) y[idx] = fma(beta, y[idx], __dmul_rn(alpha, dot));
+    else             y[idx] = __dmul_rn(alpha, dot);
   }
   __device__ __forceinline__ void finish(double *) {}
 };
@@ -125,17 +131,17 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
         const u32 c0 = s_col[j], c1 = s_col[j + 1], c2 = s_col[j + 2], c3 = s_col[j + 3];
         const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
         const double x2 = x[(size_t)c2 * xv.inc + xv.off], x3 = x[(size_t)c3 * xv.inc + xv.off];
-        dot = fma(s_val[j], x0, dot); dot = fma(s_val[j + 1], x1, dot);
-        dot = fma(s_val[j + 2], x2, dot); dot = fma(s_val[j + 3], x3, dot);
+        dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
+        dot = madd(s_val[j + 2], x2, dot); dot = madd(s_val[j + 3], x3, dot);
       }
       if (j + 2 <= e)
       {
         const u32 c0 = s_col[j], c1 = s_col[j + 1];
         const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
-        dot = fma(s_val[j], x0, dot); dot = fma(s_val[j + 1], x1, dot);
+        dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
         j += 2;
       }
-      if (j < e) dot = fma(s_val[j], x[(size_t)s_col[j] * xv.inc + xv.off], dot);
+      if (j < e) dot = madd(s_val[j], x[(size_t)s_col[j] * xv.inc + xv.off], dot);
       epi.row(r0 + tid, dot);
     }
     __syncthreads();
@@ -157,7 +163,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
     double dot = 0.0;
     const u32 e = A.rp[r + 1];
     for (u32 k = A.rp[r]; k < e; ++k)
-      dot = fma(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], dot);
+      dot = madd(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], dot);
     epi.row((u32)r, dot);
   }
   epi.finish(s_red);
