@@ -1,0 +1,247 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SpMV + Krylov hot path (contract: see the task statement / DESIGN.md section (d)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload spmv|cg512]
+
+Metric (BASELINE.json): "SpMV eff. GB/s (% HBM peak); CG iterations/sec at 1/2/4/8 B200".
+  * default workload `spmv` = BASELINE configs[1]: y = A*x, 3-D 7-point Laplacian 256^3 per GPU (16.7M rows, 117M nnz, double
+    CSR; SELL-32 reported beside it).  A step is one SpMV over the whole matrix.  With N > 1 GPUs the grid grows to
+    256 x 256 x (256*N), row-partitioned one slab per rank with NVLink halo exchange (weak scaling).
+    value = algorithmic bytes (12*nnz + 20*rows) of all ranks / time.
+  * `cg512` = BASELINE configs[4]: pipelined CG on the 512^3 Laplacian, fixed budget of iterations, row-partitioned over
+    N ranks (strong scaling); a step is one CG iteration; value = iterations / s.  The default run reports it under "cg".
+Inputs are synthetic (device-side stencil generator; x = seeded uniform[1,2)) and far larger than the 126 MB L2, so no L2
+flush is needed between steps.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max
+over ranks.  One process per GPU (torchrun); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, device copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own OpenMP host backend (oracle/_ref, compiled from /root/reference) timed on the
+    host cores on the SAME workload/metric; rank 0 only."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    o = ol.oracle()
+    kind = "reference" if ol.have_ref() else "port"
+    r = ol.ref() if kind == "reference" else o
+    cores = r.max_threads()
+    r.set_threads(cores); o.set_threads(cores)
+    n1 = 256
+    if args.workload == "spmv":
+        A = o.stencil3d(n1, n1, n1)
+        x = o.uniform(A.cols, 1, 1.0, 2.0)
+        steps, warm = max(1, args.steps), max(1, args.warmup)
+        if kind == "reference":
+            r.time_csr_spmv(A, x, warm)
+            sec = r.time_csr_spmv(A, x, steps)
+        else:
+            y = np.zeros(A.rows)
+            for _ in range(warm):
+                o.csr_spmv(A, x, y)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                o.csr_spmv(A, x, y)
+            sec = time.perf_counter() - t0
+        nbytes = 12 * A.nnz + 20 * A.rows
+        val = nbytes * steps / sec / 1e9
+        line = {"metric": "spmv_effective_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": "csr_spmv_lap3d_7pt_256^3", "rows": A.rows, "nnz": A.nnz, "format": "CSR", "index": "u32",
+                           "note": "reference OpenMP host backend (viennacl/linalg/host_based), all host threads, same matrix/vector as the GPU arm (per-GPU slab; the CPU arm does not grow with N)"},
+                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind, "sample": "%d SpMV passes over the full 256^3 matrix" % steps},
+                "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    else:
+        # CG on 512^3 needs ~12 GB of host CSR and minutes per iteration budget: bounded sample = 256^3, fixed iterations
+        A = o.stencil3d(n1, n1, n1)
+        b = np.ones(A.rows)
+        its = max(2, min(args.steps, 20))
+        res = r.solve("cg", A, b, tol=0.0, maxit=its) if kind == "reference" else None
+        if res is None:
+            t0 = time.perf_counter(); o.cg(A, b, tol=0.0, maxit=its); sec = time.perf_counter() - t0
+        else:
+            sec = res["seconds"]
+        # scale to the 512^3 problem by bytes per iteration (8x rows/nnz): iterations/s on the full workload
+        val = its / sec / 8.0
+        line = {"metric": "cg_iterations_per_sec", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": its, "warmup": 0,
+                "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": "cg_lap3d_7pt_512^3", "note": "bounded sample: %d CG iterations on the 256^3 Laplacian, scaled by the 8x byte ratio to 512^3" % its},
+                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": kind, "sample": "%d iterations on 256^3, x1/8" % its},
+                "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_baseline_spmv(n1, reps=10):
+    """Reference OpenMP host backend on the box's host cores, bounded sample (rank 0, N = 1 only)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    o = ol.oracle()
+    kind = "reference" if ol.have_ref() else "port"
+    cores = o.max_threads()
+    o.set_threads(cores)
+    A = o.stencil3d(n1, n1, n1)
+    x = o.uniform(A.cols, 1, 1.0, 2.0)
+    if kind == "reference":
+        r = ol.ref(); r.set_threads(cores)
+        r.time_csr_spmv(A, x, 2)
+        sec = r.time_csr_spmv(A, x, reps)
+    else:
+        y = np.zeros(A.rows)
+        o.csr_spmv(A, x, y)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o.csr_spmv(A, x, y)
+        sec = time.perf_counter() - t0
+    nbytes = 12 * A.nnz + 20 * A.rows
+    return {"value": nbytes * reps / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+            "sample": "%d CSR SpMV passes over the full 256^3 matrix (reference host_based::prod_impl, OpenMP)" % reps,
+            "ms_per_step": sec / reps * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="spmv", choices=["spmv", "cg512"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the SELL / CG side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    be = pkg.Backend(local)             # raises without a B200: there is no CPU fallback
+    if world > 1:
+        ids = [be.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        be.comm_init(ids[0], rank, world)
+
+    def barrier():
+        be.sync()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = load_peaks()
+    n1 = 256
+    line = None
+    sampler = ClockSampler(local)
+
+    if args.workload == "spmv":
+        import bench_workloads as bw
+        line = bw.spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampler, peak, peak_src)
+        if rank == 0 and not args.no_extras:
+            line["sell"] = bw.sell_side(pkg, be, args, n1, peak) if world == 1 else None
+        if not args.no_extras:
+            cg = bw.cg_side(pkg, be, args, rank, world, barrier, max_over_ranks)
+            if rank == 0:
+                line["cg"] = cg
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_spmv(n1)
+    else:
+        import bench_workloads as bw
+        line = bw.cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler, peak, peak_src)
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    barrier()
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

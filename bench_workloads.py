@@ -1,0 +1,203 @@
+"""Workloads behind bench.py (kept separate so bench.py stays a readable statement of the contract)."""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _traffic_from_profiles(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
+
+
+def partition_rows(rows, world, rank):
+    """Contiguous 1-D row partition: rank g owns [g*rows//world, (g+1)*rows//world)."""
+    return rows * rank // world, rows * (rank + 1) // world
+
+
+def _slab(pkg, be, rank, world, n1):
+    """Rank's slab of the 256 x 256 x (256*world) 7-point Laplacian: (matrix, rows, nnz, global rows, row range)."""
+    nz = n1 * world
+    rows_per = n1 * n1 * n1
+    rb, re_ = rank * rows_per, (rank + 1) * rows_per
+    A = pkg.CsrMatrix.stencil(be, n1, n1, nz, row_begin=rb, row_end=re_)
+    return A, rb, re_, n1 * n1 * nz
+
+
+def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampler, peak, peak_src):
+    A, rb, re_, global_rows = _slab(pkg, be, rank, world, n1)
+    n = A.rows
+    x, y = be.empty(n), be.zeros(n)
+    be.check(be.L.ViennaCLCUDADfill_uniform(be.h, n, x.ptr, 1, rb, 1.0, 2.0))
+    if world > 1:
+        D = pkg.DistCsr(be, global_rows, rb, re_, A)
+        step = lambda: D.spmv(x, y)
+    else:
+        D = None
+        step = lambda: A.spmv(x, y)
+    nbytes = 12 * A.nnz + 20 * n                      # SURVEY 8d, per rank (halo planes not counted)
+
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = be.launches()
+    be.timer_begin()
+    for _ in range(args.steps):
+        step()
+    ms = be.timer_end()
+    l1 = be.launches()
+    barrier()
+    ms = max_over_ranks(ms)
+    value = nbytes * world * args.steps / (ms * 1e-3) / 1e9
+    per_gpu = value / world
+
+    # ---- end to end through the public call with HOST vectors: x host->device, y = A*x, y device->host, every step ----
+    hx, hy = C.c_void_p(), C.c_void_p()
+    be.check(be.L.ViennaCLHostAllocPinned(be.h, C.byref(hx), 8 * n))
+    be.check(be.L.ViennaCLHostAllocPinned(be.h, C.byref(hy), 8 * n))
+    be.check(be.L.ViennaCLCUDAMemRead(be.h, x.ptr, 0, hx, 8 * n, 0))
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        be.check(be.L.ViennaCLCUDAMemWrite(be.h, x.ptr, 0, hx, 8 * n, 1))
+        step()
+        be.check(be.L.ViennaCLCUDAMemRead(be.h, y.ptr, 0, hy, 8 * n, 0))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    be.sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    sampler.stop_flag.set()
+    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_val = nbytes * world * e2e_steps / (e2e_ms * 1e-3) / 1e9
+    checksum = float(np.ctypeslib.as_array(C.cast(hy, C.POINTER(C.c_double)), shape=(n,))[:1024].sum())
+    be.check(be.L.ViennaCLHostFreePinned(be.h, hx)); be.check(be.L.ViennaCLHostFreePinned(be.h, hy))
+
+    if rank != 0:
+        return None
+    kernel = "csr_stream_kernel<EpiAxpby>"
+    return {
+        "metric": "spmv_effective_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "csr_spmv_lap3d_7pt_256^3_per_gpu", "grid": [n1, n1, n1 * world], "rows_per_gpu": n, "nnz_per_gpu": A.nnz,
+                   "format": "CSR (u32 indices) row blocks <=256 rows/<=2048 nnz", "bytes_per_step_per_gpu": nbytes,
+                   "l2_policy": "inputs (1.74 GB per step) are larger than the 126 MB L2; no flush needed",
+                   "partition": "none" if world == 1 else "1-D row slabs, NVLink halo of one 256x256 plane per neighbour"},
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                     "frac_of_nominal_8TBps": per_gpu / 8000.0, "peak_source": peak_src, "kernel": kernel,
+                     "algorithmic_bytes_per_launch": nbytes, "traffic": _traffic_from_profiles("csr_spmv_256")},
+        "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
+                "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "checksum": checksum,
+                "note": "host x -> device, y = prod(A, x) through the C-ABI, y -> host; the matrix stays resident like a viennacl::compressed_matrix"},
+        "gpu_launches": int(l1 - l0),
+        "clocks": sampler.summary(),
+    }
+
+
+def sell_side(pkg, be, args, n1, peak):
+    """Same matrix in SELL-32 (sigma = 1), same x: BASELINE configs[1] asks for CSR vs sliced-ELL."""
+    A = pkg.CsrMatrix.stencil(be, n1, n1, n1)
+    S = A.to_sell(32)
+    n = A.rows
+    x, y = be.empty(n), be.zeros(n)
+    be.check(be.L.ViennaCLCUDADfill_uniform(be.h, n, x.ptr, 1, 0, 1.0, 2.0))
+    for _ in range(args.warmup):
+        S.spmv(x, y)
+    be.sync()
+    be.timer_begin()
+    for _ in range(args.steps):
+        S.spmv(x, y)
+    ms = be.timer_end()
+    nbytes = S.bytes_spmv()
+    gbs = nbytes * args.steps / (ms * 1e-3) / 1e9
+    return {"metric": "sell32_spmv_effective_GBps", "value": gbs, "ms_per_step": ms / args.steps, "bytes_per_step": nbytes,
+            "padded_nnz": S.padded_nnz, "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBps": gbs / 8000.0,
+            "traffic": _traffic_from_profiles("sell_spmv_256")}
+
+
+def _cg_run(pkg, be, solve, iters):
+    """Fixed iteration budget (tolerance 0 never triggers): returns (ms, iterations done)."""
+    tag = pkg.SolverTag(tol=0.0, max_iterations=iters)
+    be.sync()
+    be.timer_begin()
+    solve(tag)
+    ms = be.timer_end()
+    return ms, tag.iters
+
+
+def cg_side(pkg, be, args, rank, world, barrier, max_over_ranks):
+    """CG iterations/s: BASELINE configs[0] (1024^2, N = 1 only) and configs[4] (512^3, row-partitioned over all ranks)."""
+    out = {}
+    if world == 1:
+        A = pkg.CsrMatrix.stencil(be, 1024, 1024, 1)
+        b, x = be.array(np.ones(A.rows)), be.zeros(A.rows)
+        _cg_run(pkg, be, lambda t: t.solve("cg", A, b, x), 64)
+        ms, its = _cg_run(pkg, be, lambda t: t.solve("cg", A, b, x), 1898)
+        nb = 12 * A.nnz + 76 * A.rows
+        out["lap2d_1024"] = {"iterations_per_sec": its / (ms * 1e-3), "iterations": its, "ms": ms,
+                             "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb,
+                             "note": "includes solver set-up (3 reductions, state upload); working set ~100 MB is L2-resident on B200"}
+        del A, b, x
+    out["lap3d_512"] = cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters=100, warm=10)
+    return out
+
+
+def cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters, warm):
+    n1 = 512
+    rows = n1 ** 3
+    rb, re_ = partition_rows(rows, world, rank)
+    A = pkg.CsrMatrix.stencil(be, n1, n1, n1, row_begin=rb, row_end=re_)
+    n = A.rows
+    b, x = be.empty(n), be.zeros(n)
+    be.check(be.L.ViennaCLCUDADfill_uniform(be.h, n, b.ptr, 0, 0, 1.0, 1.0))       # b = 1
+    if world > 1:
+        D = pkg.DistCsr(be, rows, rb, re_, A)
+        solve = lambda t: D.cg(b, x, t)
+    else:
+        solve = lambda t: t.solve("cg", A, b, x)
+    _cg_run(pkg, be, solve, warm)
+    barrier()
+    ms, its = _cg_run(pkg, be, solve, iters)
+    barrier()
+    ms = max_over_ranks(ms)
+    nb = 12 * (7 * rows - 6 * n1 * n1) + 76 * rows
+    return {"iterations_per_sec": its / (ms * 1e-3), "iterations": its, "ms": ms, "n_gpus": world,
+            "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb,
+            "note": "pipelined CG, fixed %d-iteration budget, b = 1, includes solver set-up" % iters}
+
+
+def cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler, peak, peak_src):
+    sampler.start()
+    l0 = be.launches()
+    r = cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters=args.steps, warm=args.warmup)
+    l1 = be.launches()
+    sampler.stop_flag.set()
+    if rank != 0:
+        return None
+    per_gpu = r["effective_GBps"] / world
+    return {"metric": "cg_iterations_per_sec", "value": r["iterations_per_sec"], "unit": "it/s", "n_gpus": world, "steps": r["iterations"],
+            "warmup": args.warmup, "ms_per_step": r["ms"] / max(r["iterations"], 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cg_lap3d_7pt_512^3", "rows": 512 ** 3, "nnz": 7 * 512 ** 3 - 6 * 512 * 512,
+                       "partition": "none" if world == 1 else "1-D row slabs, halo + 3-scalar allreduce per iteration",
+                       "l2_policy": "21.5 GB per iteration, larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                         "peak_source": peak_src, "kernel": "cg iteration = cg_update_kernel + csr_stream_kernel<EpiFused>",
+                         "algorithmic_bytes_per_launch": r["bytes_per_iteration"] // world, "traffic": None},
+            "e2e": {"value": r["iterations_per_sec"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "solve() keeps all vectors on the device; per-iteration host traffic is one 200-byte state read per 32 iterations"},
+            "gpu_launches": int(l1 - l0), "clocks": sampler.summary()}

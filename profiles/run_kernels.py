@@ -1,0 +1,49 @@
+"""Launches every hot kernel a few times at benchmark size so that ncu can capture it (never a bench number).
+
+    ncu --set full --clock-control none --import-source on -k regex:<name> -s 1 -c 2 -o gpurun_out/prof_<name> \
+        python profiles/run_kernels.py <what>
+
+what: spmv (CSR + SELL, 256^3) | cg (3 iterations at 256^3, CSR) | cg_sell | bicgstab | bicgstab_jacobi | gmres | cg1024
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+pkg = ge.load_package()
+what = sys.argv[1] if len(sys.argv) > 1 else "spmv"
+be = pkg.Backend(0)
+n1 = 256
+
+if what == "cg1024":
+    A = pkg.CsrMatrix.stencil(be, 1024, 1024, 1)
+else:
+    c = (0.5, 0.25, 0.125) if what.startswith("bicgstab") or what == "gmres" else (0.0, 0.0, 0.0)
+    A = pkg.CsrMatrix.stencil(be, n1, n1, n1, *c)
+n = A.rows
+x, y = be.empty(n), be.zeros(n)
+be.check(be.L.ViennaCLCUDADfill_uniform(be.h, n, x.ptr, 1, 0, 1.0, 2.0))
+b = be.array(np.ones(n))
+
+if what == "spmv":
+    S = A.to_sell(32)
+    for _ in range(3):
+        A.spmv(x, y)
+        S.spmv(x, y)
+elif what in ("cg", "cg1024"):
+    pkg.SolverTag(tol=0.0, max_iterations=4).solve("cg", A, b, y)
+elif what == "cg_sell":
+    pkg.SolverTag(tol=0.0, max_iterations=4).solve("cg", A.to_sell(32), b, y)
+elif what == "bicgstab":
+    pkg.SolverTag(tol=0.0, max_iterations=3).solve("bicgstab", A, b, y)
+elif what == "bicgstab_jacobi":
+    pkg.SolverTag(tol=0.0, max_iterations=3, precond=1).solve("bicgstab", A, b, y)
+elif what == "gmres":
+    pkg.SolverTag(tol=0.0, max_iterations=30, krylov_dim=30).solve("gmres", A, b, y)
+be.sync()
+print("done", what, be.launches(), "launches")
+be.close()

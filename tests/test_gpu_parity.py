@@ -189,6 +189,28 @@ def test_stencil_generator_and_spmv_vs_oracle(pkg, be, orc, shape):
     assert np.abs(ys - y_ref).max() <= 1e-13 * 24
 
 
+@pytest.mark.parametrize("Cs", [4, 32, 48, 64, 256, 512])
+def test_sell_other_slice_heights(pkg, be, orc, Cs):
+    """rows_per_block other than the default 32 (sliced_ell_matrix.hpp:59-63), incl. the non-staged kernel paths."""
+    A = orc.stencil3d(19, 17, 23, 0.5, 0.25, 0.125)
+    x = orc.uniform(A.cols, 9, 1.0, 2.0)
+    S = orc.sell_build(A, Cs)
+    dA = dev_csr(pkg, be, A)
+    dS = dA.to_sell(Cs)
+    assert dS.padded_nnz == S["padded_nnz"]
+    assert np.array_equal(dS.va.download()[:S["padded_nnz"]], S["elements"])
+    dx, dy = be.array(x), be.array(np.full(A.rows, np.nan))
+    dS.spmv(dx, dy)
+    assert np.array_equal(dy.download(), orc.sell_spmv(S, x))
+    dy = be.array(x[:A.rows].copy())
+    dS.spmv(dx, dy, 0.5, 2.0)
+    assert ol.rel_err(dy.download(), orc.sell_spmv(S, x, x[:A.rows].copy(), 0.5, 2.0)).max() <= 1e-14
+    dS2 = pkg.SellMatrix.from_host(be, S)                 # arrays uploaded in the reference layout
+    dy.fill0()
+    dS2.spmv(dx, dy)
+    assert np.array_equal(dy.download(), orc.sell_spmv(S, x))
+
+
 def test_partial_row_generator(pkg, be, orc):
     nx, ny, nz = 20, 15, 12
     A = orc.stencil3d(nx, ny, nz, 0.1, 0.2, 0.3)

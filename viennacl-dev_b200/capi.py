@@ -413,3 +413,33 @@ class SolverTag:
         s = A.struct()
         A.b.check(fn(A.b.h, C.byref(s), b.ptr, x.ptr, C.byref(self.t)))
         return self
+
+
+class DistCsr:
+    """Row-partitioned CSR (one slab per rank): wraps ViennaCLB200DistCsr.  `A_local` holds the rank's rows with GLOBAL column
+    indices; Backend.comm_init must have been called when world > 1."""
+
+    def __init__(self, backend, global_rows, row_begin, row_end, A_local):
+        self.b = backend
+        self.A = A_local                    # keeps the device arrays alive
+        self.h = c_vp()
+        backend.check(backend.L.ViennaCLCUDADdist_csr_create(backend.h, global_rows, row_begin, row_end, A_local.nnz,
+                                                             A_local.rp.ptr, A_local.ci.ptr, A_local.va.ptr, C.byref(self.h)))
+
+    def spmv(self, x, y):
+        self.b.check(self.b.L.ViennaCLCUDADdist_csrmv(self.b.h, self.h, x.ptr, y.ptr))
+
+    def cg(self, b, x, tag):
+        self.b.check(self.b.L.ViennaCLCUDADdist_csr_cg(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))
+        return tag
+
+    def close(self):
+        if self.h:
+            self.b.L.ViennaCLCUDADdist_csr_destroy(self.b.h, C.byref(self.h))
+            self.h = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -55,7 +55,11 @@ static ViennaCLStatus backend_init(ViennaCLBackend b, int device, void *stream)
   b->l2_bytes = (size_t)prop.l2CacheSize;
   if (stream) { b->stream = (cudaStream_t)stream; b->owns_stream = false; }
   else { VCL_CUDA(b, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->owns_stream = true; }
-  VCL_CUDA(b, cudaStreamCreateWithFlags(&b->comm_stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;                       // communication outranks compute: its few CTAs must not queue behind SpMV CTAs
+    VCL_CUDA(b, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VCL_CUDA(b, cudaStreamCreateWithPriority(&b->comm_stream, cudaStreamNonBlocking, hi));
+  }
   VCL_CUDA(b, cudaEventCreateWithFlags(&b->ev_a, cudaEventDisableTiming));
   VCL_CUDA(b, cudaEventCreateWithFlags(&b->ev_b, cudaEventDisableTiming));
   VCL_CUDA(b, cudaEventCreate(&b->tm_begin));

@@ -46,7 +46,7 @@ struct ViennaCLBackend_impl
   int rank = 0, world = 1;
 };
 
-#define VCL_MAX_BLOCKS 2048     // upper bound on the grid of any reducing kernel
+#define VCL_MAX_BLOCKS 16384    // upper bound on the grid of any reducing kernel (partials: 64 x 16384 doubles = 8 MB)
 #define VCL_MAX_QUANT  64       // quantities reduced at once (GMRES stage 1 reduces up to VCL_GMRES_MAX_KRYLOV dots)
 
 ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, const char *file, int line);

@@ -57,6 +57,7 @@ struct EpiFused
   SolverState *st;                 // NULL in per-op API mode
   double *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
   double acc[3];
+  const double *add_from;          // optional: 3 totals of an earlier launch over a disjoint row subset (interior + boundary split)
   static constexpr int NQ = 3;
 
   __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
@@ -72,6 +73,7 @@ struct EpiFused
   {
     if (grid_sum_last_block<3>(acc, partials, ticket, smem) && threadIdx.x == 0)
     {
+      if (add_from) { acc[0] += add_from[0]; acc[1] += add_from[1]; if (USE_R0) acc[2] += add_from[2]; }
       if (out0) *out0 = acc[0];
       if (out1) *out1 = acc[1];
       if (USE_R0 && out2) *out2 = acc[2];
@@ -92,7 +94,7 @@ __device__ __forceinline__ void st2(double *p, long long i, double2 v) { *reinte
 // ------------------------------------------------------------------------------------------------
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap, double alpha_v, double beta_v,
                  SolverState *st, double *partials, unsigned int *ticket, double *out_rr)
 {
@@ -129,7 +131,7 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
 // BiCGStab: s = r - alpha Ap with alpha = <r,r0*>/<Ap,r0*> taken from device memory; <s,s>
 // (host_based/iterative_operations.hpp:518-563; cuda K9 :733-788 recomputes alpha in every CTA, here it is two loads)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *Ap,
                          const double *in_r_r0, const double *in_Ap_r0,
                          SolverState *st, double *partials, unsigned int *ticket, double *out_ss)
@@ -159,7 +161,7 @@ bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *
 }
 
 // x += alpha p + omega s;  r = s - omega As;  p = r + beta (p - omega Ap);  <r,r0*>     (host_based/iterative_operations.hpp:572-621)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double omega_v, const double *s,
                        double *r, const double *As, double beta_v, const double *Ap, const double *r0,
                        SolverState *st, double *partials, unsigned int *ticket, double *out_r_r0)
@@ -203,7 +205,7 @@ bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double
 // Left-preconditioned BiCGStab (bicgstab.hpp:398-489), device-resident scalars
 // ------------------------------------------------------------------------------------------------
 // s = r - alpha t0                                            (bicgstab.hpp:451)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 pbicg_s_kernel(long long n, double *s, const double *r, const double *t0, const SolverState *st)
 {
   if (st->done != VCL_RUNNING || st->need_restart) return;
@@ -213,7 +215,7 @@ pbicg_s_kernel(long long n, double *s, const double *r, const double *t0, const 
 }
 
 // x += alpha p + omega s; r = s - omega t1; ||r||^2, <r,r0*>; then beta / restart bookkeeping   (bicgstab.hpp:458-474)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double *r, const double *t1, const double *r0,
                 SolverState *st, double *partials, unsigned int *ticket)
 {
@@ -247,7 +249,7 @@ pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double
 }
 
 // p -= omega t0; p = r + beta p                               (bicgstab.hpp:479-480)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 pbicg_p_kernel(long long n, double *p, const double *r, const double *t0, const SolverState *st)
 {
   if (st->done != VCL_RUNNING || st->need_restart) return;
@@ -258,7 +260,7 @@ pbicg_p_kernel(long long n, double *p, const double *r, const double *t0, const 
 
 // restart: r = (b - r) [/ diag]; p = r; r0 = r; ip_rr0 = ||r||^2     (bicgstab.hpp:430-442; r holds A*x on entry)
 template<bool JACOBI>
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double *r0, const double *diag,
                      SolverState *st, double *partials, unsigned int *ticket)
 {
@@ -286,7 +288,7 @@ pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double 
 // stage 1: h_j = <v_j, v_k>, j < k, ALL k vectors in one pass (the reference sweeps 7 at a time and re-reads v_k,
 // cuda/iterative_operations.hpp:1690-1735).  KMAX = compile-time bound on k.
 template<int KMAX>
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double *out_h, int out_stride,
                  double *partials, unsigned int *ticket)
 {
@@ -311,7 +313,7 @@ gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double 
 }
 
 // stage 2: v_k -= sum_j h_j v_j; R[j + k*m] = h_j; ||v_k||^2       (host_based/iterative_operations.hpp:852-893)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double *h, int h_stride,
                  double *R, int krylov_dim, double *out_norm_sq, double *partials, unsigned int *ticket)
 {
@@ -336,7 +338,7 @@ gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double 
 }
 
 // normalize: R[off] = ||v_k||; v_k /= ||v_k||; xi_k = <r, v_k>      (host_based/iterative_operations.hpp:733-778)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, int offset_in_R, const double *in_norm_sq,
                        double *out_r_dot_vk, double *partials, unsigned int *ticket)
 {
@@ -354,7 +356,7 @@ gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, in
 }
 
 // x += c_0 r + sum_{j=1}^{k-1} c_j v_{j-1}                         (host_based/iterative_operations.hpp:895-922)
-__global__ void __launch_bounds__(VEC_THREADS)
+static __global__ void __launch_bounds__(VEC_THREADS)
 gmres_update_kernel(long long n, double *x, const double *res, const double *basis, long long isz, const double *coef, int k)
 {
   __shared__ double s_c[VCL_GMRES_MAX_KRYLOV];

@@ -1,6 +1,7 @@
 // launch.cuh -- grid sizing + launch of the SpMV kernel templates (shared by spmv.cu and solvers.cu).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include "spmv_kernels.cuh"
 
 // Resident CTAs per SM for a kernel, queried once per instantiation (all B200s of a box are identical).
@@ -24,12 +25,12 @@ static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintp
 template<class Epi>
 static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &A, XVec xv, Epi epi)
 {
-  CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.num_blocks};
+  CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.num_blocks, nullptr};
   if (A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx))
   {
-    const int occ = vcl_occupancy(csr_stream_kernel<Epi>, CSR_BLOCK_THREADS);
+    const int occ = vcl_occupancy(csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS);
     int grid = std::min(A.num_blocks, std::min(b->sm_count * occ, VCL_MAX_BLOCKS));
-    csr_stream_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+    csr_stream_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
     VCL_LAUNCHED(b, "csr_stream_kernel");
   }
   else
@@ -42,13 +43,34 @@ static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &
   return ViennaCLSuccess;
 }
 
+// Row-partitioned variant: a subset of the row blocks (interior or boundary list), x addressed as [owned | halo].
+template<class Epi>
+static ViennaCLStatus vcl_launch_csr_split(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi epi, cudaStream_t stream)
+{
+  if (d.nblk <= 0) return ViennaCLSuccess;
+  // Persistent by default.  VCL_B200_SPLIT_CHUNK=k (experiment knob) makes CTAs retire after ~k row blocks so that
+  // communication kernels on the high-priority stream find SM slots while the interior blocks run.
+  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS);
+  const int resident = b->sm_count * occ;
+  static int chunk = -1;
+  if (chunk < 0) { const char *e = getenv("VCL_B200_SPLIT_CHUNK"); chunk = e ? atoi(e) : 0; }
+  int grid = std::min(d.nblk, std::min(resident, VCL_MAX_BLOCKS));
+  if (chunk > 0) grid = std::min(d.nblk, std::min(std::max(resident, vcl_div_up(d.nblk, chunk)), VCL_MAX_BLOCKS));
+  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, 0, stream>>>(d, xv, epi);
+  VCL_LAUNCHED(b, "csr_stream_kernel(split)");
+  return ViennaCLSuccess;
+}
+
 template<class Epi>
 static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
 {
   SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values};
-  const int occ = vcl_occupancy(sell_kernel<Epi>, 256);
-  int grid = std::max(1, std::min(vcl_div_up(A.rows, 256), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
-  sell_kernel<Epi><<<grid, 256, 0, b->stream>>>(d, xv, epi);
+  const int occ = vcl_occupancy(sell_kernel<Epi>, CSR_BLOCK_THREADS);
+  const int C = A.rows_per_block;
+  const int nslices = (A.rows - 1) / C + 1;
+  const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
+  int grid = std::max(1, std::min(vcl_div_up(nslices, spb), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+  sell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "sell_kernel");
   return ViennaCLSuccess;
 }

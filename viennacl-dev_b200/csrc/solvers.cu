@@ -123,7 +123,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, do
     {
       cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, &st->sums[0]);
       VCL_LAUNCHED(b, "cg_update_kernel");
-      EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}};
+      EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, epi));
     }
     launched += nb;
@@ -172,11 +172,11 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const doubl
     const int nb = std::min(batch, tag->max_iterations - launched);
     for (int k = 0; k < nb; ++k)
     {
-      EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}};
+      EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, e1));
       bicgstab_update_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, &st->sums[0], &st->sums[3], st, b->partials, b->tickets, &st->sums[5]);
       VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
-      EpiFused<STEP_BICGSTAB, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[4], {0.0, 0.0, 0.0}};
+      EpiFused<STEP_BICGSTAB, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[4], {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, s, e2));
       if (tag->monitor)
       {
@@ -242,11 +242,11 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *
     const int nb = std::min(batch, remaining);
     for (int k = 0; k < nb; ++k)
     {
-      EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}};
+      EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, e1));
       pbicg_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, t0, st);
       VCL_LAUNCHED(b, "pbicg_s_kernel");
-      EpiFused<STEP_PBICG_OMEGA, false, true> e2 = {t1, s, nullptr, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}};
+      EpiFused<STEP_PBICG_OMEGA, false, true> e2 = {t1, s, nullptr, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, s, e2));
       pbicg_xr_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, s, r, t1, r0, st, b->partials, b->tickets);
       VCL_LAUNCHED(b, "pbicg_xr_kernel");
@@ -366,7 +366,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs,
     {
       double *vk = V + (size_t)k * isz;
       const double *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
-      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, b->partials, b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}};
+      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, b->partials, b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, src, e));
       if (k > 0)
       {
@@ -436,10 +436,10 @@ ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p
   VCL_REQUIRE(b, p && Ap && p != Ap, "bad vectors");
   if (r0)
   {
-    EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}};
+    EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}, nullptr};
     return launch_prod(b, A, p, e);
   }
-  EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, nullptr, {0.0, 0.0, 0.0}};
+  EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, nullptr, {0.0, 0.0, 0.0}, nullptr};
   return launch_prod(b, A, p, e);
 }
 

@@ -24,6 +24,7 @@ struct CsrDev
   int rows; u32 nnz;
   const u32 *rp, *ci; const double *va;
   const u32 *blk; int nblk;
+  const u32 *blk_list;     // optional indirection: process row blocks blk_list[0..nblk) (interior / boundary subsets)
 };
 
 struct SellDev
@@ -32,7 +33,15 @@ struct SellDev
   const u32 *cpb, *ci, *bs; const double *va;
 };
 
-struct XVec { const double *x; int off, inc; };
+// x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
+struct XVec { const double *x; int off, inc; const double *x2; u32 split; };
+
+template<bool SPLIT>
+__device__ __forceinline__ double xload(const XVec &xv, u32 c)
+{
+  if (SPLIT) return (c >= xv.split) ? xv.x2[c - xv.split] : xv.x[c];
+  return xv.x[(size_t)c * xv.inc + xv.off];
+}
 
 // In-row CSR accumulation step.  The reference host backend (host_based/sparse_matrix_operations.hpp:167-184), built with
 // g++ -O3 for x86-64-v3, evaluates `dot += a*x` as a rounded multiply followed by a rounded add (GCC does not form FMA
@@ -69,7 +78,7 @@ struct EpiAxpby
 // ------------------------------------------------------------------------------------------------
 // CSR, row-block streaming
 // ------------------------------------------------------------------------------------------------
-template<class Epi>
+template<class Epi, bool SPLIT>
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS)
 csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 {
@@ -80,10 +89,10 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 
   if (epi.skip()) return;
   const int tid = threadIdx.x;
-  const double * __restrict__ x = xv.x;
 
-  for (int b = blockIdx.x; b < A.nblk; b += gridDim.x)
+  for (int bi = blockIdx.x; bi < A.nblk; bi += gridDim.x)
   {
+    const u32 b = A.blk_list ? A.blk_list[bi] : (u32)bi;
     const u32 r0 = A.blk[b], r1 = A.blk[b + 1];
     const u32 nrows = r1 - r0;
     const u32 n0 = A.rp[r0], n1 = A.rp[r1];
@@ -93,7 +102,7 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       double part[1] = {0.0};
       for (u32 k = n0 + tid; k < n1; k += CSR_BLOCK_THREADS)
-        part[0] = fma(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], part[0]);
+        part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
       __shared__ double s_long[32];
       block_sum<1>(part, s_long);
       if (tid == 0) epi.row(r0, part[0]);
@@ -129,19 +138,19 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
       for (; j + 4 <= e; j += 4)
       {
         const u32 c0 = s_col[j], c1 = s_col[j + 1], c2 = s_col[j + 2], c3 = s_col[j + 3];
-        const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
-        const double x2 = x[(size_t)c2 * xv.inc + xv.off], x3 = x[(size_t)c3 * xv.inc + xv.off];
+        const double x0 = xload<SPLIT>(xv, c0), x1 = xload<SPLIT>(xv, c1);
+        const double x2 = xload<SPLIT>(xv, c2), x3 = xload<SPLIT>(xv, c3);
         dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
         dot = madd(s_val[j + 2], x2, dot); dot = madd(s_val[j + 3], x3, dot);
       }
       if (j + 2 <= e)
       {
         const u32 c0 = s_col[j], c1 = s_col[j + 1];
-        const double x0 = x[(size_t)c0 * xv.inc + xv.off], x1 = x[(size_t)c1 * xv.inc + xv.off];
+        const double x0 = xload<SPLIT>(xv, c0), x1 = xload<SPLIT>(xv, c1);
         dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
         j += 2;
       }
-      if (j < e) dot = madd(s_val[j], x[(size_t)s_col[j] * xv.inc + xv.off], dot);
+      if (j < e) dot = madd(s_val[j], xload<SPLIT>(xv, s_col[j]), dot);
       epi.row(r0 + tid, dot);
     }
     __syncthreads();
@@ -170,46 +179,117 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 }
 
 // ------------------------------------------------------------------------------------------------
-// SELL-C-sigma (sigma = 1): one thread per row, slice-column-major storage gives fully coalesced 8-/4-byte loads per
-// warp for C a multiple of 32.  Entry loads are issued four slice-columns ahead of the fma chain.
-// Zero-valued (padding) slots never touch x: cuda/sparse_matrix_operations.hpp:2231, host :1833.
+// SELL-C-sigma (sigma = 1).  Slices are stored back to back, so the slices of a CTA (256/C of them: 8 for the default
+// C = 32) form ONE contiguous range of values and of column indices: it is streamed global->shared with 16-byte cp.async
+// exactly like a CSR row block, then one thread per row walks its slice-column-major entries (stride C in shared memory:
+// consecutive rows hit consecutive banks) with one fma chain.  Zero-valued (padding) slots never touch x
+// (cuda/sparse_matrix_operations.hpp:2231, host :1833).  Slices wider than the staging buffer take the direct path.
+// The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
 template<class Epi>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
+  __shared__ __align__(16) double s_val[CSR_STAGE];
+  __shared__ __align__(16) u32    s_col[CSR_STAGE];
   __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
   if (epi.skip()) return;
   const double * __restrict__ x = xv.x;
   const double * __restrict__ va = A.va;
   const u32 * __restrict__ ci = A.ci;
-  const size_t C = (size_t)A.C;
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
+  const int tid = threadIdx.x;
+  const u32 C = (u32)A.C;
+  const u32 nslices = (u32)((A.rows - 1) / A.C + 1);
+  const u32 spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1u;      // slices per CTA pass
+  const u32 nblocks = (nslices + spb - 1) / spb;
+  const bool can_stage = (C % 4u) == 0u && C <= CSR_BLOCK_THREADS &&
+                         ((reinterpret_cast<uintptr_t>(va) | reinterpret_cast<uintptr_t>(ci)) & 15u) == 0u;
+
+  for (u32 b = blockIdx.x; b < nblocks; b += gridDim.x)
   {
-    const u32 slice = (u32)(r / A.C);
-    const u32 w = A.cpb[slice];
-    size_t idx = (size_t)A.bs[slice] + (size_t)(r - (long long)slice * A.C);
-    double acc = 0.0;
-    u32 j = 0;
-    for (; j + 4 <= w; j += 4, idx += 4 * C)
+    const u32 s0 = b * spb, s1 = min(s0 + spb, nslices);
+    const u32 base = A.bs[s0];
+    const u32 end = A.bs[s1 - 1] + A.cpb[s1 - 1] * C;
+    const u32 cnt = end - base;
+    const bool staged = can_stage && cnt <= CSR_CAP;
+    if (staged)
     {
-      const double v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * C], v3 = va[idx + 3 * C];
-      const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * C], c3 = ci[idx + 3 * C];
-      const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
-      const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
-      const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
-      const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
-      if (v0 != 0.0) acc = fma(x0, v0, acc);
-      if (v1 != 0.0) acc = fma(x1, v1, acc);
-      if (v2 != 0.0) acc = fma(x2, v2, acc);
-      if (v3 != 0.0) acc = fma(x3, v3, acc);
+      // base is a multiple of C (hence of 4) and cnt a multiple of C: whole 16-byte packets, never past the arrays
+      for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2) cp_async16(&s_val[i], va + base + i);
+      for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4) cp_async16(&s_col[i], ci + base + i);
+      cp_async_commit();
+      // (s1 - s0) * C <= 256 here: one row per thread
+      const bool active = (u32)tid < (s1 - s0) * C;
+      u32 w = 0, idx = 0;
+      long long r = 0;
+      if (active)
+      {
+        const u32 slice = s0 + tid / C;
+        r = (long long)slice * C + (tid % C);
+        w = A.cpb[slice];
+        idx = A.bs[slice] + (tid % C) - base;
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      if (active && r < A.rows)
+      {
+        double acc = 0.0;
+        u32 j = 0;
+        for (; j + 4 <= w; j += 4, idx += 4 * C)
+        {
+          const double v0 = s_val[idx], v1 = s_val[idx + C], v2 = s_val[idx + 2 * C], v3 = s_val[idx + 3 * C];
+          const u32 c0 = s_col[idx], c1 = s_col[idx + C], c2 = s_col[idx + 2 * C], c3 = s_col[idx + 3 * C];
+          const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
+          const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
+          const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
+          const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
+          if (v0 != 0.0) acc = fma(x0, v0, acc);
+          if (v1 != 0.0) acc = fma(x1, v1, acc);
+          if (v2 != 0.0) acc = fma(x2, v2, acc);
+          if (v3 != 0.0) acc = fma(x3, v3, acc);
+        }
+        for (; j < w; ++j, idx += C)
+        {
+          const double v0 = s_val[idx];
+          if (v0 != 0.0) acc = fma(x[(size_t)s_col[idx] * xv.inc + xv.off], v0, acc);
+        }
+        epi.row((u32)r, acc);
+      }
+      __syncthreads();
     }
-    for (; j < w; ++j, idx += C)
+    else
     {
-      const double v0 = va[idx];
-      if (v0 != 0.0) acc = fma(x[(size_t)ci[idx] * xv.inc + xv.off], v0, acc);
+      // direct path (very wide slices, C not a multiple of 4, or C > 256): coalesced 8-/4-byte loads straight from global
+      for (u32 t = tid; t < (s1 - s0) * C; t += CSR_BLOCK_THREADS)
+      {
+        const u32 slice = s0 + t / C;
+        const long long r = (long long)slice * C + (t % C);
+        if (r >= A.rows) continue;
+        const u32 w = A.cpb[slice];
+        size_t idx = (size_t)A.bs[slice] + (t % C);
+        double acc = 0.0;
+        u32 j = 0;
+        for (; j + 4 <= w; j += 4, idx += 4 * (size_t)C)
+        {
+          const double v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * (size_t)C], v3 = va[idx + 3 * (size_t)C];
+          const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * (size_t)C], c3 = ci[idx + 3 * (size_t)C];
+          const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
+          const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
+          const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
+          const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
+          if (v0 != 0.0) acc = fma(x0, v0, acc);
+          if (v1 != 0.0) acc = fma(x1, v1, acc);
+          if (v2 != 0.0) acc = fma(x2, v2, acc);
+          if (v3 != 0.0) acc = fma(x3, v3, acc);
+        }
+        for (; j < w; ++j, idx += C)
+        {
+          const double v0 = va[idx];
+          if (v0 != 0.0) acc = fma(x[(size_t)ci[idx] * xv.inc + xv.off], v0, acc);
+        }
+        epi.row((u32)r, acc);
+      }
     }
-    epi.row((u32)r, acc);
   }
   epi.finish(s_red);
 }
