@@ -152,8 +152,48 @@ def cg_side(pkg, be, args, rank, world, barrier, max_over_ranks):
                              "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb,
                              "note": "includes solver set-up (3 reductions, state upload); working set ~100 MB is L2-resident on B200"}
         del A, b, x
+        out["config3_bicgstab_jacobi_cd3d_256"] = bicgstab_side(pkg, be)
+        out["config4_gmres30_cd2d_4096"] = gmres_side(pkg, be)
     out["lap3d_512"] = cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters=100, warm=10)
     return out
+
+
+def bicgstab_side(pkg, be):
+    """BASELINE configs[2]: BiCGStab + Jacobi on the nonsymmetric 3-D 7-point convection-diffusion matrix 256^3 (first-order
+    upwind, c = (0.5, 0.25, 0.125)), b = 1, tol 1e-8; also the unpreconditioned pipelined variant."""
+    A = pkg.CsrMatrix.stencil(be, 256, 256, 256, 0.5, 0.25, 0.125)
+    n = A.rows
+    b, x = be.array(np.ones(n)), be.zeros(n)
+    out = {}
+    for name, pre, per_it in (("jacobi", 1, 24 * A.nnz + 168 * n), ("pipelined_noprecond", 0, 24 * A.nnz + 152 * n)):
+        pkg.SolverTag(tol=0.0, max_iterations=5, precond=pre).solve("bicgstab", A, b, x)        # warm-up
+        be.sync()
+        tag = pkg.SolverTag(tol=1e-8, max_iterations=2000, precond=pre)
+        be.timer_begin()
+        tag.solve("bicgstab", A, b, x)
+        ms = be.timer_end()
+        out[name] = {"iterations": tag.iters, "error": tag.error, "ms": ms, "iterations_per_sec": tag.iters / (ms * 1e-3),
+                     "bytes_per_iteration": per_it, "effective_GBps": per_it * tag.iters / (ms * 1e-3) / 1e9}
+    return out
+
+
+def gmres_side(pkg, be):
+    """BASELINE configs[3]: restarted GMRES(30), fused Gram-Schmidt, 2-D upwind convection-diffusion 4096 x 4096 (16.7M rows);
+    a fixed budget of 10 restart cycles (300 inner iterations) is timed -- convergence on this grid needs >> 10^4 iterations
+    (SURVEY 8d); convergence parity is covered by the GPU tests on reduced grids."""
+    A = pkg.CsrMatrix.stencil(be, 4096, 4096, 1, 0.5, 0.25, 0.0)
+    n = A.rows
+    b, x = be.array(np.ones(n)), be.zeros(n)
+    pkg.SolverTag(tol=1e-10, max_iterations=30, krylov_dim=30).solve("gmres", A, b, x)           # warm-up: one cycle
+    be.sync()
+    tag = pkg.SolverTag(tol=1e-10, max_iterations=300, krylov_dim=30)
+    be.timer_begin()
+    tag.solve("gmres", A, b, x)
+    ms = be.timer_end()
+    cycles = max(tag.iters // 30, 1)
+    per_cycle = 372 * A.nnz + 9300 * n                 # SURVEY 8d (m = 30)
+    return {"iterations": tag.iters, "error_estimate": tag.error, "ms": ms, "iterations_per_sec": tag.iters / (ms * 1e-3),
+            "bytes_per_restart_cycle": per_cycle, "effective_GBps": per_cycle * cycles / (ms * 1e-3) / 1e9}
 
 
 def cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters, warm):

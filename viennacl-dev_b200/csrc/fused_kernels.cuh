@@ -88,6 +88,12 @@ struct EpiFused
 // ------------------------------------------------------------------------------------------------
 // Helpers for streaming vector kernels: every thread handles pairs (16-byte accesses); a scalar tail covers odd n.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool aligned16(const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
+                                          const void *e = nullptr, const void *f = nullptr, const void *g = nullptr)
+{
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d) |
+           reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0u;
+}
 __device__ __forceinline__ double2 ld2(const double *p, long long i) { return *reinterpret_cast<const double2*>(p + i); }
 __device__ __forceinline__ void st2(double *p, long long i, double2 v) { *reinterpret_cast<double2*>(p + i) = v; }
 
@@ -103,7 +109,7 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
   const double alpha = st ? st->alpha : alpha_v;
   const double beta  = st ? st->beta  : beta_v;
   double acc[1] = {0.0};
-  const long long npairs = n >> 1;
+  const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
@@ -114,9 +120,8 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
     acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const long long k = n - 1;
     double vp = p[k], vr = r[k];
     x[k] = fma(alpha, vp, x[k]);
     vr = fma(-alpha, Ap[k], vr);
@@ -140,7 +145,7 @@ bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *
   if (st != nullptr && st->done != VCL_RUNNING) return;
   const double alpha = (*in_r_r0) / (*in_Ap_r0);
   double acc[1] = {0.0};
-  const long long npairs = n >> 1;
+  const long long npairs = aligned16(s, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
@@ -150,9 +155,8 @@ bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *
     acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
     st2(s, k, vs);
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const long long k = n - 1;
     const double vs = fma(-alpha, Ap[k], r[k]);
     acc[0] = fma(vs, vs, acc[0]);
     s[k] = vs;
@@ -172,7 +176,7 @@ bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double
   const double beta  = st ? st->beta  : beta_v;
   const double omega = st ? st->omega : omega_v;
   double acc[1] = {0.0};
-  const long long npairs = n >> 1;
+  const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
@@ -184,9 +188,8 @@ bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double
     acc[0] = fma(vr.x, v0.x, acc[0]);                acc[0] = fma(vr.y, v0.y, acc[0]);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const long long k = n - 1;
     double vp = p[k]; const double vs = s[k];
     x[k] += alpha * vp + omega * vs;
     const double vr = fma(-omega, As[k], vs);
@@ -223,7 +226,19 @@ pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double
   if (st->done != VCL_RUNNING || st->need_restart) return;
   const double alpha = st->alpha, omega = st->omega;
   double acc[2] = {0.0, 0.0};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const long long npairs = aligned16(x, p, s, r, t1, r0) ? (n >> 1) : 0;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = 2 * pi;
+    const double2 vs = ld2(s, k), vp = ld2(p, k), vt = ld2(t1, k), v0 = ld2(r0, k);
+    double2 vx = ld2(x, k), vr;
+    vx.x += alpha * vp.x + omega * vs.x;   vx.y += alpha * vp.y + omega * vs.y;
+    vr.x = fma(-omega, vt.x, vs.x);        vr.y = fma(-omega, vt.y, vs.y);
+    acc[0] = fma(vr.x, vr.x, acc[0]);      acc[0] = fma(vr.y, vr.y, acc[0]);
+    acc[1] = fma(vr.x, v0.x, acc[1]);      acc[1] = fma(vr.y, v0.y, acc[1]);
+    st2(x, k, vx); st2(r, k, vr);
+  }
+  for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     const double vs = s[i];
     x[i] += alpha * p[i] + omega * vs;
@@ -285,31 +300,81 @@ pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double 
 // ------------------------------------------------------------------------------------------------
 // GMRES (classical Gram-Schmidt, gmres.hpp:241-284)
 // ------------------------------------------------------------------------------------------------
-// stage 1: h_j = <v_j, v_k>, j < k, ALL k vectors in one pass (the reference sweeps 7 at a time and re-reads v_k,
-// cuda/iterative_operations.hpp:1690-1735).  KMAX = compile-time bound on k.
-template<int KMAX>
+// stage 1: h_j = <v_j, v_k>, j < k, ALL k vectors in one pass over the basis (the reference sweeps 7 vectors at a time and
+// re-reads v_k for every sweep, cuda/iterative_operations.hpp:1690-1735).
+// Work split inside a CTA (8 warps): the k columns are dealt round-robin to NG column groups (NG = 1, 2, 4 or 8 warps),
+// the remaining 8/NG warps of a group take different row sub-ranges.  A thread therefore carries only CPW = ceil(k/NG)
+// accumulators (<= 8 for k <= 64) instead of k, and every load is a 16-byte double2; v_k is re-read by the NG column-group
+// warps of a CTA, which hits L1.  DRAM traffic: (k+1)*8*n bytes, the compulsory amount.
+template<int CPW>
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double *out_h, int out_stride,
+gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, int NG, double *out_h, int out_stride,
                  double *partials, unsigned int *ticket)
 {
-  __shared__ double s_red[KMAX * 32];
+  __shared__ double s_part[8][CPW];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cg = w % NG, rs = w / NG, RS = 8 / NG;
   const double *vk = basis + (size_t)k * isz;
-  double acc[KMAX];
+  double acc[CPW];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) acc[j] = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  for (int q = 0; q < CPW; ++q) acc[q] = 0.0;
+  const long long npairs = n >> 1;
+  const long long stride = (long long)gridDim.x * RS * 32;
+  for (long long pi = ((long long)blockIdx.x * RS + rs) * 32 + lane; pi < npairs; pi += stride)
   {
-    const double v = vk[i];
+    const double2 v = ld2(vk, 2 * pi);
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < k) acc[j] = fma(basis[(size_t)j * isz + i], v, acc[j]);
+    for (int q = 0; q < CPW; ++q)
+    {
+      const int j = cg + q * NG;
+      if (j < k)
+      {
+        const double2 a = ld2(basis + (size_t)j * isz, 2 * pi);
+        acc[q] = fma(a.x, v.x, acc[q]);
+        acc[q] = fma(a.y, v.y, acc[q]);
+      }
+    }
   }
-  if (grid_sum_last_block<KMAX>(acc, partials, ticket, s_red) && threadIdx.x == 0)
+  if ((n & 1) && blockIdx.x == 0 && rs == 0 && lane == 0)
   {
+    const double v = vk[n - 1];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < k) out_h[(size_t)j * out_stride] = acc[j];
+    for (int q = 0; q < CPW; ++q)
+    {
+      const int j = cg + q * NG;
+      if (j < k) acc[q] = fma(basis[(size_t)j * isz + n - 1], v, acc[q]);
+    }
   }
+#pragma unroll
+  for (int q = 0; q < CPW; ++q)
+  {
+    const double t = warp_sum(acc[q]);
+    if (lane == 0) s_part[w][q] = t;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < k)
+  {
+    const int j = threadIdx.x, jc = j % NG, jq = j / NG;
+    double t = 0.0;
+    for (int r = 0; r < RS; ++r) t += s_part[jc + r * NG][jq];
+    partials[(size_t)j * VCL_MAX_BLOCKS + blockIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: warp w finishes columns w, w+8, ... in a fixed order
+  for (int j = w; j < k; j += 8)
+  {
+    double t = 0.0;
+    for (unsigned int i = lane; i < gridDim.x; i += 32) t += __ldcg(partials + (size_t)j * VCL_MAX_BLOCKS + i);
+    t = warp_sum(t);
+    if (lane == 0) out_h[(size_t)j * out_stride] = t;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // stage 2: v_k -= sum_j h_j v_j; R[j + k*m] = h_j; ||v_k||^2       (host_based/iterative_operations.hpp:852-893)
@@ -323,12 +388,34 @@ gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double 
   __syncthreads();
   double *vk = basis + (size_t)k * isz;
   double acc[1] = {0.0};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const long long npairs = n >> 1;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
-    double v = vk[i];
-    for (int j = 0; j < k; ++j) v = fma(-s_h[j], basis[(size_t)j * isz + i], v);
+    double2 v = ld2(vk, 2 * pi);
+    int j = 0;
+    for (; j + 4 <= k; j += 4)
+    {
+      const double2 a0 = ld2(basis + (size_t)j * isz, 2 * pi), a1 = ld2(basis + (size_t)(j + 1) * isz, 2 * pi);
+      const double2 a2 = ld2(basis + (size_t)(j + 2) * isz, 2 * pi), a3 = ld2(basis + (size_t)(j + 3) * isz, 2 * pi);
+      v.x = fma(-s_h[j], a0.x, v.x);     v.y = fma(-s_h[j], a0.y, v.y);
+      v.x = fma(-s_h[j + 1], a1.x, v.x); v.y = fma(-s_h[j + 1], a1.y, v.y);
+      v.x = fma(-s_h[j + 2], a2.x, v.x); v.y = fma(-s_h[j + 2], a2.y, v.y);
+      v.x = fma(-s_h[j + 3], a3.x, v.x); v.y = fma(-s_h[j + 3], a3.y, v.y);
+    }
+    for (; j < k; ++j)
+    {
+      const double2 a0 = ld2(basis + (size_t)j * isz, 2 * pi);
+      v.x = fma(-s_h[j], a0.x, v.x); v.y = fma(-s_h[j], a0.y, v.y);
+    }
+    acc[0] = fma(v.x, v.x, acc[0]); acc[0] = fma(v.y, v.y, acc[0]);
+    st2(vk, 2 * pi, v);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    double v = vk[n - 1];
+    for (int j = 0; j < k; ++j) v = fma(-s_h[j], basis[(size_t)j * isz + n - 1], v);
     acc[0] = fma(v, v, acc[0]);
-    vk[i] = v;
+    vk[n - 1] = v;
   }
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
   {
@@ -346,7 +433,16 @@ gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, in
   const double nrm = sqrt(*in_norm_sq);
   if (blockIdx.x == 0 && threadIdx.x == 0) R[offset_in_R] = nrm;
   double acc[1] = {0.0};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const bool vec = ((reinterpret_cast<uintptr_t>(vk) | reinterpret_cast<uintptr_t>(res)) & 15u) == 0u;
+  const long long npairs = vec ? (n >> 1) : 0;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
+  {
+    double2 v = ld2(vk, 2 * pi); const double2 rr = ld2(res, 2 * pi);
+    v.x = v.x / nrm; v.y = v.y / nrm;
+    acc[0] = fma(rr.x, v.x, acc[0]); acc[0] = fma(rr.y, v.y, acc[0]);
+    st2(vk, 2 * pi, v);
+  }
+  for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     const double v = vk[i] / nrm;
     acc[0] = fma(res[i], v, acc[0]);
@@ -362,7 +458,20 @@ gmres_update_kernel(long long n, double *x, const double *res, const double *bas
   __shared__ double s_c[VCL_GMRES_MAX_KRYLOV];
   for (int j = threadIdx.x; j < max(k, 1); j += blockDim.x) s_c[j] = coef[j];
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(basis)) & 15u) == 0u && (isz & 1) == 0;
+  const long long npairs = vec ? (n >> 1) : 0;
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
+  {
+    double2 v = ld2(x, 2 * pi); const double2 rr = ld2(res, 2 * pi);
+    v.x = fma(s_c[0], rr.x, v.x); v.y = fma(s_c[0], rr.y, v.y);
+    for (int j = 1; j < k; ++j)
+    {
+      const double2 a = ld2(basis + (size_t)(j - 1) * isz, 2 * pi);
+      v.x = fma(s_c[j], a.x, v.x); v.y = fma(s_c[j], a.y, v.y);
+    }
+    st2(x, 2 * pi, v);
+  }
+  for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
     double v = x[i];
     v = fma(s_c[0], res[i], v);

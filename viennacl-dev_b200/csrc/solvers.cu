@@ -294,10 +294,16 @@ residual_kernel(long long n, double *res, const double *rhs)     // res = rhs - 
 
 ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const double *basis, long long n, long long isz, int k, double *out_h, int stride)
 {
-  if (k <= 8)       gmres_gs1_kernel<8><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
-  else if (k <= 16) gmres_gs1_kernel<16><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
-  else if (k <= 32) gmres_gs1_kernel<32><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
-  else              gmres_gs1_kernel<64><<<grid, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  VCL_REQUIRE(b, (isz & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u,
+              "Krylov basis must be 16-byte aligned with an even internal size (the reference pads vectors to 128 entries, forwards.h:385)");
+  const int NG = k >= 5 ? 8 : (k >= 3 ? 4 : (k == 2 ? 2 : 1));      // column groups (warps) per CTA
+  const int cpw = (k + NG - 1) / NG;                                 // columns per warp
+  (void)grid;
+  const int g = std::max(1, std::min(vcl_div_up(n / 2, 256 / NG * 1), std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+  if (cpw <= 1)      gmres_gs1_kernel<1><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
+  else if (cpw <= 2) gmres_gs1_kernel<2><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
+  else if (cpw <= 4) gmres_gs1_kernel<4><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
+  else               gmres_gs1_kernel<8><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
   VCL_LAUNCHED(b, "gmres_gs1_kernel");
   return ViennaCLSuccess;
 }
@@ -574,6 +580,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend 
     chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, b->dscal + 16 + j);
     VCL_LAUNCHED(b, "chunk_sum_kernel");
   }
+  VCL_REQUIRE(b, (internal_n & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u, "Krylov basis must be 16-byte aligned with an even internal size");
   gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, b->dscal + 16, 1, R, krylov_dim,
                                                                    buf + chunk, b->partials, b->tickets);
   VCL_LAUNCHED(b, "gmres_gs2_kernel");
