@@ -1,0 +1,47 @@
+"""The C++ drop-in facade (viennacl-dev_b200/include/viennacl/...) is exercised by plain-g++ programs that restate the
+reference's own tests/tutorials (tests/src/sparse.cpp, self_assign.cpp, examples/tutorial/iterative*.cpp,
+wrap-cuda-buffer.cu) -- see viennacl-dev_b200/facade_tests/.  CPU: they build without nvcc and refuse to run without a
+device (no CPU fallback).  GPU: they pass."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FACADE = os.path.join(ROOT, "viennacl-dev_b200", "lib", "facade")
+PROGS = ["sparse_prod", "iterative", "wrap_cuda_buffer"]
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "viennacl-dev_b200", "facade_tests")])
+
+
+def test_facade_programs_build_with_plain_gxx(pkg):
+    if not pkg.library_available():
+        pkg.build_library()
+    _build()
+    for p in PROGS + ["bench_sparse_solver"]:
+        assert os.access(os.path.join(FACADE, p), os.X_OK), p
+
+
+def test_facade_refuses_to_run_without_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    _build()
+    r = subprocess.run([os.path.join(FACADE, "wrap_cuda_buffer")], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", PROGS)
+def test_facade_program_passes_on_gpu(prog):
+    exe = os.path.join(FACADE, prog)
+    if not os.access(exe, os.X_OK):
+        _build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "COMPLETED SUCCESSFULLY" in r.stdout

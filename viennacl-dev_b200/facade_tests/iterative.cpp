@@ -1,0 +1,167 @@
+// iterative.cpp -- the user code of the reference's solver tutorials (examples/tutorial/iterative.cpp:190-290 and
+// iterative-custom.cpp:55-200) against the B200 facade: solve(A, b, tag[, precond]) for CG / BiCGStab / GMRES on
+// compressed_matrix and sliced_ell_matrix, the *_solver functors with set_initial_guess() and set_monitor().
+// The tutorials' fixture mat65k.mtx is not shipped; the systems are the FDM matrices of SURVEY 8(d) at small sizes.
+// Each result is verified by its TRUE relative residual ||b - A x|| / ||b|| computed with prod() + norm_2().
+#include <cstdlib>
+#include <cmath>
+#include <iostream>
+#include <vector>
+
+#include "viennacl/vector.hpp"
+#include "viennacl/compressed_matrix.hpp"
+#include "viennacl/sliced_ell_matrix.hpp"
+#include "viennacl/linalg/prod.hpp"
+#include "viennacl/linalg/norm_2.hpp"
+#include "viennacl/linalg/jacobi_precond.hpp"
+#include "viennacl/linalg/cg.hpp"
+#include "viennacl/linalg/bicgstab.hpp"
+#include "viennacl/linalg/gmres.hpp"
+#include "viennacl/tools/matrix_generation.hpp"
+
+typedef double ScalarType;
+typedef viennacl::vector<ScalarType> VectorT;
+typedef viennacl::compressed_matrix<ScalarType> MatrixT;
+
+template<typename MatT>
+static ScalarType true_residual(MatT const & A, VectorT const & x, VectorT const & b)
+{
+  VectorT r = viennacl::linalg::prod(A, x);
+  r = b - r;
+  return ScalarType(viennacl::linalg::norm_2(r)) / ScalarType(viennacl::linalg::norm_2(b));
+}
+
+static int failures = 0;
+static void expect(bool ok, const char *what)
+{
+  std::cout << (ok ? "  ok  " : "# FAILED: ") << what << std::endl;
+  if (!ok) ++failures;
+}
+
+// iterative-custom.cpp:55-100
+template<typename MatT>
+struct monitor_user_data
+{
+  monitor_user_data(MatT const & A, VectorT const & b, VectorT const & guess) : A_ptr(&A), b_ptr(&b), guess_ptr(&guess), calls(0), last_true(0), last_est(0) {}
+  MatT const *A_ptr;
+  VectorT const *b_ptr;
+  VectorT const *guess_ptr;
+  int calls;
+  ScalarType last_true, last_est;
+};
+
+template<typename MatT>
+bool my_custom_monitor(VectorT const & current_approx, ScalarType residual_estimate, void *user_data)
+{
+  monitor_user_data<MatT> *data = reinterpret_cast<monitor_user_data<MatT>*>(user_data);
+  VectorT x = current_approx + *data->guess_ptr;          // the solver works on the shifted system
+  data->last_true = true_residual(*data->A_ptr, x, *data->b_ptr);
+  data->last_est = residual_estimate;
+  ++data->calls;
+  return data->last_true < 1e-4;                           // custom termination criterion
+}
+
+int main()
+{
+  MatrixT A;                                               // 2-D Laplacian, SPD
+  viennacl::tools::generate_fdm_laplace(A, 96, 80);
+  MatrixT C;                                               // 3-D upwind convection-diffusion, nonsymmetric
+  viennacl::tools::generate_fdm_stencil(C, 24, 20, 18, 0.5, 0.25, 0.125);
+  viennacl::sliced_ell_matrix<ScalarType> A_sell, C_sell;
+  viennacl::copy(A, A_sell);
+  viennacl::copy(C, C_sell);
+
+  VectorT b = viennacl::scalar_vector<ScalarType>(A.size1(), 1.0);
+  VectorT c = viennacl::scalar_vector<ScalarType>(C.size1(), 1.0);
+
+  std::cout << "----- CG Method -----" << std::endl;
+  {
+    VectorT x;
+    viennacl::linalg::cg_tag tag(1e-8, 1000);
+    x = viennacl::linalg::solve(A, b, tag);
+    std::cout << "  CSR : " << tag.iters() << " iterations, estimate " << tag.error() << ", true " << true_residual(A, x, b) << std::endl;
+    expect(tag.iters() > 10 && tag.iters() < 1000 && tag.error() < 1e-8 && true_residual(A, x, b) < 1e-7, "solve(compressed_matrix, b, cg_tag)");
+    viennacl::linalg::cg_tag tag2(1e-8, 1000);
+    VectorT x2 = viennacl::linalg::solve(A_sell, b, tag2);
+    expect(std::abs(int(tag2.iters()) - int(tag.iters())) <= 2 && true_residual(A, x2, b) < 1e-7, "solve(sliced_ell_matrix, b, cg_tag)");
+    viennacl::linalg::cg_tag few(1e-8, 20);
+    x = viennacl::linalg::solve(A, b, few);
+    expect(few.iters() == 20 && few.error() > 1e-8, "cg_tag(1e-8, 20) stops at max_iterations and reports the estimate");
+    x = viennacl::linalg::solve(A, b, viennacl::linalg::cg_tag(), viennacl::linalg::no_precond());
+    expect(x.size() == b.size(), "solve(A, b, cg_tag(), no_precond())");
+  }
+
+  std::cout << "----- BiCGStab Method -----" << std::endl;
+  {
+    VectorT x;
+    viennacl::linalg::bicgstab_tag tag(1e-8, 1000);
+    x = viennacl::linalg::solve(C, c, tag);
+    std::cout << "  CSR : " << tag.iters() << " iterations, estimate " << tag.error() << ", true " << true_residual(C, x, c) << std::endl;
+    expect(tag.iters() > 3 && tag.iters() < 1000 && true_residual(C, x, c) < 1e-6, "solve(compressed_matrix, b, bicgstab_tag)");
+    viennacl::linalg::bicgstab_tag tag2(1e-8, 1000);
+    VectorT x2 = viennacl::linalg::solve(C_sell, c, tag2);
+    expect(tag2.iters() < 1000 && true_residual(C, x2, c) < 1e-6, "solve(sliced_ell_matrix, b, bicgstab_tag)");
+    viennacl::linalg::jacobi_precond<MatrixT> vcl_jacobi(C, viennacl::linalg::jacobi_tag());
+    viennacl::linalg::bicgstab_tag tag3(1e-8, 1000);
+    x = viennacl::linalg::solve(C, c, tag3, vcl_jacobi);
+    std::cout << "  CSR + Jacobi : " << tag3.iters() << " iterations, estimate " << tag3.error() << ", true " << true_residual(C, x, c) << std::endl;
+    expect(tag3.iters() > 3 && tag3.iters() < 1000 && true_residual(C, x, c) < 1e-6, "solve(compressed_matrix, b, bicgstab_tag, jacobi_precond)");
+    VectorT y = c;
+    vcl_jacobi.apply(y);                                   // stand-alone apply: y = c ./ diag(C)
+    expect(std::fabs(ScalarType(y[5]) - 1.0 / (6.0 + 0.5 + 0.25 + 0.125)) < 1e-15, "jacobi_precond::apply");
+  }
+
+  std::cout << "----- GMRES Method -----" << std::endl;
+  {
+    VectorT x;
+    viennacl::linalg::gmres_tag tag(1e-8, 600, 30);
+    x = viennacl::linalg::solve(C, c, tag);
+    std::cout << "  CSR : " << tag.iters() << " iterations, estimate " << tag.error() << ", true " << true_residual(C, x, c) << std::endl;
+    expect(tag.iters() > 3 && tag.iters() < 600 && true_residual(C, x, c) < 1e-7, "solve(compressed_matrix, b, gmres_tag)");
+    viennacl::linalg::gmres_tag tag2(1e-8, 600, 30);
+    VectorT x2 = viennacl::linalg::solve(C_sell, c, tag2);
+    expect(tag2.iters() == tag.iters() && true_residual(C, x2, c) < 1e-7, "solve(sliced_ell_matrix, b, gmres_tag)");
+    expect(viennacl::linalg::gmres_tag(1e-8, 90, 30).max_restarts() == 2 && viennacl::linalg::gmres_tag(1e-8, 100, 30).max_restarts() == 3,
+           "gmres_tag::max_restarts() (gmres.hpp:74-80)");
+  }
+
+  std::cout << "----- solver objects: initial guess + monitor (iterative-custom.cpp) -----" << std::endl;
+  {
+    VectorT init_guess = viennacl::scalar_vector<ScalarType>(b.size(), 0.9);
+    init_guess[0] = 0;
+    monitor_user_data<MatrixT> data(A, b, init_guess);
+
+    viennacl::linalg::cg_solver<VectorT> my_cg_solver(viennacl::linalg::cg_tag(1e-10, 2000));
+    my_cg_solver.set_monitor(my_custom_monitor<MatrixT>, &data);
+    my_cg_solver.set_initial_guess(init_guess);
+    VectorT x = my_cg_solver(A, b);
+    std::cout << "  CG : monitor called " << data.calls << " times, stopped at true residual " << data.last_true << " (estimate " << data.last_est << ")" << std::endl;
+    expect(data.calls > 5 && data.last_true < 1e-4 && true_residual(A, x, b) < 1e-4 && true_residual(A, x, b) > 1e-9, "cg_solver with monitor stops early");
+
+    monitor_user_data<MatrixT> data2(C, c, c);
+    VectorT guess2 = viennacl::scalar_vector<ScalarType>(c.size(), 0.1);
+    data2.guess_ptr = &guess2;
+    viennacl::linalg::bicgstab_solver<VectorT> my_bicgstab_solver(viennacl::linalg::bicgstab_tag(1e-10, 2000));
+    my_bicgstab_solver.set_monitor(my_custom_monitor<MatrixT>, &data2);
+    my_bicgstab_solver.set_initial_guess(guess2);
+    VectorT xc = my_bicgstab_solver(C, c);
+    expect(data2.calls > 1 && true_residual(C, xc, c) < 1e-3, "bicgstab_solver with monitor + initial guess");
+
+    monitor_user_data<MatrixT> data3(C, c, guess2);
+    viennacl::linalg::gmres_solver<VectorT> my_gmres_solver(viennacl::linalg::gmres_tag(1e-10, 600, 20));
+    my_gmres_solver.set_monitor(my_custom_monitor<MatrixT>, &data3);
+    my_gmres_solver.set_initial_guess(guess2);
+    xc = my_gmres_solver(C, c);
+    std::cout << "  GMRES : monitor called " << data3.calls << " times (once per restart)" << std::endl;
+    expect(data3.calls >= 1 && true_residual(C, xc, c) < 1e-4, "gmres_solver with monitor + initial guess");
+
+    viennacl::linalg::cg_solver<VectorT> plain(viennacl::linalg::cg_tag(1e-8, 1000));
+    plain.set_initial_guess(init_guess);
+    x = plain(A, b);
+    expect(true_residual(A, x, b) < 1e-6, "cg_solver with initial guess, no monitor");
+  }
+
+  if (failures) { std::cout << failures << " check(s) FAILED" << std::endl; return EXIT_FAILURE; }
+  std::cout << "!!!! TUTORIAL COMPLETED SUCCESSFULLY !!!!" << std::endl;
+  return EXIT_SUCCESS;
+}

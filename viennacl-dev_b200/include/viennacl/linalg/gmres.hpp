@@ -1,0 +1,113 @@
+// viennacl/linalg/gmres.hpp -- restarted GMRES(m), pipelined simpler-GMRES with fused classical Gram-Schmidt (reference: linalg/gmres.hpp:49-101, 181-367, 635-732).
+// The tag keeps the reference's fields and defaults; solve() forwards to the whole-solve entry point of the C-ABI
+// (ViennaCLCUDAD{csr,sell}_gmres), whose loop runs next to the kernels with device-resident scalars.
+#ifndef VIENNACL_B200_LINALG_GMRES_HPP
+#define VIENNACL_B200_LINALG_GMRES_HPP
+#include "viennacl/linalg/detail_solver_call.hpp"
+namespace viennacl
+{
+namespace linalg
+{
+
+/** @brief Solver configuration and result carrier; iters()/error() are mutable so that a const tag reports back (gmres.hpp:49-101) */
+class gmres_tag
+{
+public:
+  gmres_tag(double tol = 1e-10, unsigned int max_iterations = 300, unsigned int krylov_dim = 20)
+    : tol_(tol), abs_tol_(0), iterations_(max_iterations), krylov_dim_(krylov_dim), iters_taken_(0), last_error_(0) {}
+  double tolerance() const { return tol_; }
+  double abs_tolerance() const { return abs_tol_; }
+  void abs_tolerance(double new_tol) { if (new_tol >= 0) abs_tol_ = new_tol; }
+  unsigned int max_iterations() const { return iterations_; }
+  unsigned int krylov_dim() const { return krylov_dim_; }
+  unsigned int max_restarts() const
+  {
+    unsigned int ret = iterations_ / krylov_dim_;
+    if (ret > 0 && (ret * krylov_dim_ == iterations_)) return ret - 1;
+    return ret;
+  }
+  unsigned int iters() const { return iters_taken_; }
+  void iters(unsigned int i) const { iters_taken_ = i; }
+  double error() const { return last_error_; }
+  void error(double e) const { last_error_ = e; }
+private:
+  double tol_;
+  double abs_tol_;
+  unsigned int iterations_;
+  unsigned int krylov_dim_;
+  mutable unsigned int iters_taken_;
+  mutable double last_error_;
+};
+
+namespace detail
+{
+  inline ViennaCLB200SolverTag to_abi(gmres_tag const & tag)
+  {
+    ViennaCLB200SolverTag t;
+    t.tolerance = tag.tolerance(); t.abs_tolerance = tag.abs_tolerance(); t.max_iterations = ViennaCLInt(tag.max_iterations());
+    t.krylov_dim = ViennaCLInt(tag.krylov_dim()); t.max_iterations_before_restart = 0; t.precond = ViennaCLB200PrecondNone;
+    t.monitor = NULL; t.monitor_user = NULL; t.iters = 0; t.error = 0;
+    return t;
+  }
+
+  template<typename MatrixT, typename NumericT>
+  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag, viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  {
+    ViennaCLB200SolverTag t = to_abi(tag);
+    viennacl::vector<NumericT> x = run(SOLVER_GMRES, A, rhs, t, monitor, monitor_data);
+    tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
+    return x;
+  }
+
+}
+
+/** @brief x = solve(A, b, gmres_tag(...)) for compressed_matrix / sliced_ell_matrix (gmres.hpp:635-673) */
+template<typename MatrixT, typename NumericT, typename PreconditionerT>
+viennacl::vector<NumericT> solve(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag, PreconditionerT const & precond)
+{ return detail::solve_impl(A, rhs, tag, precond); }
+
+template<typename MatrixT, typename NumericT>
+viennacl::vector<NumericT> solve(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag)
+{ return detail::solve_impl(A, rhs, tag, viennacl::linalg::no_precond()); }
+
+/** @brief Functor form with initial guess and monitor (gmres.hpp:677-732) */
+template<typename VectorT>
+class gmres_solver
+{
+public:
+  typedef typename VectorT::value_type numeric_type;
+
+  gmres_solver(gmres_tag const & tag) : tag_(tag), monitor_callback_(NULL), user_data_(NULL) {}
+
+  template<typename MatrixT, typename PreconditionerT>
+  VectorT operator()(MatrixT const & A, VectorT const & b, PreconditionerT const & precond) const
+  {
+    if (viennacl::traits::size(init_guess_) > 0)          // A y = b - A x0, x = x0 + y
+    {
+      VectorT mod_rhs = viennacl::linalg::prod(A, init_guess_);
+      mod_rhs = b - mod_rhs;
+      VectorT y = detail::solve_impl(A, mod_rhs, tag_, precond, monitor_callback_, user_data_);
+      VectorT x = init_guess_ + y;
+      return x;
+    }
+    return detail::solve_impl(A, b, tag_, precond, monitor_callback_, user_data_);
+  }
+
+  template<typename MatrixT>
+  VectorT operator()(MatrixT const & A, VectorT const & b) const { return operator()(A, b, viennacl::linalg::no_precond()); }
+
+  void set_initial_guess(VectorT const & x) { init_guess_ = x; }
+  void set_monitor(bool (*monitor_fun)(VectorT const &, numeric_type, void *), void *user_data) { monitor_callback_ = monitor_fun; user_data_ = user_data; }
+  gmres_tag const & tag() const { return tag_; }
+
+private:
+  gmres_tag tag_;
+  VectorT init_guess_;
+  bool (*monitor_callback_)(VectorT const &, numeric_type, void *);
+  void *user_data_;
+};
+
+}
+}
+#endif
