@@ -249,6 +249,10 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend backend, long long g
                                             const double *values, ViennaCLB200DistCsr *out);
 ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend backend, ViennaCLB200DistCsr *A);
 ViennaCLStatus ViennaCLCUDADdist_csrmv(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *x_local, double *y_local);
+/* Which transport the object uses: 1 = peer memory (CUDA IPC windows over NVLink; halo pushes and the reduction are done
+ * by the solver's own kernels), 0 = NCCL send/recv + allreduce.  Also returns the halo size and the interior/boundary split. */
+ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend backend, ViennaCLB200DistCsr A, ViennaCLInt *peer_memory,
+                                          ViennaCLInt *halo_entries, ViennaCLInt *interior_blocks, ViennaCLInt *boundary_blocks);
 ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *b_local, double *x_local,
                                         ViennaCLB200SolverTag *tag);
 

@@ -69,6 +69,9 @@ def main():
         rp, ci, va = slab(A, rb, re_)
         dA = pkg.CsrMatrix.from_host(be, re_ - rb, n, rp, ci, va, with_blocks=False)
         D = pkg.DistCsr(be, n, rb, re_, dA)
+        info = D.info()
+        if world > 1 and os.environ.get("VCL_B200_DIST_TRANSPORT", "p2p") != "nccl" and os.environ.get("VCL_EXPECT_P2P", "1") == "1":
+            ok &= info["transport"] == "peer-memory"      # NVLink box: the IPC windows must map
         x = o.uniform(n, 11, 1.0, 2.0)
         y_ref = o.csr_spmv(A, x)
         dx, dy = be.array(x[rb:re_]), be.zeros(re_ - rb)
@@ -85,7 +88,7 @@ def main():
         good = same and abs(tag.iters - ref["iters"]) <= 2 and err < 1e-6 and (tag.error < 1e-9 or ref["error"] >= 1e-9)   # (CG on the nonsymmetric case stagnates, identically)
         ok &= good
         print("[rank %d/%d] %-22s spmv bit-exact=%s  cg iters %d (oracle %d) err %.2e rel-x-diff %.2e  %s"
-              % (rank, world, name, same, tag.iters, ref["iters"], tag.error, err, "OK" if good else "FAIL"), flush=True)
+              % (rank, world, name, same, tag.iters, ref["iters"], tag.error, err, "OK" if good else "FAIL") + " [%s]" % info["transport"], flush=True)
         # budget exhaustion must report the same iterate on every partitioning
         tag = D.cg(db, dsol, pkg.SolverTag(tol=1e-30, max_iterations=9))
         ref9 = o.cg(A, b, tol=1e-30, maxit=9)

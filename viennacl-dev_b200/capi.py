@@ -146,6 +146,7 @@ def lib():
     sig("ViennaCLCUDADdist_csr_create", c_vp, c_ll, c_ll, c_ll, c_int, c_vp, c_vp, c_vp, p_vp)
     sig("ViennaCLCUDADdist_csr_destroy", c_vp, p_vp)
     sig("ViennaCLCUDADdist_csrmv", c_vp, c_vp, c_vp, c_vp)
+    sig("ViennaCLCUDADdist_csr_info", c_vp, c_vp, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int))
     sig("ViennaCLCUDADdist_csr_cg", c_vp, c_vp, c_vp, c_vp, pt)
     _lib = L
     return L
@@ -428,6 +429,12 @@ class DistCsr:
 
     def spmv(self, x, y):
         self.b.check(self.b.L.ViennaCLCUDADdist_csrmv(self.b.h, self.h, x.ptr, y.ptr))
+
+    def info(self):
+        p, hl, ni, nb = c_int(), c_int(), c_int(), c_int()
+        self.b.check(self.b.L.ViennaCLCUDADdist_csr_info(self.b.h, self.h, C.byref(p), C.byref(hl), C.byref(ni), C.byref(nb)))
+        return {"transport": "peer-memory" if p.value else "nccl", "halo_entries": hl.value, "interior_blocks": ni.value,
+                "boundary_blocks": nb.value}
 
     def cg(self, b, x, tag):
         self.b.check(self.b.L.ViennaCLCUDADdist_csr_cg(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))

@@ -5,11 +5,17 @@
 // device: columns outside the owned range become the halo; they are renumbered to [owned | halo] (halo sorted by global id,
 // hence grouped by owner), every owner learns which of its entries each peer needs (send lists), and the CSR row blocks
 // are split into INTERIOR blocks (no halo column) and BOUNDARY blocks.
-// One product:   pack owned entries -> ncclSend/ncclRecv with the peers on the communication stream
-//                || interior row blocks on the compute stream            (overlap)
-//                then boundary row blocks once the halo has landed.
-// One CG iteration adds a single 3-double allreduce (<r,r>, <Ap,Ap>, <p,Ap>) -- the property Chronopoulos/Gear CG was
-// chosen for (cg.hpp:116-118) -- after which a one-thread kernel advances alpha/beta/convergence on every rank identically.
+// Transport "p2p" (default; peer.cuh): every rank maps a window of every other rank's memory (CUDA IPC over NVLink).
+//   One product    = halo_push_kernel (entries -> the neighbours' receive buffers + flag)
+//                    + ONE csr_stream_kernel launch: interior row blocks first, boundary blocks wait for the flags.
+//   One CG iteration = cg_update_kernel + halo_push_kernel + the fused SpMV kernel whose last CTA all-reduces
+//                    {<r,r>, <Ap,Ap>, <p,Ap>} through the windows and advances alpha/beta/convergence -- 3 launches,
+//                    one stream, no communication kernels, no host round trip.
+// Transport "nccl" (VCL_B200_DIST_TRANSPORT=nccl, or when IPC mapping is not possible): pack -> ncclSend/ncclRecv on the
+//   communication stream || interior blocks; boundary blocks after the halo event; ncclAllReduce of 3 doubles; a
+//   one-thread kernel advances the scalars.
+// Both sum the rank-local totals so that every rank takes the same decisions (Chronopoulos/Gear CG needs a single
+// reduction per iteration, cg.hpp:116-118).
 #include "fused_kernels.cuh"
 #include "launch.cuh"
 #include "blas1.cuh"
@@ -32,6 +38,16 @@ struct ViennaCLB200DistCsr_impl
   u32 *interior = nullptr, *boundary = nullptr; int n_interior = 0, n_boundary = 0;
   double *tmp_sums = nullptr;        // 3 doubles: interior totals
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
+  // ---- peer-memory transport ----
+  bool p2p = false;
+  void *win_mem = nullptr; size_t win_bytes = 0;
+  void *peer_base[VCL_MAX_PEERS] = {nullptr};
+  PeerWindow hwin; PeerWindow *d_win = nullptr;
+  HaloPush push;
+  unsigned int wait_mask = 0;
+  u32 *all_list = nullptr;           // [interior | boundary] row-block list for the single fused launch
+  u64 halo_seq = 0, red_seq = 0;     // exchanges EXECUTED so far (identical on every rank)
+  int *d_err = nullptr;
 };
 
 namespace {
@@ -81,6 +97,42 @@ __global__ void classify_blocks_kernel(int nblk, const u32 * __restrict__ blk, c
 __global__ void pack_kernel(int cnt, const u32 * __restrict__ idx, const double * __restrict__ x, double *out)
 {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) out[i] = x[idx[i]];
+}
+
+// x entries -> the neighbours' halo receive buffers (remote stores over NVLink); the CTA that finishes last publishes the
+// sequence number to every destination with a release store.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(HaloPush hp, const u32 * __restrict__ idx, const double * __restrict__ x, u64 seq, unsigned int *ticket,
+                 const SolverState *st)
+{
+  __shared__ bool s_last;
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  const int par = (int)(seq & 1ULL);
+  const int total = hp.begin[hp.ndst];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+  {
+    int d = 0;
+    while (i >= hp.begin[d + 1]) ++d;
+    hp.dst[d][(size_t)par * hp.stride[d] + (size_t)(i - hp.begin[d])] = x[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < hp.ndst) st_release_sys(hp.flag[threadIdx.x] + par * hp.W + hp.me, seq);
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// stand-alone all-reduce of n <= 4 doubles (solver set-up)
+__global__ void peer_allreduce_kernel(const PeerWindow *win, u64 seq, double *vals, int n)
+{
+  __shared__ double s_v[4], s_g[VCL_MAX_PEERS * 4];
+  if (threadIdx.x < 4) s_v[threadIdx.x] = (int)threadIdx.x < n ? vals[threadIdx.x] : 0.0;
+  peer_allreduce<4>(win, seq, s_v, s_g);
+  __syncthreads();
+  if ((int)threadIdx.x < n) vals[threadIdx.x] = s_v[threadIdx.x];
 }
 
 __global__ void cg_advance_kernel(SolverState *st)
@@ -135,6 +187,51 @@ ViennaCLStatus wait_halo(ViennaCLBackend b, ViennaCLB200DistCsr A)
   return ViennaCLSuccess;
 }
 
+// ---- peer-memory transport ----
+ViennaCLStatus p2p_push(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *x, u64 seq, const SolverState *st)
+{
+  if (A->push.ndst == 0) return ViennaCLSuccess;
+  const int total = A->push.begin[A->push.ndst];
+  const int grid = std::max(1, std::min(vcl_div_up(total, 256 * 4), b->sm_count));
+  halo_push_kernel<<<grid, 256, 0, b->stream>>>(A->push, A->send_idx, x, seq, b->tickets + 8, st);
+  VCL_LAUNCHED(b, "halo_push_kernel");
+  return ViennaCLSuccess;
+}
+
+// all row blocks in one launch: interior first, boundary blocks (which wait for halo sequence number `seq`) last
+CsrDev p2p_all_blocks(ViennaCLB200DistCsr A, u64 seq)
+{
+  const int par = (int)(seq & 1ULL);
+  CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->blk, A->n_interior + A->n_boundary, A->all_list,
+              A->n_interior, A->wait_mask, A->hwin.halo_flag[A->hwin.me] + par * A->hwin.W, seq, A->d_err};
+  return d;
+}
+
+template<class Epi>
+ViennaCLStatus p2p_launch_csr(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi epi)
+{
+  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS);
+  const int grid = std::max(1, std::min(d.nblk, std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+  VCL_LAUNCHED(b, "csr_stream_kernel(peer)");
+  return ViennaCLSuccess;
+}
+
+XVec p2p_xvec(ViennaCLB200DistCsr A, const double *x, u64 seq)
+{
+  const PeerWindow &w = A->hwin;
+  XVec xv = {x, 0, 1, w.halo[w.me] + (size_t)(seq & 1ULL) * (size_t)w.halo_len[w.me], (u32)A->n};
+  return xv;
+}
+
+ViennaCLStatus p2p_check(ViennaCLBackend b, ViennaCLB200DistCsr A)      // after a stream synchronisation
+{
+  int err = 0;
+  VCL_CUDA(b, cudaMemcpy(&err, A->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return vcl_fail(b, ViennaCLB200CommError, "peer-memory exchange timed out (a partner rank did not arrive)", __FILE__, __LINE__);
+  return ViennaCLSuccess;
+}
+
 CsrDev subset(ViennaCLB200DistCsr A, bool boundary)
 {
   CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->blk, boundary ? A->n_boundary : A->n_interior,
@@ -142,9 +239,15 @@ CsrDev subset(ViennaCLB200DistCsr A, bool boundary)
   return d;
 }
 
-ViennaCLStatus allreduce_sum(ViennaCLBackend b, double *buf, int count)
+ViennaCLStatus allreduce_sum(ViennaCLBackend b, ViennaCLB200DistCsr A, double *buf, int count)
 {
   if (b->world == 1) return ViennaCLSuccess;
+  if (A->p2p)
+  {
+    peer_allreduce_kernel<<<1, 32, 0, b->stream>>>(A->d_win, ++A->red_seq, buf, count);
+    VCL_LAUNCHED(b, "peer_allreduce_kernel");
+    return ViennaCLSuccess;
+  }
   const NcclApi *api = vcl_nccl(nullptr);
   VCL_NCCL(b, api, api->AllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)b->nccl_comm, b->stream));
   return ViennaCLSuccess;
@@ -153,12 +256,132 @@ ViennaCLStatus allreduce_sum(ViennaCLBackend b, double *buf, int count)
 // y = A x with overlap; epilogue factory gives the interior / boundary epilogues
 ViennaCLStatus dist_plain_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *x, double *y)
 {
-  XVec xv = {x, 0, 1, A->halo_buf, (u32)A->n};
   EpiAxpby epi = {y, 0, 1, 1.0, 0.0};
+  if (A->p2p)
+  {
+    const u64 seq = ++A->halo_seq;
+    VCL_TRY(p2p_push(b, A, x, seq, nullptr));
+    return p2p_launch_csr(b, p2p_all_blocks(A, seq), p2p_xvec(A, x, seq), epi);
+  }
+  XVec xv = {x, 0, 1, A->halo_buf, (u32)A->n};
   VCL_TRY(start_halo(b, A, x));
   VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, epi, b->stream));
   VCL_TRY(wait_halo(b, A));
   VCL_TRY(vcl_launch_csr_split(b, subset(A, true), xv, epi, b->stream));
+  return ViennaCLSuccess;
+}
+
+// ---- peer-memory transport set-up: allocate the window, exchange IPC handles (NCCL all-gather), map the peers ----
+// M[p*W + q] = number of halo entries rank p receives from rank q (known to every rank).
+static size_t win_off_rflag(int W) { return (size_t)2 * W * sizeof(u64); }
+static size_t win_off_red(int W)   { return (size_t)4 * W * sizeof(u64); }
+static size_t win_off_halo(int W)  { return ((size_t)4 * W * sizeof(u64) + (size_t)8 * W * sizeof(double) + 255) / 256 * 256; }
+
+struct PeerHello { cudaIpcMemHandle_t handle; long long n_halo; int device; int ok; };
+
+ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::vector<int> &M)
+{
+  const int W = b->world, me = b->rank;
+  const NcclApi *api = vcl_nccl(nullptr);
+  ncclComm_t comm = (ncclComm_t)b->nccl_comm;
+  const char *env = getenv("VCL_B200_DIST_TRANSPORT");
+  int want = (W <= VCL_MAX_PEERS) && !(env && std::string(env) == "nccl");
+
+  // own window (>= 2 MiB so that the allocation is not carved out of a shared driver block)
+  A->win_bytes = std::max<size_t>(win_off_halo(W) + (size_t)2 * std::max(A->n_halo, 1) * sizeof(double), (size_t)2 << 20);
+  PeerHello hello;
+  std::memset(&hello, 0, sizeof(hello));
+  hello.n_halo = A->n_halo; hello.device = b->device; hello.ok = want;
+  if (want)
+  {
+    if (cudaMalloc(&A->win_mem, A->win_bytes) != cudaSuccess || cudaMemsetAsync(A->win_mem, 0, A->win_bytes, b->stream) != cudaSuccess ||
+        cudaIpcGetMemHandle(&hello.handle, A->win_mem) != cudaSuccess)
+    { cudaGetLastError(); hello.ok = 0; }
+  }
+  // all-gather the hellos (byte-wise through NCCL; set-up only)
+  PeerHello *d_h = nullptr;
+  std::vector<PeerHello> all(W);
+  VCL_CUDA(b, cudaMalloc(&d_h, sizeof(PeerHello) * (W + 1)));
+  VCL_CUDA(b, cudaMemcpyAsync(d_h + W, &hello, sizeof(PeerHello), cudaMemcpyHostToDevice, b->stream));
+  VCL_NCCL(b, api, api->AllGather(d_h + W, d_h, sizeof(PeerHello), ncclChar, comm, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(all.data(), d_h, sizeof(PeerHello) * W, cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  int ok = 1;
+  for (int q = 0; q < W; ++q) ok &= all[q].ok;
+  if (ok)
+  {
+    for (int q = 0; q < W && ok; ++q)
+    {
+      if (q == me) { A->peer_base[q] = A->win_mem; continue; }
+      if (cudaIpcOpenMemHandle(&A->peer_base[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      { cudaGetLastError(); A->peer_base[q] = nullptr; ok = 0; }
+    }
+  }
+  // everybody must agree (and this collective is also the barrier between "windows zeroed" and the first push)
+  int *d_ok = reinterpret_cast<int*>(d_h);
+  VCL_CUDA(b, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  VCL_NCCL(b, api, api->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, comm, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  VCL_CUDA(b, cudaFree(d_h));
+  if (!ok)
+  {
+    for (int q = 0; q < W; ++q) if (q != me && A->peer_base[q]) { cudaIpcCloseMemHandle(A->peer_base[q]); A->peer_base[q] = nullptr; }
+    if (A->win_mem) { cudaFree(A->win_mem); A->win_mem = nullptr; }
+    if (want && me == 0) fprintf(stderr, "libvcl_b200: peer-memory (CUDA IPC) mapping unavailable, using the NCCL transport\n");
+    A->p2p = false;
+    return ViennaCLSuccess;
+  }
+
+  PeerWindow &w = A->hwin;
+  std::memset(&w, 0, sizeof(w));
+  w.W = W; w.me = me;
+  for (int q = 0; q < W; ++q)
+  {
+    char *base = static_cast<char*>(A->peer_base[q]);
+    w.halo_flag[q] = reinterpret_cast<u64*>(base);
+    w.red_flag[q]  = reinterpret_cast<u64*>(base + win_off_rflag(W));
+    w.red[q]       = reinterpret_cast<double*>(base + win_off_red(W));
+    w.halo[q]      = reinterpret_cast<double*>(base + win_off_halo(W));
+    w.halo_len[q]  = std::max<long long>(all[q].n_halo, 1);
+  }
+  VCL_CUDA(b, cudaMalloc(&A->d_err, sizeof(int)));
+  VCL_CUDA(b, cudaMemset(A->d_err, 0, sizeof(int)));
+  w.err = A->d_err;
+#ifdef VCL_PEER_DEBUG
+  VCL_CUDA(b, cudaMalloc(&w.dbg, sizeof(u64) * 4096));
+  VCL_CUDA(b, cudaMemset(w.dbg, 0, sizeof(u64) * 4096));
+#endif
+  VCL_CUDA(b, cudaMalloc(&A->d_win, sizeof(PeerWindow)));
+  VCL_CUDA(b, cudaMemcpy(A->d_win, &w, sizeof(PeerWindow), cudaMemcpyHostToDevice));
+
+  // destinations: every rank with traffic in EITHER direction (symmetric pairs bound how far a rank can run ahead)
+  HaloPush &hp = A->push;
+  std::memset(&hp, 0, sizeof(hp));
+  hp.me = me; hp.W = W;
+  A->wait_mask = 0;
+  for (int q = 0; q < W; ++q)
+  {
+    if (q == me || (A->send_cnt[q] == 0 && A->recv_cnt[q] == 0)) continue;
+    const int d = hp.ndst++;
+    hp.begin[d] = A->send_off[q];
+    long long off_in_q = 0;                      // where my segment starts in q's halo: after the segments of ranks < me
+    for (int p2 = 0; p2 < me; ++p2) off_in_q += M[(size_t)q * W + p2];
+    hp.dst[d] = w.halo[q] + off_in_q;
+    hp.stride[d] = w.halo_len[q];
+    hp.flag[d] = w.halo_flag[q];
+    A->wait_mask |= 1u << q;
+  }
+  // send segments are contiguous and ordered by destination rank; ranks without entries contribute empty segments
+  hp.begin[hp.ndst] = A->total_send;
+  // [interior | boundary] list
+  {
+    const int tot = A->n_interior + A->n_boundary;
+    VCL_CUDA(b, cudaMalloc(&A->all_list, sizeof(u32) * std::max(tot, 1)));
+    if (A->n_interior) VCL_CUDA(b, cudaMemcpy(A->all_list, A->interior, sizeof(u32) * A->n_interior, cudaMemcpyDeviceToDevice));
+    if (A->n_boundary) VCL_CUDA(b, cudaMemcpy(A->all_list + A->n_interior, A->boundary, sizeof(u32) * A->n_boundary, cudaMemcpyDeviceToDevice));
+  }
+  A->p2p = true;
   return ViennaCLSuccess;
 }
 
@@ -254,13 +477,13 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend b, long long global_
     A->ci_local = const_cast<u32*>(col_idx_global);      // single rank: global == local numbering
 
   // ---- 4. send lists: everyone learns what every peer needs from it ----
+  std::vector<int> M((size_t)W * W, 0);
   if (W > 1)
   {
     int *d_cnt = nullptr;
     VCL_CUDA(b, cudaMalloc(&d_cnt, sizeof(int) * (size_t)W * (W + 1)));
     VCL_CUDA(b, cudaMemcpyAsync(d_cnt + (size_t)W * W, A->recv_cnt.data(), sizeof(int) * W, cudaMemcpyHostToDevice, b->stream));
     VCL_NCCL(b, api, api->AllGather(d_cnt + (size_t)W * W, d_cnt, (size_t)W, ncclInt32, comm, b->stream));
-    std::vector<int> M((size_t)W * W);
     VCL_CUDA(b, cudaMemcpyAsync(M.data(), d_cnt, sizeof(int) * (size_t)W * W, cudaMemcpyDeviceToHost, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
     VCL_CUDA(b, cudaFree(d_cnt));
@@ -315,6 +538,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend b, long long global_
   }
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   if (d_halo) VCL_CUDA(b, cudaFree(d_halo));
+  if (W > 1) VCL_TRY(setup_p2p(b, A, M));
   *out = A;
   return ViennaCLSuccess;
 }
@@ -328,10 +552,34 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
   if (A->ci_local && A->ci_local != A->ci_global) cudaFree(A->ci_local);
   cudaFree(A->send_idx); cudaFree(A->send_buf); cudaFree(A->halo_buf); cudaFree(A->blk); cudaFree(A->interior); cudaFree(A->boundary);
   cudaFree(A->tmp_sums);
+  if (A->p2p)
+  {
+    // nobody may unmap or free a window that a partner is still writing to
+    const NcclApi *api = vcl_nccl(nullptr);
+    if (api && b->nccl_comm)
+    {
+      api->AllReduce(A->d_err, A->d_err, 1, ncclInt32, ncclMax, (ncclComm_t)b->nccl_comm, b->stream);
+      cudaStreamSynchronize(b->stream);
+    }
+    for (int q = 0; q < b->world; ++q) if (q != b->rank && A->peer_base[q]) cudaIpcCloseMemHandle(A->peer_base[q]);
+    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err); cudaFree(A->all_list);
+  }
   if (A->ev_x) cudaEventDestroy(A->ev_x);
   if (A->ev_halo) cudaEventDestroy(A->ev_halo);
   delete A;
   *pA = nullptr;
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend b, ViennaCLB200DistCsr A, ViennaCLInt *peer_memory, ViennaCLInt *halo_entries,
+                                          ViennaCLInt *interior_blocks, ViennaCLInt *boundary_blocks)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, A, "null matrix");
+  if (peer_memory) *peer_memory = A->p2p ? 1 : 0;
+  if (halo_entries) *halo_entries = A->n_halo;
+  if (interior_blocks) *interior_blocks = A->n_interior;
+  if (boundary_blocks) *boundary_blocks = A->n_boundary;
   return ViennaCLSuccess;
 }
 
@@ -369,7 +617,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
     VCL_TRY(vcl_dot_async(b, n, p, 0, 1, Ap, 0, 1, b->dscal + 1));
     VCL_TRY(vcl_dot_async(b, n, Ap, 0, 1, Ap, 0, 1, b->dscal + 2));
   }
-  VCL_TRY(allreduce_sum(b, b->dscal, 3));
+  VCL_TRY(allreduce_sum(b, A, b->dscal, 3));
   VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 3 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
 
@@ -388,14 +636,67 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
   SolverState *st = b->dstate;
 
   const int grid = (int)std::max(1LL, std::min((n / 2 + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+  const int kBatch = 32;
+  int launched = 0;
+
+  if (A->p2p)
+  {
+    // ---- peer-memory transport: 3 launches per iteration on one stream, scalars advanced by the SpMV kernel's last CTA ----
+    double *loc_rr = b->dscal + 32;
+    const u64 halo_base = A->halo_seq, red_base = A->red_seq;
+    while (launched < tag->max_iterations)
+    {
+      const int nb = std::min(kBatch, tag->max_iterations - launched);
+      for (int k = 0; k < nb; ++k)
+      {
+        // iteration i = launched + k + 1 uses exchange numbers base + i; once st->done is set every later kernel returns
+        // at once on every rank (same sums -> same decision), so the exchanges executed are exactly 1..iters
+        const u64 hseq = halo_base + (u64)(launched + k + 1), rseq = red_base + (u64)(launched + k + 1);
+        cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr);
+        VCL_LAUNCHED(b, "cg_update_kernel");
+        VCL_TRY(p2p_push(b, A, p, hseq, st));
+        EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
+                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr};
+        CsrDev dd = p2p_all_blocks(A, hseq);
+#ifdef VCL_PEER_DEBUG
+        dd.dbg = A->hwin.dbg; dd.dbg_seq = rseq;
+#endif
+        VCL_TRY(p2p_launch_csr(b, dd, p2p_xvec(A, p, hseq), e));
+      }
+      launched += nb;
+      VCL_CUDA(b, cudaMemcpyAsync(h, st, sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
+      VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+      VCL_TRY(p2p_check(b, A));
+      if (h->done != VCL_RUNNING) break;
+    }
+    A->halo_seq = halo_base + (u64)h->iters;
+    A->red_seq = red_base + (u64)h->iters;
+#ifdef VCL_PEER_DEBUG
+    {
+      std::vector<u64> d(4096);
+      cudaMemcpy(d.data(), A->hwin.dbg, sizeof(u64) * 4096, cudaMemcpyDeviceToHost);
+      double s_kernel = 0, s_red = 0, s_wait = 0; int cnt = 0;
+      for (u64 q = red_base + 1; q <= red_base + (u64)h->iters && cnt < 1000; ++q, ++cnt)
+      {
+        const u64 *e = &d[(q % 1024) * 4];
+        s_kernel += (double)(e[0] - e[2]); s_red += (double)(e[1] - e[0]); s_wait += (double)e[3];
+      }
+      if (cnt) fprintf(stderr, "[rank %d] peer debug over %d iterations: kernel start -> last CTA enters reduction %.1f us, reduction (push + wait + sum) %.1f us, max halo-flag wait per launch %.1f us\n",
+                       b->rank, cnt, s_kernel / cnt * 1e-3, s_red / cnt * 1e-3, s_wait / cnt * 1e-3);
+      cudaMemset(A->hwin.dbg, 0, sizeof(u64) * 4096);
+    }
+#endif
+    tag->iters = h->iters;
+    tag->error = std::sqrt(std::fabs(h->sums[0]) / norm_rhs_squared);
+    return ViennaCLSuccess;
+  }
+
   XVec xv = {p, 0, 1, A->halo_buf, (u32)A->n};
   // rank-local sums land in `loc`, the allreduce writes the global sums into st->sums (out of place, so that re-issuing the
   // collective after convergence -- kernels skipped, `loc` unchanged -- reproduces the same global sums)
   double *loc = b->world > 1 ? b->dscal + 32 : &st->sums[0];
   if (b->world > 1) VCL_CUDA(b, cudaMemsetAsync(loc, 0, 3 * sizeof(double), b->stream));
   const NcclApi *api = b->world > 1 ? vcl_nccl(nullptr) : nullptr;
-  const int kBatch = 32;
-  int launched = 0;
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(kBatch, tag->max_iterations - launched);

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "solver_state.cuh"
+#include "peer.cuh"
 
 #define VEC_THREADS 256
 
@@ -58,20 +59,42 @@ struct EpiFused
   double *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
   double acc[3];
   const double *add_from;          // optional: 3 totals of an earlier launch over a disjoint row subset (interior + boundary split)
+  // row-partitioned CG over peer memory (peer.cuh): the last CTA all-reduces {*loc_rr, <Ap,Ap>, <p,Ap>} across the ranks
+  // and then advances the CG scalars -- identical on every rank.  win == NULL: single-domain behaviour.
+  const PeerWindow *win; unsigned long long red_seq; const double *loc_rr;
   static constexpr int NQ = 3;
 
   __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
-  __device__ __forceinline__ void row(u32 r, double dot)
+  __device__ __forceinline__ double pre(u32 r) const { return p[r]; }
+  __device__ __forceinline__ void row(u32 r, double dot, double p_r)
   {
     if (JACOBI) dot = dot / diag[r];
     Ap[r] = dot;
     acc[0] = fma(dot, dot, acc[0]);
-    acc[1] = fma(p[r], dot, acc[1]);
+    acc[1] = fma(p_r, dot, acc[1]);
     if (USE_R0) acc[2] = fma(dot, r0[r], acc[2]);
   }
   __device__ __forceinline__ void finish(double *smem)
   {
-    if (grid_sum_last_block<3>(acc, partials, ticket, smem) && threadIdx.x == 0)
+    if (!grid_sum_last_block<3>(acc, partials, ticket, smem)) return;
+    if (win != nullptr)
+    {
+#ifdef VCL_PEER_DEBUG
+      const u64 t_a = global_ns();
+#endif
+      if (threadIdx.x == 0) { smem[0] = *loc_rr; smem[1] = acc[0]; smem[2] = acc[1]; }
+      peer_allreduce<3>(win, red_seq, smem, smem + 32);
+      if (threadIdx.x == 0)
+      {
+        st->sums[0] = smem[0]; st->sums[1] = smem[1]; st->sums[2] = smem[2];
+        cg_advance(st);
+#ifdef VCL_PEER_DEBUG
+        if (win->dbg) { u64 *d = win->dbg + (red_seq % 1024) * 4; d[0] = t_a; d[1] = global_ns(); }
+#endif
+      }
+      return;
+    }
+    if (threadIdx.x == 0)
     {
       if (add_from) { acc[0] += add_from[0]; acc[1] += add_from[1]; if (USE_R0) acc[2] += add_from[2]; }
       if (out0) *out0 = acc[0];

@@ -1,0 +1,108 @@
+// peer.cuh -- peer-memory (NVLink / NVSwitch) primitives of the row-partitioned path: every rank maps a small "window" of
+// every other rank's device memory (CUDA IPC) and the kernels of the solver push halo entries and reduction partials
+// straight into the consumer's memory, followed by a release-store of a sequence number; consumers spin on their OWN
+// memory with acquire loads.  No communication kernel, no second stream, no host involvement inside an iteration:
+//   halo_push_kernel     x entries -> the neighbours' halo receive buffers + flag            (1 launch per product)
+//   csr_stream_kernel    interior row blocks first; boundary blocks wait for the flags        (the SpMV launch itself)
+//   peer_allreduce()     called by the LAST CTA of the reducing kernel: push the rank-local totals to all ranks, wait
+//                        for everyone's, sum in rank order -> bit-identical global sums on every rank
+// Buffers are double-buffered by the parity of the sequence number; every exchange pair is symmetric (a rank that sends
+// to q also waits for q), which bounds any rank to at most one exchange ahead of its partners.
+// No counterpart in the reference (doc/manual/multi-device.dox:9).
+#pragma once
+#include "common.cuh"
+
+#define VCL_MAX_PEERS 16
+#define VCL_PEER_TIMEOUT_NS 8000000000ULL      // a spin that lasts 8 s is reported (error word) instead of hanging the GPU
+
+typedef unsigned long long u64;
+
+// All pointers are valid in THIS process (own window: the allocation itself; peers: cudaIpcOpenMemHandle mappings).
+struct PeerWindow
+{
+  int W, me;
+  double *halo[VCL_MAX_PEERS];          // rank q: halo receive area  [2][halo_len[q]]
+  long long halo_len[VCL_MAX_PEERS];
+  u64 *halo_flag[VCL_MAX_PEERS];        // rank q: [2][W]  (indexed by source rank)
+  double *red[VCL_MAX_PEERS];           // rank q: [2][W][4]
+  u64 *red_flag[VCL_MAX_PEERS];         // rank q: [2][W]
+  int *err;                             // own error word (set on time-out)
+  u64 *dbg;                             // VCL_PEER_DEBUG builds: [1024][4] time stamps (kernel start, last CTA enters the
+                                        // reduction, reduction done) -- NULL otherwise
+};
+
+// One destination of a halo push (passed by value to the kernel).
+struct HaloPush
+{
+  int ndst, me, W;
+  int begin[VCL_MAX_PEERS + 1];         // segment of the send list per destination
+  double *dst[VCL_MAX_PEERS];           // destination's halo area, already offset to this rank's segment (parity 0)
+  long long stride[VCL_MAX_PEERS];      // destination's halo_len (parity stride)
+  u64 *flag[VCL_MAX_PEERS];             // destination's halo_flag (parity 0), entry of this rank added in the kernel
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
+{
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u64 global_ns()
+{
+  u64 t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Spins until *flag >= seq (acquire).  Returns false on time-out after raising *err.
+__device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err)
+{
+  if (ld_acquire_sys(flag) >= seq) return true;
+  const u64 t0 = global_ns();
+  for (;;)
+  {
+    __nanosleep(40);
+    if (ld_acquire_sys(flag) >= seq) return true;
+    if (global_ns() - t0 > VCL_PEER_TIMEOUT_NS) { if (err) atomicExch(err, 1); return false; }
+  }
+}
+
+// All-reduce (sum) of N <= 4 doubles across the ranks, executed by ONE CTA per rank (>= W threads).
+// vals: shared memory, N inputs (valid before the call, written by thread 0) -> N global sums (valid for thread 0 after).
+// gather: shared memory, >= W*4 doubles.
+template<int N>
+__device__ __forceinline__ void peer_allreduce(const PeerWindow *win, u64 seq, double *vals, double *gather)
+{
+  const int W = win->W, me = win->me, par = (int)(seq & 1ULL), tid = threadIdx.x;
+  __syncthreads();
+  if (tid < W)
+  {
+    double *slot = win->red[tid] + (size_t)(par * W + me) * 4;
+#pragma unroll
+    for (int j = 0; j < N; ++j) __stcg(slot + j, vals[j]);
+    __threadfence_system();
+    st_release_sys(win->red_flag[tid] + par * W + me, seq);
+    // every rank's contribution lands in my own window
+    peer_wait(win->red_flag[me] + par * W + tid, seq, win->err);
+    const double *mine = win->red[me] + (size_t)(par * W + tid) * 4;
+#pragma unroll
+    for (int j = 0; j < N; ++j) gather[tid * 4 + j] = __ldcg(mine + j);
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+    {
+      double s = 0.0;
+      for (int q = 0; q < W; ++q) s += gather[q * 4 + j];      // rank order: identical on every rank
+      vals[j] = s;
+    }
+  }
+}
+#endif

@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "solver_state.cuh"
+#include "peer.cuh"
 
 #define CSR_BLOCK_THREADS 256
 #define CSR_CAP (VCL_B200_CSR_BLOCK_NNZ)          // staged non-zeros per row block
@@ -25,6 +26,10 @@ struct CsrDev
   const u32 *rp, *ci; const double *va;
   const u32 *blk; int nblk;
   const u32 *blk_list;     // optional indirection: process row blocks blk_list[0..nblk) (interior / boundary subsets)
+  // peer-memory halo (row-partitioned path, peer.cuh): list positions >= wait_from read halo columns and must first see
+  // wait_flags[q] >= wait_seq for every source rank q in wait_mask.  wait_mask == 0: nothing to wait for.
+  int wait_from; unsigned int wait_mask; const unsigned long long *wait_flags; unsigned long long wait_seq; int *err;
+  unsigned long long *dbg; unsigned long long dbg_seq;     // VCL_PEER_DEBUG builds only
 };
 
 struct SellDev
@@ -36,10 +41,16 @@ struct SellDev
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
 struct XVec { const double *x; int off, inc; const double *x2; u32 split; };
 
+// SPLIT: one load from a selected base (no branch).  Halo entries are written by peer GPUs; reading them through L1 is safe
+// because a CTA touches the halo only after its acquire on the arrival flag (peer.cuh) and L1 does not outlive a launch.
 template<bool SPLIT>
 __device__ __forceinline__ double xload(const XVec &xv, u32 c)
 {
-  if (SPLIT) return (c >= xv.split) ? xv.x2[c - xv.split] : xv.x[c];
+  if (SPLIT)
+  {
+    const double *base = (c >= xv.split) ? (xv.x2 - xv.split) : xv.x;
+    return base[c];
+  }
   return xv.x[(size_t)c * xv.inc + xv.off];
 }
 
@@ -48,10 +59,18 @@ __device__ __forceinline__ double xload(const XVec &xv, u32 c)
 // chains in reductions under generic tuning); the same two roundings are used here so that CSR results match it bit for bit.
 __device__ __forceinline__ double madd(double a, double x, double acc) { return __dadd_rn(acc, __dmul_rn(a, x)); }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+// The matrix arrays are read exactly once per product: they are streamed with an L2 evict-first policy so that they do not
+// push the gathered x entries (re-used by the rows of the next planes, tens of MB of streamed matrix data later) out of L2.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, unsigned long long pol)
 {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem_src), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
@@ -65,11 +84,16 @@ struct EpiAxpby
   double *y; int off, inc; double alpha, beta;
   static constexpr int NQ = 0;
   __device__ __forceinline__ bool skip() const { return false; }
-  __device__ __forceinline__ void row(u32 r, double dot)
+  // pre(): the epilogue's own per-row operand, requested BEFORE the row's gather chain so that its latency overlaps
+  __device__ __forceinline__ double pre(u32 r) const
+  {
+    return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0;
+  }
+  __device__ __forceinline__ void row(u32 r, double dot, double y_old)
   {
     size_t idx = (size_t)r * (size_t)inc + (size_t)off;
     // same operations as the reference host build: t = alpha*dot (rounded), then one fused beta*y + t
-    if (beta != 0.0) y[idx] = fma(beta, y[idx], __dmul_rn(alpha, dot));
+    if (beta != 0.0) y[idx] = fma(beta, y_old, __dmul_rn(alpha, dot));
     else             y[idx] = __dmul_rn(alpha, dot);
   }
   __device__ __forceinline__ void finish(double *) {}
@@ -79,7 +103,7 @@ struct EpiAxpby
 // CSR, row-block streaming
 // ------------------------------------------------------------------------------------------------
 template<class Epi, bool SPLIT>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 8)
 csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 {
   __shared__ __align__(16) double s_val[CSR_STAGE];
@@ -89,9 +113,27 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 
   if (epi.skip()) return;
   const int tid = threadIdx.x;
+  const unsigned long long pol = l2_evict_first_policy();
+#ifdef VCL_PEER_DEBUG
+  if (SPLIT && A.dbg && blockIdx.x == 0 && tid == 0) A.dbg[(A.dbg_seq % 1024) * 4 + 2] = global_ns();
+#endif
+  bool halo_ready = !(SPLIT && A.wait_mask != 0u);
 
   for (int bi = blockIdx.x; bi < A.nblk; bi += gridDim.x)
   {
+    if (SPLIT && !halo_ready && bi >= A.wait_from)
+    {
+      // boundary row blocks come last in the list: by now the neighbours' pushes have normally landed
+#ifdef VCL_PEER_DEBUG
+      const u64 t_w = global_ns();
+#endif
+      if (tid < VCL_MAX_PEERS && ((A.wait_mask >> tid) & 1u)) peer_wait(A.wait_flags + tid, A.wait_seq, A.err);
+      __syncthreads();
+#ifdef VCL_PEER_DEBUG
+      if (A.dbg && tid == 0) atomicMax(A.dbg + (A.dbg_seq % 1024) * 4 + 3, global_ns() - t_w);
+#endif
+      halo_ready = true;
+    }
     const u32 b = A.blk_list ? A.blk_list[bi] : (u32)bi;
     const u32 r0 = A.blk[b], r1 = A.blk[b + 1];
     const u32 nrows = r1 - r0;
@@ -105,7 +147,7 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
         part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
       __shared__ double s_long[32];
       block_sum<1>(part, s_long);
-      if (tid == 0) epi.row(r0, part[0]);
+      if (tid == 0) epi.row(r0, part[0], epi.pre(r0));
       __syncthreads();
       continue;
     }
@@ -115,17 +157,18 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
     const u32 cnt = n1 - a0;
     for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2)
     {
-      if (a0 + i + 2 <= A.nnz) cp_async16(&s_val[i], A.va + a0 + i);
+      if (a0 + i + 2 <= A.nnz) cp_async16(&s_val[i], A.va + a0 + i, pol);
       else if (a0 + i < A.nnz) s_val[i] = A.va[a0 + i];
     }
     for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4)
     {
-      if (a0 + i + 4 <= A.nnz) cp_async16(&s_col[i], A.ci + a0 + i);
+      if (a0 + i + 4 <= A.nnz) cp_async16(&s_col[i], A.ci + a0 + i, pol);
       else { for (u32 k = 0; k < 4 && a0 + i + k < A.nnz; ++k) s_col[i + k] = A.ci[a0 + i + k]; }
     }
     cp_async_commit();
     if ((u32)tid <= nrows) s_rp[tid] = A.rp[r0 + tid];
     if (tid == 0 && nrows == CSR_BLOCK_THREADS) s_rp[CSR_BLOCK_THREADS] = n1;
+    const double pre = ((u32)tid < nrows) ? epi.pre(r0 + tid) : 0.0;      // in flight together with the staging copies
     cp_async_wait<0>();
     __syncthreads();
 
@@ -151,7 +194,7 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
         j += 2;
       }
       if (j < e) dot = madd(s_val[j], xload<SPLIT>(xv, s_col[j]), dot);
-      epi.row(r0 + tid, dot);
+      epi.row(r0 + tid, dot, pre);
     }
     __syncthreads();
   }
@@ -173,7 +216,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
     const u32 e = A.rp[r + 1];
     for (u32 k = A.rp[r]; k < e; ++k)
       dot = madd(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], dot);
-    epi.row((u32)r, dot);
+    epi.row((u32)r, dot, epi.pre((u32)r));
   }
   epi.finish(s_red);
 }
@@ -187,7 +230,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
 template<class Epi>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 8)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
   __shared__ __align__(16) double s_val[CSR_STAGE];
@@ -198,6 +241,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   const double * __restrict__ va = A.va;
   const u32 * __restrict__ ci = A.ci;
   const int tid = threadIdx.x;
+  const unsigned long long pol = l2_evict_first_policy();
   const u32 C = (u32)A.C;
   const u32 nslices = (u32)((A.rows - 1) / A.C + 1);
   const u32 spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1u;      // slices per CTA pass
@@ -215,8 +259,8 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
     if (staged)
     {
       // base is a multiple of C (hence of 4) and cnt a multiple of C: whole 16-byte packets, never past the arrays
-      for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2) cp_async16(&s_val[i], va + base + i);
-      for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4) cp_async16(&s_col[i], ci + base + i);
+      for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2) cp_async16(&s_val[i], va + base + i, pol);
+      for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4) cp_async16(&s_col[i], ci + base + i, pol);
       cp_async_commit();
       // (s1 - s0) * C <= 256 here: one row per thread
       const bool active = (u32)tid < (s1 - s0) * C;
@@ -229,6 +273,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         w = A.cpb[slice];
         idx = A.bs[slice] + (tid % C) - base;
       }
+      const double pre = (active && r < A.rows) ? epi.pre((u32)r) : 0.0;
       cp_async_wait<0>();
       __syncthreads();
       if (active && r < A.rows)
@@ -253,7 +298,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
           const double v0 = s_val[idx];
           if (v0 != 0.0) acc = fma(x[(size_t)s_col[idx] * xv.inc + xv.off], v0, acc);
         }
-        epi.row((u32)r, acc);
+        epi.row((u32)r, acc, pre);
       }
       __syncthreads();
     }
@@ -287,7 +332,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
           const double v0 = va[idx];
           if (v0 != 0.0) acc = fma(x[(size_t)ci[idx] * xv.inc + xv.off], v0, acc);
         }
-        epi.row((u32)r, acc);
+        epi.row((u32)r, acc, epi.pre((u32)r));
       }
     }
   }
