@@ -12,7 +12,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "lib", "libvcl_b200.so")
+LIB_PATH = os.environ.get("VCL_B200_LIB_OVERRIDE") or os.path.join(HERE, "lib", "libvcl_b200.so")   # override: kernel-variant experiments only
 HEADER = os.path.join(ROOT, "include", "vcl_b200.h")
 
 c_int, c_dbl, c_ll, c_vp, c_sz = C.c_int, C.c_double, C.c_longlong, C.c_void_p, C.c_size_t

@@ -35,7 +35,7 @@ struct ViennaCLB200DistCsr_impl
   u32 *send_idx = nullptr;           // local indices to pack, grouped by destination
   double *send_buf = nullptr, *halo_buf = nullptr;
   u32 *blk = nullptr; int nblk = 0;
-  u32 *interior = nullptr, *boundary = nullptr; int n_interior = 0, n_boundary = 0;
+  int n_interior = 0, n_boundary = 0;
   double *tmp_sums = nullptr;        // 3 doubles: interior totals
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
   // ---- peer-memory transport ----
@@ -45,7 +45,7 @@ struct ViennaCLB200DistCsr_impl
   PeerWindow hwin; PeerWindow *d_win = nullptr;
   HaloPush push;
   unsigned int wait_mask = 0;
-  u32 *all_list = nullptr;           // [interior | boundary] row-block list for the single fused launch
+  u32 *ord_start = nullptr, *ord_end = nullptr;   // row ranges of the blocks in the order [interior | boundary]
   u64 halo_seq = 0, red_seq = 0;     // exchanges EXECUTED so far (identical on every rank)
   int *d_err = nullptr;
 };
@@ -202,7 +202,7 @@ ViennaCLStatus p2p_push(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *
 CsrDev p2p_all_blocks(ViennaCLB200DistCsr A, u64 seq)
 {
   const int par = (int)(seq & 1ULL);
-  CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->blk, A->n_interior + A->n_boundary, A->all_list,
+  CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->ord_start, A->ord_end, A->n_interior + A->n_boundary,
               A->n_interior, A->wait_mask, A->hwin.halo_flag[A->hwin.me] + par * A->hwin.W, seq, A->d_err};
   return d;
 }
@@ -210,9 +210,9 @@ CsrDev p2p_all_blocks(ViennaCLB200DistCsr A, u64 seq)
 template<class Epi>
 ViennaCLStatus p2p_launch_csr(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi epi)
 {
-  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS);
+  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int grid = std::max(1, std::min(d.nblk, std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
-  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "csr_stream_kernel(peer)");
   return ViennaCLSuccess;
 }
@@ -234,8 +234,9 @@ ViennaCLStatus p2p_check(ViennaCLBackend b, ViennaCLB200DistCsr A)      // after
 
 CsrDev subset(ViennaCLB200DistCsr A, bool boundary)
 {
-  CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->blk, boundary ? A->n_boundary : A->n_interior,
-              boundary ? A->boundary : A->interior};
+  const int off = boundary ? A->n_interior : 0;
+  CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->ord_start + off, A->ord_end + off,
+              boundary ? A->n_boundary : A->n_interior};
   return d;
 }
 
@@ -374,13 +375,6 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
   }
   // send segments are contiguous and ordered by destination rank; ranks without entries contribute empty segments
   hp.begin[hp.ndst] = A->total_send;
-  // [interior | boundary] list
-  {
-    const int tot = A->n_interior + A->n_boundary;
-    VCL_CUDA(b, cudaMalloc(&A->all_list, sizeof(u32) * std::max(tot, 1)));
-    if (A->n_interior) VCL_CUDA(b, cudaMemcpy(A->all_list, A->interior, sizeof(u32) * A->n_interior, cudaMemcpyDeviceToDevice));
-    if (A->n_boundary) VCL_CUDA(b, cudaMemcpy(A->all_list + A->n_interior, A->boundary, sizeof(u32) * A->n_boundary, cudaMemcpyDeviceToDevice));
-  }
   A->p2p = true;
   return ViennaCLSuccess;
 }
@@ -531,10 +525,15 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend b, long long global_
     std::vector<u32> in, bd;
     for (int i = 0; i < A->nblk; ++i) (flags[i] ? bd : in).push_back((u32)i);
     A->n_interior = (int)in.size(); A->n_boundary = (int)bd.size();
-    VCL_CUDA(b, cudaMalloc(&A->interior, sizeof(u32) * std::max<size_t>(in.size(), 1)));
-    VCL_CUDA(b, cudaMalloc(&A->boundary, sizeof(u32) * std::max<size_t>(bd.size(), 1)));
-    if (!in.empty()) VCL_CUDA(b, cudaMemcpyAsync(A->interior, in.data(), sizeof(u32) * in.size(), cudaMemcpyHostToDevice, b->stream));
-    if (!bd.empty()) VCL_CUDA(b, cudaMemcpyAsync(A->boundary, bd.data(), sizeof(u32) * bd.size(), cudaMemcpyHostToDevice, b->stream));
+    // row ranges in the order [interior | boundary]: the kernels read them without an indirection
+    std::vector<u32> os, oe;
+    for (u32 i : in) { os.push_back(blk[i]); oe.push_back(blk[i + 1]); }
+    for (u32 i : bd) { os.push_back(blk[i]); oe.push_back(blk[i + 1]); }
+    VCL_CUDA(b, cudaMalloc(&A->ord_start, sizeof(u32) * std::max<size_t>(os.size(), 1)));
+    VCL_CUDA(b, cudaMalloc(&A->ord_end, sizeof(u32) * std::max<size_t>(oe.size(), 1)));
+    VCL_CUDA(b, cudaMemcpyAsync(A->ord_start, os.data(), sizeof(u32) * os.size(), cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(A->ord_end, oe.data(), sizeof(u32) * oe.size(), cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   }
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   if (d_halo) VCL_CUDA(b, cudaFree(d_halo));
@@ -550,7 +549,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
   ViennaCLB200DistCsr A = *pA;
   cudaStreamSynchronize(b->stream); cudaStreamSynchronize(b->comm_stream);
   if (A->ci_local && A->ci_local != A->ci_global) cudaFree(A->ci_local);
-  cudaFree(A->send_idx); cudaFree(A->send_buf); cudaFree(A->halo_buf); cudaFree(A->blk); cudaFree(A->interior); cudaFree(A->boundary);
+  cudaFree(A->send_idx); cudaFree(A->send_buf); cudaFree(A->halo_buf); cudaFree(A->blk); cudaFree(A->ord_start); cudaFree(A->ord_end);
   cudaFree(A->tmp_sums);
   if (A->p2p)
   {
@@ -562,7 +561,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
       cudaStreamSynchronize(b->stream);
     }
     for (int q = 0; q < b->world; ++q) if (q != b->rank && A->peer_base[q]) cudaIpcCloseMemHandle(A->peer_base[q]);
-    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err); cudaFree(A->all_list);
+    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err);
   }
   if (A->ev_x) cudaEventDestroy(A->ev_x);
   if (A->ev_halo) cudaEventDestroy(A->ev_halo);

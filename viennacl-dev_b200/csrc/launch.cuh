@@ -6,13 +6,14 @@
 
 // Resident CTAs per SM for a kernel, queried once per instantiation (all B200s of a box are identical).
 template<class K>
-static int vcl_occupancy(K kernel, int threads)
+static int vcl_occupancy(K kernel, int threads, int dyn_smem = 0)
 {
   static int cached = 0;
   if (cached == 0)
   {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) != cudaSuccess || n <= 0) n = 1;
+    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess || n <= 0) n = 1;
     cached = n;
   }
   return cached;
@@ -25,12 +26,12 @@ static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintp
 template<class Epi>
 static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &A, XVec xv, Epi epi)
 {
-  CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.num_blocks, nullptr};
+  CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.row_blocks ? A.row_blocks + 1 : nullptr, A.num_blocks};
   if (A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx))
   {
-    const int occ = vcl_occupancy(csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS);
+    const int occ = vcl_occupancy(csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     int grid = std::min(A.num_blocks, std::min(b->sm_count * occ, VCL_MAX_BLOCKS));
-    csr_stream_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+    csr_stream_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
     VCL_LAUNCHED(b, "csr_stream_kernel");
   }
   else
@@ -50,13 +51,13 @@ static ViennaCLStatus vcl_launch_csr_split(ViennaCLBackend b, const CsrDev &d, X
   if (d.nblk <= 0) return ViennaCLSuccess;
   // Persistent by default.  VCL_B200_SPLIT_CHUNK=k (experiment knob) makes CTAs retire after ~k row blocks so that
   // communication kernels on the high-priority stream find SM slots while the interior blocks run.
-  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS);
+  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int resident = b->sm_count * occ;
   static int chunk = -1;
   if (chunk < 0) { const char *e = getenv("VCL_B200_SPLIT_CHUNK"); chunk = e ? atoi(e) : 0; }
   int grid = std::min(d.nblk, std::min(resident, VCL_MAX_BLOCKS));
   if (chunk > 0) grid = std::min(d.nblk, std::min(std::max(resident, vcl_div_up(d.nblk, chunk)), VCL_MAX_BLOCKS));
-  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, 0, stream>>>(d, xv, epi);
+  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "csr_stream_kernel(split)");
   return ViennaCLSuccess;
 }

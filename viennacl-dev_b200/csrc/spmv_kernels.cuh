@@ -24,8 +24,8 @@ struct CsrDev
 {
   int rows; u32 nnz;
   const u32 *rp, *ci; const double *va;
-  const u32 *blk; int nblk;
-  const u32 *blk_list;     // optional indirection: process row blocks blk_list[0..nblk) (interior / boundary subsets)
+  const u32 *blk_start, *blk_end; int nblk;     // row block i covers rows [blk_start[i], blk_end[i]); for a plain plan
+                                                // blk_end == blk_start + 1 (compressed_matrix handle3() layout)
   // peer-memory halo (row-partitioned path, peer.cuh): list positions >= wait_from read halo columns and must first see
   // wait_flags[q] >= wait_seq for every source rank q in wait_mask.  wait_mask == 0: nothing to wait for.
   int wait_from; unsigned int wait_mask; const unsigned long long *wait_flags; unsigned long long wait_seq; int *err;
@@ -100,27 +100,148 @@ struct EpiAxpby
 };
 
 // ------------------------------------------------------------------------------------------------
-// CSR, row-block streaming
+// CSR, row-block streaming: persistent CTAs, two-deep TMA pipeline.
+//
+// Every CTA walks its row blocks bi = blockIdx.x, +gridDim.x, ...  While the 256 threads work on block j (one thread per
+// row, entries read from shared memory), ONE elected thread has already issued two bulk copies (cp.async.bulk, the 1-D TMA
+// path, L2 evict-first) that bring the value and column-index ranges of block j+1 into the other shared-memory buffer;
+// completion is signalled through an mbarrier (complete_tx bytes), so no thread spends issue slots on the copy and the CTA
+// always has a block in flight.  The block descriptors (row range, nnz range) are themselves software-pipelined in
+// registers two and three blocks ahead, so that no dependent global load sits on the critical path.
+//   class 0  normal block: 16-byte aligned enclosing range, <= CSR_CAP entries           -> TMA
+//   class 1  one row longer than CSR_CAP: the whole CTA strides over it straight from global memory
+//   class 2  range whose 16-byte padded end would pass the end of the arrays (last block) -> guarded synchronous staging
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar, unsigned long long pol)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+#ifndef CSR_NSTAGE
+#define CSR_NSTAGE 2                                                               // shared-memory ring depth (blocks)
+#endif
+#define CSR_SMEM_BYTES (CSR_NSTAGE * CSR_STAGE * (int)(sizeof(double) + sizeof(u32)))  // dynamic shared memory
+#define CSR_MIN_CTAS (CSR_NSTAGE <= 2 ? 4 : (CSR_NSTAGE == 3 ? 3 : 2))
+
+struct CsrBlockDesc { u32 r0, r1, n0, n1; };
+
+__device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
+{
+  if (d.n1 - d.n0 > CSR_CAP) return 1;
+  const u32 a0 = d.n0 & ~3u;
+  const u32 cnt4 = (d.n1 - a0 + 3u) & ~3u;
+  return (cnt4 == 0u || a0 + cnt4 > nnz) ? 2 : 0;
+}
+
+// One row, entries [j, e) of the staged block, sequential accumulation chain in storage order.  All gathers of up to 8
+// entries are issued before the first multiply-add (predicated, so a 7-point row costs ONE round trip to L2, not three).
+template<bool SPLIT>
+__device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv)
+{
+  double dot = 0.0;
+  for (; j < e; j += 8)
+  {
+    double v[8], xx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      const bool ok = j + k < e;
+      xx[k] = ok ? xload<SPLIT>(xv, s_col[j + k]) : 0.0;
+      v[k] = ok ? s_val[j + k] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (j + k < e) dot = madd(v[k], xx[k], dot);
+  }
+  return dot;
+}
+
 template<class Epi, bool SPLIT>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 8)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 {
-  __shared__ __align__(16) double s_val[CSR_STAGE];
-  __shared__ __align__(16) u32    s_col[CSR_STAGE];
-  __shared__ u32 s_rp[CSR_BLOCK_THREADS + 1];
+  constexpr int S = CSR_NSTAGE;
+  extern __shared__ __align__(128) unsigned char csr_smem[];
+  __shared__ __align__(8) unsigned long long s_bar[S];
   __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  double *s_val0 = reinterpret_cast<double*>(csr_smem);
+  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(double));
 
   if (epi.skip()) return;
   const int tid = threadIdx.x;
+  const int step = (int)gridDim.x;
   const unsigned long long pol = l2_evict_first_policy();
 #ifdef VCL_PEER_DEBUG
   if (SPLIT && A.dbg && blockIdx.x == 0 && tid == 0) A.dbg[(A.dbg_seq % 1024) * 4 + 2] = global_ns();
 #endif
   bool halo_ready = !(SPLIT && A.wait_mask != 0u);
 
-  for (int bi = blockIdx.x; bi < A.nblk; bi += gridDim.x)
+  if (tid == 0)
   {
+#pragma unroll
+    for (int i = 0; i < S; ++i) mbar_init(&s_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // elected thread: bring block `d` into buffer `buf`
+  auto issue = [&](const CsrBlockDesc &d, int buf)
+  {
+    const u32 a0 = d.n0 & ~3u;
+    const u32 cnt4 = (d.n1 - a0 + 3u) & ~3u;
+    fence_proxy_async();                                   // earlier generic-proxy accesses to this buffer are done (barrier)
+    mbar_expect_tx(&s_bar[buf], cnt4 * 12u);
+    tma_load_1d(s_val0 + buf * CSR_STAGE, A.va + a0, cnt4 * 8u, &s_bar[buf], pol);
+    tma_load_1d(s_col0 + buf * CSR_STAGE, A.ci + a0, cnt4 * 4u, &s_bar[buf], pol);
+  };
+
+  // ---- prologue: D[i] = descriptor of this CTA's i-th block, (r0_S, r1_S) = row range of the S-th ----
+  int bi = blockIdx.x;
+  CsrBlockDesc D[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i)
+  {
+    D[i].r0 = D[i].r1 = D[i].n0 = D[i].n1 = 0;
+    if (bi + i * step < A.nblk) { D[i].r0 = A.blk_start[bi + i * step]; D[i].r1 = A.blk_end[bi + i * step]; }
+  }
+  u32 r0_S = 0, r1_S = 0;
+  if (bi + S * step < A.nblk) { r0_S = A.blk_start[bi + S * step]; r1_S = A.blk_end[bi + S * step]; }
+#pragma unroll
+  for (int i = 0; i < S; ++i)
+    if (bi + i * step < A.nblk) { D[i].n0 = A.rp[D[i].r0]; D[i].n1 = A.rp[D[i].r1]; }
+  u32 my_s = 0, my_e = 0;                                  // this thread's row of the current block
+  if (bi < A.nblk && (u32)tid < D[0].r1 - D[0].r0) { my_s = A.rp[D[0].r0 + tid]; my_e = A.rp[D[0].r0 + tid + 1]; }
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int i = 0; i < S - 1; ++i)
+      if (bi + i * step < A.nblk && csr_block_class(D[i], A.nnz) == 0) issue(D[i], i);
+  }
+  unsigned phase = 0;                                      // bit b: parity to wait for on buffer b
+  int buf = 0;                                             // buffer of the current block
+
+  for (; bi < A.nblk; bi += step)
+  {
+    // ---- keep the pipeline full: copy of block j+S-1, row pointers of j+1, nnz range of j+S, row range of j+S+1 ----
+    const int buf_issue = (buf == 0) ? S - 1 : buf - 1;    // == (buf + S - 1) % S: the buffer block j-1 has just released
+    if (tid == 0 && bi + (S - 1) * step < A.nblk && csr_block_class(D[S - 1], A.nnz) == 0) issue(D[S - 1], buf_issue);
+    u32 nx_s = 0, nx_e = 0, n0_S = 0, n1_S = 0, r0_T = 0, r1_T = 0;
+    if (bi + step < A.nblk && (u32)tid < D[1].r1 - D[1].r0) { nx_s = A.rp[D[1].r0 + tid]; nx_e = A.rp[D[1].r0 + tid + 1]; }
+    if (bi + S * step < A.nblk) { n0_S = A.rp[r0_S]; n1_S = A.rp[r1_S]; }
+    if (bi + (S + 1) * step < A.nblk) { r0_T = A.blk_start[bi + (S + 1) * step]; r1_T = A.blk_end[bi + (S + 1) * step]; }
+
     if (SPLIT && !halo_ready && bi >= A.wait_from)
     {
       // boundary row blocks come last in the list: by now the neighbours' pushes have normally landed
@@ -134,69 +255,48 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 #endif
       halo_ready = true;
     }
-    const u32 b = A.blk_list ? A.blk_list[bi] : (u32)bi;
-    const u32 r0 = A.blk[b], r1 = A.blk[b + 1];
-    const u32 nrows = r1 - r0;
-    const u32 n0 = A.rp[r0], n1 = A.rp[r1];
 
-    if (n1 - n0 > CSR_CAP)
+    const CsrBlockDesc cur = D[0];
+    const u32 nrows = cur.r1 - cur.r0;
+    const int cls = csr_block_class(cur, A.nnz);
+    if (cls == 1)
     {
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       double part[1] = {0.0};
-      for (u32 k = n0 + tid; k < n1; k += CSR_BLOCK_THREADS)
+      for (u32 k = cur.n0 + tid; k < cur.n1; k += CSR_BLOCK_THREADS)
         part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
       __shared__ double s_long[32];
       block_sum<1>(part, s_long);
-      if (tid == 0) epi.row(r0, part[0], epi.pre(r0));
-      __syncthreads();
-      continue;
+      if (tid == 0) epi.row(cur.r0, part[0], epi.pre(cur.r0));
     }
-
-    // ---- stage values / column indices: 16-byte cp.async from the enclosing 16-byte aligned range ----
-    const u32 a0 = n0 & ~3u;
-    const u32 cnt = n1 - a0;
-    for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2)
+    else
     {
-      if (a0 + i + 2 <= A.nnz) cp_async16(&s_val[i], A.va + a0 + i, pol);
-      else if (a0 + i < A.nnz) s_val[i] = A.va[a0 + i];
-    }
-    for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4)
-    {
-      if (a0 + i + 4 <= A.nnz) cp_async16(&s_col[i], A.ci + a0 + i, pol);
-      else { for (u32 k = 0; k < 4 && a0 + i + k < A.nnz; ++k) s_col[i + k] = A.ci[a0 + i + k]; }
-    }
-    cp_async_commit();
-    if ((u32)tid <= nrows) s_rp[tid] = A.rp[r0 + tid];
-    if (tid == 0 && nrows == CSR_BLOCK_THREADS) s_rp[CSR_BLOCK_THREADS] = n1;
-    const double pre = ((u32)tid < nrows) ? epi.pre(r0 + tid) : 0.0;      // in flight together with the staging copies
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // ---- one thread per row, sequential fma chain in storage order ----
-    if ((u32)tid < nrows)
-    {
-      u32 j = s_rp[tid] - a0;
-      const u32 e = s_rp[tid + 1] - a0;
-      double dot = 0.0;
-      for (; j + 4 <= e; j += 4)
+      const double pre = ((u32)tid < nrows) ? epi.pre(cur.r0 + tid) : 0.0;
+      const u32 a0 = cur.n0 & ~3u;
+      const double *s_val = s_val0 + buf * CSR_STAGE;
+      const u32 *s_col = s_col0 + buf * CSR_STAGE;
+      if (cls == 0)
       {
-        const u32 c0 = s_col[j], c1 = s_col[j + 1], c2 = s_col[j + 2], c3 = s_col[j + 3];
-        const double x0 = xload<SPLIT>(xv, c0), x1 = xload<SPLIT>(xv, c1);
-        const double x2 = xload<SPLIT>(xv, c2), x3 = xload<SPLIT>(xv, c3);
-        dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
-        dot = madd(s_val[j + 2], x2, dot); dot = madd(s_val[j + 3], x3, dot);
+        mbar_wait(&s_bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
       }
-      if (j + 2 <= e)
+      else
       {
-        const u32 c0 = s_col[j], c1 = s_col[j + 1];
-        const double x0 = xload<SPLIT>(xv, c0), x1 = xload<SPLIT>(xv, c1);
-        dot = madd(s_val[j], x0, dot); dot = madd(s_val[j + 1], x1, dot);
-        j += 2;
+        // guarded staging of the last few entries of the arrays (never reads past nnz)
+        double *wv = s_val0 + buf * CSR_STAGE; u32 *wc = s_col0 + buf * CSR_STAGE;
+        for (u32 i = tid; a0 + i < cur.n1; i += CSR_BLOCK_THREADS) { wv[i] = A.va[a0 + i]; wc[i] = A.ci[a0 + i]; }
+        __syncthreads();
       }
-      if (j < e) dot = madd(s_val[j], xload<SPLIT>(xv, s_col[j]), dot);
-      epi.row(r0 + tid, dot, pre);
+      if ((u32)tid < nrows) epi.row(cur.r0 + tid, csr_row_dot<SPLIT>(s_val, s_col, my_s - a0, my_e - a0, xv), pre);
     }
-    __syncthreads();
+    __syncthreads();                                       // buffer `buf` may be refilled from the next iteration on
+    // ---- rotate the descriptor pipeline ----
+#pragma unroll
+    for (int i = 0; i + 1 < S; ++i) D[i] = D[i + 1];
+    D[S - 1].r0 = r0_S; D[S - 1].r1 = r1_S; D[S - 1].n0 = n0_S; D[S - 1].n1 = n1_S;
+    r0_S = r0_T; r1_S = r1_T;
+    my_s = nx_s; my_e = nx_e;
+    buf = (buf + 1 == S) ? 0 : buf + 1;
   }
   epi.finish(s_red);
 }
