@@ -54,6 +54,12 @@ def main():
         for _ in range(20):
             spmv()
         be.sync()
+        if world == 1 and n1 <= 256:
+            S = A.to_sell(32)
+            pkg.SolverTag(tol=1e-30, max_iterations=iters).solve("cg", S, b, x)
+            for _ in range(20):
+                S.spmv(b, x)
+            be.sync()
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda e: e.time_range.start)
     if rank in (0, world - 1):

@@ -220,7 +220,7 @@ ViennaCLStatus p2p_launch_csr(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi e
 XVec p2p_xvec(ViennaCLB200DistCsr A, const double *x, u64 seq)
 {
   const PeerWindow &w = A->hwin;
-  XVec xv = {x, 0, 1, w.halo[w.me] + (size_t)(seq & 1ULL) * (size_t)w.halo_len[w.me], (u32)A->n};
+  XVec xv = make_xvec(x, 0, 1, w.halo[w.me] + (size_t)(seq & 1ULL) * (size_t)w.halo_len[w.me], (u32)A->n);
   return xv;
 }
 
@@ -264,7 +264,7 @@ ViennaCLStatus dist_plain_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const d
     VCL_TRY(p2p_push(b, A, x, seq, nullptr));
     return p2p_launch_csr(b, p2p_all_blocks(A, seq), p2p_xvec(A, x, seq), epi);
   }
-  XVec xv = {x, 0, 1, A->halo_buf, (u32)A->n};
+  XVec xv = make_xvec(x, 0, 1, A->halo_buf, (u32)A->n);
   VCL_TRY(start_halo(b, A, x));
   VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, epi, b->stream));
   VCL_TRY(wait_halo(b, A));
@@ -690,7 +690,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
     return ViennaCLSuccess;
   }
 
-  XVec xv = {p, 0, 1, A->halo_buf, (u32)A->n};
+  XVec xv = make_xvec(p, 0, 1, A->halo_buf, (u32)A->n);
   // rank-local sums land in `loc`, the allreduce writes the global sums into st->sums (out of place, so that re-issuing the
   // collective after convergence -- kernels skipped, `loc` unchanged -- reproduces the same global sums)
   double *loc = b->world > 1 ? b->dscal + 32 : &st->sums[0];

@@ -66,12 +66,12 @@ template<class Epi>
 static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
 {
   SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values};
-  const int occ = vcl_occupancy(sell_kernel<Epi>, CSR_BLOCK_THREADS);
+  const int occ = vcl_occupancy(sell_kernel<Epi>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int C = A.rows_per_block;
   const int nslices = (A.rows - 1) / C + 1;
   const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
   int grid = std::max(1, std::min(vcl_div_up(nslices, spb), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
-  sell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+  sell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "sell_kernel");
   return ViennaCLSuccess;
 }

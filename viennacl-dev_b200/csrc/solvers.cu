@@ -22,7 +22,7 @@ struct MatOp
 template<class Epi>
 ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const double *x, Epi epi)
 {
-  XVec xv = {x, 0, 1};
+  XVec xv = make_xvec(x, 0, 1);
   if (A.fmt == 0) return vcl_launch_csr(b, A.csr, xv, epi);
   return vcl_launch_sell(b, A.sell, xv, epi);
 }

@@ -64,7 +64,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsrmv(ViennaCLBackend b, ViennaCLInt rows
   VCL_REQUIRE(b, x != y, "x and y alias: the facade resolves x = A*x through a temporary (compressed_matrix.hpp:1237-1242)");
   ViennaCLCUDADcsr A = {rows, cols, nnz, row_ptr, col_idx, values, row_blocks, num_blocks};
   EpiAxpby epi = {y, offy, incy, alpha, beta};
-  XVec xv = {x, offx, incx};
+  XVec xv = make_xvec(x, offx, incx);
   return vcl_launch_csr(b, A, xv, epi);
 }
 
@@ -82,7 +82,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADsellmv(ViennaCLBackend b, ViennaCLInt row
   VCL_REQUIRE(b, x != y, "x and y alias");
   ViennaCLCUDADsell A = {rows, cols, rows_per_block, columns_per_block, col_idx, block_start, values};
   EpiAxpby epi = {y, offy, incy, alpha, beta};
-  XVec xv = {x, offx, incx};
+  XVec xv = make_xvec(x, offx, incx);
   return vcl_launch_sell(b, A, xv, epi);
 }
 

@@ -39,7 +39,15 @@ struct SellDev
 };
 
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
-struct XVec { const double *x; int off, inc; const double *x2; u32 split; };
+// `x` already points at the first entry (start offset folded in); inc8 = stride in BYTES, so an entry address is ONE
+// 32x32+64-bit multiply-add.  Build with make_xvec().
+struct XVec { const double *x; u32 inc8; const double *x2; u32 split; };
+
+static inline XVec make_xvec(const double *x, long long off, long long inc, const double *x2 = nullptr, u32 split = 0)
+{
+  XVec v = {x + off, (u32)(inc * 8), x2, split};
+  return v;
+}
 
 // SPLIT: one load from a selected base (no branch).  Halo entries are written by peer GPUs; reading them through L1 is safe
 // because a CTA touches the halo only after its acquire on the arrival flag (peer.cuh) and L1 does not outlive a launch.
@@ -51,13 +59,16 @@ __device__ __forceinline__ double xload(const XVec &xv, u32 c)
     const double *base = (c >= xv.split) ? (xv.x2 - xv.split) : xv.x;
     return base[c];
   }
-  return xv.x[(size_t)c * xv.inc + xv.off];
+  return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(xv.x) + (unsigned long long)c * xv.inc8);
 }
 
 // In-row CSR accumulation step.  The reference host backend (host_based/sparse_matrix_operations.hpp:167-184), built with
 // g++ -O3 for x86-64-v3, evaluates `dot += a*x` as a rounded multiply followed by a rounded add (GCC does not form FMA
 // chains in reductions under generic tuning); the same two roundings are used here so that CSR results match it bit for bit.
 __device__ __forceinline__ double madd(double a, double x, double acc) { return __dadd_rn(acc, __dmul_rn(a, x)); }
+
+// v != 0.0 without the FP64 pipe (true for NaN, false for +-0.0, like the floating-point comparison)
+__device__ __forceinline__ bool nonzero(double v) { return (__double_as_longlong(v) << 1) != 0; }
 
 // The matrix arrays are read exactly once per product: they are streamed with an L2 evict-first policy so that they do not
 // push the gathered x entries (re-used by the rows of the next planes, tens of MB of streamed matrix data later) out of L2.
@@ -161,9 +172,10 @@ __device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_
       xx[k] = ok ? xload<SPLIT>(xv, s_col[j + k]) : 0.0;
       v[k] = ok ? s_val[j + k] : 0.0;
     }
+    // empty slots hold v = x = +0.0: adding +0.0 never changes the bits of `dot` (a round-to-nearest sum that starts at
+    // +0.0 cannot be -0.0), so the chain needs no predicates and stays bit-identical to the sequential reference
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (j + k < e) dot = madd(v[k], xx[k], dot);
+    for (int k = 0; k < 8; ++k) dot = madd(v[k], xx[k], dot);
   }
   return dot;
 }
@@ -309,98 +321,128 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 {
   __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
   if (epi.skip()) return;
-  const double * __restrict__ x = xv.x;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
     double dot = 0.0;
     const u32 e = A.rp[r + 1];
     for (u32 k = A.rp[r]; k < e; ++k)
-      dot = madd(A.va[k], x[(size_t)A.ci[k] * xv.inc + xv.off], dot);
+      dot = madd(A.va[k], xload<false>(xv, A.ci[k]), dot);
     epi.row((u32)r, dot, epi.pre((u32)r));
   }
   epi.finish(s_red);
 }
 
 // ------------------------------------------------------------------------------------------------
-// SELL-C-sigma (sigma = 1).  Slices are stored back to back, so the slices of a CTA (256/C of them: 8 for the default
-// C = 32) form ONE contiguous range of values and of column indices: it is streamed global->shared with 16-byte cp.async
-// exactly like a CSR row block, then one thread per row walks its slice-column-major entries (stride C in shared memory:
-// consecutive rows hit consecutive banks) with one fma chain.  Zero-valued (padding) slots never touch x
-// (cuda/sparse_matrix_operations.hpp:2231, host :1833).  Slices wider than the staging buffer take the direct path.
+// SELL-C-sigma (sigma = 1).  Slices are stored back to back, so the slices of one CTA pass (256/C of them: 8 for the default
+// C = 32) form ONE contiguous, 16-byte aligned range of values and of column indices: it is brought into shared memory
+// by the same two-stage TMA pipeline as a CSR row block (block j+1 is in flight while block j is computed), then one
+// thread per row walks its slice-column-major entries (stride C in shared memory: consecutive rows hit consecutive banks)
+// with one fma chain, all gathers of up to 8 entries issued before the first fma.  Zero-valued (padding) slots never
+// touch x (cuda/sparse_matrix_operations.hpp:2231, host :1833).  Passes whose range does not fit the staging buffer, or
+// C not a multiple of 4 / larger than the CTA, take the direct path.
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
 template<class Epi>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 8)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
-  __shared__ __align__(16) double s_val[CSR_STAGE];
-  __shared__ __align__(16) u32    s_col[CSR_STAGE];
+  constexpr int S = CSR_NSTAGE;
+  extern __shared__ __align__(128) unsigned char csr_smem[];
+  __shared__ __align__(8) unsigned long long s_bar[S];
   __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  double *s_val0 = reinterpret_cast<double*>(csr_smem);
+  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(double));
+  static_assert(CSR_NSTAGE == 2, "sell_kernel is written for a two-stage ring");
+
   if (epi.skip()) return;
-  const double * __restrict__ x = xv.x;
   const double * __restrict__ va = A.va;
   const u32 * __restrict__ ci = A.ci;
   const int tid = threadIdx.x;
+  const int step = (int)gridDim.x;
   const unsigned long long pol = l2_evict_first_policy();
   const u32 C = (u32)A.C;
   const u32 nslices = (u32)((A.rows - 1) / A.C + 1);
   const u32 spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1u;      // slices per CTA pass
-  const u32 nblocks = (nslices + spb - 1) / spb;
+  const int nblocks = (int)((nslices + spb - 1) / spb);
   const bool can_stage = (C % 4u) == 0u && C <= CSR_BLOCK_THREADS &&
                          ((reinterpret_cast<uintptr_t>(va) | reinterpret_cast<uintptr_t>(ci)) & 15u) == 0u;
 
-  for (u32 b = blockIdx.x; b < nblocks; b += gridDim.x)
+  if (tid == 0)
   {
-    const u32 s0 = b * spb, s1 = min(s0 + spb, nslices);
-    const u32 base = A.bs[s0];
-    const u32 end = A.bs[s1 - 1] + A.cpb[s1 - 1] * C;
-    const u32 cnt = end - base;
-    const bool staged = can_stage && cnt <= CSR_CAP;
-    if (staged)
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  // element range [base, end) of pass b
+  auto range_of = [&](int b, u32 &base, u32 &end)
+  {
+    const u32 s0 = (u32)b * spb, s1 = min(s0 + spb, nslices);
+    base = A.bs[s0];
+    end = A.bs[s1 - 1] + A.cpb[s1 - 1] * C;
+  };
+  auto staged = [&](u32 base, u32 end) { return can_stage && end > base && end - base <= CSR_CAP; };
+  auto issue = [&](u32 base, u32 end, int buf)
+  {
+    const u32 cnt = end - base;                            // multiple of C, hence of 4; base likewise
+    fence_proxy_async();
+    mbar_expect_tx(&s_bar[buf], cnt * 12u);
+    tma_load_1d(s_val0 + buf * CSR_STAGE, va + base, cnt * 8u, &s_bar[buf], pol);
+    tma_load_1d(s_col0 + buf * CSR_STAGE, ci + base, cnt * 4u, &s_bar[buf], pol);
+  };
+  // this thread's row of pass b: slice width and offset of its first entry
+  auto my_row = [&](int b, u32 &w, u32 &first)
+  {
+    const u32 slice = (u32)b * spb + (u32)tid / C;
+    w = 0; first = 0;
+    if ((u32)tid < spb * C && slice < nslices) { w = A.cpb[slice]; first = A.bs[slice] + (u32)tid % C; }
+  };
+
+  int b = blockIdx.x;
+  u32 base_c = 0, end_c = 0, base_n = 0, end_n = 0, w_c = 0, first_c = 0;
+  if (b < nblocks) { range_of(b, base_c, end_c); my_row(b, w_c, first_c); }
+  if (b + step < nblocks) range_of(b + step, base_n, end_n);
+  if (tid == 0 && b < nblocks && staged(base_c, end_c)) issue(base_c, end_c, 0);
+  unsigned phase = 0;
+  int buf = 0;
+
+  for (; b < nblocks; b += step, buf ^= 1)
+  {
+    if (tid == 0 && b + step < nblocks && staged(base_n, end_n)) issue(base_n, end_n, buf ^ 1);
+    u32 base_2 = 0, end_2 = 0, w_n = 0, first_n = 0;
+    if (b + 2 * step < nblocks) range_of(b + 2 * step, base_2, end_2);
+    if (b + step < nblocks) my_row(b + step, w_n, first_n);
+
+    const u32 s0 = (u32)b * spb, s1 = min(s0 + spb, nslices);
+    if (staged(base_c, end_c))
     {
-      // base is a multiple of C (hence of 4) and cnt a multiple of C: whole 16-byte packets, never past the arrays
-      for (u32 i = tid * 2; i < cnt; i += CSR_BLOCK_THREADS * 2) cp_async16(&s_val[i], va + base + i, pol);
-      for (u32 i = tid * 4; i < cnt; i += CSR_BLOCK_THREADS * 4) cp_async16(&s_col[i], ci + base + i, pol);
-      cp_async_commit();
       // (s1 - s0) * C <= 256 here: one row per thread
-      const bool active = (u32)tid < (s1 - s0) * C;
-      u32 w = 0, idx = 0;
-      long long r = 0;
+      const long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);
+      const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
+      const double pre = active ? epi.pre((u32)r) : 0.0;
+      const double *s_val = s_val0 + buf * CSR_STAGE;
+      const u32 *s_col = s_col0 + buf * CSR_STAGE;
+      mbar_wait(&s_bar[buf], (phase >> buf) & 1u);
+      phase ^= 1u << buf;
       if (active)
       {
-        const u32 slice = s0 + tid / C;
-        r = (long long)slice * C + (tid % C);
-        w = A.cpb[slice];
-        idx = A.bs[slice] + (tid % C) - base;
-      }
-      const double pre = (active && r < A.rows) ? epi.pre((u32)r) : 0.0;
-      cp_async_wait<0>();
-      __syncthreads();
-      if (active && r < A.rows)
-      {
         double acc = 0.0;
-        u32 j = 0;
-        for (; j + 4 <= w; j += 4, idx += 4 * C)
+        u32 idx = first_c - base_c;
+        for (u32 j = 0; j < w_c; j += 8, idx += 8 * C)
         {
-          const double v0 = s_val[idx], v1 = s_val[idx + C], v2 = s_val[idx + 2 * C], v3 = s_val[idx + 3 * C];
-          const u32 c0 = s_col[idx], c1 = s_col[idx + C], c2 = s_col[idx + 2 * C], c3 = s_col[idx + 3 * C];
-          const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
-          const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
-          const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
-          const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
-          if (v0 != 0.0) acc = fma(x0, v0, acc);
-          if (v1 != 0.0) acc = fma(x1, v1, acc);
-          if (v2 != 0.0) acc = fma(x2, v2, acc);
-          if (v3 != 0.0) acc = fma(x3, v3, acc);
-        }
-        for (; j < w; ++j, idx += C)
-        {
-          const double v0 = s_val[idx];
-          if (v0 != 0.0) acc = fma(x[(size_t)s_col[idx] * xv.inc + xv.off], v0, acc);
+          double v[8], xx[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+          {
+            v[k] = (j + k < w_c) ? s_val[idx + k * C] : 0.0;
+            xx[k] = nonzero(v[k]) ? xload<false>(xv, s_col[idx + k * C]) : 0.0;
+          }
+          // zero (padding / empty) slots have v = x = +0.0 and leave the bits of `acc` unchanged: no predicates needed
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fma(xx[k], v[k], acc);
         }
         epi.row((u32)r, acc, pre);
       }
-      __syncthreads();
     }
     else
     {
@@ -418,10 +460,10 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         {
           const double v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * (size_t)C], v3 = va[idx + 3 * (size_t)C];
           const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * (size_t)C], c3 = ci[idx + 3 * (size_t)C];
-          const double x0 = (v0 != 0.0) ? x[(size_t)c0 * xv.inc + xv.off] : 0.0;
-          const double x1 = (v1 != 0.0) ? x[(size_t)c1 * xv.inc + xv.off] : 0.0;
-          const double x2 = (v2 != 0.0) ? x[(size_t)c2 * xv.inc + xv.off] : 0.0;
-          const double x3 = (v3 != 0.0) ? x[(size_t)c3 * xv.inc + xv.off] : 0.0;
+          const double x0 = (v0 != 0.0) ? xload<false>(xv, c0) : 0.0;
+          const double x1 = (v1 != 0.0) ? xload<false>(xv, c1) : 0.0;
+          const double x2 = (v2 != 0.0) ? xload<false>(xv, c2) : 0.0;
+          const double x3 = (v3 != 0.0) ? xload<false>(xv, c3) : 0.0;
           if (v0 != 0.0) acc = fma(x0, v0, acc);
           if (v1 != 0.0) acc = fma(x1, v1, acc);
           if (v2 != 0.0) acc = fma(x2, v2, acc);
@@ -430,11 +472,13 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         for (; j < w; ++j, idx += C)
         {
           const double v0 = va[idx];
-          if (v0 != 0.0) acc = fma(x[(size_t)ci[idx] * xv.inc + xv.off], v0, acc);
+          if (v0 != 0.0) acc = fma(xload<false>(xv, ci[idx]), v0, acc);
         }
         epi.row((u32)r, acc, epi.pre((u32)r));
       }
     }
+    __syncthreads();                                       // buffer `buf` may be refilled from the next iteration on
+    base_c = base_n; end_c = end_n; base_n = base_2; end_n = end_2; w_c = w_n; first_c = first_n;
   }
   epi.finish(s_red);
 }
