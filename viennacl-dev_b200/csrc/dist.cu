@@ -44,6 +44,8 @@ struct ViennaCLB200DistCsr_impl
   void *peer_base[VCL_MAX_PEERS] = {nullptr};
   PeerWindow hwin; PeerWindow *d_win = nullptr;
   HaloPush push;
+  bool fused_push = false;           // every destination's send list is one contiguous range: cg_update_kernel pushes
+  long long push_lo[VCL_MAX_PUSH_RANGES] = {0}, push_hi[VCL_MAX_PUSH_RANGES] = {0};
   unsigned int wait_mask = 0;
   u32 *ord_start = nullptr, *ord_end = nullptr;   // row ranges of the blocks in the order [interior | boundary]
   u64 halo_seq = 0, red_seq = 0;     // exchanges EXECUTED so far (identical on every rank)
@@ -375,6 +377,22 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
   }
   // send segments are contiguous and ordered by destination rank; ranks without entries contribute empty segments
   hp.begin[hp.ndst] = A->total_send;
+  // contiguous send ranges?  (slab partitions of banded matrices: yes) -> the producing kernel can push by itself
+  A->fused_push = false;
+  if (hp.ndst > 0 && hp.ndst <= VCL_MAX_PUSH_RANGES && !(getenv("VCL_B200_NO_FUSED_PUSH")))
+  {
+    std::vector<u32> idx((size_t)std::max(A->total_send, 1));
+    if (A->total_send) VCL_CUDA(b, cudaMemcpy(idx.data(), A->send_idx, sizeof(u32) * A->total_send, cudaMemcpyDeviceToHost));
+    bool contiguous = true;
+    for (int d = 0; d < hp.ndst && contiguous; ++d)
+    {
+      const int b0 = hp.begin[d], b1 = hp.begin[d + 1];
+      A->push_lo[d] = b1 > b0 ? (long long)idx[b0] : 0;
+      A->push_hi[d] = A->push_lo[d] + (b1 - b0);
+      for (int i = b0; i < b1; ++i) if (idx[i] != idx[b0] + (u32)(i - b0)) { contiguous = false; break; }
+    }
+    A->fused_push = contiguous;
+  }
   A->p2p = true;
   return ViennaCLSuccess;
 }
@@ -651,9 +669,21 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         // iteration i = launched + k + 1 uses exchange numbers base + i; once st->done is set every later kernel returns
         // at once on every rank (same sums -> same decision), so the exchanges executed are exactly 1..iters
         const u64 hseq = halo_base + (u64)(launched + k + 1), rseq = red_base + (u64)(launched + k + 1);
-        cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr);
+        PushRanges pr = PushRanges();
+        if (A->fused_push)
+        {
+          const int par = (int)(hseq & 1ULL);
+          pr.n = A->push.ndst; pr.me = A->push.me; pr.W = A->push.W; pr.seq = hseq;
+          for (int d = 0; d < pr.n; ++d)
+          {
+            pr.lo[d] = A->push_lo[d]; pr.hi[d] = A->push_hi[d];
+            pr.dst[d] = A->push.dst[d] + (size_t)par * (size_t)A->push.stride[d];
+            pr.flag[d] = A->push.flag[d] + par * pr.W + pr.me;
+          }
+        }
+        cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr, pr);
         VCL_LAUNCHED(b, "cg_update_kernel");
-        VCL_TRY(p2p_push(b, A, p, hseq, st));
+        if (!A->fused_push) VCL_TRY(p2p_push(b, A, p, hseq, st));
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr};
         CsrDev dd = p2p_all_blocks(A, hseq);

@@ -125,7 +125,7 @@ __device__ __forceinline__ void st2(double *p, long long i, double2 v) { *reinte
 // ------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(VEC_THREADS)
 cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap, double alpha_v, double beta_v,
-                 SolverState *st, double *partials, unsigned int *ticket, double *out_rr)
+                 SolverState *st, double *partials, unsigned int *ticket, double *out_rr, const PushRanges pr = PushRanges())
 {
   __shared__ double s_red[32];
   if (st != nullptr && st->done != VCL_RUNNING) return;
@@ -142,6 +142,7 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
     vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
     acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+    if (pr.n) { push_entry(pr, k, vp.x); push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
@@ -151,8 +152,15 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
     vp = fma(beta, vp, vr);
     acc[0] = fma(vr, vr, acc[0]);
     p[k] = vp; r[k] = vr;
+    if (pr.n) push_entry(pr, k, vp);
   }
-  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_rr = acc[0];
+  if (pr.n) __threadfence_system();                 // this thread's remote stores are performed before its CTA takes a ticket
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
+  {
+    if (threadIdx.x == 0) *out_rr = acc[0];
+    // every CTA has fenced its pushes: publish the sequence number to the destinations
+    if ((int)threadIdx.x < pr.n) { __threadfence_system(); st_release_sys(pr.flag[threadIdx.x], pr.seq); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

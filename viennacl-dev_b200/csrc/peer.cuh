@@ -41,6 +41,18 @@ struct HaloPush
   u64 *flag[VCL_MAX_PEERS];             // destination's halo_flag (parity 0), entry of this rank added in the kernel
 };
 
+// Halo push fused into the kernel that PRODUCES the vector (cg_update_kernel): usable when every destination's send list
+// is one contiguous index range [lo, hi) -- slab partitions of banded / stencil matrices.  n == 0: nothing to push.
+#define VCL_MAX_PUSH_RANGES 4
+struct PushRanges
+{
+  int n, me, W;
+  long long lo[VCL_MAX_PUSH_RANGES], hi[VCL_MAX_PUSH_RANGES];
+  double *dst[VCL_MAX_PUSH_RANGES];     // destination's halo area, offset to this rank's segment AND to the parity buffer
+  u64 *flag[VCL_MAX_PUSH_RANGES];       // destination's halo_flag entry for (parity, this rank)
+  u64 seq;
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
 {
@@ -70,6 +82,13 @@ __device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err)
     if (ld_acquire_sys(flag) >= seq) return true;
     if (global_ns() - t0 > VCL_PEER_TIMEOUT_NS) { if (err) atomicExch(err, 1); return false; }
   }
+}
+
+__device__ __forceinline__ void push_entry(const PushRanges &pr, long long k, double v)
+{
+#pragma unroll
+  for (int d = 0; d < VCL_MAX_PUSH_RANGES; ++d)
+    if (d < pr.n && k >= pr.lo[d] && k < pr.hi[d]) pr.dst[d][k - pr.lo[d]] = v;
 }
 
 // All-reduce (sum) of N <= 4 doubles across the ranks, executed by ONE CTA per rank (>= W threads).
