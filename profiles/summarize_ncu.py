@@ -25,7 +25,8 @@ def to_bytes(val, unit):
 
 
 rows_out = []
-for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "prof_*.ncu-rep"))):
+pattern = "prof_%s_*.ncu-rep" % tag if glob.glob(os.path.join(ROOT, "gpurun_out", "prof_%s_*.ncu-rep" % tag)) else "prof_*.ncu-rep"
+for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", pattern))):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -63,9 +64,9 @@ with open(os.path.join(ROOT, "profiles", "ncu_summary_%s.md" % tag), "w") as f:
 # per-launch DRAM traffic of the two headline kernels, read by bench.py (roofline.traffic)
 traffic = {}
 for d in rows_out:
-    if d["capture"] == "prof_spmv" and "csr_stream_kernel<EpiAxpby" in d["kernel"]:
+    if d["capture"].endswith("spmv") and "csr_stream_kernel<EpiAxpby" in d["kernel"]:
         traffic["csr_spmv_256"] = d["dram_total"]
-    if d["capture"] == "prof_spmv" and "sell_kernel<EpiAxpby" in d["kernel"]:
+    if d["capture"].endswith("spmv") and "sell_kernel<EpiAxpby" in d["kernel"]:
         traffic["sell_spmv_256"] = d["dram_total"]
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 print(open(os.path.join(ROOT, "profiles", "ncu_summary_%s.md" % tag)).read())

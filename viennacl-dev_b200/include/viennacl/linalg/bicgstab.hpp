@@ -3,7 +3,10 @@
 // (ViennaCLCUDAD{csr,sell}_bicgstab), whose loop runs next to the kernels with device-resident scalars.
 #ifndef VIENNACL_B200_LINALG_BICGSTAB_HPP
 #define VIENNACL_B200_LINALG_BICGSTAB_HPP
+#include <cmath>
 #include "viennacl/linalg/detail_solver_call.hpp"
+#include "viennacl/linalg/inner_prod.hpp"
+#include "viennacl/linalg/norm_2.hpp"
 namespace viennacl
 {
 namespace linalg
@@ -44,14 +47,80 @@ namespace detail
     return t;
   }
 
+  /** @brief Pipelined BiCGStab on the device (bicgstab.hpp:97-215): compressed_matrix / sliced_ell_matrix without preconditioner */
   template<typename MatrixT, typename NumericT>
-  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag, viennacl::linalg::no_precond,
-                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  viennacl::vector<NumericT> fused_bicgstab(MatrixT const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag, ViennaCLB200Precond pc,
+                                            bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data)
   {
     ViennaCLB200SolverTag t = to_abi(tag);
+    t.precond = pc;
     viennacl::vector<NumericT> x = run(SOLVER_BICGSTAB, A, rhs, t, monitor, monitor_data);
     tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
     return x;
+  }
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondNone, monitor, monitor_data); }
+  template<typename NumericT, typename IndexT>
+  viennacl::vector<NumericT> solve_impl(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondNone, monitor, monitor_data); }
+
+  /** @brief Left-preconditioned BiCGStab for ANY operator and ANY preconditioner with `apply(v)`: the reference's generic
+   *  path (bicgstab.hpp:398-489) including its restart rule, built from prod / inner_prod / norm_2 / vector expressions. */
+  template<typename MatrixT, typename NumericT, typename PreconditionerT>
+  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag, PreconditionerT const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  {
+    typedef viennacl::vector<NumericT> VectorT;
+    const vcl_size_t n = rhs.size();
+    VectorT result(n), residual = rhs, r0star = rhs, p = rhs, s(n), t0(n), t1(n);
+    const NumericT norm_rhs = viennacl::linalg::norm_2(rhs);
+    NumericT ip_rr0star = norm_rhs * norm_rhs, residual_norm = norm_rhs;
+    tag.iters(0); tag.error(0);
+    if (norm_rhs <= tag.abs_tolerance()) return result;
+
+    bool restart = true;
+    unsigned int last_restart = 0;
+    for (unsigned int i = 0; i < tag.max_iterations(); ++i)
+    {
+      if (restart)
+      {
+        residual = rhs - viennacl::linalg::prod(A, result);
+        precond.apply(residual);
+        p = residual;
+        r0star = residual;
+        ip_rr0star = viennacl::linalg::norm_2(residual);
+        ip_rr0star *= ip_rr0star;
+        restart = false;
+        last_restart = i;
+      }
+      tag.iters(i + 1);
+      t0 = viennacl::linalg::prod(A, p);
+      precond.apply(t0);
+      const NumericT alpha = ip_rr0star / NumericT(viennacl::linalg::inner_prod(t0, r0star));
+      s = residual - alpha * t0;
+      t1 = viennacl::linalg::prod(A, s);
+      precond.apply(t1);
+      const NumericT norm_t1 = viennacl::linalg::norm_2(t1);
+      const NumericT omega = NumericT(viennacl::linalg::inner_prod(t1, s)) / (norm_t1 * norm_t1);
+      result += alpha * p + omega * s;
+      residual = s - omega * t1;
+      residual_norm = viennacl::linalg::norm_2(residual);
+      if (monitor && monitor(result, std::fabs(residual_norm / norm_rhs), monitor_data)) break;
+      if (residual_norm / norm_rhs < tag.tolerance() || residual_norm < tag.abs_tolerance()) break;
+      const NumericT new_ip = viennacl::linalg::inner_prod(residual, r0star);
+      const NumericT beta = new_ip / ip_rr0star * alpha / omega;
+      ip_rr0star = new_ip;
+      if (ip_rr0star == NumericT(0) || omega == NumericT(0) || i - last_restart > tag.max_iterations_before_restart()) restart = true;
+      p -= omega * t0;                    // p = residual + beta * (p - omega * t0)
+      p = residual + beta * p;
+    }
+    tag.error(residual_norm / norm_rhs);
+    return result;
   }
 
   /** @brief Left-preconditioned BiCGStab with Jacobi (bicgstab.hpp:398-489): fused on the device, 5 kernels per iteration */
@@ -59,13 +128,7 @@ namespace detail
   viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
                                         jacobi_precond< compressed_matrix<NumericT, AlignmentV> > const &,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
-  {
-    ViennaCLB200SolverTag t = to_abi(tag);
-    t.precond = ViennaCLB200PrecondJacobi;
-    viennacl::vector<NumericT> x = run(SOLVER_BICGSTAB, A, rhs, t, monitor, monitor_data);
-    tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
-    return x;
-  }
+  { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondJacobi, monitor, monitor_data); }
 }
 
 /** @brief x = solve(A, b, bicgstab_tag(...)) for compressed_matrix / sliced_ell_matrix (bicgstab.hpp:495-533) */

@@ -3,7 +3,10 @@
 // (ViennaCLCUDAD{csr,sell}_cg), whose loop runs next to the kernels with device-resident scalars.
 #ifndef VIENNACL_B200_LINALG_CG_HPP
 #define VIENNACL_B200_LINALG_CG_HPP
+#include <cmath>
 #include "viennacl/linalg/detail_solver_call.hpp"
+#include "viennacl/linalg/inner_prod.hpp"
+#include "viennacl/linalg/norm_2.hpp"
 namespace viennacl
 {
 namespace linalg
@@ -43,14 +46,66 @@ namespace detail
     return t;
   }
 
+  /** @brief Pipelined CG on the device (cg.hpp:128-187): compressed_matrix / sliced_ell_matrix without preconditioner */
   template<typename MatrixT, typename NumericT>
-  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, cg_tag const & tag, viennacl::linalg::no_precond,
-                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  viennacl::vector<NumericT> fused_cg(MatrixT const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
+                                      bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data)
   {
     ViennaCLB200SolverTag t = to_abi(tag);
     viennacl::vector<NumericT> x = run(SOLVER_CG, A, rhs, t, monitor, monitor_data);
     tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
     return x;
+  }
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_cg(A, rhs, tag, monitor, monitor_data); }
+  template<typename NumericT, typename IndexT>
+  viennacl::vector<NumericT> solve_impl(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_cg(A, rhs, tag, monitor, monitor_data); }
+
+  /** @brief Preconditioned CG for ANY operator (matrix-free `apply()`) and ANY preconditioner with `apply(v)`:
+   *  the reference's generic path (cg.hpp:257-322; Saad, Alg. 9.1), built from prod / inner_prod / vector expressions.
+   *  One blocking reduction per inner product, exactly like the reference -- the fused paths above avoid that. */
+  template<typename MatrixT, typename NumericT, typename PreconditionerT>
+  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, cg_tag const & tag, PreconditionerT const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  {
+    typedef viennacl::vector<NumericT> VectorT;
+    VectorT result(rhs.size());
+    VectorT residual = rhs;
+    VectorT z = rhs;
+    precond.apply(z);
+    VectorT p = z;
+    VectorT Ap(rhs.size());
+    NumericT ip_rz = viennacl::linalg::inner_prod(residual, z);
+    const NumericT norm_rhs_squared = ip_rz;
+    NumericT new_ip_rz = 0;
+    tag.iters(0); tag.error(0);
+    if (std::fabs(norm_rhs_squared) <= tag.abs_tolerance() * tag.abs_tolerance()) return result;
+
+    for (unsigned int i = 0; i < tag.max_iterations(); ++i)
+    {
+      tag.iters(i + 1);
+      Ap = viennacl::linalg::prod(A, p);
+      const NumericT alpha = ip_rz / NumericT(viennacl::linalg::inner_prod(Ap, p));
+      result += alpha * p;
+      residual -= alpha * Ap;
+      z = residual;
+      precond.apply(z);
+      new_ip_rz = viennacl::linalg::inner_prod(residual, z);
+      const NumericT rel_sq = new_ip_rz / norm_rhs_squared;
+      if (monitor && monitor(result, std::sqrt(std::fabs(rel_sq)), monitor_data)) break;
+      if (std::fabs(rel_sq) < tag.tolerance() * tag.tolerance() || std::fabs(new_ip_rz) < tag.abs_tolerance() * tag.abs_tolerance()) break;
+      const NumericT beta = new_ip_rz / ip_rz;
+      ip_rz = new_ip_rz;
+      p = z + beta * p;
+    }
+    tag.error(std::sqrt(std::fabs(new_ip_rz / norm_rhs_squared)));
+    return result;
   }
 
 }

@@ -3,7 +3,12 @@
 // (ViennaCLCUDAD{csr,sell}_gmres), whose loop runs next to the kernels with device-resident scalars.
 #ifndef VIENNACL_B200_LINALG_GMRES_HPP
 #define VIENNACL_B200_LINALG_GMRES_HPP
+#include <cmath>
+#include <vector>
+#include <algorithm>
 #include "viennacl/linalg/detail_solver_call.hpp"
+#include "viennacl/linalg/inner_prod.hpp"
+#include "viennacl/linalg/norm_2.hpp"
 namespace viennacl
 {
 namespace linalg
@@ -50,14 +55,104 @@ namespace detail
     return t;
   }
 
+  /** @brief Pipelined GMRES(m) on the device (gmres.hpp:181-367): compressed_matrix / sliced_ell_matrix without preconditioner */
   template<typename MatrixT, typename NumericT>
-  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag, viennacl::linalg::no_precond,
-                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  viennacl::vector<NumericT> fused_gmres(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data)
   {
     ViennaCLB200SolverTag t = to_abi(tag);
     viennacl::vector<NumericT> x = run(SOLVER_GMRES, A, rhs, t, monitor, monitor_data);
     tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
     return x;
+  }
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_gmres(A, rhs, tag, monitor, monitor_data); }
+  template<typename NumericT, typename IndexT>
+  viennacl::vector<NumericT> solve_impl(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_gmres(A, rhs, tag, monitor, monitor_data); }
+
+  /** @brief Left-preconditioned restarted GMRES(m) for ANY operator and ANY preconditioner with `apply(v)`.
+   *  Same problem statement, stopping rule and bookkeeping as the reference's generic path (gmres.hpp:449-631): the residual
+   *  M^-1 (b - A x) is minimised over the Krylov space of M^-1 A, the estimate |rho * rho_0| / ||b|| is tested after every
+   *  inner iteration, tag.iters() counts inner iterations, the monitor runs once per restart.  The reference orthogonalises
+   *  with Householder reflections; here the basis is built by modified Gram-Schmidt and the least-squares problem is kept
+   *  triangular with Givens rotations -- the same minimiser, so iteration counts agree to within rounding. */
+  template<typename MatrixT, typename NumericT, typename PreconditionerT>
+  viennacl::vector<NumericT> solve_impl(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag, PreconditionerT const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  {
+    typedef viennacl::vector<NumericT> VectorT;
+    const vcl_size_t n = rhs.size();
+    vcl_size_t m = tag.krylov_dim();
+    if (n < m) m = n;
+    VectorT result(n), w(n);
+    const NumericT norm_rhs = viennacl::linalg::norm_2(rhs);
+    tag.iters(0); tag.error(0);
+    if (norm_rhs <= tag.abs_tolerance() || m == 0) return result;
+
+    std::vector<VectorT> V(m + 1);
+    std::vector< std::vector<NumericT> > H(m + 1, std::vector<NumericT>(m, NumericT(0)));   // H[i][k], upper triangular after rotations
+    std::vector<NumericT> cs(m), sn(m), g(m + 1), y(m);
+
+    for (unsigned int it = 0; it <= tag.max_restarts(); ++it)
+    {
+      w = rhs - viennacl::linalg::prod(A, result);
+      precond.apply(w);
+      const NumericT rho_0 = viennacl::linalg::norm_2(w);
+      if (rho_0 / norm_rhs < tag.tolerance() || rho_0 < tag.abs_tolerance()) { tag.error(rho_0 / norm_rhs); return result; }
+      V[0] = (NumericT(1) / rho_0) * w;
+      std::fill(g.begin(), g.end(), NumericT(0));
+      g[0] = rho_0;
+      NumericT estimate = rho_0 / norm_rhs;
+
+      vcl_size_t k = 0;
+      for (k = 0; k < m; ++k)
+      {
+        tag.iters(tag.iters() + 1);
+        w = viennacl::linalg::prod(A, V[k]);
+        precond.apply(w);
+        for (vcl_size_t i = 0; i <= k; ++i)                  // modified Gram-Schmidt
+        {
+          H[i][k] = viennacl::linalg::inner_prod(w, V[i]);
+          w -= H[i][k] * V[i];
+        }
+        const NumericT h_next = viennacl::linalg::norm_2(w);
+        for (vcl_size_t i = 0; i < k; ++i)                   // earlier rotations on the new column
+        {
+          const NumericT t = cs[i] * H[i][k] + sn[i] * H[i + 1][k];
+          H[i + 1][k] = -sn[i] * H[i][k] + cs[i] * H[i + 1][k];
+          H[i][k] = t;
+        }
+        const NumericT denom = std::sqrt(H[k][k] * H[k][k] + h_next * h_next);
+        cs[k] = denom > 0 ? H[k][k] / denom : NumericT(1);
+        sn[k] = denom > 0 ? h_next / denom : NumericT(0);
+        H[k][k] = denom;
+        g[k + 1] = -sn[k] * g[k];
+        g[k] = cs[k] * g[k];
+        estimate = std::fabs(g[k + 1]) / norm_rhs;
+        if (h_next > 0 && k + 1 < m + 1) V[k + 1] = (NumericT(1) / h_next) * w;
+        if (estimate < tag.tolerance() || h_next <= 0) { ++k; break; }
+      }
+
+      for (vcl_size_t i2 = k; i2 > 0; --i2)                  // back substitution on the k x k triangle
+      {
+        const vcl_size_t i = i2 - 1;
+        NumericT sum = g[i];
+        for (vcl_size_t j = i + 1; j < k; ++j) sum -= H[i][j] * y[j];
+        y[i] = sum / H[i][i];
+      }
+      for (vcl_size_t i = 0; i < k; ++i) result += y[i] * V[i];
+
+      tag.error(estimate);
+      if (monitor && monitor(result, estimate, monitor_data)) break;
+      if (tag.error() < tag.tolerance()) return result;
+    }
+    return result;
   }
 
 }

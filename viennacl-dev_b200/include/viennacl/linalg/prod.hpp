@@ -19,6 +19,11 @@ namespace linalg
   viennacl::detail::matvec_expr<sliced_ell_matrix<NumericT, IndexT>, NumericT>
   prod(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & x)
   { viennacl::detail::matvec_expr<sliced_ell_matrix<NumericT, IndexT>, NumericT> e = {&A, &x}; return e; }
+
+  /** @brief User-defined (matrix-free) operators: any type with `apply(x, y)` and `size1()` (linalg/prod.hpp:350-361 + vector.hpp:3315-3319) */
+  template<typename OperatorT, typename NumericT>
+  viennacl::detail::matvec_expr<OperatorT, NumericT> prod(OperatorT const & A, vector_base<NumericT> const & x)
+  { viennacl::detail::matvec_expr<OperatorT, NumericT> e = {&A, &x}; return e; }
 }
 }
 #endif

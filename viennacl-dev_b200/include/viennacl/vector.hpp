@@ -152,6 +152,18 @@ private:
 
 template<typename NumericT> void fast_copy_to_host(vector_base<NumericT> const & gpu_vec, NumericT *host);
 
+namespace detail
+{
+  /** @brief y = alpha * A x + beta * y for any operator type: sparse matrix types bring vec_mul(); user-defined operators
+   *  only need `apply(x, y)` computing y = A x and `size1()` (the matrix-free hook, vector.hpp:3315-3319, examples/tutorial/matrix-free.cpp) */
+  template<typename MatrixT, typename NumericT>
+  auto vec_mul_dispatch(MatrixT const & A, vector_base<NumericT> const & x, NumericT alpha, vector_base<NumericT> & y, NumericT beta, int)
+    -> decltype(A.vec_mul(x, alpha, y, beta), void())
+  { A.vec_mul(x, alpha, y, beta); }
+  template<typename MatrixT, typename NumericT>
+  void vec_mul_dispatch(MatrixT const & A, vector_base<NumericT> const & x, NumericT alpha, vector_base<NumericT> & y, NumericT beta, long);
+}
+
 // ---------------------------------------------------------------------------------------------- vector_base
 template<typename NumericT>
 class vector_base
@@ -226,7 +238,7 @@ public:
     if (e.Ax.x->handle() == elements_ && e.v->handle() != elements_)      // x = b - A*x: the product needs the old x
     {
       vector_base temp(size_);
-      e.Ax.A->vec_mul(*e.Ax.x, NumericT(1), temp, NumericT(0));
+      detail::vec_mul_dispatch(*e.Ax.A, *e.Ax.x, NumericT(1), temp, NumericT(0), 0);
       detail::lincomb<NumericT> l; l.push(e.v, NumericT(1)); l.push(&temp, e.sign);
       eval(l, false);
       return *this;
@@ -314,16 +326,16 @@ protected:
   template<typename MatrixT>
   void matvec(detail::matvec_expr<MatrixT, NumericT> const & e, NumericT alpha, NumericT beta)
   {
-    assert(e.A->size1() == size_ && e.A->size2() == e.x->size() && bool("Size check failed for matrix-vector product"));
+    assert(e.A->size1() == size_ && bool("Size check failed for matrix-vector product"));
     if (e.x->handle() == elements_)         // x = A*x and friends: go through a temporary (compressed_matrix.hpp:1237-1242)
     {
       vector_base temp(size_);
-      e.A->vec_mul(*e.x, NumericT(1), temp, NumericT(0));
+      detail::vec_mul_dispatch(*e.A, *e.x, NumericT(1), temp, NumericT(0), 0);
       detail::lincomb<NumericT> l; l.push(&temp, alpha);
       if (beta != NumericT(0)) eval(l, true); else eval(l, false);
     }
     else
-      e.A->vec_mul(*e.x, alpha, *this, beta);
+      detail::vec_mul_dispatch(*e.A, *e.x, alpha, *this, beta, 0);
   }
   void eval(detail::lincomb<NumericT> const & e, bool accumulate)
   {
@@ -432,6 +444,19 @@ std::ostream & operator<<(std::ostream & os, vector_base<T> const & val)
   for (vcl_size_t i = 0; i < tmp.size(); ++i) { if (i > 0) os << ","; os << tmp[i]; }
   os << ")";
   return os;
+}
+
+namespace detail
+{
+  template<typename MatrixT, typename NumericT>
+  void vec_mul_dispatch(MatrixT const & A, vector_base<NumericT> const & x, NumericT alpha, vector_base<NumericT> & y, NumericT beta, long)
+  {
+    if (alpha == NumericT(1) && beta == NumericT(0)) { A.apply(x, y); return; }
+    vector<NumericT> t(y.size());
+    A.apply(x, t);
+    if (beta == NumericT(0)) y = alpha * t;
+    else y = alpha * t + beta * y;
+  }
 }
 
 namespace linalg
