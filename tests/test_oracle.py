@@ -1,5 +1,7 @@
 """CPU tests: the plain-C oracle (oracle/vcl_oracle.c) against the golden vectors produced by the unmodified reference
 (tests/golden/make_golden.py), and -- where oracle/_ref was built -- against the reference itself."""
+import os
+
 import numpy as np
 import pytest
 
@@ -134,3 +136,22 @@ def test_oracle_vs_live_reference(orc):
     d = ol.ref(True); d.set_threads(1)
     e = d.solve("gmres", A, b, precond="none", tol=1e-9, maxit=600, krylov=20)
     assert abs(a["iters"] - e["iters"]) <= 2
+
+
+def test_generic_solver_counts_pinned():
+    """tests/golden/generic_solver_counts.json (used by facade_tests/matrix_free.cpp) equals a live run of the reference's
+    generic solver paths when the reference tree is present; the constants in matrix_free.cpp equal the JSON."""
+    import json
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "generic_solver_counts.json")))
+    src = open(os.path.join(root, "viennacl-dev_b200", "facade_tests", "matrix_free.cpp")).read()
+    for key, val in gold.items():
+        m = re.search(r"REF_%s = (\d+)" % key.upper(), src)
+        assert m and int(m.group(1)) == val, key
+    if os.path.isdir("/root/reference/viennacl"):
+        exe = os.path.join(root, "oracle", "_ref", "ref_generic_counts")
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-I/root/reference", "-o", exe, os.path.join(root, "oracle", "ref_generic_counts.cpp")])
+        live = json.loads(subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")).stdout)
+        assert live == gold
