@@ -333,67 +333,61 @@ pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double 
 // ------------------------------------------------------------------------------------------------
 // stage 1: h_j = <v_j, v_k>, j < k, ALL k vectors in one pass over the basis (the reference sweeps 7 vectors at a time and
 // re-reads v_k for every sweep, cuda/iterative_operations.hpp:1690-1735).
-// Work split inside a CTA (8 warps): the k columns are dealt round-robin to NG column groups (NG = 1, 2, 4 or 8 warps),
-// the remaining 8/NG warps of a group take different row sub-ranges.  A thread therefore carries only CPW = ceil(k/NG)
-// accumulators (<= 8 for k <= 64) instead of k, and every load is a 16-byte double2; v_k is re-read by the NG column-group
-// warps of a CTA, which hits L1.  DRAM traffic: (k+1)*8*n bytes, the compulsory amount.
-template<int CPW>
+// Work split: a 2-D grid.  blockIdx.y selects a group of <= GS1_COLS columns, blockIdx.x a persistent share of the rows.
+// Every thread of a CTA does the same work (its 16-byte slice of v_k against the <= 8 columns of the group, 8 accumulators),
+// so the warps of a CTA are balanced for every k -- a first version dealt columns to warps and lost up to 44 % at
+// k = 9, 17, 25 (profiles/ncu_summary_r1b.md: gs1<4> at 3.5 TB/s).  The column groups of one row share are resident at
+// the same time and re-read the same slice of v_k, which L2 serves: DRAM traffic stays (k+1)*8*n bytes.
+#define GS1_COLS 8
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, int NG, double *out_h, int out_stride,
+gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double *out_h, int out_stride,
                  double *partials, unsigned int *ticket)
 {
-  __shared__ double s_part[8][CPW];
+  __shared__ double s_part[8][GS1_COLS];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cg = w % NG, rs = w / NG, RS = 8 / NG;
+  const int c0 = blockIdx.y * GS1_COLS;
+  const int nc = min(GS1_COLS, k - c0);
   const double *vk = basis + (size_t)k * isz;
-  double acc[CPW];
+  const double *col = basis + (size_t)c0 * isz;
+  double acc[GS1_COLS];
 #pragma unroll
-  for (int q = 0; q < CPW; ++q) acc[q] = 0.0;
+  for (int q = 0; q < GS1_COLS; ++q) acc[q] = 0.0;
   const long long npairs = n >> 1;
-  const long long stride = (long long)gridDim.x * RS * 32;
-  for (long long pi = ((long long)blockIdx.x * RS + rs) * 32 + lane; pi < npairs; pi += stride)
+  for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
     const double2 v = ld2(vk, 2 * pi);
+    double2 a[GS1_COLS];
 #pragma unroll
-    for (int q = 0; q < CPW; ++q)
-    {
-      const int j = cg + q * NG;
-      if (j < k)
-      {
-        const double2 a = ld2(basis + (size_t)j * isz, 2 * pi);
-        acc[q] = fma(a.x, v.x, acc[q]);
-        acc[q] = fma(a.y, v.y, acc[q]);
-      }
-    }
+    for (int q = 0; q < GS1_COLS; ++q)
+      if (q < nc) a[q] = ld2(col + (size_t)q * isz, 2 * pi);
+#pragma unroll
+    for (int q = 0; q < GS1_COLS; ++q)
+      if (q < nc) { acc[q] = fma(a[q].x, v.x, acc[q]); acc[q] = fma(a[q].y, v.y, acc[q]); }
   }
-  if ((n & 1) && blockIdx.x == 0 && rs == 0 && lane == 0)
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
   {
     const double v = vk[n - 1];
 #pragma unroll
-    for (int q = 0; q < CPW; ++q)
-    {
-      const int j = cg + q * NG;
-      if (j < k) acc[q] = fma(basis[(size_t)j * isz + n - 1], v, acc[q]);
-    }
+    for (int q = 0; q < GS1_COLS; ++q)
+      if (q < nc) acc[q] = fma(col[(size_t)q * isz + n - 1], v, acc[q]);
   }
 #pragma unroll
-  for (int q = 0; q < CPW; ++q)
+  for (int q = 0; q < GS1_COLS; ++q)
   {
     const double t = warp_sum(acc[q]);
     if (lane == 0) s_part[w][q] = t;
   }
   __syncthreads();
-  if ((int)threadIdx.x < k)
+  if ((int)threadIdx.x < nc)
   {
-    const int j = threadIdx.x, jc = j % NG, jq = j / NG;
     double t = 0.0;
-    for (int r = 0; r < RS; ++r) t += s_part[jc + r * NG][jq];
-    partials[(size_t)j * VCL_MAX_BLOCKS + blockIdx.x] = t;
+    for (int r = 0; r < 8; ++r) t += s_part[r][threadIdx.x];
+    partials[(size_t)(c0 + threadIdx.x) * VCL_MAX_BLOCKS + blockIdx.x] = t;
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence();

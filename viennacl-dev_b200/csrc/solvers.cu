@@ -296,14 +296,10 @@ ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const double *basis, long
 {
   VCL_REQUIRE(b, (isz & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u,
               "Krylov basis must be 16-byte aligned with an even internal size (the reference pads vectors to 128 entries, forwards.h:385)");
-  const int NG = k >= 5 ? 8 : (k >= 3 ? 4 : (k == 2 ? 2 : 1));      // column groups (warps) per CTA
-  const int cpw = (k + NG - 1) / NG;                                 // columns per warp
   (void)grid;
-  const int g = std::max(1, std::min(vcl_div_up(n / 2, 256 / NG * 1), std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
-  if (cpw <= 1)      gmres_gs1_kernel<1><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
-  else if (cpw <= 2) gmres_gs1_kernel<2><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
-  else if (cpw <= 4) gmres_gs1_kernel<4><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
-  else               gmres_gs1_kernel<8><<<g, VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, NG, out_h, stride, b->partials, b->tickets);
+  const int gy = (k + GS1_COLS - 1) / GS1_COLS;                      // column groups
+  const int gx = std::max(1, std::min(vcl_div_up(n / 2, VEC_THREADS), std::min(std::max(b->sm_count * 8 / gy, b->sm_count), VCL_MAX_BLOCKS)));
+  gmres_gs1_kernel<<<dim3(gx, gy), VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
   VCL_LAUNCHED(b, "gmres_gs1_kernel");
   return ViennaCLSuccess;
 }
