@@ -327,9 +327,11 @@ class CsrMatrix:
         return CsrStruct(self.rows, self.cols, self.nnz, self.rp.ptr, self.ci.ptr, self.va.ptr,
                          self.blocks.ptr if self.blocks is not None else None, self.nblocks)
 
-    def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1, use_blocks=True):
+    def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1, use_blocks=True, backend=None):
+        """y = alpha*A*x + beta*y.  `backend`: another handle (stream) of the same device -- the matrix arrays are only read."""
         blocks = self.blocks.ptr if (use_blocks and self.blocks is not None) else None
-        self.b.check(self.b.L.ViennaCLCUDADcsrmv(self.b.h, self.rows, self.cols, self.nnz, self.rp.ptr, self.ci.ptr, self.va.ptr,
+        b = backend or self.b
+        b.check(b.L.ViennaCLCUDADcsrmv(b.h, self.rows, self.cols, self.nnz, self.rp.ptr, self.ci.ptr, self.va.ptr,
                                                  blocks, self.nblocks if blocks else 0, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
     def row_info(self, option=3):
