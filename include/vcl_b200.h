@@ -131,6 +131,45 @@ ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend backend, ViennaCLInt rows, 
                                      unsigned int *columns_per_block, unsigned int *block_start, long long *padded_nnz,
                                      unsigned int *col_idx, double *values);
 
+/* ELL (ell_matrix.hpp:36-119) and HYB (hyb_matrix.hpp:36-126), AlignmentV = 1 layouts:
+ * ELL entry j of row r at j*internal_rows + r (coords / elements hold internal_rows*maxnnz entries, padding value 0, column 0);
+ * HYB = ELL part of width ell.maxnnz + CSR tail (csr_rows[rows+1], csr_cols, csr_elements).
+ * Products: cuda/sparse_matrix_operations.hpp:1747-1838 (ELL), :2298-2400 (HYB); zero-valued ELL slots never touch x. */
+typedef struct
+{
+  ViennaCLInt rows, cols, internal_rows, maxnnz;
+  const unsigned int *coords;
+  const double *elements;
+} ViennaCLCUDADell;
+
+typedef struct
+{
+  ViennaCLCUDADell ell;
+  const unsigned int *csr_rows, *csr_cols;
+  const double *csr_elements;
+  ViennaCLInt csr_nnz;
+} ViennaCLCUDADhyb;
+
+ViennaCLStatus ViennaCLCUDADellmv(ViennaCLBackend backend, const ViennaCLCUDADell *A,
+                                  const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta);
+ViennaCLStatus ViennaCLCUDADhybmv(ViennaCLBackend backend, const ViennaCLCUDADhyb *A,
+                                  const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta);
+/* Device-side CSR -> ELL (layout of ell_matrix.hpp:122-166).  Call 1 (coords == NULL): *maxnnz = longest row.
+ * Call 2: coords / elements sized rows * (*maxnnz) are filled (internal_rows = rows). */
+ViennaCLStatus ViennaCLCUDADcsr2ell(ViennaCLBackend backend, ViennaCLInt rows, const unsigned int *row_ptr,
+                                    const unsigned int *csr_col, const double *csr_val, ViennaCLInt *maxnnz,
+                                    unsigned int *coords, double *elements);
+/* Device-side CSR -> HYB (layout and width rule of hyb_matrix.hpp:127-214: the smallest width that covers at least
+ * `csr_threshold` (reference default 0.8) of the rows).  Call 1 (ell_coords == NULL): *ell_width and *csr_nnz (>= 1: the
+ * reference stores one dummy entry when the tail is empty).  Call 2 fills all five arrays. */
+ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt cols, const unsigned int *row_ptr,
+                                    const unsigned int *csr_col, const double *csr_val, double csr_threshold,
+                                    ViennaCLInt *ell_width, ViennaCLInt *csr_nnz,
+                                    unsigned int *ell_coords, double *ell_elements,
+                                    unsigned int *csr_rows, unsigned int *csr_cols, double *csr_elements);
+
 /* detail::row_info: linalg/sparse_matrix_operations.hpp:48-74 -> cuda/sparse_matrix_operations.hpp:53-119.
  * option: 0 inf-norm, 1 1-norm, 2 2-norm, 3 diagonal (forwards.h row_info_types order). */
 ViennaCLStatus ViennaCLCUDADcsr_row_info(ViennaCLBackend backend, ViennaCLInt rows,
@@ -204,6 +243,19 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_csr(ViennaCLBackend backend, co
                                                      double *buf, ViennaCLInt buf_size);
 ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_sell(ViennaCLBackend backend, const ViennaCLCUDADsell *A, const double *p, double *Ap,
                                                       double *buf, ViennaCLInt buf_size);
+/* the same fused products for ell_matrix / hyb_matrix (cuda/iterative_operations.hpp:330-727, :1138-1593) */
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_ell(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *p, double *Ap,
+                                                  double *buf, ViennaCLInt buf_size);
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_hyb(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *p, double *Ap,
+                                                  double *buf, ViennaCLInt buf_size);
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_ell(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *p, double *Ap,
+                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset);
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_hyb(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *p, double *Ap,
+                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset);
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_ell(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *p, double *Ap,
+                                                     double *buf, ViennaCLInt buf_size);
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *p, double *Ap,
+                                                     double *buf, ViennaCLInt buf_size);
 
 /* ---------------------------------------------------------------- whole solves ------------------------------------------------------------ */
 /* The loop lives next to the kernels (device-resident scalars, no per-iteration host round trip); the C++ `solve()` keeps its
@@ -236,6 +288,13 @@ ViennaCLStatus ViennaCLCUDADcsr_bicgstab(ViennaCLBackend backend, const ViennaCL
 ViennaCLStatus ViennaCLCUDADsell_bicgstab(ViennaCLBackend backend, const ViennaCLCUDADsell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
 ViennaCLStatus ViennaCLCUDADcsr_gmres(ViennaCLBackend backend, const ViennaCLCUDADcsr *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
 ViennaCLStatus ViennaCLCUDADsell_gmres(ViennaCLBackend backend, const ViennaCLCUDADsell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+/* ell_matrix / hyb_matrix overloads of solve() (cg.hpp:204-254 and siblings) */
+ViennaCLStatus ViennaCLCUDADell_cg(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+ViennaCLStatus ViennaCLCUDADhyb_cg(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+ViennaCLStatus ViennaCLCUDADell_bicgstab(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+ViennaCLStatus ViennaCLCUDADhyb_bicgstab(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+ViennaCLStatus ViennaCLCUDADell_gmres(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
+ViennaCLStatus ViennaCLCUDADhyb_gmres(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
 
 /* ---------------------------------------------------------------- row-partitioned (multi-GPU) CG ------------------------------------------ */
 /* New (no reference counterpart).  Rank g owns a contiguous block of rows of a square matrix; `A_local` holds those rows with

@@ -14,6 +14,8 @@
 //   viennacl/linalg/bicgstab.hpp:97-215     pipelined BiCGStab; :398-489 preconditioned BiCGStab
 //   viennacl/linalg/gmres.hpp:181-367       pipelined GMRES;    :449-631 Householder GMRES
 //   viennacl/linalg/jacobi_precond.hpp:103-130
+//   viennacl/ell_matrix.hpp:122-166, viennacl/hyb_matrix.hpp:127-214 (host -> ELL / HYB layout),
+//   viennacl/linalg/host_based/sparse_matrix_operations.hpp:1503-1538 (ELL), :1873-1927 (HYB)
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -25,6 +27,8 @@
 #include "viennacl/vector.hpp"
 #include "viennacl/compressed_matrix.hpp"
 #include "viennacl/sliced_ell_matrix.hpp"
+#include "viennacl/ell_matrix.hpp"
+#include "viennacl/hyb_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/inner_prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
@@ -37,6 +41,8 @@ typedef unsigned int u32;
 typedef viennacl::compressed_matrix<double> csr_t;
 typedef viennacl::sliced_ell_matrix<double> sell_t;
 typedef viennacl::vector<double> vec_t;
+typedef viennacl::ell_matrix<double> ell_t;
+typedef viennacl::hyb_matrix<double> hyb_t;
 
 namespace {
 
@@ -229,6 +235,70 @@ int vclref_sell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const dou
   return 0;
 }
 
+// ELL / HYB built by the reference's own copy(); arrays malloc'ed here (vclref_free).  ELL: coords/elements hold
+// internal_size1 * internal_maxnnz entries, entry j of row r at j*internal_size1 + r.  HYB: ELL part of width ell_width
+// (csr_threshold 0.8) + CSR remainder.
+int vclref_ell_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
+                     u32 **coords, double **elements, int *maxnnz, int *internal_rows)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  ell_t E(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, E);
+  std::size_t tot = E.internal_nnz();
+  *maxnnz = int(E.internal_maxnnz()); *internal_rows = int(E.internal_size1());
+  *coords = (u32*)std::malloc(sizeof(u32) * (tot ? tot : 1));
+  *elements = (double*)std::malloc(sizeof(double) * (tot ? tot : 1));
+  std::memcpy(*coords, E.handle2().ram_handle().get(), sizeof(u32) * tot);
+  std::memcpy(*elements, E.handle().ram_handle().get(), sizeof(double) * tot);
+  return 0;
+}
+
+int vclref_ell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
+                    double *x, double alpha, double *y, double beta)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  ell_t E(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, E);
+  vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(cols));
+  vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
+  viennacl::linalg::prod_impl(E, vx, alpha, vy, beta);
+  return 0;
+}
+
+int vclref_hyb_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
+                     u32 **ell_coords, double **ell_elements, int *ell_width, int *internal_rows,
+                     u32 **csr_rows, u32 **csr_cols, double **csr_elements, int *csr_nnz)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  hyb_t H(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, H);
+  std::size_t tot = H.internal_size1() * H.internal_ellnnz();
+  *ell_width = int(H.internal_ellnnz()); *internal_rows = int(H.internal_size1()); *csr_nnz = int(H.csr_nnz());
+  *ell_coords = (u32*)std::malloc(sizeof(u32) * (tot ? tot : 1));
+  *ell_elements = (double*)std::malloc(sizeof(double) * (tot ? tot : 1));
+  *csr_rows = (u32*)std::malloc(sizeof(u32) * (std::size_t(rows) + 1));
+  *csr_cols = (u32*)std::malloc(sizeof(u32) * H.csr_nnz());
+  *csr_elements = (double*)std::malloc(sizeof(double) * H.csr_nnz());
+  std::memcpy(*ell_coords, H.handle2().ram_handle().get(), sizeof(u32) * tot);
+  std::memcpy(*ell_elements, H.handle().ram_handle().get(), sizeof(double) * tot);
+  std::memcpy(*csr_rows, H.handle3().ram_handle().get(), sizeof(u32) * (std::size_t(rows) + 1));
+  std::memcpy(*csr_cols, H.handle4().ram_handle().get(), sizeof(u32) * H.csr_nnz());
+  std::memcpy(*csr_elements, H.handle5().ram_handle().get(), sizeof(double) * H.csr_nnz());
+  return 0;
+}
+
+int vclref_hyb_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
+                    double *x, double alpha, double *y, double beta)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  hyb_t H(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, H);
+  vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(cols));
+  vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
+  viennacl::linalg::prod_impl(H, vx, alpha, vy, beta);
+  return 0;
+}
+
 // diag[r] = A(r,r) (0 when absent): detail::row_info(A, vec, SPARSE_ROW_DIAGONAL)
 int vclref_csr_diag(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const double *v, double *diag)
 {
@@ -254,7 +324,7 @@ double vclref_inner_prod(const double *x, const double *y, int n)
 }
 
 // solver: 0 CG, 1 BiCGStab, 2 GMRES;  precond: 0 none (pipelined path), 1 Jacobi, 2 identity functor (generic path)
-// format: 0 CSR, 1 SELL-32 (rows % 32 != 0 required)
+// format: 0 CSR, 1 SELL-32 (rows % 32 != 0 required), 2 ELL, 3 HYB
 // hist (optional): monitor estimates, hist_len receives the number of monitor calls.
 int vclref_solve(int solver, int precond, int format,
                  int rows, int nnz, const u32 *rp, const u32 *ci, const double *v,
@@ -271,6 +341,24 @@ int vclref_solve(int solver, int precond, int format,
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   if (format == 0)
     rc = run_solver(A, solver, precond, &A, vb, vx, tol, abs_tol, maxit, krylov, restart_every, iters, err, hp);
+  else if (format == 2 || format == 3)
+  {
+    raw_csr_view view = {std::size_t(rows), std::size_t(rows), rp, ci, v};
+    if (format == 2)
+    {
+      ell_t E(viennacl::context(viennacl::MAIN_MEMORY));
+      viennacl::copy(view, E);
+      t0 = std::chrono::steady_clock::now();
+      rc = run_solver(E, solver, precond, &A, vb, vx, tol, abs_tol, maxit, krylov, restart_every, iters, err, hp);
+    }
+    else
+    {
+      hyb_t H(viennacl::context(viennacl::MAIN_MEMORY));
+      viennacl::copy(view, H);
+      t0 = std::chrono::steady_clock::now();
+      rc = run_solver(H, solver, precond, &A, vb, vx, tol, abs_tol, maxit, krylov, restart_every, iters, err, hp);
+    }
+  }
   else
   {
     if (rows % 32 == 0) return 3;

@@ -213,6 +213,115 @@ void vclo_sell_spmv(int rows, int C, const u32 *cols_per_block, const u32 *block
   }
 }
 
+/* ----------------------------------------------------------------------------------------------
+ * ELL (ell_matrix.hpp:122-166) and HYB (hyb_matrix.hpp:127-214) layouts and products, AlignmentV = 1.
+ * ELL: entry j of row r at j*rows + r, width = longest row, padding value 0 / column 0.
+ * HYB: ELL part of width w = the smallest row length L such that at least csr_threshold (0.8) of the rows have
+ *      <= L entries; the remaining entries of longer rows go to a CSR tail (one dummy entry when the tail is empty).
+ * Products: host_based/sparse_matrix_operations.hpp:1503-1538 (ELL), :1873-1927 (HYB) -- serial loops, zero-valued ELL
+ * slots never touch x.  ARITHMETIC (pinned against the live reference build, tests/test_oracle.py): the conditional ELL
+ * update `sum += x*val` is contracted to an fma by GCC, the unconditional CSR-tail update of HYB is not.
+ * ---------------------------------------------------------------------------------------------- */
+#ifndef ELL_FUSED
+#define ELL_FUSED 1
+#endif
+static inline double ell_madd(double x, double v, double acc)
+{
+#if ELL_FUSED
+  return fma(x, v, acc);
+#else
+  return acc + x * v;       /* two roundings (file is compiled with -ffp-contract=off) */
+#endif
+}
+
+int vclo_ell_width(int rows, const u32 *rp)
+{
+  u32 w = 0;
+  for (int r = 0; r < rows; ++r) if (rp[r + 1] - rp[r] > w) w = rp[r + 1] - rp[r];
+  return (int)w;
+}
+
+void vclo_ell_build(int rows, const u32 *rp, const u32 *ci, const double *v, int width, u32 *coords, double *elements)
+{
+  memset(coords, 0, sizeof(u32) * (size_t)rows * (size_t)width);
+  memset(elements, 0, sizeof(double) * (size_t)rows * (size_t)width);
+  for (int r = 0; r < rows; ++r)
+  {
+    u32 j = 0;
+    for (u32 k = rp[r]; k < rp[r + 1] && j < (u32)width; ++k, ++j)
+    {
+      coords[(size_t)j * (size_t)rows + (size_t)r] = ci[k];
+      elements[(size_t)j * (size_t)rows + (size_t)r] = v[k];
+    }
+  }
+}
+
+int vclo_hyb_width(int rows, int cols, const u32 *rp, double threshold)
+{
+  int maxw = vclo_ell_width(rows, rp);
+  long *hist = (long*)calloc((size_t)cols + 2, sizeof(long));
+  for (int r = 0; r < rows; ++r) hist[rp[r + 1] - rp[r]] += 1;
+  long sum = 0;
+  int w = maxw;
+  for (int ind = 0; ind <= maxw; ++ind)
+  {
+    sum += hist[ind];
+    if ((double)sum >= threshold * (double)rows) { w = ind; break; }
+  }
+  free(hist);
+  return w;
+}
+
+/* csr_rows[rows+1]; csr_cols / csr_elements sized vclo_hyb_tail_nnz() (>= 1: dummy entry when empty) */
+long long vclo_hyb_tail_nnz(int rows, const u32 *rp, int width)
+{
+  long long t = 0;
+  for (int r = 0; r < rows; ++r) if (rp[r + 1] - rp[r] > (u32)width) t += (long long)(rp[r + 1] - rp[r]) - width;
+  return t > 0 ? t : 1;
+}
+
+void vclo_hyb_build(int rows, const u32 *rp, const u32 *ci, const double *v, int width,
+                    u32 *ell_coords, double *ell_elements, u32 *csr_rows, u32 *csr_cols, double *csr_elements)
+{
+  vclo_ell_build(rows, rp, ci, v, width, ell_coords, ell_elements);
+  u32 t = 0;
+  for (int r = 0; r < rows; ++r)
+  {
+    csr_rows[r] = t;
+    for (u32 k = rp[r] + (u32)width; k < rp[r + 1]; ++k, ++t) { csr_cols[t] = ci[k]; csr_elements[t] = v[k]; }
+  }
+  csr_rows[rows] = t;
+  if (t == 0) { csr_cols[0] = 0; csr_elements[0] = 0; }
+}
+
+void vclo_hyb_spmv(int rows, int width, const u32 *ell_coords, const double *ell_elements,
+                   const u32 *csr_rows, const u32 *csr_cols, const double *csr_elements,
+                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta)
+{
+  for (int r = 0; r < rows; ++r)
+  {
+    double sum = 0;
+    for (int j = 0; j < width; ++j)
+    {
+      size_t idx = (size_t)j * (size_t)rows + (size_t)r;
+      double val = ell_elements[idx];
+      if (val > 0 || val < 0) sum = ell_madd(x[(size_t)ell_coords[idx] * (size_t)incx + (size_t)offx], val, sum);
+    }
+    if (csr_rows)
+      for (u32 k = csr_rows[r]; k < csr_rows[r + 1]; ++k)
+        sum = sum + x[(size_t)csr_cols[k] * (size_t)incx + (size_t)offx] * csr_elements[k];   /* tail: NOT contracted in the reference build */
+    size_t yi = (size_t)r * (size_t)incy + (size_t)offy;
+    if (beta < 0 || beta > 0) y[yi] = fma(beta, y[yi], alpha * sum);
+    else                      y[yi] = alpha * sum;
+  }
+}
+
+void vclo_ell_spmv(int rows, int width, const u32 *coords, const double *elements,
+                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta)
+{
+  vclo_hyb_spmv(rows, width, coords, elements, NULL, NULL, NULL, x, offx, incx, alpha, y, offy, incy, beta);
+}
+
 /* detail::row_info(A, vec, SPARSE_ROW_DIAGONAL): host_based/sparse_matrix_operations.hpp:52-98 (0 if absent). */
 void vclo_csr_diag(int rows, const u32 *rp, const u32 *ci, const double *v, double *diag)
 {

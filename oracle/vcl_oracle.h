@@ -24,6 +24,18 @@ void vclo_sell_spmv(int rows, int C, const vclo_u32 *cols_per_block, const vclo_
                     const vclo_u32 *col_idx, const double *elements,
                     const double *x, int offx, int incx, double alpha,
                     double *y, int offy, int incy, double beta);
+/* ELL / HYB (AlignmentV = 1): layouts of ell_matrix.hpp:122-166 / hyb_matrix.hpp:127-214 */
+int  vclo_ell_width(int rows, const vclo_u32 *rp);
+void vclo_ell_build(int rows, const vclo_u32 *rp, const vclo_u32 *ci, const double *v, int width, vclo_u32 *coords, double *elements);
+void vclo_ell_spmv(int rows, int width, const vclo_u32 *coords, const double *elements,
+                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta);
+int  vclo_hyb_width(int rows, int cols, const vclo_u32 *rp, double threshold);
+long long vclo_hyb_tail_nnz(int rows, const vclo_u32 *rp, int width);
+void vclo_hyb_build(int rows, const vclo_u32 *rp, const vclo_u32 *ci, const double *v, int width,
+                    vclo_u32 *ell_coords, double *ell_elements, vclo_u32 *csr_rows, vclo_u32 *csr_cols, double *csr_elements);
+void vclo_hyb_spmv(int rows, int width, const vclo_u32 *ell_coords, const double *ell_elements,
+                   const vclo_u32 *csr_rows, const vclo_u32 *csr_cols, const double *csr_elements,
+                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta);
 void vclo_csr_diag(int rows, const vclo_u32 *rp, const vclo_u32 *ci, const double *v, double *diag);
 
 /* ---- BLAS-1 ---- */

@@ -1,0 +1,48 @@
+"""Golden vectors for the ELL / HYB formats, produced by the UNMODIFIED reference (oracle/_ref, 1 thread) on the
+matrices of reference_vectors.npz:  python tests/golden/make_golden_formats.py  ->  tests/golden/formats_vectors.npz"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib as ol  # noqa: E402
+
+
+def main():
+    o = ol.oracle(); r = ol.ref()
+    r.set_threads(1)
+    g = np.load(os.path.join(HERE, "reference_vectors.npz"))
+    out = {}
+    for name in ["lap2d_13x11", "cd3d_9x8x7", "ragged_200x180", "ragged_97x97"]:
+        rows, cols = g[name + "/shape"]
+        A = ol.CSR(rows, cols, g[name + "/rp"], g[name + "/ci"], g[name + "/v"])
+        x, y0 = g[name + "/x"], g[name + "/y0"]
+        E = r.ell_build(A)
+        out[name + "/ell/width"] = np.array([E["width"], E["internal_rows"]])
+        out[name + "/ell/coords"] = E["coords"]; out[name + "/ell/elements"] = E["elements"]
+        out[name + "/ell/y"] = r.ell_spmv(A, x.copy())
+        out[name + "/ell/y_ab"] = r.ell_spmv(A, x.copy(), y0.copy(), 1.5, -0.25)
+        H = r.hyb_build(A)
+        out[name + "/hyb/width"] = np.array([H["width"], H["internal_rows"], H["csr_nnz"]])
+        for k in ("ell_coords", "ell_elements", "csr_rows", "csr_cols", "csr_elements"):
+            out[name + "/hyb/" + k] = H[k]
+        out[name + "/hyb/y"] = r.hyb_spmv(A, x.copy())
+        out[name + "/hyb/y_ab"] = r.hyb_spmv(A, x.copy(), y0.copy(), 1.5, -0.25)
+    # solvers on the other formats (pipelined paths, cg.hpp:204-254 overloads): iteration counts at 1 thread
+    L = o.stencil2d(63, 65)
+    Cd = o.stencil2d(48, 50, 0.5, 0.0)
+    for name, A, solvers in (("lap2d_63x65", L, ("cg", "bicgstab")), ("cd2d_48x50", Cd, ("bicgstab",))):
+        b = np.ones(A.rows)
+        for fmt, fname in ((2, "ell"), (3, "hyb")):
+            for solver in solvers:
+                res = r.solve(solver, A, b, precond="none", fmt=fmt, tol=1e-8, maxit=1000)
+                key = "solve/%s/%s_%s" % (name, solver, fname)
+                out[key + "/iters"] = np.array([res["iters"]]); out[key + "/error"] = np.array([res["error"]]); out[key + "/x"] = res["x"]
+    np.savez_compressed(os.path.join(HERE, "formats_vectors.npz"), **out)
+    print("wrote", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,16 @@ class _Oracle:
         lib.vclo_sell_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, u32p, u32p, f64p]
         lib.vclo_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
         lib.vclo_csr_diag.argtypes = [c_int, u32p, u32p, f64p, f64p]
+        lib.vclo_ell_width.restype = c_int
+        lib.vclo_ell_width.argtypes = [c_int, u32p]
+        lib.vclo_ell_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, f64p]
+        lib.vclo_ell_spmv.argtypes = [c_int, c_int, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
+        lib.vclo_hyb_width.restype = c_int
+        lib.vclo_hyb_width.argtypes = [c_int, c_int, u32p, c_dbl]
+        lib.vclo_hyb_tail_nnz.restype = c_ll
+        lib.vclo_hyb_tail_nnz.argtypes = [c_int, u32p, c_int]
+        lib.vclo_hyb_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, f64p, u32p, u32p, f64p]
+        lib.vclo_hyb_spmv.argtypes = [c_int, c_int, u32p, f64p, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
         lib.vclo_norm2.restype = c_dbl
         lib.vclo_norm2.argtypes = [f64p, c_ll]
         lib.vclo_inner_prod.restype = c_dbl
@@ -128,6 +138,40 @@ class _Oracle:
         self.lib.vclo_csr_diag(A.rows, A.rp, A.ci, A.v, d)
         return d
 
+    # -- ELL / HYB (ell_matrix.hpp:122-166, hyb_matrix.hpp:127-214) ---------------------------
+    def ell_build(self, A):
+        w = self.lib.vclo_ell_width(A.rows, A.rp)
+        tot = max(A.rows * w, 1)
+        co = np.zeros(tot, np.uint32); el = np.zeros(tot, np.float64)
+        self.lib.vclo_ell_build(A.rows, A.rp, A.ci, A.v, w, co, el)
+        return dict(rows=A.rows, cols=A.cols, width=w, internal_rows=A.rows, coords=co[:A.rows * w], elements=el[:A.rows * w])
+
+    def ell_spmv(self, E, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        if y is None:
+            y = np.zeros(offy + E["rows"] * incy, np.float64)
+        pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt))
+        self.lib.vclo_ell_spmv(E["rows"], E["width"], pad(E["coords"], np.uint32), pad(E["elements"], np.float64),
+                               x, offx, incx, alpha, y, offy, incy, beta)
+        return y
+
+    def hyb_build(self, A, threshold=0.8):
+        w = self.lib.vclo_hyb_width(A.rows, A.cols, A.rp, threshold)
+        tn = int(self.lib.vclo_hyb_tail_nnz(A.rows, A.rp, w))
+        tot = max(A.rows * w, 1)
+        co = np.zeros(tot, np.uint32); el = np.zeros(tot, np.float64)
+        cr = np.zeros(A.rows + 1, np.uint32); cc = np.zeros(tn, np.uint32); ce = np.zeros(tn, np.float64)
+        self.lib.vclo_hyb_build(A.rows, A.rp, A.ci, A.v, w, co, el, cr, cc, ce)
+        return dict(rows=A.rows, cols=A.cols, width=w, internal_rows=A.rows, ell_coords=co[:A.rows * w], ell_elements=el[:A.rows * w],
+                    csr_rows=cr, csr_cols=cc, csr_elements=ce, csr_nnz=tn)
+
+    def hyb_spmv(self, H, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        if y is None:
+            y = np.zeros(offy + H["rows"] * incy, np.float64)
+        pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt))
+        self.lib.vclo_hyb_spmv(H["rows"], H["width"], pad(H["ell_coords"], np.uint32), pad(H["ell_elements"], np.float64),
+                               H["csr_rows"], H["csr_cols"], H["csr_elements"], x, offx, incx, alpha, y, offy, incy, beta)
+        return y
+
     def norm2(self, x):
         return self.lib.vclo_norm2(np.ascontiguousarray(x), x.size)
 
@@ -180,6 +224,12 @@ class _Ref:
         lib.vclref_free.argtypes = [C.c_void_p]
         lib.vclref_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, c_int, f64p, c_dbl, f64p, c_dbl]
         lib.vclref_csr_diag.argtypes = [c_int, c_int, c_int, u32p, u32p, f64p, f64p]
+        vpp = C.POINTER(C.c_void_p)
+        if hasattr(lib, "vclref_ell_build"):
+            lib.vclref_ell_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip, ip]
+            lib.vclref_ell_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
+            lib.vclref_hyb_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip, ip, vpp, vpp, vpp, ip]
+            lib.vclref_hyb_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
         lib.vclref_norm2.restype = c_dbl
         lib.vclref_norm2.argtypes = [f64p, c_int]
         lib.vclref_inner_prod.restype = c_dbl
@@ -232,6 +282,47 @@ class _Ref:
         d = np.empty(A.rows, np.float64)
         self.lib.vclref_csr_diag(A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, d)
         return d
+
+    @staticmethod
+    def _grab(ptr, n, ct, dt):
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(max(n, 1),))[:n].astype(dt, copy=True)
+
+    def ell_build(self, A):
+        p = [C.c_void_p() for _ in range(2)]
+        w, ir = c_int(0), c_int(0)
+        self.lib.vclref_ell_build(A.rows, A.cols, A.rp, A.ci, A.v, C.byref(p[0]), C.byref(p[1]), C.byref(w), C.byref(ir))
+        tot = w.value * ir.value
+        out = dict(rows=A.rows, cols=A.cols, width=w.value, internal_rows=ir.value,
+                   coords=self._grab(p[0], tot, C.c_uint32, np.uint32), elements=self._grab(p[1], tot, C.c_double, np.float64))
+        for q in p:
+            self.lib.vclref_free(q)
+        return out
+
+    def ell_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
+        if y is None:
+            y = np.zeros(A.rows, np.float64)
+        self.lib.vclref_ell_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
+        return y
+
+    def hyb_build(self, A):
+        p = [C.c_void_p() for _ in range(5)]
+        w, ir, cn = c_int(0), c_int(0), c_int(0)
+        self.lib.vclref_hyb_build(A.rows, A.cols, A.rp, A.ci, A.v, C.byref(p[0]), C.byref(p[1]), C.byref(w), C.byref(ir),
+                                  C.byref(p[2]), C.byref(p[3]), C.byref(p[4]), C.byref(cn))
+        tot = w.value * ir.value
+        out = dict(rows=A.rows, cols=A.cols, width=w.value, internal_rows=ir.value, csr_nnz=cn.value,
+                   ell_coords=self._grab(p[0], tot, C.c_uint32, np.uint32), ell_elements=self._grab(p[1], tot, C.c_double, np.float64),
+                   csr_rows=self._grab(p[2], A.rows + 1, C.c_uint32, np.uint32), csr_cols=self._grab(p[3], cn.value, C.c_uint32, np.uint32),
+                   csr_elements=self._grab(p[4], cn.value, C.c_double, np.float64))
+        for q in p:
+            self.lib.vclref_free(q)
+        return out
+
+    def hyb_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
+        if y is None:
+            y = np.zeros(A.rows, np.float64)
+        self.lib.vclref_hyb_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
+        return y
 
     def norm2(self, x):
         return self.lib.vclref_norm2(np.ascontiguousarray(x), x.size)

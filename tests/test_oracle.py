@@ -155,3 +155,30 @@ def test_generic_solver_counts_pinned():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-I/root/reference", "-o", exe, os.path.join(root, "oracle", "ref_generic_counts.cpp")])
         live = json.loads(subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")).stdout)
         assert live == gold
+
+
+# ----------------------------------------------------------------------------------------------- ELL / HYB
+@pytest.fixture(scope="module")
+def golden_formats():
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "formats_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", ["lap2d_13x11", "cd3d_9x8x7", "ragged_200x180", "ragged_97x97"])
+def test_ell_hyb_layout_and_spmv_bitexact(golden, golden_formats, orc, name):
+    """Layouts equal the reference's copy() (ell_matrix.hpp:122-166, hyb_matrix.hpp:127-214); products are bit-identical to
+    host_based/sparse_matrix_operations.hpp:1503-1538 / :1873-1927 as built (ELL update fused, HYB tail not)."""
+    gf = golden_formats
+    A = load_csr(golden, name)
+    x, y0 = golden[name + "/x"], golden[name + "/y0"]
+    E = orc.ell_build(A)
+    assert [E["width"], E["internal_rows"]] == list(gf[name + "/ell/width"])
+    assert np.array_equal(E["coords"], gf[name + "/ell/coords"]) and np.array_equal(E["elements"], gf[name + "/ell/elements"])
+    assert np.array_equal(orc.ell_spmv(E, x), gf[name + "/ell/y"])
+    assert np.array_equal(orc.ell_spmv(E, x, y0.copy(), 1.5, -0.25), gf[name + "/ell/y_ab"])
+    H = orc.hyb_build(A)
+    assert [H["width"], H["internal_rows"], H["csr_nnz"]] == list(gf[name + "/hyb/width"])
+    for k in ("ell_coords", "ell_elements", "csr_rows", "csr_cols", "csr_elements"):
+        assert np.array_equal(H[k], gf[name + "/hyb/" + k]), k
+    assert np.array_equal(orc.hyb_spmv(H, x), gf[name + "/hyb/y"])
+    assert np.array_equal(orc.hyb_spmv(H, x, y0.copy(), 1.5, -0.25), gf[name + "/hyb/y_ab"])
+    assert ol.rel_err(gf[name + "/hyb/y"], golden[name + "/y_assign"]).max() <= 1e-12

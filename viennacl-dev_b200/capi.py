@@ -38,6 +38,14 @@ class SellStruct(C.Structure):
                 ("block_start", c_vp), ("values", c_vp)]
 
 
+class EllStruct(C.Structure):
+    _fields_ = [("rows", c_int), ("cols", c_int), ("internal_rows", c_int), ("maxnnz", c_int), ("coords", c_vp), ("elements", c_vp)]
+
+
+class HybStruct(C.Structure):
+    _fields_ = [("ell", EllStruct), ("csr_rows", c_vp), ("csr_cols", c_vp), ("csr_elements", c_vp), ("csr_nnz", c_int)]
+
+
 MONITOR = C.CFUNCTYPE(c_int, c_vp, c_dbl, c_vp)
 
 
@@ -140,9 +148,20 @@ def lib():
     sig("ViennaCLCUDADpipelined_gmres_update_result", c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int)
     sig("ViennaCLCUDADpipelined_gmres_prod_csr", c_vp, pc, c_vp, c_vp, c_vp, c_int)
     sig("ViennaCLCUDADpipelined_gmres_prod_sell", c_vp, ps, c_vp, c_vp, c_vp, c_int)
+    pe, ph = C.POINTER(EllStruct), C.POINTER(HybStruct)
+    sig("ViennaCLCUDADellmv", c_vp, pe, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
+    sig("ViennaCLCUDADhybmv", c_vp, ph, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
+    sig("ViennaCLCUDADcsr2ell", c_vp, c_int, c_vp, c_vp, c_vp, p_int, c_vp, c_vp)
+    sig("ViennaCLCUDADcsr2hyb", c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, p_int, p_int, c_vp, c_vp, c_vp, c_vp, c_vp)
+    for fmt, pp in (("ell", pe), ("hyb", ph)):
+        sig("ViennaCLCUDADpipelined_cg_prod_" + fmt, c_vp, pp, c_vp, c_vp, c_vp, c_int)
+        sig("ViennaCLCUDADpipelined_bicgstab_prod_" + fmt, c_vp, pp, c_vp, c_vp, c_vp, c_vp, c_int, c_int)
+        sig("ViennaCLCUDADpipelined_gmres_prod_" + fmt, c_vp, pp, c_vp, c_vp, c_vp, c_int)
     for nm in ("cg", "bicgstab", "gmres"):
         sig("ViennaCLCUDADcsr_" + nm, c_vp, pc, c_vp, c_vp, pt)
         sig("ViennaCLCUDADsell_" + nm, c_vp, ps, c_vp, c_vp, pt)
+        sig("ViennaCLCUDADell_" + nm, c_vp, pe, c_vp, c_vp, pt)
+        sig("ViennaCLCUDADhyb_" + nm, c_vp, ph, c_vp, c_vp, pt)
     sig("ViennaCLCUDADdist_csr_create", c_vp, c_ll, c_ll, c_ll, c_int, c_vp, c_vp, c_vp, p_vp)
     sig("ViennaCLCUDADdist_csr_destroy", c_vp, p_vp)
     sig("ViennaCLCUDADdist_csrmv", c_vp, c_vp, c_vp, c_vp)
@@ -388,6 +407,73 @@ class SellMatrix:
         return 12 * self.padded_nnz + 8 * ns + 16 * self.rows
 
 
+class EllMatrix:
+    """ell_matrix mirror (ell_matrix.hpp:36-119, AlignmentV = 1): coords / elements, entry j of row r at j*internal_rows + r."""
+    kind = "ell"
+
+    def __init__(self, backend, rows, cols, internal_rows, width, coords, elements):
+        self.b = backend
+        self.rows, self.cols, self.internal_rows, self.width = int(rows), int(cols), int(internal_rows), int(width)
+        self.coords, self.elements = coords, elements
+
+    @classmethod
+    def from_csr(cls, A):
+        b = A.b
+        w = c_int(0)
+        b.check(b.L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), None, None))
+        tot = max(A.rows * w.value, 1)
+        co = b.empty(tot, np.uint32); el = b.empty(tot, np.float64)
+        b.check(b.L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), co.ptr, el.ptr))
+        return cls(b, A.rows, A.cols, A.rows, w.value, co, el)
+
+    @classmethod
+    def from_host(cls, backend, E):
+        pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt), dtype=dt)
+        return cls(backend, E["rows"], E["cols"], E["internal_rows"], E["width"], backend.array(pad(E["coords"], np.uint32)),
+                   backend.array(pad(E["elements"], np.float64)))
+
+    def struct(self):
+        return EllStruct(self.rows, self.cols, self.internal_rows, self.width, self.coords.ptr, self.elements.ptr)
+
+    def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        s = self.struct()
+        self.b.check(self.b.L.ViennaCLCUDADellmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+
+    def bytes_spmv(self):
+        return 12 * self.internal_rows * self.width + 16 * self.rows
+
+
+class HybMatrix:
+    """hyb_matrix mirror (hyb_matrix.hpp:36-126): ELL part + CSR tail."""
+    kind = "hyb"
+
+    def __init__(self, backend, ell, csr_rows, csr_cols, csr_elements, csr_nnz):
+        self.b = backend
+        self.ell = ell
+        self.rows, self.cols = ell.rows, ell.cols
+        self.csr_rows, self.csr_cols, self.csr_elements, self.csr_nnz = csr_rows, csr_cols, csr_elements, int(csr_nnz)
+
+    @classmethod
+    def from_csr(cls, A, threshold=0.8):
+        b = A.b
+        w, tn = c_int(0), c_int(0)
+        b.check(b.L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
+                                         None, None, None, None, None))
+        tot = max(A.rows * w.value, 1)
+        co = b.empty(tot, np.uint32); el = b.empty(tot, np.float64)
+        cr = b.empty(A.rows + 1, np.uint32); cc = b.empty(max(tn.value, 1), np.uint32); ce = b.empty(max(tn.value, 1), np.float64)
+        b.check(b.L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
+                                         co.ptr, el.ptr, cr.ptr, cc.ptr, ce.ptr))
+        return cls(b, EllMatrix(b, A.rows, A.cols, A.rows, w.value, co, el), cr, cc, ce, tn.value)
+
+    def struct(self):
+        return HybStruct(self.ell.struct(), self.csr_rows.ptr, self.csr_cols.ptr, self.csr_elements.ptr, self.csr_nnz)
+
+    def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        s = self.struct()
+        self.b.check(self.b.L.ViennaCLCUDADhybmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+
+
 class SolverTag:
     """cg_tag / bicgstab_tag / gmres_tag in one (cg.hpp:48-87, bicgstab.hpp:47-90, gmres.hpp:49-101)."""
 
@@ -411,7 +497,7 @@ class SolverTag:
 
     def solve(self, solver, A, b, x):
         """solver in {'cg','bicgstab','gmres'}; A a CsrMatrix or SellMatrix; b, x DeviceArrays."""
-        kind = "csr" if isinstance(A, CsrMatrix) else "sell"
+        kind = "csr" if isinstance(A, CsrMatrix) else getattr(A, "kind", "sell")
         fn = getattr(A.b.L, "ViennaCLCUDAD%s_%s" % (kind, solver))
         s = A.struct()
         A.b.check(fn(A.b.h, C.byref(s), b.ptr, x.ptr, C.byref(self.t)))

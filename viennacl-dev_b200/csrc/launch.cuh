@@ -75,3 +75,14 @@ static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell
   VCL_LAUNCHED(b, "sell_kernel");
   return ViennaCLSuccess;
 }
+
+template<class Epi>
+static ViennaCLStatus vcl_launch_ell(ViennaCLBackend b, const ViennaCLCUDADhyb &A, XVec xv, Epi epi)
+{
+  EllDev d = {A.ell.rows, A.ell.internal_rows, A.ell.maxnnz, A.ell.coords, A.ell.elements, A.csr_rows, A.csr_cols, A.csr_elements};
+  const int occ = vcl_occupancy(ell_kernel<Epi>, CSR_BLOCK_THREADS);
+  int grid = std::max(1, std::min(vcl_div_up(A.ell.rows, CSR_BLOCK_THREADS), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+  ell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
+  VCL_LAUNCHED(b, "ell_kernel");
+  return ViennaCLSuccess;
+}

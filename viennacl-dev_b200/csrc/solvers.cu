@@ -12,11 +12,12 @@ namespace {
 
 struct MatOp
 {
-  int fmt;                 // 0 CSR, 1 SELL
+  int fmt;                 // 0 CSR, 1 SELL, 2 ELL / HYB (plain ELL = HYB without tail)
   ViennaCLCUDADcsr csr;
   ViennaCLCUDADsell sell;
-  int rows() const { return fmt == 0 ? csr.rows : sell.rows; }
-  int cols() const { return fmt == 0 ? csr.cols : sell.cols; }
+  ViennaCLCUDADhyb hyb;
+  int rows() const { return fmt == 0 ? csr.rows : (fmt == 1 ? sell.rows : hyb.ell.rows); }
+  int cols() const { return fmt == 0 ? csr.cols : (fmt == 1 ? sell.cols : hyb.ell.cols); }
 };
 
 template<class Epi>
@@ -24,7 +25,8 @@ ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const double *x, E
 {
   XVec xv = make_xvec(x, 0, 1);
   if (A.fmt == 0) return vcl_launch_csr(b, A.csr, xv, epi);
-  return vcl_launch_sell(b, A.sell, xv, epi);
+  if (A.fmt == 1) return vcl_launch_sell(b, A.sell, xv, epi);
+  return vcl_launch_ell(b, A.hyb, xv, epi);
 }
 
 ViennaCLStatus plain_prod(ViennaCLBackend b, const MatOp &A, const double *x, double *y)
@@ -43,7 +45,19 @@ ViennaCLStatus check_matrix(ViennaCLBackend b, const MatOp &A)
 {
   VCL_REQUIRE(b, A.rows() >= 0 && A.rows() == A.cols(), "solvers need a square matrix");
   if (A.fmt == 0) VCL_REQUIRE(b, A.rows() == 0 || (A.csr.row_ptr && (A.csr.nnz == 0 || (A.csr.col_idx && A.csr.values))), "null CSR array");
-  else VCL_REQUIRE(b, A.rows() == 0 || (A.sell.columns_per_block && A.sell.block_start && A.sell.rows_per_block > 0), "bad SELL matrix");
+  else if (A.fmt == 1) VCL_REQUIRE(b, A.rows() == 0 || (A.sell.columns_per_block && A.sell.block_start && A.sell.rows_per_block > 0), "bad SELL matrix");
+  else VCL_REQUIRE(b, A.rows() == 0 || (A.hyb.ell.maxnnz >= 0 && A.hyb.ell.internal_rows >= A.hyb.ell.rows &&
+                                        (A.hyb.ell.maxnnz == 0 || (A.hyb.ell.coords && A.hyb.ell.elements)) &&
+                                        (!A.hyb.csr_rows || (A.hyb.csr_cols && A.hyb.csr_elements))), "bad ELL / HYB matrix");
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus check_matrix_any(ViennaCLBackend b, const MatOp &A)       // like check_matrix, rectangular allowed (plain products)
+{
+  VCL_REQUIRE(b, A.rows() >= 0 && A.cols() >= 0, "negative size");
+  VCL_REQUIRE(b, A.rows() == 0 || (A.hyb.ell.maxnnz >= 0 && A.hyb.ell.internal_rows >= A.hyb.ell.rows &&
+                                   (A.hyb.ell.maxnnz == 0 || (A.hyb.ell.coords && A.hyb.ell.elements)) &&
+                                   (!A.hyb.csr_rows || (A.hyb.csr_cols && A.hyb.csr_elements))), "bad ELL / HYB matrix");
   return ViennaCLSuccess;
 }
 
@@ -426,8 +440,10 @@ __global__ void chunk_sum_kernel(const double *in, int chunk, double *out)
   if (threadIdx.x == 0) out[0] = acc[0];
 }
 
-MatOp from_csr(const ViennaCLCUDADcsr *A) { MatOp m; m.fmt = 0; m.csr = *A; m.sell = ViennaCLCUDADsell(); return m; }
-MatOp from_sell(const ViennaCLCUDADsell *A) { MatOp m; m.fmt = 1; m.sell = *A; m.csr = ViennaCLCUDADcsr(); return m; }
+MatOp from_csr(const ViennaCLCUDADcsr *A) { MatOp m; m.fmt = 0; m.csr = *A; m.sell = ViennaCLCUDADsell(); m.hyb = ViennaCLCUDADhyb(); return m; }
+MatOp from_sell(const ViennaCLCUDADsell *A) { MatOp m; m.fmt = 1; m.sell = *A; m.csr = ViennaCLCUDADcsr(); m.hyb = ViennaCLCUDADhyb(); return m; }
+MatOp from_hyb(const ViennaCLCUDADhyb *A) { MatOp m; m.fmt = 2; m.hyb = *A; m.csr = ViennaCLCUDADcsr(); m.sell = ViennaCLCUDADsell(); return m; }
+MatOp from_ell(const ViennaCLCUDADell *A) { ViennaCLCUDADhyb h = ViennaCLCUDADhyb(); h.ell = *A; return from_hyb(&h); }
 
 ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p, double *Ap, const double *r0,
                               double *out_ApAp, double *out_pAp, double *out_Apr0)
@@ -464,6 +480,52 @@ ViennaCLStatus ViennaCLCUDADcsr_gmres(ViennaCLBackend b, const ViennaCLCUDADcsr 
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_csr(A), rhs, x, tag); }
 ViennaCLStatus ViennaCLCUDADsell_gmres(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_sell(A), rhs, x, tag); }
+
+#define VCL_SOLVER_ENTRY(name, type, conv, fn) \
+ViennaCLStatus name(ViennaCLBackend b, const type *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag) \
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return fn(b, conv(A), rhs, x, tag); }
+VCL_SOLVER_ENTRY(ViennaCLCUDADell_cg, ViennaCLCUDADell, from_ell, cg_solve)
+VCL_SOLVER_ENTRY(ViennaCLCUDADhyb_cg, ViennaCLCUDADhyb, from_hyb, cg_solve)
+VCL_SOLVER_ENTRY(ViennaCLCUDADell_bicgstab, ViennaCLCUDADell, from_ell, bicgstab_solve)
+VCL_SOLVER_ENTRY(ViennaCLCUDADhyb_bicgstab, ViennaCLCUDADhyb, from_hyb, bicgstab_solve)
+VCL_SOLVER_ENTRY(ViennaCLCUDADell_gmres, ViennaCLCUDADell, from_ell, gmres_solve)
+VCL_SOLVER_ENTRY(ViennaCLCUDADhyb_gmres, ViennaCLCUDADhyb, from_hyb, gmres_solve)
+
+// plain products for the other formats (linalg/sparse_matrix_operations.hpp:90-121 dispatch)
+static ViennaCLStatus ellhyb_mv(ViennaCLBackend b, const MatOp &A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+{
+  VCL_TRY(check_matrix_any(b, A));
+  if (A.rows() == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, x && y && incx != 0 && incy != 0 && x != y, "bad vectors");
+  EpiAxpby epi = {y, offy, incy, alpha, beta};
+  return vcl_launch_ell(b, A.hyb, make_xvec(x, offx, incx), epi);
+}
+ViennaCLStatus ViennaCLCUDADellmv(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return ellhyb_mv(b, from_ell(A), x, offx, incx, alpha, y, offy, incy, beta); }
+ViennaCLStatus ViennaCLCUDADhybmv(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return ellhyb_mv(b, from_hyb(A), x, offx, incx, alpha, y, offy, incy, beta); }
+
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
+  return fused_prod_api(b, from_ell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
+  return fused_prod_api(b, from_hyb(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap,
+                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
+  return fused_prod_api(b, from_ell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap,
+                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+{ VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
+  return fused_prod_api(b, from_hyb(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+{ return ViennaCLCUDADpipelined_cg_prod_ell(b, A, p, Ap, buf, buf_size); }
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+{ return ViennaCLCUDADpipelined_cg_prod_hyb(b, A, p, Ap, buf, buf_size); }
 
 // ---- per-step entry points (linalg/iterative_operations.hpp) ----
 ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend b, ViennaCLInt n, double *result, double alpha,

@@ -192,3 +192,113 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend b, ViennaCLInt r
   VCL_LAUNCHED(b, "sell_fill_kernel");
   return ViennaCLSuccess;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CSR -> ELL (ell_matrix.hpp:122-166) and CSR -> HYB (hyb_matrix.hpp:127-214), AlignmentV = 1.  Row lengths are analysed
+// on the host from a D2H copy of row_ptr (set-up path, like the reference, which builds both formats entirely on the
+// host); the entries are scattered on the device.
+// ------------------------------------------------------------------------------------------------
+__global__ void ell_fill_kernel(int rows, int width, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const double * __restrict__ cva,
+                                u32 *coords, double *elements, const u32 * __restrict__ tail_rows, u32 *tail_cols, double *tail_elements)
+{
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    const u32 b0 = rp[r], e = rp[r + 1];
+    size_t idx = (size_t)r;
+    u32 k = b0;
+    int j = 0;
+    for (; j < width && k < e; ++j, ++k, idx += (size_t)rows) { coords[idx] = cci[k]; elements[idx] = cva[k]; }
+    for (; j < width; ++j, idx += (size_t)rows) { coords[idx] = 0u; elements[idx] = 0.0; }
+    if (tail_rows)
+    {
+      u32 t = tail_rows[r];
+      for (; k < e; ++k, ++t) { tail_cols[t] = cci[k]; tail_elements[t] = cva[k]; }
+    }
+  }
+}
+
+static ViennaCLStatus fetch_row_ptr(ViennaCLBackend b, int rows, const u32 *row_ptr, std::vector<u32> &rp)
+{
+  rp.resize((size_t)rows + 1);
+  VCL_CUDA(b, cudaMemcpyAsync(rp.data(), row_ptr, sizeof(u32) * ((size_t)rows + 1), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  return ViennaCLSuccess;
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADcsr2ell(ViennaCLBackend b, ViennaCLInt rows, const unsigned int *row_ptr,
+                                               const unsigned int *csr_col, const double *csr_val, ViennaCLInt *maxnnz,
+                                               unsigned int *coords, double *elements)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && maxnnz, "bad arguments");
+  if (rows == 0) { *maxnnz = 0; return ViennaCLSuccess; }
+  VCL_REQUIRE(b, row_ptr, "null row_ptr");
+  if (!coords || !elements)
+  {
+    std::vector<u32> rp;
+    VCL_TRY(fetch_row_ptr(b, rows, row_ptr, rp));
+    u32 w = 0;
+    for (int r = 0; r < rows; ++r) w = std::max(w, rp[r + 1] - rp[r]);
+    VCL_REQUIRE(b, (unsigned long long)w * (unsigned long long)rows <= 0x7FFFFFFFull, "ELL storage exceeds 32-bit sizes");
+    *maxnnz = (ViennaCLInt)w;
+    return ViennaCLSuccess;
+  }
+  if (*maxnnz == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, csr_col && csr_val, "null CSR array");
+  ell_fill_kernel<<<std::min(vcl_div_up(rows, 256), b->sm_count * 8), 256, 0, b->stream>>>(rows, *maxnnz, row_ptr, csr_col, csr_val, coords, elements,
+                                                                                         nullptr, nullptr, nullptr);
+  VCL_LAUNCHED(b, "ell_fill_kernel");
+  return ViennaCLSuccess;
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, const unsigned int *row_ptr,
+                                               const unsigned int *csr_col, const double *csr_val, double csr_threshold,
+                                               ViennaCLInt *ell_width, ViennaCLInt *csr_nnz,
+                                               unsigned int *ell_coords, double *ell_elements,
+                                               unsigned int *csr_rows, unsigned int *csr_cols, double *csr_elements)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && cols >= 0 && ell_width && csr_nnz, "bad arguments");
+  if (rows == 0) { *ell_width = 0; *csr_nnz = 0; return ViennaCLSuccess; }
+  VCL_REQUIRE(b, row_ptr, "null row_ptr");
+  std::vector<u32> rp;
+  VCL_TRY(fetch_row_ptr(b, rows, row_ptr, rp));
+  if (!ell_coords || !csr_rows)
+  {
+    // hyb_matrix.hpp:139-166: histogram of row lengths, smallest width covering >= threshold of the rows
+    u32 maxw = 0;
+    for (int r = 0; r < rows; ++r) maxw = std::max(maxw, rp[r + 1] - rp[r]);
+    std::vector<size_t> hist((size_t)maxw + 1, 0);
+    for (int r = 0; r < rows; ++r) hist[rp[r + 1] - rp[r]] += 1;
+    size_t sum = 0; u32 w = maxw;
+    for (u32 ind = 0; ind <= maxw; ++ind)
+    {
+      sum += hist[ind];
+      if ((double)sum >= csr_threshold * (double)rows) { w = ind; break; }
+    }
+    unsigned long long tail = 0;
+    for (int r = 0; r < rows; ++r) if (rp[r + 1] - rp[r] > w) tail += (rp[r + 1] - rp[r]) - w;
+    VCL_REQUIRE(b, (unsigned long long)w * (unsigned long long)rows <= 0x7FFFFFFFull && tail <= 0x7FFFFFFFull, "HYB storage exceeds 32-bit sizes");
+    *ell_width = (ViennaCLInt)w;
+    *csr_nnz = (ViennaCLInt)(tail > 0 ? tail : 1);            // one dummy entry when empty (hyb_matrix.hpp:209-213)
+    return ViennaCLSuccess;
+  }
+  VCL_REQUIRE(b, csr_cols && csr_elements && (*ell_width == 0 || ell_elements), "null output array");
+  const u32 w = (u32)*ell_width;
+  std::vector<u32> tr((size_t)rows + 1);
+  u32 t = 0;
+  for (int r = 0; r < rows; ++r) { tr[r] = t; if (rp[r + 1] - rp[r] > w) t += (rp[r + 1] - rp[r]) - w; }
+  tr[rows] = t;
+  VCL_CUDA(b, cudaMemcpyAsync(csr_rows, tr.data(), sizeof(u32) * ((size_t)rows + 1), cudaMemcpyHostToDevice, b->stream));
+  if (t == 0)
+  {
+    VCL_CUDA(b, cudaMemsetAsync(csr_cols, 0, sizeof(u32), b->stream));
+    VCL_CUDA(b, cudaMemsetAsync(csr_elements, 0, sizeof(double), b->stream));
+  }
+  VCL_REQUIRE(b, rp[rows] == 0 || (csr_col && csr_val), "null CSR array");
+  ell_fill_kernel<<<std::min(vcl_div_up(rows, 256), b->sm_count * 8), 256, 0, b->stream>>>(rows, (int)w, row_ptr, csr_col, csr_val, ell_coords, ell_elements,
+                                                                                         csr_rows, csr_cols, csr_elements);
+  VCL_LAUNCHED(b, "ell_fill_kernel");
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));              // tr (pageable) must outlive the copy
+  return ViennaCLSuccess;
+}

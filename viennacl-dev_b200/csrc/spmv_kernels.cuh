@@ -482,3 +482,71 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   }
   epi.finish(s_red);
 }
+
+// ------------------------------------------------------------------------------------------------
+// ELL / HYB (cuda/sparse_matrix_operations.hpp:1747-1838, :2298-2400).  The ELL arrays are column-major over the rows, so
+// a warp that owns 32 consecutive rows reads 256 / 128 contiguous bytes per slot: the loads are coalesced as they are and
+// need no staging; they are issued 8 slots at a time (values and column indices together, L2 evict-first, no L1
+// allocation), then the gathers of the non-zero slots, then one fma chain -- the reference host build fuses the ELL
+// update (oracle/vcl_oracle.c, ARITHMETIC).  HYB: the same thread then walks its CSR tail with the unfused multiply-add
+// the reference build uses there.  One thread per row, persistent grid-stride over rows.
+// ------------------------------------------------------------------------------------------------
+struct EllDev
+{
+  int rows, internal_rows, width;
+  const u32 *coords; const double *elements;
+  const u32 *csr_rows, *csr_cols; const double *csr_elements;      // HYB tail, NULL for plain ELL
+};
+
+__device__ __forceinline__ double ldg_stream(const double *p, unsigned long long pol)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ u32 ldg_stream(const u32 *p, unsigned long long pol)
+{
+  u32 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;\n" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+#ifndef ELL_ILP
+#define ELL_ILP 4
+#endif
+template<class Epi>
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 6)
+ell_kernel(EllDev A, XVec xv, Epi epi)
+{
+  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  if (epi.skip()) return;
+  const unsigned long long pol = l2_evict_first_policy();
+  const size_t IR = (size_t)A.internal_rows;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    const double pre = epi.pre((u32)r);
+    u32 t0 = 0, t1 = 0;
+    if (A.csr_rows) { t0 = A.csr_rows[r]; t1 = A.csr_rows[r + 1]; }
+    double acc = 0.0;
+    const double *pv = A.elements + r;
+    const u32 *pc = A.coords + r;
+    for (int j = 0; j < A.width; j += ELL_ILP, pv += ELL_ILP * IR, pc += ELL_ILP * IR)
+    {
+      double v[ELL_ILP], xx[ELL_ILP]; u32 c[ELL_ILP];
+#pragma unroll
+      for (int k = 0; k < ELL_ILP; ++k)
+      {
+        const bool ok = j + k < A.width;
+        v[k] = ok ? ldg_stream(pv + k * IR, pol) : 0.0;
+        c[k] = ok ? ldg_stream(pc + k * IR, pol) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < ELL_ILP; ++k) xx[k] = nonzero(v[k]) ? xload<false>(xv, c[k]) : 0.0;
+#pragma unroll
+      for (int k = 0; k < ELL_ILP; ++k) acc = fma(xx[k], v[k], acc);      // zero slots: +0.0, bits unchanged
+    }
+    for (u32 k = t0; k < t1; ++k) acc = madd(A.csr_elements[k], xload<false>(xv, A.csr_cols[k]), acc);
+    epi.row((u32)r, acc, pre);
+  }
+  epi.finish(s_red);
+}

@@ -11,6 +11,8 @@
 #include "viennacl/vector.hpp"
 #include "viennacl/compressed_matrix.hpp"
 #include "viennacl/sliced_ell_matrix.hpp"
+#include "viennacl/ell_matrix.hpp"
+#include "viennacl/hyb_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
@@ -123,6 +125,30 @@ int main()
     expect(tag2.iters() == tag.iters() && true_residual(C, x2, c) < 1e-7, "solve(sliced_ell_matrix, b, gmres_tag)");
     expect(viennacl::linalg::gmres_tag(1e-8, 90, 30).max_restarts() == 2 && viennacl::linalg::gmres_tag(1e-8, 100, 30).max_restarts() == 3,
            "gmres_tag::max_restarts() (gmres.hpp:74-80)");
+  }
+
+  std::cout << "----- ell_matrix / hyb_matrix in the solvers (cg.hpp:204-254 overloads) -----" << std::endl;
+  {
+    viennacl::ell_matrix<ScalarType> A_ell, C_ell;
+    viennacl::hyb_matrix<ScalarType> A_hyb, C_hyb;
+    viennacl::copy(A, A_ell); viennacl::copy(C, C_ell);
+    viennacl::copy(A, A_hyb);
+    C_hyb.csr_threshold(0.2);                              // ELL width 6: the 7-entry interior rows spill into the CSR tail
+    viennacl::copy(C, C_hyb);
+    viennacl::linalg::cg_tag ref_tag(1e-8, 1000), t1(1e-8, 1000), t2(1e-8, 1000);
+    VectorT x0 = viennacl::linalg::solve(A, b, ref_tag);
+    VectorT x1 = viennacl::linalg::solve(A_ell, b, t1);
+    VectorT x2 = viennacl::linalg::solve(A_hyb, b, t2);
+    expect(std::abs(int(t1.iters()) - int(ref_tag.iters())) <= 2 && std::abs(int(t2.iters()) - int(ref_tag.iters())) <= 2 &&
+           true_residual(A, x1, b) < 1e-7 && true_residual(A, x2, b) < 1e-7, "solve(ell_matrix / hyb_matrix, b, cg_tag)");
+    viennacl::linalg::bicgstab_tag t3(1e-8, 1000), t4(1e-8, 1000);
+    VectorT x3 = viennacl::linalg::solve(C_ell, c, t3);
+    VectorT x4 = viennacl::linalg::solve(C_hyb, c, t4);
+    expect(C_hyb.csr_nnz() > 1 && true_residual(C, x3, c) < 1e-6 && true_residual(C, x4, c) < 1e-6, "solve(ell_matrix / hyb_matrix, b, bicgstab_tag)");
+    viennacl::linalg::gmres_tag t5(1e-8, 600, 30), t6(1e-8, 600, 30);
+    VectorT x5 = viennacl::linalg::solve(C_ell, c, t5);
+    VectorT x6 = viennacl::linalg::solve(C_hyb, c, t6);
+    expect(t5.iters() == t6.iters() && true_residual(C, x5, c) < 1e-7 && true_residual(C, x6, c) < 1e-7, "solve(ell_matrix / hyb_matrix, b, gmres_tag)");
   }
 
   std::cout << "----- solver objects: initial guess + monitor (iterative-custom.cpp) -----" << std::endl;

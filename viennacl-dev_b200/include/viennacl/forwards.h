@@ -51,6 +51,8 @@ template<typename NumericT> class vector_base;
 template<typename NumericT, unsigned int AlignmentV = 1> class vector;
 template<typename NumericT, unsigned int AlignmentV = 1> class compressed_matrix;
 template<typename NumericT, typename IndexT = unsigned int> class sliced_ell_matrix;
+template<typename NumericT, unsigned int AlignmentV = 1> class ell_matrix;
+template<typename NumericT, unsigned int AlignmentV = 1> class hyb_matrix;
 
 namespace linalg
 {

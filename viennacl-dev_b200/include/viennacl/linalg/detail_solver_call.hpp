@@ -4,6 +4,8 @@
 #include "viennacl/vector.hpp"
 #include "viennacl/compressed_matrix.hpp"
 #include "viennacl/sliced_ell_matrix.hpp"
+#include "viennacl/ell_matrix.hpp"
+#include "viennacl/hyb_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
 namespace viennacl
@@ -42,6 +44,21 @@ namespace detail
     if (k == SOLVER_CG) return ViennaCLCUDADsell_cg(h, &A, b, x, t);
     if (k == SOLVER_BICGSTAB) return ViennaCLCUDADsell_bicgstab(h, &A, b, x, t);
     return ViennaCLCUDADsell_gmres(h, &A, b, x, t);
+  }
+
+  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADell const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
+  {
+    ViennaCLBackend h = backend::b200::handle();
+    if (k == SOLVER_CG) return ViennaCLCUDADell_cg(h, &A, b, x, t);
+    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADell_bicgstab(h, &A, b, x, t);
+    return ViennaCLCUDADell_gmres(h, &A, b, x, t);
+  }
+  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADhyb const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
+  {
+    ViennaCLBackend h = backend::b200::handle();
+    if (k == SOLVER_CG) return ViennaCLCUDADhyb_cg(h, &A, b, x, t);
+    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADhyb_bicgstab(h, &A, b, x, t);
+    return ViennaCLCUDADhyb_gmres(h, &A, b, x, t);
   }
 
   /** @brief Runs one solve on the device; rhs may be a strided view (it is compacted first). */
