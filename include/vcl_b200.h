@@ -170,6 +170,20 @@ ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend backend, ViennaCLInt rows, V
                                     unsigned int *ell_coords, double *ell_elements,
                                     unsigned int *csr_rows, unsigned int *csr_cols, double *csr_elements);
 
+/* COO (coordinate_matrix.hpp:47-102): coords = (row, col) pairs, entries sorted by row as the reference's copy() produces
+ * them.  SpMV and the solvers run on a CSR index of the same entries, built once on the device:
+ * row_ptr[rows+1] and col_idx[nnz] are filled, the value array is shared with the COO matrix (no copy).
+ * Fails with ViennaCLB200InvalidArgument when the entries are not sorted by row. */
+ViennaCLStatus ViennaCLCUDAcoo2csr(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt nnz, const unsigned int *coords,
+                                   unsigned int *row_ptr, unsigned int *col_idx);
+/* coordinate_matrix product with the reference's arithmetic (host_based/sparse_matrix_operations.hpp:1222-1247):
+ * y <- beta*y (or 0), then y[row] += (alpha*a) * x[col] entry by entry; (row_ptr, col_idx) from ViennaCLCUDAcoo2csr. */
+ViennaCLStatus ViennaCLCUDADcoomv(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
+                                  const unsigned int *row_ptr, const unsigned int *col_idx, const double *elements,
+                                  const unsigned int *row_blocks, ViennaCLInt num_blocks,
+                                  const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta);
+
 /* detail::row_info: linalg/sparse_matrix_operations.hpp:48-74 -> cuda/sparse_matrix_operations.hpp:53-119.
  * option: 0 inf-norm, 1 1-norm, 2 2-norm, 3 diagonal (forwards.h row_info_types order). */
 ViennaCLStatus ViennaCLCUDADcsr_row_info(ViennaCLBackend backend, ViennaCLInt rows,

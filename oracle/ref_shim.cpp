@@ -29,6 +29,7 @@
 #include "viennacl/sliced_ell_matrix.hpp"
 #include "viennacl/ell_matrix.hpp"
 #include "viennacl/hyb_matrix.hpp"
+#include "viennacl/coordinate_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/inner_prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
@@ -296,6 +297,33 @@ int vclref_hyb_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const doub
   vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(cols));
   vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
   viennacl::linalg::prod_impl(H, vx, alpha, vy, beta);
+  return 0;
+}
+
+// COO built by the reference's copy() (coordinate_matrix.hpp:47-102): coords = (row, col) pairs; product host_based/...:1222-1247
+int vclref_coo_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v, u32 **coords, double **elements, int *nnz)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  viennacl::coordinate_matrix<double> M(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, M);
+  std::size_t n = M.nnz();
+  *nnz = int(n);
+  *coords = (u32*)std::malloc(sizeof(u32) * 2 * (n ? n : 1));
+  *elements = (double*)std::malloc(sizeof(double) * (n ? n : 1));
+  std::memcpy(*coords, M.handle12().ram_handle().get(), sizeof(u32) * 2 * n);
+  std::memcpy(*elements, M.handle().ram_handle().get(), sizeof(double) * n);
+  return 0;
+}
+
+int vclref_coo_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
+                    double *x, double alpha, double *y, double beta)
+{
+  raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
+  viennacl::coordinate_matrix<double> M(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::copy(view, M);
+  vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(cols));
+  vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
+  viennacl::linalg::prod_impl(M, vx, alpha, vy, beta);
   return 0;
 }
 

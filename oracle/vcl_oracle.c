@@ -322,6 +322,27 @@ void vclo_ell_spmv(int rows, int width, const u32 *coords, const double *element
   vclo_hyb_spmv(rows, width, coords, elements, NULL, NULL, NULL, x, offx, incx, alpha, y, offy, incy, beta);
 }
 
+/* COO (coordinate_matrix.hpp:47-102: (row, col) pairs in row-major order) product, host_based/sparse_matrix_operations.hpp:
+ * 1222-1247: y is first scaled by beta (or cleared), then every entry adds (alpha * a) * x[col] IN STORAGE ORDER. */
+#ifndef COO_FUSED
+#define COO_FUSED 1
+#endif
+void vclo_coo_spmv(int rows, long long nnz, const u32 *coords, const double *elements,
+                   const double *x, double alpha, double *y, double beta)
+{
+  if (beta < 0 || beta > 0) for (int i = 0; i < rows; ++i) y[i] *= beta;
+  else                      for (int i = 0; i < rows; ++i) y[i] = 0;
+  for (long long i = 0; i < nnz; ++i)
+  {
+    double t = alpha * elements[i];
+#if COO_FUSED
+    y[coords[2 * i]] = fma(t, x[coords[2 * i + 1]], y[coords[2 * i]]);
+#else
+    y[coords[2 * i]] = y[coords[2 * i]] + t * x[coords[2 * i + 1]];
+#endif
+  }
+}
+
 /* detail::row_info(A, vec, SPARSE_ROW_DIAGONAL): host_based/sparse_matrix_operations.hpp:52-98 (0 if absent). */
 void vclo_csr_diag(int rows, const u32 *rp, const u32 *ci, const double *v, double *diag)
 {

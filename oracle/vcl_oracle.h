@@ -36,6 +36,8 @@ void vclo_hyb_build(int rows, const vclo_u32 *rp, const vclo_u32 *ci, const doub
 void vclo_hyb_spmv(int rows, int width, const vclo_u32 *ell_coords, const double *ell_elements,
                    const vclo_u32 *csr_rows, const vclo_u32 *csr_cols, const double *csr_elements,
                    const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta);
+void vclo_coo_spmv(int rows, long long nnz, const vclo_u32 *coords, const double *elements,
+                   const double *x, double alpha, double *y, double beta);
 void vclo_csr_diag(int rows, const vclo_u32 *rp, const vclo_u32 *ci, const double *v, double *diag);
 
 /* ---- BLAS-1 ---- */

@@ -1,4 +1,4 @@
-"""Golden vectors for the ELL / HYB formats, produced by the UNMODIFIED reference (oracle/_ref, 1 thread) on the
+"""Golden vectors for the ELL / HYB / COO formats, produced by the UNMODIFIED reference (oracle/_ref, 1 thread) on the
 matrices of reference_vectors.npz:  python tests/golden/make_golden_formats.py  ->  tests/golden/formats_vectors.npz"""
 import os
 import sys
@@ -30,6 +30,10 @@ def main():
             out[name + "/hyb/" + k] = H[k]
         out[name + "/hyb/y"] = r.hyb_spmv(A, x.copy())
         out[name + "/hyb/y_ab"] = r.hyb_spmv(A, x.copy(), y0.copy(), 1.5, -0.25)
+        M = r.coo_build(A)
+        out[name + "/coo/coords"] = M["coords"]; out[name + "/coo/elements"] = M["elements"]
+        out[name + "/coo/y"] = r.coo_spmv(A, x.copy())
+        out[name + "/coo/y_ab"] = r.coo_spmv(A, x.copy(), y0.copy(), 1.5, -0.25)
     # solvers on the other formats (pipelined paths, cg.hpp:204-254 overloads): iteration counts at 1 thread
     L = o.stencil2d(63, 65)
     Cd = o.stencil2d(48, 50, 0.5, 0.0)

@@ -71,6 +71,7 @@ class _Oracle:
         lib.vclo_hyb_tail_nnz.argtypes = [c_int, u32p, c_int]
         lib.vclo_hyb_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, f64p, u32p, u32p, f64p]
         lib.vclo_hyb_spmv.argtypes = [c_int, c_int, u32p, f64p, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
+        lib.vclo_coo_spmv.argtypes = [c_int, c_ll, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
         lib.vclo_norm2.restype = c_dbl
         lib.vclo_norm2.argtypes = [f64p, c_ll]
         lib.vclo_inner_prod.restype = c_dbl
@@ -137,6 +138,20 @@ class _Oracle:
         d = np.empty(A.rows, np.float64)
         self.lib.vclo_csr_diag(A.rows, A.rp, A.ci, A.v, d)
         return d
+
+    # -- COO (coordinate_matrix.hpp:47-102) ----------------------------------------------------
+    def coo_build(self, A):
+        rows = np.repeat(np.arange(A.rows, dtype=np.uint32), np.diff(A.rp.astype(np.int64)))
+        coords = np.empty(2 * A.nnz, np.uint32)
+        coords[0::2] = rows; coords[1::2] = A.ci
+        return dict(rows=A.rows, cols=A.cols, nnz=A.nnz, coords=coords, elements=A.v.copy())
+
+    def coo_spmv(self, M, x, y=None, alpha=1.0, beta=0.0):
+        if y is None:
+            y = np.zeros(M["rows"], np.float64)
+        pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(2, dt))
+        self.lib.vclo_coo_spmv(M["rows"], M["nnz"], pad(M["coords"], np.uint32), pad(M["elements"], np.float64), x, alpha, y, beta)
+        return y
 
     # -- ELL / HYB (ell_matrix.hpp:122-166, hyb_matrix.hpp:127-214) ---------------------------
     def ell_build(self, A):
@@ -230,6 +245,9 @@ class _Ref:
             lib.vclref_ell_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
             lib.vclref_hyb_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip, ip, vpp, vpp, vpp, ip]
             lib.vclref_hyb_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
+        if hasattr(lib, "vclref_coo_build"):
+            lib.vclref_coo_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip]
+            lib.vclref_coo_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
         lib.vclref_norm2.restype = c_dbl
         lib.vclref_norm2.argtypes = [f64p, c_int]
         lib.vclref_inner_prod.restype = c_dbl
@@ -302,6 +320,22 @@ class _Ref:
         if y is None:
             y = np.zeros(A.rows, np.float64)
         self.lib.vclref_ell_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
+        return y
+
+    def coo_build(self, A):
+        p = [C.c_void_p() for _ in range(2)]
+        n = c_int(0)
+        self.lib.vclref_coo_build(A.rows, A.cols, A.rp, A.ci, A.v, C.byref(p[0]), C.byref(p[1]), C.byref(n))
+        out = dict(rows=A.rows, cols=A.cols, nnz=n.value, coords=self._grab(p[0], 2 * n.value, C.c_uint32, np.uint32),
+                   elements=self._grab(p[1], n.value, C.c_double, np.float64))
+        for q in p:
+            self.lib.vclref_free(q)
+        return out
+
+    def coo_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
+        if y is None:
+            y = np.zeros(A.rows, np.float64)
+        self.lib.vclref_coo_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
         return y
 
     def hyb_build(self, A):

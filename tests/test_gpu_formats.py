@@ -127,3 +127,33 @@ def test_ell_hyb_full_size_vs_csr(pkg, be):
     ref = y0.download()
     # 6*x_i - (neighbours) cancels: compare against the scale of the terms (sum |a||x| <= 24), not of the result
     assert np.abs(y1.download() - ref).max() <= 24 * 1e-15 and np.abs(y2.download() - ref).max() <= 24 * 1e-15
+
+
+@pytest.mark.parametrize("name", MATS)
+def test_coo_index_and_spmv_bitexact(pkg, be, golden, gf, name):
+    """coordinate_matrix: the CSR index built on the device equals the original CSR structure; the product is bit-identical
+    to the reference's COO arithmetic for both the plain and the alpha/beta form."""
+    A = load_csr(golden, name)
+    M = pkg.CooMatrix(be, A.rows, A.cols, gf[name + "/coo/coords"], gf[name + "/coo/elements"])
+    assert np.array_equal(M.index.rp.download(), A.rp)
+    assert np.array_equal(M.index.ci.download()[:A.nnz], A.ci)
+    x, y0 = golden[name + "/x"], golden[name + "/y0"]
+    dx = be.array(x)
+    dy = be.array(np.full(A.rows, np.nan))
+    M.spmv(dx, dy)
+    assert np.array_equal(dy.download(), gf[name + "/coo/y"])
+    dy = be.array(y0)
+    M.spmv(dx, dy, 1.5, -0.25)
+    assert np.array_equal(dy.download(), gf[name + "/coo/y_ab"])
+    # solvers run on the index like on any compressed_matrix
+    if A.rows == A.cols and name.startswith("lap"):
+        b = np.ones(A.rows)
+        dsol = be.zeros(A.rows)
+        tag = pkg.SolverTag(tol=1e-9, max_iterations=500).solve("cg", M.index, be.array(b), dsol)
+        assert tag.error < 1e-9 and np.linalg.norm(b - A.to_scipy() @ dsol.download()) / np.linalg.norm(b) < 1e-8
+
+
+def test_coo_unsorted_is_refused(pkg, be):
+    coords = np.array([1, 0, 0, 1], np.uint32)           # row 1 before row 0
+    with pytest.raises(pkg.VclError):
+        pkg.CooMatrix(be, 2, 2, coords, np.array([1.0, 2.0]))

@@ -182,3 +182,16 @@ def test_ell_hyb_layout_and_spmv_bitexact(golden, golden_formats, orc, name):
     assert np.array_equal(orc.hyb_spmv(H, x), gf[name + "/hyb/y"])
     assert np.array_equal(orc.hyb_spmv(H, x, y0.copy(), 1.5, -0.25), gf[name + "/hyb/y_ab"])
     assert ol.rel_err(gf[name + "/hyb/y"], golden[name + "/y_assign"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["lap2d_13x11", "cd3d_9x8x7", "ragged_200x180", "ragged_97x97"])
+def test_coo_layout_and_spmv_bitexact(golden, golden_formats, orc, name):
+    """coordinate_matrix: (row, col) pairs as produced by coordinate_matrix.hpp:47-102; product bit-identical to
+    host_based/sparse_matrix_operations.hpp:1222-1247 as built (beta*y first, then fma(alpha*a, x, y) in storage order)."""
+    gf = golden_formats
+    A = load_csr(golden, name)
+    M = orc.coo_build(A)
+    assert np.array_equal(M["coords"], gf[name + "/coo/coords"]) and np.array_equal(M["elements"], gf[name + "/coo/elements"])
+    x, y0 = golden[name + "/x"], golden[name + "/y0"]
+    assert np.array_equal(orc.coo_spmv(M, x), gf[name + "/coo/y"])
+    assert np.array_equal(orc.coo_spmv(M, x, y0.copy(), 1.5, -0.25), gf[name + "/coo/y_ab"])

@@ -148,6 +148,8 @@ def lib():
     sig("ViennaCLCUDADpipelined_gmres_update_result", c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int)
     sig("ViennaCLCUDADpipelined_gmres_prod_csr", c_vp, pc, c_vp, c_vp, c_vp, c_int)
     sig("ViennaCLCUDADpipelined_gmres_prod_sell", c_vp, ps, c_vp, c_vp, c_vp, c_int)
+    sig("ViennaCLCUDAcoo2csr", c_vp, c_int, c_int, c_vp, c_vp, c_vp)
+    sig("ViennaCLCUDADcoomv", c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
     pe, ph = C.POINTER(EllStruct), C.POINTER(HybStruct)
     sig("ViennaCLCUDADellmv", c_vp, pe, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
     sig("ViennaCLCUDADhybmv", c_vp, ph, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
@@ -472,6 +474,29 @@ class HybMatrix:
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         s = self.struct()
         self.b.check(self.b.L.ViennaCLCUDADhybmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+
+
+class CooMatrix:
+    """coordinate_matrix mirror (coordinate_matrix.hpp:186-400): (row, col) pairs + elements, plus the CSR index of the same
+    entries that products and solvers run on (ViennaCLCUDAcoo2csr)."""
+
+    def __init__(self, backend, rows, cols, coords_host, elements_host):
+        self.b = backend
+        self.rows, self.cols = int(rows), int(cols)
+        self.nnz = int(len(elements_host))
+        pad = lambda a, dt, m: np.ascontiguousarray(a if a.size else np.zeros(m, dt), dtype=dt)
+        self.coords = backend.array(pad(np.asarray(coords_host), np.uint32, 2))
+        self.elements = backend.array(pad(np.asarray(elements_host), np.float64, 1))
+        rp = backend.empty(self.rows + 1, np.uint32); ci = backend.empty(max(self.nnz, 1), np.uint32)
+        backend.check(backend.L.ViennaCLCUDAcoo2csr(backend.h, self.rows, self.nnz, self.coords.ptr, rp.ptr, ci.ptr))
+        self.index = CsrMatrix(backend, self.rows, self.cols, rp, ci, self.elements)      # shares the value array
+        self.index.nnz = self.nnz
+
+    def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        i = self.index
+        blocks = i.blocks.ptr if i.blocks is not None else None
+        self.b.check(self.b.L.ViennaCLCUDADcoomv(self.b.h, i.rows, i.cols, self.nnz, i.rp.ptr, i.ci.ptr, i.va.ptr, blocks,
+                                                 i.nblocks if blocks else 0, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
 
 class SolverTag:

@@ -63,6 +63,9 @@ struct EpiFused
   // and then advances the CG scalars -- identical on every rank.  win == NULL: single-domain behaviour.
   const PeerWindow *win; unsigned long long red_seq; const double *loc_rr;
   static constexpr int NQ = 3;
+  static constexpr bool COO = false;
+  __device__ __forceinline__ double init(double) const { return 0.0; }
+  __device__ __forceinline__ double term_scale() const { return 1.0; }
 
   __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
   __device__ __forceinline__ double pre(u32 r) const { return p[r]; }

@@ -94,6 +94,9 @@ struct EpiAxpby
 {
   double *y; int off, inc; double alpha, beta;
   static constexpr int NQ = 0;
+  static constexpr bool COO = false;
+  __device__ __forceinline__ double init(double) const { return 0.0; }
+  __device__ __forceinline__ double term_scale() const { return 1.0; }
   __device__ __forceinline__ bool skip() const { return false; }
   // pre(): the epilogue's own per-row operand, requested BEFORE the row's gather chain so that its latency overlaps
   __device__ __forceinline__ double pre(u32 r) const
@@ -107,6 +110,20 @@ struct EpiAxpby
     if (beta != 0.0) y[idx] = fma(beta, y_old, __dmul_rn(alpha, dot));
     else             y[idx] = __dmul_rn(alpha, dot);
   }
+  __device__ __forceinline__ void finish(double *) {}
+};
+
+// coordinate_matrix product on the CSR index of the COO entries: y = (beta*y) + sum_k fma(alpha*a_k, x_k, .) in storage order
+struct EpiCoo
+{
+  double *y; int off, inc; double alpha, beta;
+  static constexpr int NQ = 0;
+  static constexpr bool COO = true;
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ double pre(u32 r) const { return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0; }
+  __device__ __forceinline__ double init(double y_old) const { return (beta != 0.0) ? __dmul_rn(y_old, beta) : 0.0; }
+  __device__ __forceinline__ double term_scale() const { return alpha; }
+  __device__ __forceinline__ void row(u32 r, double dot, double) { y[(size_t)r * (size_t)inc + (size_t)off] = dot; }
   __device__ __forceinline__ void finish(double *) {}
 };
 
@@ -158,10 +175,13 @@ __device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
 
 // One row, entries [j, e) of the staged block, sequential accumulation chain in storage order.  All gathers of up to 8
 // entries are issued before the first multiply-add (predicated, so a 7-point row costs ONE round trip to L2, not three).
-template<bool SPLIT>
-__device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv)
+// COO == true: coordinate_matrix semantics (host_based/sparse_matrix_operations.hpp:1233-1246): the chain starts at beta*y
+// and every term is fma(alpha*a, x, .) -- what the reference build does for that format.
+template<bool SPLIT, bool COO>
+__device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv,
+                                              double init = 0.0, double alpha = 1.0)
 {
-  double dot = 0.0;
+  double dot = COO ? init : 0.0;
   for (; j < e; j += 8)
   {
     double v[8], xx[8];
@@ -175,7 +195,7 @@ __device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_
     // empty slots hold v = x = +0.0: adding +0.0 never changes the bits of `dot` (a round-to-nearest sum that starts at
     // +0.0 cannot be -0.0), so the chain needs no predicates and stays bit-identical to the sequential reference
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dot = madd(v[k], xx[k], dot);
+    for (int k = 0; k < 8; ++k) dot = COO ? fma(__dmul_rn(alpha, v[k]), xx[k], dot) : madd(v[k], xx[k], dot);
   }
   return dot;
 }
@@ -279,7 +299,11 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
         part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
       __shared__ double s_long[32];
       block_sum<1>(part, s_long);
-      if (tid == 0) epi.row(cur.r0, part[0], epi.pre(cur.r0));
+      if (tid == 0)
+      {
+        const double pre = epi.pre(cur.r0);
+        epi.row(cur.r0, Epi::COO ? fma(epi.term_scale(), part[0], epi.init(pre)) : part[0], pre);
+      }
     }
     else
     {
@@ -299,7 +323,8 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
         for (u32 i = tid; a0 + i < cur.n1; i += CSR_BLOCK_THREADS) { wv[i] = A.va[a0 + i]; wc[i] = A.ci[a0 + i]; }
         __syncthreads();
       }
-      if ((u32)tid < nrows) epi.row(cur.r0 + tid, csr_row_dot<SPLIT>(s_val, s_col, my_s - a0, my_e - a0, xv), pre);
+      if ((u32)tid < nrows)
+        epi.row(cur.r0 + tid, csr_row_dot<SPLIT, Epi::COO>(s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale()), pre);
     }
     __syncthreads();                                       // buffer `buf` may be refilled from the next iteration on
     // ---- rotate the descriptor pipeline ----
@@ -323,11 +348,12 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
   if (epi.skip()) return;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
-    double dot = 0.0;
+    const double pre = epi.pre((u32)r);
+    double dot = Epi::COO ? epi.init(pre) : 0.0;
     const u32 e = A.rp[r + 1];
     for (u32 k = A.rp[r]; k < e; ++k)
-      dot = madd(A.va[k], xload<false>(xv, A.ci[k]), dot);
-    epi.row((u32)r, dot, epi.pre((u32)r));
+      dot = Epi::COO ? fma(__dmul_rn(epi.term_scale(), A.va[k]), xload<false>(xv, A.ci[k]), dot) : madd(A.va[k], xload<false>(xv, A.ci[k]), dot);
+    epi.row((u32)r, dot, pre);
   }
   epi.finish(s_red);
 }

@@ -13,6 +13,7 @@
 #include "viennacl/sliced_ell_matrix.hpp"
 #include "viennacl/ell_matrix.hpp"
 #include "viennacl/hyb_matrix.hpp"
+#include "viennacl/coordinate_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
@@ -149,6 +150,15 @@ int main()
     VectorT x5 = viennacl::linalg::solve(C_ell, c, t5);
     VectorT x6 = viennacl::linalg::solve(C_hyb, c, t6);
     expect(t5.iters() == t6.iters() && true_residual(C, x5, c) < 1e-7 && true_residual(C, x6, c) < 1e-7, "solve(ell_matrix / hyb_matrix, b, gmres_tag)");
+    // coordinate_matrix (iterative.cpp:126-128, 160: the tutorial copies the system into a coordinate_matrix as well)
+    std::vector< std::map<unsigned int, ScalarType> > stl_A;
+    viennacl::copy(A, stl_A);
+    viennacl::coordinate_matrix<ScalarType> A_coo;
+    viennacl::copy(stl_A, A_coo);
+    viennacl::linalg::cg_tag t7(1e-8, 1000);
+    VectorT x7 = viennacl::linalg::solve(A_coo, b, t7);
+    expect(std::abs(int(t7.iters()) - int(ref_tag.iters())) <= 2 && true_residual(A, x7, b) < 1e-7 && A_coo.nnz() == A.nnz(),
+           "solve(coordinate_matrix, b, cg_tag)");
   }
 
   std::cout << "----- solver objects: initial guess + monitor (iterative-custom.cpp) -----" << std::endl;

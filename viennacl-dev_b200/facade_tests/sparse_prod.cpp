@@ -15,6 +15,7 @@
 #include "viennacl/sliced_ell_matrix.hpp"
 #include "viennacl/ell_matrix.hpp"
 #include "viennacl/hyb_matrix.hpp"
+#include "viennacl/coordinate_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/inner_prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
@@ -179,6 +180,17 @@ int main()
   if (product_tests< viennacl::compressed_matrix<NumericT> >("compressed_matrix", epsilon, std_matrix, rhs) != EXIT_SUCCESS) return EXIT_FAILURE;
   if (product_tests< viennacl::sliced_ell_matrix<NumericT> >("sliced_ell_matrix", epsilon, std_matrix, rhs) != EXIT_SUCCESS) return EXIT_FAILURE;
   if (product_tests< viennacl::hyb_matrix<NumericT> >("hyb_matrix", epsilon, std_matrix, rhs) != EXIT_SUCCESS) return EXIT_FAILURE;
+  if (product_tests< viennacl::coordinate_matrix<NumericT> >("coordinate_matrix", epsilon, std_matrix, rhs) != EXIT_SUCCESS) return EXIT_FAILURE;
+  {
+    viennacl::coordinate_matrix<NumericT> M;
+    viennacl::copy(std_matrix, M);
+    StlMatrix back;
+    viennacl::copy(M, back);
+    bool same = back.size() == std_matrix.size();
+    for (std::size_t i = 0; same && i < n; ++i) same = back[i] == std_matrix[i];
+    if (!same) { std::cout << "# coordinate_matrix round trip differs" << std::endl; return EXIT_FAILURE; }
+    std::cout << "  ok  copy(host -> coordinate_matrix -> host) is the identity" << std::endl;
+  }
   {
     // ell_matrix stores rows * (longest row) entries: tests/src/sparse.cpp:805-828 uses the same matrix; here the 5000-entry
     // rows are dropped so that the padded storage stays small

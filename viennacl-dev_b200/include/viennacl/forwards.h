@@ -53,6 +53,7 @@ template<typename NumericT, unsigned int AlignmentV = 1> class compressed_matrix
 template<typename NumericT, typename IndexT = unsigned int> class sliced_ell_matrix;
 template<typename NumericT, unsigned int AlignmentV = 1> class ell_matrix;
 template<typename NumericT, unsigned int AlignmentV = 1> class hyb_matrix;
+template<typename NumericT, unsigned int AlignmentV = 128> class coordinate_matrix;
 
 namespace linalg
 {

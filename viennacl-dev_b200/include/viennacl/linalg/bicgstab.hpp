@@ -73,6 +73,11 @@ namespace detail
                                         viennacl::linalg::no_precond,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondNone, monitor, monitor_data); }
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(coordinate_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondNone, monitor, monitor_data); }
   template<typename NumericT, typename IndexT>
   viennacl::vector<NumericT> solve_impl(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
                                         viennacl::linalg::no_precond,

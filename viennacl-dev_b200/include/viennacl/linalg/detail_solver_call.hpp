@@ -6,6 +6,7 @@
 #include "viennacl/sliced_ell_matrix.hpp"
 #include "viennacl/ell_matrix.hpp"
 #include "viennacl/hyb_matrix.hpp"
+#include "viennacl/coordinate_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
 namespace viennacl

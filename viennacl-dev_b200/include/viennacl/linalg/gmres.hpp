@@ -80,6 +80,11 @@ namespace detail
                                         viennacl::linalg::no_precond,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_gmres(A, rhs, tag, monitor, monitor_data); }
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(coordinate_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                        viennacl::linalg::no_precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_gmres(A, rhs, tag, monitor, monitor_data); }
   template<typename NumericT, typename IndexT>
   viennacl::vector<NumericT> solve_impl(sliced_ell_matrix<NumericT, IndexT> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
                                         viennacl::linalg::no_precond,

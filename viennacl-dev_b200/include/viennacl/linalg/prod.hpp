@@ -7,6 +7,7 @@
 #include "viennacl/sliced_ell_matrix.hpp"
 #include "viennacl/ell_matrix.hpp"
 #include "viennacl/hyb_matrix.hpp"
+#include "viennacl/coordinate_matrix.hpp"
 namespace viennacl
 {
 namespace linalg
