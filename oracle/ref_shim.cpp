@@ -113,6 +113,12 @@ int run_solver(MatT const & A, int solver, int precond, csr_t const * A_csr_for_
     if (mon) s.set_monitor(mon, h);
     if (precond == 0) x = s(A, b);
     else if (precond == 2) x = s(A, b, identity_precond());
+    else if (precond == 1)
+    {
+      if (!A_csr_for_jacobi) return 2;
+      viennacl::linalg::jacobi_precond<csr_t> jac(*A_csr_for_jacobi, viennacl::linalg::jacobi_tag());
+      x = s(A, b, jac);                          // generic PCG, cg.hpp:257-322
+    }
     else return 2;
     *iters = int(s.tag().iters()); *err = s.tag().error();
     return 0;

@@ -10,6 +10,17 @@ sys.path.insert(0, os.path.dirname(HERE))
 import oracle_lib as ol  # noqa: E402
 
 
+def vardiag_matrix(o, scale):
+    """SPD test system: 2-D 5-point Laplacian 63 x 65 plus diag(scale * ((7919 r) mod 1000) / 999)."""
+    import scipy.sparse as sp
+    L = o.stencil2d(63, 65)
+    S = L.to_scipy().tocsr()
+    n = S.shape[0]
+    S = (S + sp.diags(scale * (((np.arange(n) * 7919) % 1000) / 999.0))).tocsr()
+    S.sort_indices()
+    return ol.CSR(n, n, S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data)
+
+
 def main():
     o = ol.oracle(); r = ol.ref()
     r.set_threads(1)
@@ -44,6 +55,12 @@ def main():
                 res = r.solve(solver, A, b, precond="none", fmt=fmt, tol=1e-8, maxit=1000)
                 key = "solve/%s/%s_%s" % (name, solver, fname)
                 out[key + "/iters"] = np.array([res["iters"]]); out[key + "/error"] = np.array([res["error"]]); out[key + "/x"] = res["x"]
+    # CG with the Jacobi preconditioner: the reference's generic PCG (cg.hpp:257-322) on Laplacian + varying diagonal
+    for scale in (0.5, 5.0):
+        A = vardiag_matrix(o, scale)
+        res = r.solve("cg", A, np.ones(A.rows), precond="jacobi", tol=1e-9, maxit=2000)
+        key = "solve/vd2d_63x65_s%g/cg_jacobi" % scale
+        out[key + "/iters"] = np.array([res["iters"]]); out[key + "/error"] = np.array([res["error"]]); out[key + "/x"] = res["x"]
     np.savez_compressed(os.path.join(HERE, "formats_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

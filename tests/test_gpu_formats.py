@@ -157,3 +157,27 @@ def test_coo_unsorted_is_refused(pkg, be):
     coords = np.array([1, 0, 0, 1], np.uint32)           # row 1 before row 0
     with pytest.raises(pkg.VclError):
         pkg.CooMatrix(be, 2, 2, coords, np.array([1.0, 2.0]))
+
+
+@pytest.mark.parametrize("scale", [0.5, 5.0])
+def test_cg_jacobi_fused_vs_reference_generic_pcg(pkg, be, orc, gf, scale):
+    """solve(A, b, cg_tag, jacobi_precond): fused single-reduction PCG on the device vs the reference's generic PCG
+    (cg.hpp:257-322): iteration count within +-2, same solution, same error estimate definition."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mgf", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_formats.py"))
+    mgf = importlib.util.module_from_spec(spec); spec.loader.exec_module(mgf)
+    A = mgf.vardiag_matrix(orc, scale)
+    b = np.ones(A.rows)
+    dA = pkg.CsrMatrix.from_host(be, A.rows, A.cols, A.rp, A.ci, A.v)
+    dx = be.array(np.full(A.rows, 3.0))
+    tag = pkg.SolverTag(tol=1e-9, max_iterations=2000, precond=1).solve("cg", dA, be.array(b), dx)
+    key = "solve/vd2d_63x65_s%g/cg_jacobi" % scale
+    it = int(gf[key + "/iters"][0])
+    assert abs(tag.iters - it) <= 2, (tag.iters, it)
+    xr = gf[key + "/x"]
+    x = dx.download()
+    assert np.linalg.norm(x - xr) <= 1e-6 * np.linalg.norm(xr)
+    assert tag.error < 1e-9 and np.linalg.norm(b - A.to_scipy() @ x) / np.linalg.norm(b) < 1e-7
+    # budget exhaustion reports the estimate and the iterate after exactly max_iterations updates
+    tag = pkg.SolverTag(tol=1e-30, max_iterations=5, precond=1).solve("cg", dA, be.array(b), dx)
+    assert tag.iters == 5 and tag.error > 1e-9

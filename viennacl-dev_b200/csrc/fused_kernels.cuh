@@ -29,6 +29,23 @@ __device__ __forceinline__ void cg_advance(SolverState *st)
   st->beta = (alpha * alpha * ApAp - rr) / rr;
 }
 
+// Jacobi-preconditioned CG in the single-reduction form of Chronopoulos/Gear (the recurrence the reference's pipelined CG
+// is built on, cg.hpp:116-118, extended by the preconditioner; same iterates as the classical PCG of cg.hpp:257-322 up to
+// rounding).  sums[0] = gamma = <r, u> with u = r ./ diag (written by pcg_update_kernel), delta = <w, u> with w = A u.
+// Bookkeeping as in cg.hpp:296-309: iteration counted, estimate sqrt(|gamma / gamma_0|), squared tolerances.
+__device__ __forceinline__ void pcg_advance(SolverState *st, double delta)
+{
+  const double gamma = st->sums[0];
+  st->iters += 1;
+  st->est = sqrt(fabs(gamma / st->norm_rhs_sq));
+  if (fabs(gamma / st->norm_rhs_sq) < st->tol * st->tol || fabs(gamma) < st->abs_tol * st->abs_tol) { st->done = VCL_CONVERGED; return; }
+  if (st->iters >= st->maxit) { st->done = VCL_MAXIT; return; }
+  const double beta = gamma / st->ip_rr0;                          // ip_rr0 holds the previous gamma
+  st->alpha = gamma / (delta - beta * gamma / st->alpha);
+  st->beta = beta;
+  st->ip_rr0 = gamma;
+}
+
 // bicgstab.hpp:184-199.  chunks: 0 <r,r0*>, 1 <As,As>, 2 <As,s>, 3 <Ap,r0*>, 4 <As,r0*>, 5 <s,s>
 __device__ __forceinline__ void bicgstab_advance(SolverState *st)
 {
@@ -48,7 +65,7 @@ __device__ __forceinline__ void bicgstab_advance(SolverState *st)
 // Fused SpMV epilogue:  Ap[r] = dot (optionally / diag[r]);  <Ap,Ap>, <p,Ap>, <Ap,r0*>
 // host_based/iterative_operations.hpp:58-103.  STEP selects what the last CTA does after the reduction.
 // ------------------------------------------------------------------------------------------------
-enum { STEP_NONE = 0, STEP_CG = 1, STEP_BICGSTAB = 2, STEP_PBICG_ALPHA = 3, STEP_PBICG_OMEGA = 4 };
+enum { STEP_NONE = 0, STEP_CG = 1, STEP_BICGSTAB = 2, STEP_PBICG_ALPHA = 3, STEP_PBICG_OMEGA = 4, STEP_PCG = 5 };
 
 template<int STEP, bool USE_R0, bool JACOBI>
 struct EpiFused
@@ -105,6 +122,7 @@ struct EpiFused
       if (USE_R0 && out2) *out2 = acc[2];
       if (STEP == STEP_CG) cg_advance(st);
       if (STEP == STEP_BICGSTAB) bicgstab_advance(st);
+      if (STEP == STEP_PCG) pcg_advance(st, acc[1]);
       if (STEP == STEP_PBICG_ALPHA) st->alpha = st->ip_rr0 / acc[2];                       // bicgstab.hpp:449
       if (STEP == STEP_PBICG_OMEGA) { const double nt = sqrt(acc[0]); st->omega = acc[1] / (nt * nt); }  // bicgstab.hpp:455-456
     }
@@ -164,6 +182,59 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
     // every CTA has fenced its pushes: publish the sequence number to the destinations
     if ((int)threadIdx.x < pr.n) { __threadfence_system(); st_release_sys(pr.flag[threadIdx.x], pr.seq); }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobi-PCG update: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = r ./ diag; <r,u>
+// (one pass: 7 reads + 5 writes per entry; the reference's generic PCG makes ~10 passes and 2 blocking reductions)
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(VEC_THREADS)
+pcg_update_kernel(long long n, double *x, double *r, double *u, const double *w, double *p, double *s, const double *diag,
+                  SolverState *st, double *partials, unsigned int *ticket, double *out_gamma)
+{
+  __shared__ double s_red[32];
+  if (st->done != VCL_RUNNING) return;
+  const double alpha = st->alpha, beta = st->beta;
+  double acc[1] = {0.0};
+  const long long npairs = aligned16(x, r, u, w, p, s, diag) ? (n >> 1) : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = i * 2;
+    double2 vx = ld2(x, k), vr = ld2(r, k), vu = ld2(u, k), vp = ld2(p, k), vs = ld2(s, k);
+    const double2 vw = ld2(w, k), vd = ld2(diag, k);
+    vp.x = fma(beta, vp.x, vu.x);        vp.y = fma(beta, vp.y, vu.y);
+    vs.x = fma(beta, vs.x, vw.x);        vs.y = fma(beta, vs.y, vw.y);
+    vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
+    vr.x = fma(-alpha, vs.x, vr.x);      vr.y = fma(-alpha, vs.y, vr.y);
+    vu.x = vr.x / vd.x;                  vu.y = vr.y / vd.y;
+    acc[0] = fma(vr.x, vu.x, acc[0]);    acc[0] = fma(vr.y, vu.y, acc[0]);
+    st2(p, k, vp); st2(s, k, vs); st2(x, k, vx); st2(r, k, vr); st2(u, k, vu);
+  }
+  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+  {
+    const double vp = fma(beta, p[k], u[k]), vs = fma(beta, s[k], w[k]);
+    x[k] = fma(alpha, vp, x[k]);
+    const double vr = fma(-alpha, vs, r[k]);
+    const double vu = vr / diag[k];
+    acc[0] = fma(vr, vu, acc[0]);
+    p[k] = vp; s[k] = vs; r[k] = vr; u[k] = vu;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_gamma = acc[0];
+}
+
+// u = r ./ diag; <r,u>   (set-up of the Jacobi-PCG)
+static __global__ void __launch_bounds__(VEC_THREADS)
+pcg_init_kernel(long long n, const double *r, double *u, const double *diag, double *partials, unsigned int *ticket, double *out_gamma)
+{
+  __shared__ double s_red[32];
+  double acc[1] = {0.0};
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+  {
+    const double vu = r[k] / diag[k];
+    acc[0] = fma(r[k], vu, acc[0]);
+    u[k] = vu;
+  }
+  if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_gamma = acc[0];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -87,6 +87,64 @@ ViennaCLStatus pull_state(ViennaCLBackend b)
 const int kBatch = 32;   // iterations enqueued between two looks at the device state
 
 // ------------------------------------------------------------------------------------------------
+// CG with Jacobi preconditioner: the reference runs its generic PCG (cg.hpp:257-322: SpMV + element_div + ~6 BLAS-1
+// launches + 2 blocking reductions per iteration).  Here: single-reduction (Chronopoulos/Gear) PCG, 2 kernels per
+// iteration -- pcg_update_kernel (all vector updates, u = r ./ diag, <r,u>) and the fused SpMV w = A u with <w,u>,
+// whose last CTA advances alpha/beta/convergence on the device.  12*nnz + 116*N bytes per iteration.
+// ------------------------------------------------------------------------------------------------
+ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
+  const long long n = A.rows();
+  VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
+  Carver cv(b->ws);
+  double *r = cv.take(n), *u = cv.take(n), *w = cv.take(n), *p = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
+  const int grid = vec_grid(b, n);
+
+  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(p, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(s, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  pcg_init_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, r, u, diag, b->partials, b->tickets, b->dscal + 0);
+  VCL_LAUNCHED(b, "pcg_init_kernel");
+  VCL_TRY(plain_prod(b, A, u, w));
+  VCL_TRY(vcl_dot_async(b, n, w, 0, 1, u, 0, 1, b->dscal + 1));
+  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  const double gamma0 = b->hscal[0], delta0 = b->hscal[1];
+  if (std::fabs(gamma0) <= tag->abs_tolerance * tag->abs_tolerance) return ViennaCLSuccess;       // cg.hpp:286-287
+
+  SolverState *h = b->hstate;
+  std::memset(h, 0, sizeof(SolverState));
+  h->alpha = gamma0 / delta0; h->beta = 0.0; h->ip_rr0 = gamma0; h->norm_rhs_sq = gamma0; h->norm_rhs = std::sqrt(std::fabs(gamma0));
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = gamma0;
+  VCL_TRY(push_state(b));
+  SolverState *st = b->dstate;
+
+  const int batch = tag->monitor ? 1 : kBatch;
+  int launched = 0;
+  while (launched < tag->max_iterations)
+  {
+    const int nb = std::min(batch, tag->max_iterations - launched);
+    for (int k = 0; k < nb; ++k)
+    {
+      pcg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, r, u, w, p, s, diag, st, b->partials, b->tickets, &st->sums[0]);
+      VCL_LAUNCHED(b, "pcg_update_kernel");
+      EpiFused<STEP_PCG, false, false> epi = {w, u, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
+      VCL_TRY(launch_prod(b, A, u, epi));
+    }
+    launched += nb;
+    VCL_TRY(pull_state(b));
+    if (tag->monitor && tag->monitor(x, h->est, tag->monitor_user)) break;
+    if (h->done != VCL_RUNNING) break;
+  }
+  tag->iters = h->iters;
+  tag->error = std::sqrt(std::fabs(h->sums[0] / gamma0));                            // cg.hpp:317
+  return ViennaCLSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CG  (cg.hpp:128-187)
 // ------------------------------------------------------------------------------------------------
 ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
@@ -94,12 +152,13 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, do
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
   VCL_TRY(check_matrix(b, A));
-  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: only the unpreconditioned pipelined path is provided (DESIGN.md, next rows)");
   const long long n = A.rows();
   tag->iters = 0; tag->error = 0.0;
   if (n == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, rhs && x, "null vector");
   VCL_CUDA(b, cudaSetDevice(b->device));
+  if (tag->precond == ViennaCLB200PrecondJacobi) return pcg_jacobi(b, A, rhs, x, tag);
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: unknown preconditioner id");
   VCL_TRY(vcl_ws_reserve(b, 3 * Carver::need(n)));
   Carver cv(b->ws);
   double *r = cv.take(n), *p = cv.take(n), *Ap = cv.take(n);

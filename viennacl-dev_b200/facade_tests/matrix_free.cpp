@@ -126,7 +126,8 @@ int main()
     std::cout << "  iterations: none " << plain.iters() << ", Jacobi " << jac.iters() << ", user diagonal scaling " << user.iters() << std::endl;
     expect(true_residual(A, x1, b) < 1e-8 && within(jac.iters(), REF_VARDIAG_CG_JACOBI, 2) && within(plain.iters(), REF_VARDIAG_CG, 2),
            "solve(A, b, cg_tag[, jacobi_precond]): iterations within +-2 of the reference");
-    expect(user.iters() == jac.iters() && true_residual(A, x2, b) < 1e-8, "a user preconditioner equal to Jacobi gives the same iteration count");
+    expect(within(user.iters(), REF_VARDIAG_CG_JACOBI, 0) && std::abs(int(user.iters()) - int(jac.iters())) <= 1 && true_residual(A, x2, b) < 1e-8,
+           "generic PCG with a user preconditioner equal to Jacobi: the reference's count; fused Jacobi-PCG within 1 of it");
     VectorT diff = x0 - x1;
     expect(ScalarType(viennacl::linalg::norm_2(diff)) < 1e-7 * ScalarType(viennacl::linalg::norm_2(x0)), "same solution with and without preconditioner");
     viennacl::linalg::cg_tag few(1e-6, 20);                 // iterative.cpp:222 -- cg_tag(1e-6, 20) with a preconditioner

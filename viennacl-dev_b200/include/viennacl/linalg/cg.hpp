@@ -49,9 +49,11 @@ namespace detail
   /** @brief Pipelined CG on the device (cg.hpp:128-187): compressed_matrix / sliced_ell_matrix without preconditioner */
   template<typename MatrixT, typename NumericT>
   viennacl::vector<NumericT> fused_cg(MatrixT const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
-                                      bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data)
+                                      bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data,
+                                      ViennaCLB200Precond pc = ViennaCLB200PrecondNone)
   {
     ViennaCLB200SolverTag t = to_abi(tag);
+    t.precond = pc;
     viennacl::vector<NumericT> x = run(SOLVER_CG, A, rhs, t, monitor, monitor_data);
     tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
     return x;
@@ -81,6 +83,14 @@ namespace detail
                                         viennacl::linalg::no_precond,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_cg(A, rhs, tag, monitor, monitor_data); }
+
+  /** @brief CG with the Jacobi preconditioner on a compressed_matrix: fused single-reduction PCG on the device (2 kernels per
+   *  iteration) instead of the reference's generic path (cg.hpp:257-322) */
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
+                                        jacobi_precond< compressed_matrix<NumericT, AlignmentV> > const &,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_cg(A, rhs, tag, monitor, monitor_data, ViennaCLB200PrecondJacobi); }
 
   /** @brief Preconditioned CG for ANY operator (matrix-free `apply()`) and ANY preconditioner with `apply(v)`:
    *  the reference's generic path (cg.hpp:257-322; Saad, Alg. 9.1), built from prod / inner_prod / vector expressions.
