@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FACADE = os.path.join(ROOT, "viennacl-dev_b200", "lib", "facade")
-PROGS = ["sparse_prod", "iterative", "wrap_cuda_buffer", "matrix_free"]
+PROGS = ["sparse_prod", "iterative", "wrap_cuda_buffer", "matrix_free", "matrix_market"]
 
 
 def _build():
@@ -45,3 +45,12 @@ def test_facade_program_passes_on_gpu(prog):
     print(r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "COMPLETED SUCCESSFULLY" in r.stdout
+
+
+def test_matrix_market_host_parsing(pkg):
+    """viennacl/io/matrix_market.hpp is host code: general / symmetric / pattern headers, index bases, malformed input."""
+    if not pkg.library_available():
+        pkg.build_library()
+    _build()
+    r = subprocess.run([os.path.join(FACADE, "matrix_market"), "host-only"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "COMPLETED SUCCESSFULLY" in r.stdout, r.stdout + r.stderr
