@@ -474,7 +474,9 @@ def test_solver_edge_cases(pkg, be, orc):
     assert tag.iters == ref["iters"] and np.allclose(dx.download(), ref["x"], rtol=1e-8, atol=1e-12)
     # unsupported combinations fail loudly instead of silently taking another path
     with pytest.raises(pkg.VclError):
-        pkg.SolverTag(precond=1).solve("cg", dA, db, dx)
+        pkg.SolverTag(precond=1, krylov_dim=10).solve("gmres", dA, db, dx)     # GMRES + Jacobi: facade's generic path only
+    with pytest.raises(pkg.VclError):
+        pkg.SolverTag(precond=1).solve("cg", dA.to_sell(32), db, dx)           # Jacobi needs the CSR matrix (row_info)
 
 
 def test_config1_cg_parity_1024(pkg, be, orc):

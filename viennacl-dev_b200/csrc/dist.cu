@@ -142,22 +142,6 @@ __global__ void cg_advance_kernel(SolverState *st)
   if (st->done == VCL_RUNNING) cg_advance(st);
 }
 
-ViennaCLStatus build_row_blocks_host(const std::vector<u32> &rp, int rows, std::vector<u32> &blk)
-{
-  blk.clear(); blk.push_back(0);
-  int r = 0;
-  while (r < rows)
-  {
-    const u32 start = rp[r], slack = start & 3u;
-    int e = r;
-    while (e < rows && e - r < VCL_B200_CSR_BLOCK_ROWS && (rp[e + 1] - start) + slack <= VCL_B200_CSR_BLOCK_NNZ) ++e;
-    if (e == r) e = r + 1;
-    blk.push_back((u32)e);
-    r = e;
-  }
-  return ViennaCLSuccess;
-}
-
 // halo exchange of `x` (owned entries) into A->halo_buf, on the communication stream; compute stream is not blocked
 ViennaCLStatus start_halo(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *x)
 {
@@ -521,13 +505,15 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend b, long long global_
   // ---- 5. row blocks and their interior / boundary split ----
   if (A->n > 0)
   {
-    std::vector<u32> rp((size_t)A->n + 1), blk;
-    VCL_CUDA(b, cudaMemcpyAsync(rp.data(), row_ptr, sizeof(u32) * ((size_t)A->n + 1), cudaMemcpyDeviceToHost, b->stream));
+    // the plan of the single-domain kernels (device-side for evenly filled rows), then its block list on the host
+    ViennaCLInt nb = 0;
+    VCL_TRY(ViennaCLCUDAcsr_row_blocks(b, A->n, row_ptr, nullptr, &nb));
+    A->nblk = nb;
+    VCL_CUDA(b, cudaMalloc(&A->blk, sizeof(u32) * ((size_t)nb + 1)));
+    VCL_TRY(ViennaCLCUDAcsr_row_blocks(b, A->n, row_ptr, A->blk, &nb));
+    std::vector<u32> blk((size_t)nb + 1);
+    VCL_CUDA(b, cudaMemcpyAsync(blk.data(), A->blk, sizeof(u32) * blk.size(), cudaMemcpyDeviceToHost, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
-    build_row_blocks_host(rp, A->n, blk);
-    A->nblk = (int)blk.size() - 1;
-    VCL_CUDA(b, cudaMalloc(&A->blk, sizeof(u32) * blk.size()));
-    VCL_CUDA(b, cudaMemcpyAsync(A->blk, blk.data(), sizeof(u32) * blk.size(), cudaMemcpyHostToDevice, b->stream));
     std::vector<int> flags(A->nblk, 0);
     if (W > 1 && A->n_halo > 0)
     {

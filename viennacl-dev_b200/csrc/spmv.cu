@@ -1,6 +1,7 @@
 // spmv.cu -- C-ABI entry points for CSR / SELL SpMV, row blocks, row_info and CSR->SELL conversion.
 #include "spmv_kernels.cuh"
 #include "launch.cuh"
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------
 // Row blocks (compressed_matrix.hpp:1152-1188 analogue).  Greedy over whole rows: a block closes when the next row would
@@ -25,6 +26,61 @@ static void build_row_blocks(const u32 *rp, int rows, std::vector<u32> &blk)
   }
 }
 
+// Device-side plan for matrices whose rows are short and evenly filled (every stencil / FEM matrix of the benchmarks):
+// for G = 256, 128, ..., 1 the largest number of staged entries of any ALIGNED group of G rows is one difference of two
+// row pointers per group; the largest G whose groups all fit VCL_B200_CSR_BLOCK_NNZ gives the plan blk[i] = min(i*G, rows)
+// without copying row_ptr (4 bytes per row: 537 MB at 512^3) to the host.  Anything else (a row longer than a block, or
+// groups that only fit at G < 32) takes the greedy host scan above, like the reference (compressed_matrix.hpp:1152-1188).
+__global__ void row_group_fill_kernel(int rows, const u32 * __restrict__ rp, unsigned int *max_fill /* [9] */)
+{
+  __shared__ unsigned int s_max[9];
+  if (threadIdx.x < 9) s_max[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned int loc[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
+  {
+    const u32 start = rp[r];
+#pragma unroll
+    for (int lg = 0; lg < 9; ++lg)                       // group size G = 1 << lg; row r opens a group when r % G == 0
+    {
+      const long long G = 1LL << lg;
+      if ((r & (G - 1)) == 0)
+      {
+        const long long e = min((long long)rows, r + G);
+        loc[lg] = max(loc[lg], (rp[e] - start) + (start & 3u));
+      }
+    }
+  }
+#pragma unroll
+  for (int lg = 0; lg < 9; ++lg) if (loc[lg]) atomicMax(&s_max[lg], loc[lg]);
+  __syncthreads();
+  if (threadIdx.x < 9 && s_max[threadIdx.x]) atomicMax(&max_fill[threadIdx.x], s_max[threadIdx.x]);
+}
+
+__global__ void uniform_blocks_kernel(int rows, int G, int nb, u32 *blk)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= nb; i += (long long)gridDim.x * blockDim.x)
+    blk[i] = (u32)min((long long)rows, i * G);
+}
+
+// returns the uniform group size (0: none usable)
+static ViennaCLStatus uniform_group_size(ViennaCLBackend b, int rows, const u32 *row_ptr, int *G_out)
+{
+  *G_out = 0;
+  if (getenv("VCL_B200_HOST_ROW_BLOCKS")) return ViennaCLSuccess;
+  unsigned int *d_max = reinterpret_cast<unsigned int*>(b->dscal + 44);
+  VCL_CUDA(b, cudaMemsetAsync(d_max, 0, 9 * sizeof(unsigned int), b->stream));
+  row_group_fill_kernel<<<std::max(1, std::min(vcl_div_up(rows, 256), b->sm_count * 8)), 256, 0, b->stream>>>(rows, row_ptr, d_max);
+  VCL_LAUNCHED(b, "row_group_fill_kernel");
+  unsigned int h[9];
+  VCL_CUDA(b, cudaMemcpyAsync(h, d_max, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  static_assert(VCL_B200_CSR_BLOCK_ROWS == 256, "group sizes below assume 256-row blocks");
+  for (int lg = 8; lg >= 5; --lg)
+    if (h[lg] <= (unsigned int)VCL_B200_CSR_BLOCK_NNZ) { *G_out = 1 << lg; break; }
+  return ViennaCLSuccess;
+}
+
 extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCLInt rows, const unsigned int *row_ptr,
                                                      unsigned int *row_blocks, ViennaCLInt *num_blocks)
 {
@@ -32,6 +88,20 @@ extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCL
   VCL_REQUIRE(b, rows >= 0 && num_blocks, "bad arguments");
   if (rows == 0) { *num_blocks = 0; return ViennaCLSuccess; }
   VCL_REQUIRE(b, row_ptr, "null row_ptr");
+  int G = 0;
+  VCL_TRY(uniform_group_size(b, rows, row_ptr, &G));
+  if (G > 0)
+  {
+    const int nb = vcl_div_up(rows, G);
+    if (row_blocks)
+    {
+      VCL_REQUIRE(b, *num_blocks >= nb, "row_blocks buffer too small");
+      uniform_blocks_kernel<<<std::max(1, std::min(vcl_div_up(nb + 1, 256), b->sm_count * 4)), 256, 0, b->stream>>>(rows, G, nb, row_blocks);
+      VCL_LAUNCHED(b, "uniform_blocks_kernel");
+    }
+    *num_blocks = nb;
+    return ViennaCLSuccess;
+  }
   std::vector<u32> rp((size_t)rows + 1), blk;
   VCL_CUDA(b, cudaMemcpyAsync(rp.data(), row_ptr, sizeof(u32) * ((size_t)rows + 1), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
