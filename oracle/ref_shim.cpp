@@ -39,11 +39,17 @@
 #include "viennacl/linalg/jacobi_precond.hpp"
 
 typedef unsigned int u32;
-typedef viennacl::compressed_matrix<double> csr_t;
-typedef viennacl::sliced_ell_matrix<double> sell_t;
-typedef viennacl::vector<double> vec_t;
-typedef viennacl::ell_matrix<double> ell_t;
-typedef viennacl::hyb_matrix<double> hyb_t;
+// element type: built twice, as it is (double -> libvcl_ref.so) and with -DVCLREF_F32 (float -> libvcl_ref_f32.so)
+#ifdef VCLREF_F32
+typedef float real_t;
+#else
+typedef double real_t;
+#endif
+typedef viennacl::compressed_matrix<real_t> csr_t;
+typedef viennacl::sliced_ell_matrix<real_t> sell_t;
+typedef viennacl::vector<real_t> vec_t;
+typedef viennacl::ell_matrix<real_t> ell_t;
+typedef viennacl::hyb_matrix<real_t> hyb_t;
 
 namespace {
 
@@ -52,14 +58,14 @@ namespace {
 // std::vector<std::map<>> detour.
 struct raw_csr_view
 {
-  typedef std::size_t size_type; typedef double value_type;
-  std::size_t rows_, cols_; const u32 *rp_, *ci_; const double *v_;
+  typedef std::size_t size_type; typedef real_t value_type;
+  std::size_t rows_, cols_; const u32 *rp_, *ci_; const real_t *v_;
   struct const_iterator2
   {
     const raw_csr_view *m; std::size_t row, k;
     std::size_t index1() const { return row; }
     std::size_t index2() const { return m->ci_[k]; }
-    double operator*() const { return m->v_[k]; }
+    real_t operator*() const { return m->v_[k]; }
     const_iterator2 & operator++() { ++k; return *this; }
     bool operator!=(const_iterator2 const & o) const { return k != o.k; }
     bool operator==(const_iterator2 const & o) const { return k == o.k; }
@@ -85,7 +91,7 @@ struct history
   double *buf; int cap; int len;
 };
 
-bool monitor_cb(vec_t const &, double est, void *user)
+bool monitor_cb(vec_t const &, real_t est, void *user)
 {
   history *h = static_cast<history*>(user);
   if (h->buf && h->len < h->cap) h->buf[h->len] = est;
@@ -105,7 +111,7 @@ int run_solver(MatT const & A, int solver, int precond, csr_t const * A_csr_for_
                vec_t const & b, vec_t & x, double tol, double abs_tol, int maxit, int krylov, int restart_every,
                int *iters, double *err, history *h)
 {
-  bool (*mon)(vec_t const &, double, void*) = h ? monitor_cb : NULL;
+  bool (*mon)(vec_t const &, real_t, void*) = h ? monitor_cb : NULL;
   if (solver == 0)
   {
     viennacl::linalg::cg_tag tag(tol, maxit); tag.abs_tolerance(abs_tol);
@@ -182,13 +188,13 @@ void vclref_set_threads(int n)
 
 // y[offy + i*incy] = alpha * (A x)_i + beta * y_i     (x read at offx + col*incx)
 // mode: 0 = prod_impl(A,x,alpha,y,beta); 1 = y = prod(A,x); 2 = y += prod(A,x); 3 = y -= prod(A,x); 4 = x = prod(A,x) (aliasing, result in x)
-int vclref_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const double *v,
-                    double *x, int offx, int incx, int nx,
-                    double alpha,
-                    double *y, int offy, int incy, int ny,
-                    double beta, int mode)
+int vclref_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const real_t *v,
+                    real_t *x, int offx, int incx, int nx,
+                    real_t alpha,
+                    real_t *y, int offy, int incy, int ny,
+                    real_t beta, int mode)
 {
-  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<double*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
+  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<real_t*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
   vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(nx), std::size_t(offx), std::size_t(incx));
   vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(ny), std::size_t(offy), std::size_t(incy));
   switch (mode)
@@ -204,24 +210,24 @@ int vclref_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, c
 }
 
 // Builds SELL-C (sigma = 1) from CSR through the reference's own copy(); arrays are malloc'ed here, freed by vclref_free.
-int vclref_sell_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v, int C,
-                      u32 **cols_per_block, u32 **block_start, u32 **col_idx, double **elements,
+int vclref_sell_build(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v, int C,
+                      u32 **cols_per_block, u32 **block_start, u32 **col_idx, real_t **elements,
                       int *num_blocks, long long *padded_nnz)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
   sell_t S((std::size_t(rows)), (std::size_t(cols)), (std::size_t(C)));
   viennacl::copy(view, S);
   std::size_t nb = (std::size_t(rows) - 1) / S.rows_per_block() + 1;
-  std::size_t tot = S.handle().raw_size() / sizeof(double);
+  std::size_t tot = S.handle().raw_size() / sizeof(real_t);
   *num_blocks = int(nb); *padded_nnz = (long long)tot;
   *cols_per_block = (u32*)std::malloc(sizeof(u32) * nb);
   *block_start    = (u32*)std::malloc(sizeof(u32) * nb);
   *col_idx        = (u32*)std::malloc(sizeof(u32) * (tot ? tot : 1));
-  *elements       = (double*)std::malloc(sizeof(double) * (tot ? tot : 1));
+  *elements       = (real_t*)std::malloc(sizeof(real_t) * (tot ? tot : 1));
   std::memcpy(*cols_per_block, S.handle1().ram_handle().get(), sizeof(u32) * nb);
   std::memcpy(*block_start,    S.handle3().ram_handle().get(), sizeof(u32) * nb);
   std::memcpy(*col_idx,        S.handle2().ram_handle().get(), sizeof(u32) * tot);
-  std::memcpy(*elements,       S.handle().ram_handle().get(),  sizeof(double) * tot);
+  std::memcpy(*elements,       S.handle().ram_handle().get(),  sizeof(real_t) * tot);
   return 0;
 }
 
@@ -229,8 +235,8 @@ void vclref_free(void *p) { std::free(p); }
 
 // Reference host SELL SpMV.  Refuses rows % C == 0 because the reference over-reads its block arrays
 // there (host_based/sparse_matrix_operations.hpp:1810 vs sliced_ell_matrix.hpp:154); see SURVEY 8c-2.
-int vclref_sell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v, int C,
-                     double *x, double alpha, double *y, double beta)
+int vclref_sell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v, int C,
+                     real_t *x, real_t alpha, real_t *y, real_t beta)
 {
   if (rows % C == 0) return 3;
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
@@ -245,8 +251,8 @@ int vclref_sell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const dou
 // ELL / HYB built by the reference's own copy(); arrays malloc'ed here (vclref_free).  ELL: coords/elements hold
 // internal_size1 * internal_maxnnz entries, entry j of row r at j*internal_size1 + r.  HYB: ELL part of width ell_width
 // (csr_threshold 0.8) + CSR remainder.
-int vclref_ell_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
-                     u32 **coords, double **elements, int *maxnnz, int *internal_rows)
+int vclref_ell_build(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v,
+                     u32 **coords, real_t **elements, int *maxnnz, int *internal_rows)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
   ell_t E(viennacl::context(viennacl::MAIN_MEMORY));
@@ -254,14 +260,14 @@ int vclref_ell_build(int rows, int cols, const u32 *rp, const u32 *ci, const dou
   std::size_t tot = E.internal_nnz();
   *maxnnz = int(E.internal_maxnnz()); *internal_rows = int(E.internal_size1());
   *coords = (u32*)std::malloc(sizeof(u32) * (tot ? tot : 1));
-  *elements = (double*)std::malloc(sizeof(double) * (tot ? tot : 1));
+  *elements = (real_t*)std::malloc(sizeof(real_t) * (tot ? tot : 1));
   std::memcpy(*coords, E.handle2().ram_handle().get(), sizeof(u32) * tot);
-  std::memcpy(*elements, E.handle().ram_handle().get(), sizeof(double) * tot);
+  std::memcpy(*elements, E.handle().ram_handle().get(), sizeof(real_t) * tot);
   return 0;
 }
 
-int vclref_ell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
-                    double *x, double alpha, double *y, double beta)
+int vclref_ell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v,
+                    real_t *x, real_t alpha, real_t *y, real_t beta)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
   ell_t E(viennacl::context(viennacl::MAIN_MEMORY));
@@ -272,9 +278,9 @@ int vclref_ell_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const doub
   return 0;
 }
 
-int vclref_hyb_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
-                     u32 **ell_coords, double **ell_elements, int *ell_width, int *internal_rows,
-                     u32 **csr_rows, u32 **csr_cols, double **csr_elements, int *csr_nnz)
+int vclref_hyb_build(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v,
+                     u32 **ell_coords, real_t **ell_elements, int *ell_width, int *internal_rows,
+                     u32 **csr_rows, u32 **csr_cols, real_t **csr_elements, int *csr_nnz)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
   hyb_t H(viennacl::context(viennacl::MAIN_MEMORY));
@@ -282,20 +288,20 @@ int vclref_hyb_build(int rows, int cols, const u32 *rp, const u32 *ci, const dou
   std::size_t tot = H.internal_size1() * H.internal_ellnnz();
   *ell_width = int(H.internal_ellnnz()); *internal_rows = int(H.internal_size1()); *csr_nnz = int(H.csr_nnz());
   *ell_coords = (u32*)std::malloc(sizeof(u32) * (tot ? tot : 1));
-  *ell_elements = (double*)std::malloc(sizeof(double) * (tot ? tot : 1));
+  *ell_elements = (real_t*)std::malloc(sizeof(real_t) * (tot ? tot : 1));
   *csr_rows = (u32*)std::malloc(sizeof(u32) * (std::size_t(rows) + 1));
   *csr_cols = (u32*)std::malloc(sizeof(u32) * H.csr_nnz());
-  *csr_elements = (double*)std::malloc(sizeof(double) * H.csr_nnz());
+  *csr_elements = (real_t*)std::malloc(sizeof(real_t) * H.csr_nnz());
   std::memcpy(*ell_coords, H.handle2().ram_handle().get(), sizeof(u32) * tot);
-  std::memcpy(*ell_elements, H.handle().ram_handle().get(), sizeof(double) * tot);
+  std::memcpy(*ell_elements, H.handle().ram_handle().get(), sizeof(real_t) * tot);
   std::memcpy(*csr_rows, H.handle3().ram_handle().get(), sizeof(u32) * (std::size_t(rows) + 1));
   std::memcpy(*csr_cols, H.handle4().ram_handle().get(), sizeof(u32) * H.csr_nnz());
-  std::memcpy(*csr_elements, H.handle5().ram_handle().get(), sizeof(double) * H.csr_nnz());
+  std::memcpy(*csr_elements, H.handle5().ram_handle().get(), sizeof(real_t) * H.csr_nnz());
   return 0;
 }
 
-int vclref_hyb_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
-                    double *x, double alpha, double *y, double beta)
+int vclref_hyb_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v,
+                    real_t *x, real_t alpha, real_t *y, real_t beta)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
   hyb_t H(viennacl::context(viennacl::MAIN_MEMORY));
@@ -307,25 +313,25 @@ int vclref_hyb_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const doub
 }
 
 // COO built by the reference's copy() (coordinate_matrix.hpp:47-102): coords = (row, col) pairs; product host_based/...:1222-1247
-int vclref_coo_build(int rows, int cols, const u32 *rp, const u32 *ci, const double *v, u32 **coords, double **elements, int *nnz)
+int vclref_coo_build(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v, u32 **coords, real_t **elements, int *nnz)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
-  viennacl::coordinate_matrix<double> M(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::coordinate_matrix<real_t> M(viennacl::context(viennacl::MAIN_MEMORY));
   viennacl::copy(view, M);
   std::size_t n = M.nnz();
   *nnz = int(n);
   *coords = (u32*)std::malloc(sizeof(u32) * 2 * (n ? n : 1));
-  *elements = (double*)std::malloc(sizeof(double) * (n ? n : 1));
+  *elements = (real_t*)std::malloc(sizeof(real_t) * (n ? n : 1));
   std::memcpy(*coords, M.handle12().ram_handle().get(), sizeof(u32) * 2 * n);
-  std::memcpy(*elements, M.handle().ram_handle().get(), sizeof(double) * n);
+  std::memcpy(*elements, M.handle().ram_handle().get(), sizeof(real_t) * n);
   return 0;
 }
 
-int vclref_coo_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const double *v,
-                    double *x, double alpha, double *y, double beta)
+int vclref_coo_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const real_t *v,
+                    real_t *x, real_t alpha, real_t *y, real_t beta)
 {
   raw_csr_view view = {std::size_t(rows), std::size_t(cols), rp, ci, v};
-  viennacl::coordinate_matrix<double> M(viennacl::context(viennacl::MAIN_MEMORY));
+  viennacl::coordinate_matrix<real_t> M(viennacl::context(viennacl::MAIN_MEMORY));
   viennacl::copy(view, M);
   vec_t vx(x, viennacl::MAIN_MEMORY, std::size_t(cols));
   vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
@@ -334,26 +340,26 @@ int vclref_coo_spmv(int rows, int cols, const u32 *rp, const u32 *ci, const doub
 }
 
 // diag[r] = A(r,r) (0 when absent): detail::row_info(A, vec, SPARSE_ROW_DIAGONAL)
-int vclref_csr_diag(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const double *v, double *diag)
+int vclref_csr_diag(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const real_t *v, real_t *diag)
 {
-  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<double*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
+  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<real_t*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
   vec_t d(diag, viennacl::MAIN_MEMORY, std::size_t(rows));
   viennacl::linalg::detail::row_info(A, d, viennacl::linalg::detail::SPARSE_ROW_DIAGONAL);
   return 0;
 }
 
-double vclref_norm2(const double *x, int n)
+real_t vclref_norm2(const real_t *x, int n)
 {
-  vec_t vx(const_cast<double*>(x), viennacl::MAIN_MEMORY, std::size_t(n));
-  double r = viennacl::linalg::norm_2(vx);
+  vec_t vx(const_cast<real_t*>(x), viennacl::MAIN_MEMORY, std::size_t(n));
+  real_t r = viennacl::linalg::norm_2(vx);
   return r;
 }
 
-double vclref_inner_prod(const double *x, const double *y, int n)
+real_t vclref_inner_prod(const real_t *x, const real_t *y, int n)
 {
-  vec_t vx(const_cast<double*>(x), viennacl::MAIN_MEMORY, std::size_t(n));
-  vec_t vy(const_cast<double*>(y), viennacl::MAIN_MEMORY, std::size_t(n));
-  double r = viennacl::linalg::inner_prod(vx, vy);
+  vec_t vx(const_cast<real_t*>(x), viennacl::MAIN_MEMORY, std::size_t(n));
+  vec_t vy(const_cast<real_t*>(y), viennacl::MAIN_MEMORY, std::size_t(n));
+  real_t r = viennacl::linalg::inner_prod(vx, vy);
   return r;
 }
 
@@ -361,13 +367,13 @@ double vclref_inner_prod(const double *x, const double *y, int n)
 // format: 0 CSR, 1 SELL-32 (rows % 32 != 0 required), 2 ELL, 3 HYB
 // hist (optional): monitor estimates, hist_len receives the number of monitor calls.
 int vclref_solve(int solver, int precond, int format,
-                 int rows, int nnz, const u32 *rp, const u32 *ci, const double *v,
-                 const double *b, double *x,
+                 int rows, int nnz, const u32 *rp, const u32 *ci, const real_t *v,
+                 const real_t *b, real_t *x,
                  double tol, double abs_tol, int maxit, int krylov, int restart_every,
                  int *iters, double *err, double *hist, int hist_cap, int *hist_len, double *seconds)
 {
-  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<double*>(v), viennacl::MAIN_MEMORY, rows, rows, nnz);
-  vec_t vb(const_cast<double*>(b), viennacl::MAIN_MEMORY, std::size_t(rows));
+  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<real_t*>(v), viennacl::MAIN_MEMORY, rows, rows, nnz);
+  vec_t vb(const_cast<real_t*>(b), viennacl::MAIN_MEMORY, std::size_t(rows));
   vec_t vx(std::size_t(rows), viennacl::context(viennacl::MAIN_MEMORY));
   history h = {hist, hist_cap, 0};
   history *hp = (hist_len != NULL) ? &h : NULL;
@@ -410,11 +416,11 @@ int vclref_solve(int solver, int precond, int format,
 }
 
 // Times `reps` plain y = A*x products the way examples/benchmarks/sparse.cpp:123-130 does (one warm-up first).
-double vclref_time_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const double *v,
-                            const double *x, double *y, int reps)
+double vclref_time_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const real_t *v,
+                            const real_t *x, real_t *y, int reps)
 {
-  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<double*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
-  vec_t vx(const_cast<double*>(x), viennacl::MAIN_MEMORY, std::size_t(cols));
+  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<real_t*>(v), viennacl::MAIN_MEMORY, rows, cols, nnz);
+  vec_t vx(const_cast<real_t*>(x), viennacl::MAIN_MEMORY, std::size_t(cols));
   vec_t vy(y, viennacl::MAIN_MEMORY, std::size_t(rows));
   vy = viennacl::linalg::prod(A, vx);
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();

@@ -23,7 +23,7 @@
  * All citations are relative to /root/reference.
  */
 #include "vcl_oracle.h"
-#include <math.h>
+#include <tgmath.h>   /* sqrt / fabs / fma resolve to the float versions in the -DVCLO_F32 build */
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -56,7 +56,7 @@ void vclo_set_threads(int n)
  * Upwind convection: west/south/down = -1-c, diagonal += c, east/north/up = -1.
  * Pass rp == NULL to only count the non-zeros.
  * ---------------------------------------------------------------------------------------------- */
-long long vclo_gen_stencil2d(int nx, int ny, double cx, double cy, u32 *rp, u32 *ci, double *v)
+long long vclo_gen_stencil2d(int nx, int ny, vreal cx, vreal cy, u32 *rp, u32 *ci, vreal *v)
 {
   long long k = 0;
   for (int j = 0; j < ny; ++j)
@@ -74,7 +74,7 @@ long long vclo_gen_stencil2d(int nx, int ny, double cx, double cy, u32 *rp, u32 
   return k;
 }
 
-long long vclo_gen_stencil3d(int nx, int ny, int nz, double cx, double cy, double cz, u32 *rp, u32 *ci, double *v)
+long long vclo_gen_stencil3d(int nx, int ny, int nz, vreal cx, vreal cy, vreal cz, u32 *rp, u32 *ci, vreal *v)
 {
   long long k = 0;
   long long nxy = (long long)nx * ny;
@@ -97,7 +97,7 @@ long long vclo_gen_stencil3d(int nx, int ny, int nz, double cx, double cy, doubl
 }
 
 /* Counter-based uniform numbers (splitmix64 of seed + index): reproducible in C, numpy and CUDA alike. */
-void vclo_fill_uniform(double *x, long long n, unsigned long long seed, double lo, double hi)
+void vclo_fill_uniform(vreal *x, long long n, unsigned long long seed, vreal lo, vreal hi)
 {
   for (long long i = 0; i < n; ++i)
   {
@@ -105,7 +105,7 @@ void vclo_fill_uniform(double *x, long long n, unsigned long long seed, double l
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     z = z ^ (z >> 31);
-    double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    vreal u = (vreal)(z >> 11) * (1.0 / 9007199254740992.0);
     x[i] = lo + (hi - lo) * u;
   }
 }
@@ -114,19 +114,32 @@ void vclo_fill_uniform(double *x, long long n, unsigned long long seed, double l
  * CSR SpMV: viennacl/linalg/host_based/sparse_matrix_operations.hpp:110-186.
  * In-row accumulation is sequential in storage order; beta == 0 means "do not read y".
  * ---------------------------------------------------------------------------------------------- */
-void vclo_csr_spmv(int rows, const u32 *rp, const u32 *ci, const double *v,
-                   const double *x, int offx, int incx, double alpha,
-                   double *y, int offy, int incy, double beta)
+void vclo_csr_spmv(int rows, const u32 *rp, const u32 *ci, const vreal *v,
+                   const vreal *x, int offx, int incx, vreal alpha,
+                   vreal *y, int offy, int incy, vreal beta)
 {
 #ifdef _OPENMP
   #pragma omp parallel for
 #endif
   for (long row = 0; row < (long)rows; ++row)
   {
-    double dot = 0;
+    vreal dot = 0;
     size_t row_end = rp[row + 1];
-    for (size_t i = rp[row]; i < row_end; ++i)
+    size_t i = rp[row];
+#ifdef VCLO_F32
+    /* float instantiation of the reference build (pinned empirically, tests/test_oracle.py): GCC vectorises the gather
+     * loop 4 wide with an in-order reduction -- products rounded, then added -- and contracts the scalar remainder loop
+     * (the last (row length mod 4) entries) to fmaf -- in the loop version for x stride 1 only; the strided version and the
+     * double instantiation are neither vectorised nor contracted. */
+    size_t vec_end = (incx == 1) ? i + ((row_end - i) & ~(size_t)3) : row_end;
+    for (; i < vec_end; ++i)
       dot += v[i] * x[(size_t)ci[i] * (size_t)incx + (size_t)offx];
+    for (; i < row_end; ++i)
+      dot = fma(v[i], x[(size_t)ci[i] * (size_t)incx + (size_t)offx], dot);
+#else
+    for (; i < row_end; ++i)
+      dot += v[i] * x[(size_t)ci[i] * (size_t)incx + (size_t)offx];
+#endif
     size_t idx = (size_t)row * (size_t)incy + (size_t)offy;
     if (beta < 0 || beta > 0)
       y[idx] = fma(beta, y[idx], alpha * dot);   /* the reference build fuses this one */
@@ -153,12 +166,12 @@ long long vclo_sell_padded_nnz(int rows, const u32 *rp, int C)
   return tot;
 }
 
-void vclo_sell_build(int rows, const u32 *rp, const u32 *ci, const double *v, int C,
-                     u32 *cols_per_block, u32 *block_start, u32 *col_idx, double *elements)
+void vclo_sell_build(int rows, const u32 *rp, const u32 *ci, const vreal *v, int C,
+                     u32 *cols_per_block, u32 *block_start, u32 *col_idx, vreal *elements)
 {
   long long tot = vclo_sell_padded_nnz(rows, rp, C);
   memset(col_idx, 0, sizeof(u32) * (size_t)tot);
-  memset(elements, 0, sizeof(double) * (size_t)tot);
+  memset(elements, 0, sizeof(vreal) * (size_t)tot);
   size_t off = 0;
   int b = 0;
   for (int b0 = 0; b0 < rows; b0 += C, ++b)
@@ -185,9 +198,9 @@ void vclo_sell_build(int rows, const u32 *rp, const u32 *ci, const double *v, in
 /* SELL SpMV: host_based/sparse_matrix_operations.hpp:1796-1858 (zero-valued slots never touch x).
  * Loops over the ceil(rows/C) slices that exist (the reference loops one further when rows % C == 0: SURVEY 8c-2). */
 void vclo_sell_spmv(int rows, int C, const u32 *cols_per_block, const u32 *block_start,
-                    const u32 *col_idx, const double *elements,
-                    const double *x, int offx, int incx, double alpha,
-                    double *y, int offy, int incy, double beta)
+                    const u32 *col_idx, const vreal *elements,
+                    const vreal *x, int offx, int incx, vreal alpha,
+                    vreal *y, int offy, int incy, vreal beta)
 {
   long nb = rows > 0 ? ((long)rows - 1) / C + 1 : 0;
 #ifdef _OPENMP
@@ -199,15 +212,19 @@ void vclo_sell_spmv(int rows, int C, const u32 *cols_per_block, const u32 *block
     {
       long row = b * C + rib;
       if (row >= rows) break;
-      double acc = 0;
+      vreal acc = 0;
       for (u32 j = 0; j < cols_per_block[b]; ++j)
       {
         size_t idx = (size_t)block_start[b] + (size_t)j * (size_t)C + (size_t)rib;
-        double val = elements[idx];
+        vreal val = elements[idx];
         if (val > 0 || val < 0) acc = fma(x[(size_t)col_idx[idx] * (size_t)incx + (size_t)offx], val, acc);   /* fused in the reference build */
       }
       size_t yi = (size_t)row * (size_t)incy + (size_t)offy;
+#ifdef VCLO_F32
+      if (beta < 0 || beta > 0) y[yi] = fma(alpha, acc, beta * y[yi]);   /* float instantiation of the reference build: the other product is fused */
+#else
       if (beta < 0 || beta > 0) y[yi] = fma(beta, y[yi], alpha * acc);
+#endif
       else                      y[yi] = alpha * acc;
     }
   }
@@ -225,7 +242,7 @@ void vclo_sell_spmv(int rows, int C, const u32 *cols_per_block, const u32 *block
 #ifndef ELL_FUSED
 #define ELL_FUSED 1
 #endif
-static inline double ell_madd(double x, double v, double acc)
+static inline vreal ell_madd(vreal x, vreal v, vreal acc)
 {
 #if ELL_FUSED
   return fma(x, v, acc);
@@ -241,10 +258,10 @@ int vclo_ell_width(int rows, const u32 *rp)
   return (int)w;
 }
 
-void vclo_ell_build(int rows, const u32 *rp, const u32 *ci, const double *v, int width, u32 *coords, double *elements)
+void vclo_ell_build(int rows, const u32 *rp, const u32 *ci, const vreal *v, int width, u32 *coords, vreal *elements)
 {
   memset(coords, 0, sizeof(u32) * (size_t)rows * (size_t)width);
-  memset(elements, 0, sizeof(double) * (size_t)rows * (size_t)width);
+  memset(elements, 0, sizeof(vreal) * (size_t)rows * (size_t)width);
   for (int r = 0; r < rows; ++r)
   {
     u32 j = 0;
@@ -280,8 +297,8 @@ long long vclo_hyb_tail_nnz(int rows, const u32 *rp, int width)
   return t > 0 ? t : 1;
 }
 
-void vclo_hyb_build(int rows, const u32 *rp, const u32 *ci, const double *v, int width,
-                    u32 *ell_coords, double *ell_elements, u32 *csr_rows, u32 *csr_cols, double *csr_elements)
+void vclo_hyb_build(int rows, const u32 *rp, const u32 *ci, const vreal *v, int width,
+                    u32 *ell_coords, vreal *ell_elements, u32 *csr_rows, u32 *csr_cols, vreal *csr_elements)
 {
   vclo_ell_build(rows, rp, ci, v, width, ell_coords, ell_elements);
   u32 t = 0;
@@ -294,30 +311,42 @@ void vclo_hyb_build(int rows, const u32 *rp, const u32 *ci, const double *v, int
   if (t == 0) { csr_cols[0] = 0; csr_elements[0] = 0; }
 }
 
-void vclo_hyb_spmv(int rows, int width, const u32 *ell_coords, const double *ell_elements,
-                   const u32 *csr_rows, const u32 *csr_cols, const double *csr_elements,
-                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta)
+void vclo_hyb_spmv(int rows, int width, const u32 *ell_coords, const vreal *ell_elements,
+                   const u32 *csr_rows, const u32 *csr_cols, const vreal *csr_elements,
+                   const vreal *x, int offx, int incx, vreal alpha, vreal *y, int offy, int incy, vreal beta)
 {
   for (int r = 0; r < rows; ++r)
   {
-    double sum = 0;
+    vreal sum = 0;
     for (int j = 0; j < width; ++j)
     {
       size_t idx = (size_t)j * (size_t)rows + (size_t)r;
-      double val = ell_elements[idx];
+      vreal val = ell_elements[idx];
       if (val > 0 || val < 0) sum = ell_madd(x[(size_t)ell_coords[idx] * (size_t)incx + (size_t)offx], val, sum);
     }
     if (csr_rows)
-      for (u32 k = csr_rows[r]; k < csr_rows[r + 1]; ++k)
+    {
+      u32 k = csr_rows[r], k1 = csr_rows[r + 1];
+#ifdef VCLO_F32
+      /* float instantiation: vectorised 4 wide (rounded products, in-order adds) + contracted scalar remainder, like vclo_csr_spmv */
+      u32 kv = (incx == 1) ? k + ((k1 - k) & ~3u) : k1;
+      for (; k < kv; ++k)
+        sum = sum + x[(size_t)csr_cols[k] * (size_t)incx + (size_t)offx] * csr_elements[k];
+      for (; k < k1; ++k)
+        sum = fma(x[(size_t)csr_cols[k] * (size_t)incx + (size_t)offx], csr_elements[k], sum);
+#else
+      for (; k < k1; ++k)
         sum = sum + x[(size_t)csr_cols[k] * (size_t)incx + (size_t)offx] * csr_elements[k];   /* tail: NOT contracted in the reference build */
+#endif
+    }
     size_t yi = (size_t)r * (size_t)incy + (size_t)offy;
     if (beta < 0 || beta > 0) y[yi] = fma(beta, y[yi], alpha * sum);
     else                      y[yi] = alpha * sum;
   }
 }
 
-void vclo_ell_spmv(int rows, int width, const u32 *coords, const double *elements,
-                   const double *x, int offx, int incx, double alpha, double *y, int offy, int incy, double beta)
+void vclo_ell_spmv(int rows, int width, const u32 *coords, const vreal *elements,
+                   const vreal *x, int offx, int incx, vreal alpha, vreal *y, int offy, int incy, vreal beta)
 {
   vclo_hyb_spmv(rows, width, coords, elements, NULL, NULL, NULL, x, offx, incx, alpha, y, offy, incy, beta);
 }
@@ -327,14 +356,14 @@ void vclo_ell_spmv(int rows, int width, const u32 *coords, const double *element
 #ifndef COO_FUSED
 #define COO_FUSED 1
 #endif
-void vclo_coo_spmv(int rows, long long nnz, const u32 *coords, const double *elements,
-                   const double *x, double alpha, double *y, double beta)
+void vclo_coo_spmv(int rows, long long nnz, const u32 *coords, const vreal *elements,
+                   const vreal *x, vreal alpha, vreal *y, vreal beta)
 {
   if (beta < 0 || beta > 0) for (int i = 0; i < rows; ++i) y[i] *= beta;
   else                      for (int i = 0; i < rows; ++i) y[i] = 0;
   for (long long i = 0; i < nnz; ++i)
   {
-    double t = alpha * elements[i];
+    vreal t = alpha * elements[i];
 #if COO_FUSED
     y[coords[2 * i]] = fma(t, x[coords[2 * i + 1]], y[coords[2 * i]]);
 #else
@@ -344,11 +373,11 @@ void vclo_coo_spmv(int rows, long long nnz, const u32 *coords, const double *ele
 }
 
 /* detail::row_info(A, vec, SPARSE_ROW_DIAGONAL): host_based/sparse_matrix_operations.hpp:52-98 (0 if absent). */
-void vclo_csr_diag(int rows, const u32 *rp, const u32 *ci, const double *v, double *diag)
+void vclo_csr_diag(int rows, const u32 *rp, const u32 *ci, const vreal *v, vreal *diag)
 {
   for (int r = 0; r < rows; ++r)
   {
-    double val = 0;
+    vreal val = 0;
     for (u32 k = rp[r]; k < rp[r + 1]; ++k)
       if (ci[k] == (u32)r) { val = v[k]; break; }
     diag[r] = val;
@@ -356,18 +385,18 @@ void vclo_csr_diag(int rows, const u32 *rp, const u32 *ci, const double *v, doub
 }
 
 /* norm_2 / inner_prod: host_based/vector_operations.hpp:557-576, 463-472 -- plain sums, no scaling. */
-double vclo_norm2(const double *x, long long n)
+vreal vclo_norm2(const vreal *x, long long n)
 {
-  double s = 0;
+  vreal s = 0;
 #ifdef _OPENMP
   #pragma omp parallel for reduction(+: s) if (n > 5000)
 #endif
   for (long long i = 0; i < n; ++i) s += x[i] * x[i];
   return sqrt(s);
 }
-double vclo_inner_prod(const double *x, const double *y, long long n)
+vreal vclo_inner_prod(const vreal *x, const vreal *y, long long n)
 {
-  double s = 0;
+  vreal s = 0;
 #ifdef _OPENMP
   #pragma omp parallel for reduction(+: s) if (n > 5000)
 #endif
@@ -376,18 +405,18 @@ double vclo_inner_prod(const double *x, const double *y, long long n)
 }
 
 /* Fused SpMV + dots: host_based/iterative_operations.hpp:58-103 (pipelined_prod_impl, CSR). */
-static void fused_prod(int rows, const u32 *rp, const u32 *ci, const double *v,
-                       const double *p, double *Ap, const double *r0star,
-                       double *ApAp, double *pAp, double *Apr0)
+static void fused_prod(int rows, const u32 *rp, const u32 *ci, const vreal *v,
+                       const vreal *p, vreal *Ap, const vreal *r0star,
+                       vreal *ApAp, vreal *pAp, vreal *Apr0)
 {
-  double s_ApAp = 0, s_pAp = 0, s_Apr0 = 0;
+  vreal s_ApAp = 0, s_pAp = 0, s_Apr0 = 0;
 #ifdef _OPENMP
   #pragma omp parallel for reduction(+: s_ApAp, s_pAp, s_Apr0)
 #endif
   for (long row = 0; row < (long)rows; ++row)
   {
-    double dot = 0;
-    double pd = p[row];
+    vreal dot = 0;
+    vreal pd = p[row];
     size_t row_end = rp[row + 1];
     for (size_t i = rp[row]; i < row_end; ++i)
       dot += v[i] * p[ci[i]];
@@ -406,37 +435,37 @@ static void fused_prod(int rows, const u32 *rp, const u32 *ci, const double *v,
  * Pipelined CG (Chronopoulos/Gear): viennacl/linalg/cg.hpp:128-187 with
  * host_based/iterative_operations.hpp:378-418 (vector update) and :58-103 (SpMV + dots).
  * ---------------------------------------------------------------------------------------------- */
-int vclo_cg(int rows, const u32 *rp, const u32 *ci, const double *v,
-            const double *b, double *x, double tol, double abs_tol, int maxit,
+int vclo_cg(int rows, const u32 *rp, const u32 *ci, const vreal *v,
+            const vreal *b, vreal *x, double tol, double abs_tol, int maxit,
             int *iters, double *err, double *hist, int hist_cap, int *hist_len)
 {
   size_t n = (size_t)rows;
-  double *r = (double*)malloc(sizeof(double) * n), *p = (double*)malloc(sizeof(double) * n), *Ap = (double*)malloc(sizeof(double) * n);
+  vreal *r = (vreal*)malloc(sizeof(vreal) * n), *p = (vreal*)malloc(sizeof(vreal) * n), *Ap = (vreal*)malloc(sizeof(vreal) * n);
   if (hist_len) *hist_len = 0;
-  memset(x, 0, sizeof(double) * n);
-  memcpy(r, b, sizeof(double) * n);
-  memcpy(p, b, sizeof(double) * n);
+  memset(x, 0, sizeof(vreal) * n);
+  memcpy(r, b, sizeof(vreal) * n);
+  memcpy(p, b, sizeof(vreal) * n);
   vclo_csr_spmv(rows, rp, ci, v, p, 0, 1, 1.0, Ap, 0, 1, 0.0);
 
-  double norm_rhs_squared = vclo_norm2(r, rows); norm_rhs_squared *= norm_rhs_squared;
+  vreal norm_rhs_squared = vclo_norm2(r, rows); norm_rhs_squared *= norm_rhs_squared;
   *iters = 0; *err = 0;
   if (norm_rhs_squared <= abs_tol * abs_tol) { free(r); free(p); free(Ap); return 0; }
 
-  double rr = norm_rhs_squared;
-  double alpha = rr / vclo_inner_prod(p, Ap, rows);
-  double beta = vclo_norm2(Ap, rows); beta = (alpha * alpha * beta * beta - rr) / rr;
-  double ApAp = 0, pAp = 0;
+  vreal rr = norm_rhs_squared;
+  vreal alpha = rr / vclo_inner_prod(p, Ap, rows);
+  vreal beta = vclo_norm2(Ap, rows); beta = (alpha * alpha * beta * beta - rr) / rr;
+  vreal ApAp = 0, pAp = 0;
 
   for (int i = 0; i < maxit; ++i)
   {
     *iters = i + 1;
-    double s_rr = 0;
+    vreal s_rr = 0;
 #ifdef _OPENMP
     #pragma omp parallel for reduction(+: s_rr)
 #endif
     for (long k = 0; k < (long)rows; ++k)
     {
-      double vp = p[k], vr = r[k];
+      vreal vp = p[k], vr = r[k];
       x[k] += alpha * vp;
       vr -= alpha * Ap[k];
       vp = vr + beta * vp;
@@ -462,22 +491,22 @@ int vclo_cg(int rows, const u32 *rp, const u32 *ci, const double *v,
  * NB (reference behaviour, kept): on convergence the loop breaks BEFORE the final vector update, so the returned
  * x is the iterate of the previous step while tag.error() describes the new residual.
  * ---------------------------------------------------------------------------------------------- */
-int vclo_bicgstab(int rows, const u32 *rp, const u32 *ci, const double *v,
-                  const double *b, double *x, double tol, double abs_tol, int maxit,
+int vclo_bicgstab(int rows, const u32 *rp, const u32 *ci, const vreal *v,
+                  const vreal *b, vreal *x, double tol, double abs_tol, int maxit,
                   int *iters, double *err, double *hist, int hist_cap, int *hist_len)
 {
   size_t n = (size_t)rows;
-  double *r = (double*)malloc(sizeof(double) * n), *p = (double*)malloc(sizeof(double) * n), *r0 = (double*)malloc(sizeof(double) * n);
-  double *Ap = (double*)malloc(sizeof(double) * n), *s = (double*)malloc(sizeof(double) * n), *As = (double*)malloc(sizeof(double) * n);
+  vreal *r = (vreal*)malloc(sizeof(vreal) * n), *p = (vreal*)malloc(sizeof(vreal) * n), *r0 = (vreal*)malloc(sizeof(vreal) * n);
+  vreal *Ap = (vreal*)malloc(sizeof(vreal) * n), *s = (vreal*)malloc(sizeof(vreal) * n), *As = (vreal*)malloc(sizeof(vreal) * n);
   if (hist_len) *hist_len = 0;
-  memset(x, 0, sizeof(double) * n);
-  memcpy(r, b, sizeof(double) * n); memcpy(p, b, sizeof(double) * n); memcpy(r0, b, sizeof(double) * n);
-  memcpy(Ap, b, sizeof(double) * n); memcpy(s, b, sizeof(double) * n); memcpy(As, b, sizeof(double) * n);
+  memset(x, 0, sizeof(vreal) * n);
+  memcpy(r, b, sizeof(vreal) * n); memcpy(p, b, sizeof(vreal) * n); memcpy(r0, b, sizeof(vreal) * n);
+  memcpy(Ap, b, sizeof(vreal) * n); memcpy(s, b, sizeof(vreal) * n); memcpy(As, b, sizeof(vreal) * n);
 
-  double norm_rhs = vclo_norm2(r, rows);
-  double residual_norm = norm_rhs;
-  double r_dot_r0 = norm_rhs * norm_rhs;            /* inner_prod_buffer[0] = ||b||^2 (bicgstab.hpp:131) */
-  double As_As = 0, As_s = 0, Ap_r0 = 0, As_r0 = 0, s_s = 0, dummy1, dummy2;
+  vreal norm_rhs = vclo_norm2(r, rows);
+  vreal residual_norm = norm_rhs;
+  vreal r_dot_r0 = norm_rhs * norm_rhs;            /* inner_prod_buffer[0] = ||b||^2 (bicgstab.hpp:131) */
+  vreal As_As = 0, As_s = 0, Ap_r0 = 0, As_r0 = 0, s_s = 0, dummy1, dummy2;
   *iters = 0; *err = 0;
   if (norm_rhs <= abs_tol) goto done;
 
@@ -487,14 +516,14 @@ int vclo_bicgstab(int rows, const u32 *rp, const u32 *ci, const double *v,
     fused_prod(rows, rp, ci, v, p, Ap, r0, &dummy1, &dummy2, &Ap_r0);
 
     /* update_s: alpha on "device" from chunks 0 and 3 */
-    double alpha = r_dot_r0 / Ap_r0;
-    double t_ss = 0;
+    vreal alpha = r_dot_r0 / Ap_r0;
+    vreal t_ss = 0;
 #ifdef _OPENMP
     #pragma omp parallel for reduction(+: t_ss)
 #endif
     for (long k = 0; k < (long)rows; ++k)
     {
-      double vs = r[k] - alpha * Ap[k];
+      vreal vs = r[k] - alpha * Ap[k];
       t_ss += vs * vs;
       s[k] = vs;
     }
@@ -503,20 +532,20 @@ int vclo_bicgstab(int rows, const u32 *rp, const u32 *ci, const double *v,
     fused_prod(rows, rp, ci, v, s, As, r0, &As_As, &As_s, &As_r0);
 
     alpha = r_dot_r0 / Ap_r0;
-    double beta = -As_r0 / Ap_r0;
-    double omega = As_s / As_As;
+    vreal beta = -As_r0 / Ap_r0;
+    vreal omega = As_s / As_As;
 
     residual_norm = sqrt(s_s - 2.0 * omega * As_s + omega * omega * As_As);
     HIST_PUSH(fabs(residual_norm / norm_rhs));
     if (fabs(residual_norm / norm_rhs) < tol || residual_norm < abs_tol) break;
 
-    double t_rr0 = 0;
+    vreal t_rr0 = 0;
 #ifdef _OPENMP
     #pragma omp parallel for reduction(+: t_rr0)
 #endif
     for (long k = 0; k < (long)rows; ++k)
     {
-      double vx = x[k], vp = p[k], vs = s[k], vr, vAs = As[k], vAp = Ap[k];
+      vreal vx = x[k], vp = p[k], vs = s[k], vr, vAs = As[k], vAp = Ap[k];
       vx += alpha * vp + omega * vs;
       vr  = vs - omega * vAs;
       vp  = vr + beta * (vp - omega * vAp);
@@ -535,7 +564,7 @@ done:
  * Preconditioned (left) BiCGStab, generic path: viennacl/linalg/bicgstab.hpp:398-489;
  * Jacobi: jacobi_precond.hpp:103-130 (vec = element_div(vec, diag)).
  * ---------------------------------------------------------------------------------------------- */
-static void apply_precond(int precond, const double *diag, double *vec, int rows)
+static void apply_precond(int precond, const vreal *diag, vreal *vec, int rows)
 {
   if (precond != 1) return;
 #ifdef _OPENMP
@@ -544,22 +573,22 @@ static void apply_precond(int precond, const double *diag, double *vec, int rows
   for (long k = 0; k < (long)rows; ++k) vec[k] = vec[k] / diag[k];
 }
 
-int vclo_bicgstab_precond(int rows, const u32 *rp, const u32 *ci, const double *v, int precond,
-                          const double *b, double *x, double tol, double abs_tol, int maxit, int restart_every,
+int vclo_bicgstab_precond(int rows, const u32 *rp, const u32 *ci, const vreal *v, int precond,
+                          const vreal *b, vreal *x, double tol, double abs_tol, int maxit, int restart_every,
                           int *iters, double *err, double *hist, int hist_cap, int *hist_len)
 {
   size_t n = (size_t)rows;
-  double *r = (double*)malloc(sizeof(double) * n), *p = (double*)malloc(sizeof(double) * n), *r0 = (double*)malloc(sizeof(double) * n);
-  double *t0 = (double*)malloc(sizeof(double) * n), *t1 = (double*)malloc(sizeof(double) * n), *s = (double*)malloc(sizeof(double) * n);
-  double *diag = (double*)malloc(sizeof(double) * n);
+  vreal *r = (vreal*)malloc(sizeof(vreal) * n), *p = (vreal*)malloc(sizeof(vreal) * n), *r0 = (vreal*)malloc(sizeof(vreal) * n);
+  vreal *t0 = (vreal*)malloc(sizeof(vreal) * n), *t1 = (vreal*)malloc(sizeof(vreal) * n), *s = (vreal*)malloc(sizeof(vreal) * n);
+  vreal *diag = (vreal*)malloc(sizeof(vreal) * n);
   if (hist_len) *hist_len = 0;
   vclo_csr_diag(rows, rp, ci, v, diag);
-  memset(x, 0, sizeof(double) * n);
-  memcpy(r, b, sizeof(double) * n); memcpy(p, b, sizeof(double) * n); memcpy(r0, b, sizeof(double) * n);
+  memset(x, 0, sizeof(vreal) * n);
+  memcpy(r, b, sizeof(vreal) * n); memcpy(p, b, sizeof(vreal) * n); memcpy(r0, b, sizeof(vreal) * n);
 
-  double ip_rr0 = vclo_norm2(r, rows);
-  double norm_rhs = vclo_norm2(r, rows);
-  double residual_norm = norm_rhs, new_ip_rr0 = 0;
+  vreal ip_rr0 = vclo_norm2(r, rows);
+  vreal norm_rhs = vclo_norm2(r, rows);
+  vreal residual_norm = norm_rhs, new_ip_rr0 = 0;
   *iters = 0; *err = 0;
   if (norm_rhs <= abs_tol) goto done;
   {
@@ -572,20 +601,20 @@ int vclo_bicgstab_precond(int rows, const u32 *rp, const u32 *ci, const double *
         vclo_csr_spmv(rows, rp, ci, v, x, 0, 1, 1.0, r, 0, 1, 0.0);
         for (size_t k = 0; k < n; ++k) r[k] = b[k] - r[k];
         apply_precond(precond, diag, r, rows);
-        memcpy(p, r, sizeof(double) * n); memcpy(r0, r, sizeof(double) * n);
+        memcpy(p, r, sizeof(vreal) * n); memcpy(r0, r, sizeof(vreal) * n);
         ip_rr0 = vclo_norm2(r, rows); ip_rr0 *= ip_rr0;
         restart_flag = 0; last_restart = i;
       }
       *iters = (int)(i + 1);
       vclo_csr_spmv(rows, rp, ci, v, p, 0, 1, 1.0, t0, 0, 1, 0.0);
       apply_precond(precond, diag, t0, rows);
-      double alpha = ip_rr0 / vclo_inner_prod(t0, r0, rows);
+      vreal alpha = ip_rr0 / vclo_inner_prod(t0, r0, rows);
       for (size_t k = 0; k < n; ++k) s[k] = r[k] - alpha * t0[k];
 
       vclo_csr_spmv(rows, rp, ci, v, s, 0, 1, 1.0, t1, 0, 1, 0.0);
       apply_precond(precond, diag, t1, rows);
-      double norm_t1 = vclo_norm2(t1, rows);
-      double omega = vclo_inner_prod(t1, s, rows) / (norm_t1 * norm_t1);
+      vreal norm_t1 = vclo_norm2(t1, rows);
+      vreal omega = vclo_inner_prod(t1, s, rows) / (norm_t1 * norm_t1);
 
       for (size_t k = 0; k < n; ++k) x[k] += alpha * p[k] + omega * s[k];
       for (size_t k = 0; k < n; ++k) r[k] = s[k] - omega * t1[k];
@@ -595,7 +624,7 @@ int vclo_bicgstab_precond(int rows, const u32 *rp, const u32 *ci, const double *
       if (residual_norm / norm_rhs < tol || residual_norm < abs_tol) break;
 
       new_ip_rr0 = vclo_inner_prod(r, r0, rows);
-      double beta = new_ip_rr0 / ip_rr0 * alpha / omega;
+      vreal beta = new_ip_rr0 / ip_rr0 * alpha / omega;
       ip_rr0 = new_ip_rr0;
 
       if ((ip_rr0 >= 0 && ip_rr0 <= 0) || (omega >= 0 && omega <= 0) || i - last_restart > restart_every)
@@ -616,24 +645,24 @@ done:
  * semantics of cuda/iterative_operations.hpp:1597-1894 (== host_based/iterative_operations.hpp:733-937 minus the
  * dropped-tail defect at :820-822).  Basis vector k lives at k*internal_size (size padded to 128, gmres.hpp:192).
  * ---------------------------------------------------------------------------------------------- */
-int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const double *v,
-               const double *b, double *x, double tol, double abs_tol, int maxit, int krylov,
+int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const vreal *v,
+               const vreal *b, vreal *x, double tol, double abs_tol, int maxit, int krylov,
                int *iters, double *err, double *hist, int hist_cap, int *hist_len)
 {
   size_t n = (size_t)rows;
   size_t isz = (n + 127) / 128 * 128;
   size_t m = (size_t)krylov;
-  double *res = (double*)malloc(sizeof(double) * n);
-  double *V = (double*)calloc(isz * m, sizeof(double));
-  double *R = (double*)calloc(m * m, sizeof(double));
-  double *xi = (double*)calloc(m, sizeof(double)), *eta = (double*)calloc(m, sizeof(double)), *coef = (double*)calloc(m, sizeof(double));
-  double *h = (double*)calloc(m, sizeof(double));
+  vreal *res = (vreal*)malloc(sizeof(vreal) * n);
+  vreal *V = (vreal*)calloc(isz * m, sizeof(vreal));
+  vreal *R = (vreal*)calloc(m * m, sizeof(vreal));
+  vreal *xi = (vreal*)calloc(m, sizeof(vreal)), *eta = (vreal*)calloc(m, sizeof(vreal)), *coef = (vreal*)calloc(m, sizeof(vreal));
+  vreal *h = (vreal*)calloc(m, sizeof(vreal));
   if (hist_len) *hist_len = 0;
-  memset(x, 0, sizeof(double) * n);
-  memcpy(res, b, sizeof(double) * n);
+  memset(x, 0, sizeof(vreal) * n);
+  memcpy(res, b, sizeof(vreal) * n);
 
-  double norm_rhs = vclo_norm2(res, rows);
-  double rho_0 = norm_rhs, rho = 1.0;
+  vreal norm_rhs = vclo_norm2(res, rows);
+  vreal rho_0 = norm_rhs, rho = 1.0;
   *iters = 0; *err = 0;
 
   unsigned max_restarts = (unsigned)maxit / (unsigned)krylov;                  /* gmres.hpp:74-80 */
@@ -655,23 +684,23 @@ int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const double *v,
     size_t k;
     for (k = 0; k < m; ++k)
     {
-      double *vk = V + k * isz;
-      const double *src = (k == 0) ? res : V + (k - 1) * isz;
-      double ApAp, pAp;
+      vreal *vk = V + k * isz;
+      const vreal *src = (k == 0) ? res : V + (k - 1) * isz;
+      vreal ApAp, pAp;
       fused_prod(rows, rp, ci, v, src, vk, NULL, &ApAp, &pAp, NULL);   /* chunk 1 <- <v_k,v_k> */
-      double norm_sq = ApAp;
+      vreal norm_sq = ApAp;
       if (k > 0)
       {
         /* stage 1: h_j = <v_j, v_k>, j < k */
         for (size_t j = 0; j < k; ++j) h[j] = vclo_inner_prod(V + j * isz, vk, rows);
         /* stage 2: v_k -= sum h_j v_j ; R[j + k*m] = h_j ; ||v_k||^2 */
-        double nsq = 0;
+        vreal nsq = 0;
 #ifdef _OPENMP
         #pragma omp parallel for reduction(+: nsq)
 #endif
         for (long i = 0; i < (long)rows; ++i)
         {
-          double val = vk[i];
+          vreal val = vk[i];
           for (size_t j = 0; j < k; ++j) val -= h[j] * V[(size_t)i + j * isz];
           nsq += val * val;
           vk[i] = val;
@@ -680,15 +709,15 @@ int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const double *v,
         norm_sq = nsq;
       }
       /* normalize: R[k + k*m] = ||v_k||, v_k /= ||v_k||, xi_k = <r, v_k> */
-      double nrm = sqrt(norm_sq);
+      vreal nrm = sqrt(norm_sq);
       R[k + k * m] = nrm;
-      double rv = 0;
+      vreal rv = 0;
 #ifdef _OPENMP
       #pragma omp parallel for reduction(+: rv)
 #endif
       for (long i = 0; i < (long)rows; ++i)
       {
-        double val = vk[i] / nrm;
+        vreal val = vk[i] / nrm;
         rv += res[i] * val;
         vk[i] = val;
       }
@@ -707,7 +736,7 @@ int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const double *v,
       rho *= sin(acos(xi[i] / rho));
     }
 
-    memcpy(eta, xi, sizeof(double) * m);
+    memcpy(eta, xi, sizeof(vreal) * m);
     for (long i2 = (long)k - 1; i2 > -1; --i2)
     {
       size_t i = (size_t)i2;
@@ -723,7 +752,7 @@ int vclo_gmres(int rows, const u32 *rp, const u32 *ci, const double *v,
 #endif
     for (long i = 0; i < (long)rows; ++i)
     {
-      double val = x[i];
+      vreal val = x[i];
       val += coef[0] * res[i];
       for (size_t j = 1; j < k; ++j) val += coef[j] * V[(size_t)i + (j - 1) * isz];
       x[i] = val;

@@ -34,12 +34,15 @@ def build(force=False):
 class CSR:
     """Host CSR triple with the reference's array layout (u32 row_ptr[rows+1], u32 col[nnz], f64 val[nnz])."""
 
-    def __init__(self, rows, cols, rp, ci, v):
+    def __init__(self, rows, cols, rp, ci, v, dtype=np.float64):
         self.rows, self.cols = int(rows), int(cols)
         self.rp = np.ascontiguousarray(rp, dtype=np.uint32)
         self.ci = np.ascontiguousarray(ci, dtype=np.uint32)
-        self.v = np.ascontiguousarray(v, dtype=np.float64)
+        self.v = np.ascontiguousarray(v, dtype=dtype)
         self.nnz = int(self.rp[-1]) if self.rp.size else 0
+
+    def astype(self, dtype):
+        return CSR(self.rows, self.cols, self.rp, self.ci, self.v.astype(dtype), dtype)
 
     def to_scipy(self):
         import scipy.sparse as sp
@@ -47,40 +50,44 @@ class CSR:
 
 
 class _Oracle:
-    def __init__(self):
+    def __init__(self, dtype=np.float64):
         build()
-        self.lib = lib = C.CDLL(os.path.join(ORACLE_DIR, "libvcl_oracle.so"))
+        self.dt = np.dtype(dtype).type
+        single = self.dt is np.float32
+        fp = np.ctypeslib.ndpointer(dtype=self.dt, flags="C_CONTIGUOUS")
+        cr = C.c_float if single else C.c_double        # vreal scalars; tolerances / error / history stay double
+        self.lib = lib = C.CDLL(os.path.join(ORACLE_DIR, "libvcl_oracle_f32.so" if single else "libvcl_oracle.so"))
         lib.vclo_gen_stencil2d.restype = c_ll
-        lib.vclo_gen_stencil2d.argtypes = [c_int, c_int, c_dbl, c_dbl, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vclo_gen_stencil2d.argtypes = [c_int, c_int, cr, cr, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.vclo_gen_stencil3d.restype = c_ll
-        lib.vclo_gen_stencil3d.argtypes = [c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.vclo_fill_uniform.argtypes = [f64p, c_ll, C.c_ulonglong, c_dbl, c_dbl]
-        lib.vclo_csr_spmv.argtypes = [c_int, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
+        lib.vclo_gen_stencil3d.argtypes = [c_int, c_int, c_int, cr, cr, cr, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.vclo_fill_uniform.argtypes = [fp, c_ll, C.c_ulonglong, cr, cr]
+        lib.vclo_csr_spmv.argtypes = [c_int, u32p, u32p, fp, fp, c_int, c_int, cr, fp, c_int, c_int, cr]
         lib.vclo_sell_padded_nnz.restype = c_ll
         lib.vclo_sell_padded_nnz.argtypes = [c_int, u32p, c_int]
-        lib.vclo_sell_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, u32p, u32p, f64p]
-        lib.vclo_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
-        lib.vclo_csr_diag.argtypes = [c_int, u32p, u32p, f64p, f64p]
+        lib.vclo_sell_build.argtypes = [c_int, u32p, u32p, fp, c_int, u32p, u32p, u32p, fp]
+        lib.vclo_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, u32p, fp, fp, c_int, c_int, cr, fp, c_int, c_int, cr]
+        lib.vclo_csr_diag.argtypes = [c_int, u32p, u32p, fp, fp]
         lib.vclo_ell_width.restype = c_int
         lib.vclo_ell_width.argtypes = [c_int, u32p]
-        lib.vclo_ell_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, f64p]
-        lib.vclo_ell_spmv.argtypes = [c_int, c_int, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
+        lib.vclo_ell_build.argtypes = [c_int, u32p, u32p, fp, c_int, u32p, fp]
+        lib.vclo_ell_spmv.argtypes = [c_int, c_int, u32p, fp, fp, c_int, c_int, cr, fp, c_int, c_int, cr]
         lib.vclo_hyb_width.restype = c_int
         lib.vclo_hyb_width.argtypes = [c_int, c_int, u32p, c_dbl]
         lib.vclo_hyb_tail_nnz.restype = c_ll
         lib.vclo_hyb_tail_nnz.argtypes = [c_int, u32p, c_int]
-        lib.vclo_hyb_build.argtypes = [c_int, u32p, u32p, f64p, c_int, u32p, f64p, u32p, u32p, f64p]
-        lib.vclo_hyb_spmv.argtypes = [c_int, c_int, u32p, f64p, u32p, u32p, f64p, f64p, c_int, c_int, c_dbl, f64p, c_int, c_int, c_dbl]
-        lib.vclo_coo_spmv.argtypes = [c_int, c_ll, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
-        lib.vclo_norm2.restype = c_dbl
-        lib.vclo_norm2.argtypes = [f64p, c_ll]
-        lib.vclo_inner_prod.restype = c_dbl
-        lib.vclo_inner_prod.argtypes = [f64p, f64p, c_ll]
+        lib.vclo_hyb_build.argtypes = [c_int, u32p, u32p, fp, c_int, u32p, fp, u32p, u32p, fp]
+        lib.vclo_hyb_spmv.argtypes = [c_int, c_int, u32p, fp, u32p, u32p, fp, fp, c_int, c_int, cr, fp, c_int, c_int, cr]
+        lib.vclo_coo_spmv.argtypes = [c_int, c_ll, u32p, fp, fp, cr, fp, cr]
+        lib.vclo_norm2.restype = cr
+        lib.vclo_norm2.argtypes = [fp, c_ll]
+        lib.vclo_inner_prod.restype = cr
+        lib.vclo_inner_prod.argtypes = [fp, fp, c_ll]
         ip, dp = C.POINTER(c_int), C.POINTER(c_dbl)
-        lib.vclo_cg.argtypes = [c_int, u32p, u32p, f64p, f64p, f64p, c_dbl, c_dbl, c_int, ip, dp, C.c_void_p, c_int, ip]
+        lib.vclo_cg.argtypes = [c_int, u32p, u32p, fp, fp, fp, c_dbl, c_dbl, c_int, ip, dp, C.c_void_p, c_int, ip]
         lib.vclo_bicgstab.argtypes = lib.vclo_cg.argtypes
-        lib.vclo_bicgstab_precond.argtypes = [c_int, u32p, u32p, f64p, c_int, f64p, f64p, c_dbl, c_dbl, c_int, c_int, ip, dp, C.c_void_p, c_int, ip]
-        lib.vclo_gmres.argtypes = [c_int, u32p, u32p, f64p, f64p, f64p, c_dbl, c_dbl, c_int, c_int, ip, dp, C.c_void_p, c_int, ip]
+        lib.vclo_bicgstab_precond.argtypes = [c_int, u32p, u32p, fp, c_int, fp, fp, c_dbl, c_dbl, c_int, c_int, ip, dp, C.c_void_p, c_int, ip]
+        lib.vclo_gmres.argtypes = [c_int, u32p, u32p, fp, fp, fp, c_dbl, c_dbl, c_int, c_int, ip, dp, C.c_void_p, c_int, ip]
         lib.vclo_max_threads.restype = c_int
         lib.vclo_set_threads.argtypes = [c_int]
 
@@ -88,19 +95,19 @@ class _Oracle:
     def stencil2d(self, nx, ny, cx=0.0, cy=0.0):
         nnz = self.lib.vclo_gen_stencil2d(nx, ny, cx, cy, None, None, None)
         n = nx * ny
-        rp = np.empty(n + 1, np.uint32); ci = np.empty(nnz, np.uint32); v = np.empty(nnz, np.float64)
+        rp = np.empty(n + 1, np.uint32); ci = np.empty(nnz, np.uint32); v = np.empty(nnz, self.dt)
         self.lib.vclo_gen_stencil2d(nx, ny, cx, cy, rp.ctypes.data, ci.ctypes.data, v.ctypes.data)
-        return CSR(n, n, rp, ci, v)
+        return CSR(n, n, rp, ci, v, self.dt)
 
     def stencil3d(self, nx, ny, nz, cx=0.0, cy=0.0, cz=0.0):
         nnz = self.lib.vclo_gen_stencil3d(nx, ny, nz, cx, cy, cz, None, None, None)
         n = nx * ny * nz
-        rp = np.empty(n + 1, np.uint32); ci = np.empty(nnz, np.uint32); v = np.empty(nnz, np.float64)
+        rp = np.empty(n + 1, np.uint32); ci = np.empty(nnz, np.uint32); v = np.empty(nnz, self.dt)
         self.lib.vclo_gen_stencil3d(nx, ny, nz, cx, cy, cz, rp.ctypes.data, ci.ctypes.data, v.ctypes.data)
-        return CSR(n, n, rp, ci, v)
+        return CSR(n, n, rp, ci, v, self.dt)
 
     def uniform(self, n, seed=42, lo=0.0, hi=1.0):
-        x = np.empty(n, np.float64)
+        x = np.empty(n, self.dt)
         self.lib.vclo_fill_uniform(x, n, seed, lo, hi)
         return x
 
@@ -113,7 +120,7 @@ class _Oracle:
     # -- SpMV ----------------------------------------------------------------------------------
     def csr_spmv(self, A, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         if y is None:
-            y = np.zeros(offy + A.rows * incy, np.float64)
+            y = np.zeros(offy + A.rows * incy, self.dt)
         self.lib.vclo_csr_spmv(A.rows, A.rp, A.ci, A.v, x, offx, incx, alpha, y, offy, incy, beta)
         return y
 
@@ -121,21 +128,21 @@ class _Oracle:
         nb = (A.rows - 1) // Cs + 1 if A.rows > 0 else 0
         tot = self.lib.vclo_sell_padded_nnz(A.rows, A.rp, Cs)
         cpb = np.zeros(max(nb, 1), np.uint32); bs = np.zeros(max(nb, 1), np.uint32)
-        ci = np.zeros(max(tot, 1), np.uint32); el = np.zeros(max(tot, 1), np.float64)
+        ci = np.zeros(max(tot, 1), np.uint32); el = np.zeros(max(tot, 1), self.dt)
         self.lib.vclo_sell_build(A.rows, A.rp, A.ci, A.v, Cs, cpb, bs, ci, el)
         return dict(rows=A.rows, cols=A.cols, C=Cs, nb=nb, padded_nnz=int(tot), cols_per_block=cpb[:nb], block_start=bs[:nb],
                     col_idx=ci[:tot], elements=el[:tot])
 
     def sell_spmv(self, S, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         if y is None:
-            y = np.zeros(offy + S["rows"] * incy, np.float64)
+            y = np.zeros(offy + S["rows"] * incy, self.dt)
         pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt))
         self.lib.vclo_sell_spmv(S["rows"], S["C"], pad(S["cols_per_block"], np.uint32), pad(S["block_start"], np.uint32),
-                                pad(S["col_idx"], np.uint32), pad(S["elements"], np.float64), x, offx, incx, alpha, y, offy, incy, beta)
+                                pad(S["col_idx"], np.uint32), pad(S["elements"], self.dt), x, offx, incx, alpha, y, offy, incy, beta)
         return y
 
     def csr_diag(self, A):
-        d = np.empty(A.rows, np.float64)
+        d = np.empty(A.rows, self.dt)
         self.lib.vclo_csr_diag(A.rows, A.rp, A.ci, A.v, d)
         return d
 
@@ -148,24 +155,24 @@ class _Oracle:
 
     def coo_spmv(self, M, x, y=None, alpha=1.0, beta=0.0):
         if y is None:
-            y = np.zeros(M["rows"], np.float64)
+            y = np.zeros(M["rows"], self.dt)
         pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(2, dt))
-        self.lib.vclo_coo_spmv(M["rows"], M["nnz"], pad(M["coords"], np.uint32), pad(M["elements"], np.float64), x, alpha, y, beta)
+        self.lib.vclo_coo_spmv(M["rows"], M["nnz"], pad(M["coords"], np.uint32), pad(M["elements"], self.dt), x, alpha, y, beta)
         return y
 
     # -- ELL / HYB (ell_matrix.hpp:122-166, hyb_matrix.hpp:127-214) ---------------------------
     def ell_build(self, A):
         w = self.lib.vclo_ell_width(A.rows, A.rp)
         tot = max(A.rows * w, 1)
-        co = np.zeros(tot, np.uint32); el = np.zeros(tot, np.float64)
+        co = np.zeros(tot, np.uint32); el = np.zeros(tot, self.dt)
         self.lib.vclo_ell_build(A.rows, A.rp, A.ci, A.v, w, co, el)
         return dict(rows=A.rows, cols=A.cols, width=w, internal_rows=A.rows, coords=co[:A.rows * w], elements=el[:A.rows * w])
 
     def ell_spmv(self, E, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         if y is None:
-            y = np.zeros(offy + E["rows"] * incy, np.float64)
+            y = np.zeros(offy + E["rows"] * incy, self.dt)
         pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt))
-        self.lib.vclo_ell_spmv(E["rows"], E["width"], pad(E["coords"], np.uint32), pad(E["elements"], np.float64),
+        self.lib.vclo_ell_spmv(E["rows"], E["width"], pad(E["coords"], np.uint32), pad(E["elements"], self.dt),
                                x, offx, incx, alpha, y, offy, incy, beta)
         return y
 
@@ -173,17 +180,17 @@ class _Oracle:
         w = self.lib.vclo_hyb_width(A.rows, A.cols, A.rp, threshold)
         tn = int(self.lib.vclo_hyb_tail_nnz(A.rows, A.rp, w))
         tot = max(A.rows * w, 1)
-        co = np.zeros(tot, np.uint32); el = np.zeros(tot, np.float64)
-        cr = np.zeros(A.rows + 1, np.uint32); cc = np.zeros(tn, np.uint32); ce = np.zeros(tn, np.float64)
+        co = np.zeros(tot, np.uint32); el = np.zeros(tot, self.dt)
+        cr = np.zeros(A.rows + 1, np.uint32); cc = np.zeros(tn, np.uint32); ce = np.zeros(tn, self.dt)
         self.lib.vclo_hyb_build(A.rows, A.rp, A.ci, A.v, w, co, el, cr, cc, ce)
         return dict(rows=A.rows, cols=A.cols, width=w, internal_rows=A.rows, ell_coords=co[:A.rows * w], ell_elements=el[:A.rows * w],
                     csr_rows=cr, csr_cols=cc, csr_elements=ce, csr_nnz=tn)
 
     def hyb_spmv(self, H, x, y=None, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         if y is None:
-            y = np.zeros(offy + H["rows"] * incy, np.float64)
+            y = np.zeros(offy + H["rows"] * incy, self.dt)
         pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt))
-        self.lib.vclo_hyb_spmv(H["rows"], H["width"], pad(H["ell_coords"], np.uint32), pad(H["ell_elements"], np.float64),
+        self.lib.vclo_hyb_spmv(H["rows"], H["width"], pad(H["ell_coords"], np.uint32), pad(H["ell_elements"], self.dt),
                                H["csr_rows"], H["csr_cols"], H["csr_elements"], x, offx, incx, alpha, y, offy, incy, beta)
         return y
 
@@ -195,7 +202,7 @@ class _Oracle:
 
     # -- solvers -------------------------------------------------------------------------------
     def _run(self, fn, A, b, extra, hist_cap):
-        x = np.zeros(A.rows, np.float64)
+        x = np.zeros(A.rows, self.dt)
         it, err, hl = c_int(0), c_dbl(0), c_int(0)
         hist = np.zeros(max(hist_cap, 1), np.float64)
         fn(A.rows, A.rp, A.ci, A.v, *extra(b, x), C.byref(it), C.byref(err), hist.ctypes.data, hist_cap, C.byref(hl))
@@ -208,7 +215,7 @@ class _Oracle:
         return self._run(self.lib.vclo_bicgstab, A, b, lambda b, x: (b, x, tol, abs_tol, maxit), hist_cap)
 
     def bicgstab_precond(self, A, b, precond=1, tol=1e-8, maxit=400, abs_tol=0.0, restart_every=200, hist_cap=0):
-        x = np.zeros(A.rows, np.float64)
+        x = np.zeros(A.rows, self.dt)
         it, err, hl = c_int(0), c_dbl(0), c_int(0)
         hist = np.zeros(max(hist_cap, 1), np.float64)
         self.lib.vclo_bicgstab_precond(A.rows, A.rp, A.ci, A.v, precond, b, x, tol, abs_tol, maxit, restart_every,
@@ -222,9 +229,14 @@ class _Oracle:
 class _Ref:
     """The reference itself (OpenMP host backend).  Present only where oracle/_ref/*.so was built/prebuilt."""
 
-    def __init__(self, fixed=False):
+    def __init__(self, fixed=False, dtype=np.float64):
         build()
-        name = "libvcl_ref_gmresfix.so" if fixed else "libvcl_ref.so"
+        self.dt = np.dtype(dtype).type
+        single = self.dt is np.float32
+        fp = np.ctypeslib.ndpointer(dtype=self.dt, flags="C_CONTIGUOUS")
+        cr = C.c_float if single else C.c_double        # real_t scalars; tolerances / error / history / seconds stay double
+        self.ct = cr
+        name = ("libvcl_ref_gmresfix" if fixed else "libvcl_ref") + ("_f32.so" if single else ".so")
         path = os.path.join(ORACLE_DIR, "_ref", name)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
@@ -232,30 +244,30 @@ class _Ref:
         ip, dp = C.POINTER(c_int), C.POINTER(c_dbl)
         lib.vclref_max_threads.restype = c_int
         lib.vclref_set_threads.argtypes = [c_int]
-        lib.vclref_csr_spmv.argtypes = [c_int, c_int, c_int, u32p, u32p, f64p, f64p, c_int, c_int, c_int, c_dbl,
-                                        f64p, c_int, c_int, c_int, c_dbl, c_int]
-        lib.vclref_sell_build.argtypes = [c_int, c_int, u32p, u32p, f64p, c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+        lib.vclref_csr_spmv.argtypes = [c_int, c_int, c_int, u32p, u32p, fp, fp, c_int, c_int, c_int, cr,
+                                        fp, c_int, c_int, c_int, cr, c_int]
+        lib.vclref_sell_build.argtypes = [c_int, c_int, u32p, u32p, fp, c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), ip, C.POINTER(c_ll)]
         lib.vclref_free.argtypes = [C.c_void_p]
-        lib.vclref_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, c_int, f64p, c_dbl, f64p, c_dbl]
-        lib.vclref_csr_diag.argtypes = [c_int, c_int, c_int, u32p, u32p, f64p, f64p]
+        lib.vclref_sell_spmv.argtypes = [c_int, c_int, u32p, u32p, fp, c_int, fp, cr, fp, cr]
+        lib.vclref_csr_diag.argtypes = [c_int, c_int, c_int, u32p, u32p, fp, fp]
         vpp = C.POINTER(C.c_void_p)
         if hasattr(lib, "vclref_ell_build"):
-            lib.vclref_ell_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip, ip]
-            lib.vclref_ell_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
-            lib.vclref_hyb_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip, ip, vpp, vpp, vpp, ip]
-            lib.vclref_hyb_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
+            lib.vclref_ell_build.argtypes = [c_int, c_int, u32p, u32p, fp, vpp, vpp, ip, ip]
+            lib.vclref_ell_spmv.argtypes = [c_int, c_int, u32p, u32p, fp, fp, cr, fp, cr]
+            lib.vclref_hyb_build.argtypes = [c_int, c_int, u32p, u32p, fp, vpp, vpp, ip, ip, vpp, vpp, vpp, ip]
+            lib.vclref_hyb_spmv.argtypes = [c_int, c_int, u32p, u32p, fp, fp, cr, fp, cr]
         if hasattr(lib, "vclref_coo_build"):
-            lib.vclref_coo_build.argtypes = [c_int, c_int, u32p, u32p, f64p, vpp, vpp, ip]
-            lib.vclref_coo_spmv.argtypes = [c_int, c_int, u32p, u32p, f64p, f64p, c_dbl, f64p, c_dbl]
-        lib.vclref_norm2.restype = c_dbl
-        lib.vclref_norm2.argtypes = [f64p, c_int]
-        lib.vclref_inner_prod.restype = c_dbl
-        lib.vclref_inner_prod.argtypes = [f64p, f64p, c_int]
-        lib.vclref_solve.argtypes = [c_int, c_int, c_int, c_int, c_int, u32p, u32p, f64p, f64p, f64p,
+            lib.vclref_coo_build.argtypes = [c_int, c_int, u32p, u32p, fp, vpp, vpp, ip]
+            lib.vclref_coo_spmv.argtypes = [c_int, c_int, u32p, u32p, fp, fp, cr, fp, cr]
+        lib.vclref_norm2.restype = cr
+        lib.vclref_norm2.argtypes = [fp, c_int]
+        lib.vclref_inner_prod.restype = cr
+        lib.vclref_inner_prod.argtypes = [fp, fp, c_int]
+        lib.vclref_solve.argtypes = [c_int, c_int, c_int, c_int, c_int, u32p, u32p, fp, fp, fp,
                                      c_dbl, c_dbl, c_int, c_int, c_int, ip, dp, C.c_void_p, c_int, ip, dp]
         lib.vclref_time_csr_spmv.restype = c_dbl
-        lib.vclref_time_csr_spmv.argtypes = [c_int, c_int, c_int, u32p, u32p, f64p, f64p, f64p, c_int]
+        lib.vclref_time_csr_spmv.argtypes = [c_int, c_int, c_int, u32p, u32p, fp, fp, fp, c_int]
 
     def set_threads(self, n):
         self.lib.vclref_set_threads(n)
@@ -269,7 +281,7 @@ class _Ref:
         if ny is None:
             ny = A.rows
         if y is None:
-            y = np.zeros(offy + A.rows * incy, np.float64)
+            y = np.zeros(offy + A.rows * incy, self.dt)
         rc = self.lib.vclref_csr_spmv(A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, x, offx, incx, nx, alpha, y, offy, incy, ny, beta, mode)
         assert rc == 0
         return y
@@ -283,21 +295,21 @@ class _Ref:
             return a
         out = dict(rows=A.rows, cols=A.cols, C=Cs, nb=nb.value, padded_nnz=int(tot.value),
                    cols_per_block=grab(p[0], nb.value, C.c_uint32, np.uint32), block_start=grab(p[1], nb.value, C.c_uint32, np.uint32),
-                   col_idx=grab(p[2], tot.value, C.c_uint32, np.uint32), elements=grab(p[3], tot.value, C.c_double, np.float64))
+                   col_idx=grab(p[2], tot.value, C.c_uint32, np.uint32), elements=grab(p[3], tot.value, self.ct, self.dt))
         for q in p:
             self.lib.vclref_free(q)
         return out
 
     def sell_spmv(self, A, x, y=None, alpha=1.0, beta=0.0, Cs=32):
         if y is None:
-            y = np.zeros(A.rows, np.float64)
+            y = np.zeros(A.rows, self.dt)
         rc = self.lib.vclref_sell_spmv(A.rows, A.cols, A.rp, A.ci, A.v, Cs, x, alpha, y, beta)
         if rc == 3:
             raise ValueError("reference host SELL over-reads when rows % C == 0 (SURVEY 8c-2)")
         return y
 
     def csr_diag(self, A):
-        d = np.empty(A.rows, np.float64)
+        d = np.empty(A.rows, self.dt)
         self.lib.vclref_csr_diag(A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, d)
         return d
 
@@ -311,14 +323,14 @@ class _Ref:
         self.lib.vclref_ell_build(A.rows, A.cols, A.rp, A.ci, A.v, C.byref(p[0]), C.byref(p[1]), C.byref(w), C.byref(ir))
         tot = w.value * ir.value
         out = dict(rows=A.rows, cols=A.cols, width=w.value, internal_rows=ir.value,
-                   coords=self._grab(p[0], tot, C.c_uint32, np.uint32), elements=self._grab(p[1], tot, C.c_double, np.float64))
+                   coords=self._grab(p[0], tot, C.c_uint32, np.uint32), elements=self._grab(p[1], tot, self.ct, self.dt))
         for q in p:
             self.lib.vclref_free(q)
         return out
 
     def ell_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
         if y is None:
-            y = np.zeros(A.rows, np.float64)
+            y = np.zeros(A.rows, self.dt)
         self.lib.vclref_ell_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
         return y
 
@@ -327,14 +339,14 @@ class _Ref:
         n = c_int(0)
         self.lib.vclref_coo_build(A.rows, A.cols, A.rp, A.ci, A.v, C.byref(p[0]), C.byref(p[1]), C.byref(n))
         out = dict(rows=A.rows, cols=A.cols, nnz=n.value, coords=self._grab(p[0], 2 * n.value, C.c_uint32, np.uint32),
-                   elements=self._grab(p[1], n.value, C.c_double, np.float64))
+                   elements=self._grab(p[1], n.value, self.ct, self.dt))
         for q in p:
             self.lib.vclref_free(q)
         return out
 
     def coo_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
         if y is None:
-            y = np.zeros(A.rows, np.float64)
+            y = np.zeros(A.rows, self.dt)
         self.lib.vclref_coo_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
         return y
 
@@ -345,16 +357,16 @@ class _Ref:
                                   C.byref(p[2]), C.byref(p[3]), C.byref(p[4]), C.byref(cn))
         tot = w.value * ir.value
         out = dict(rows=A.rows, cols=A.cols, width=w.value, internal_rows=ir.value, csr_nnz=cn.value,
-                   ell_coords=self._grab(p[0], tot, C.c_uint32, np.uint32), ell_elements=self._grab(p[1], tot, C.c_double, np.float64),
+                   ell_coords=self._grab(p[0], tot, C.c_uint32, np.uint32), ell_elements=self._grab(p[1], tot, self.ct, self.dt),
                    csr_rows=self._grab(p[2], A.rows + 1, C.c_uint32, np.uint32), csr_cols=self._grab(p[3], cn.value, C.c_uint32, np.uint32),
-                   csr_elements=self._grab(p[4], cn.value, C.c_double, np.float64))
+                   csr_elements=self._grab(p[4], cn.value, self.ct, self.dt))
         for q in p:
             self.lib.vclref_free(q)
         return out
 
     def hyb_spmv(self, A, x, y=None, alpha=1.0, beta=0.0):
         if y is None:
-            y = np.zeros(A.rows, np.float64)
+            y = np.zeros(A.rows, self.dt)
         self.lib.vclref_hyb_spmv(A.rows, A.cols, A.rp, A.ci, A.v, x, alpha, y, beta)
         return y
 
@@ -368,7 +380,7 @@ class _Ref:
     PRECONDS = dict(none=0, jacobi=1, identity=2)
 
     def solve(self, solver, A, b, precond="none", fmt=0, tol=1e-8, abs_tol=0.0, maxit=300, krylov=20, restart_every=200, hist_cap=0):
-        x = np.zeros(A.rows, np.float64)
+        x = np.zeros(A.rows, self.dt)
         it, err, hl, sec = c_int(0), c_dbl(0), c_int(0), c_dbl(0)
         hist = np.zeros(max(hist_cap, 1), np.float64)
         rc = self.lib.vclref_solve(self.SOLVERS[solver], self.PRECONDS[precond], fmt, A.rows, A.nnz, A.rp, A.ci, A.v, b, x,
@@ -379,29 +391,30 @@ class _Ref:
         return dict(x=x, iters=it.value, error=err.value, history=hist[:min(hl.value, hist_cap)].copy(), seconds=sec.value)
 
     def time_csr_spmv(self, A, x, reps):
-        y = np.zeros(A.rows, np.float64)
+        y = np.zeros(A.rows, self.dt)
         return self.lib.vclref_time_csr_spmv(A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, x, y, reps)
 
 
 _cache = {}
 
 
-def oracle():
-    if "o" not in _cache:
-        _cache["o"] = _Oracle()
-    return _cache["o"]
-
-
-def ref(fixed=False):
-    key = "rf" if fixed else "r"
+def oracle(dtype=np.float64):
+    key = ("o", np.dtype(dtype).name)
     if key not in _cache:
-        _cache[key] = _Ref(fixed)
+        _cache[key] = _Oracle(dtype)
     return _cache[key]
 
 
-def have_ref():
+def ref(fixed=False, dtype=np.float64):
+    key = ("rf" if fixed else "r", np.dtype(dtype).name)
+    if key not in _cache:
+        _cache[key] = _Ref(fixed, dtype)
+    return _cache[key]
+
+
+def have_ref(dtype=np.float64):
     try:
-        ref()
+        ref(dtype=dtype)
         return True
     except (FileNotFoundError, OSError):
         return False

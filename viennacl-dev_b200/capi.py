@@ -14,9 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.environ.get("VCL_B200_LIB_OVERRIDE") or os.path.join(HERE, "lib", "libvcl_b200.so")   # override: kernel-variant experiments only
 HEADER = os.path.join(ROOT, "include", "vcl_b200.h")
+HEADER_FLOAT = os.path.join(ROOT, "include", "vcl_b200_float.h")     # generated: tools/gen_float_header.py
 
 c_int, c_dbl, c_ll, c_vp, c_sz = C.c_int, C.c_double, C.c_longlong, C.c_void_p, C.c_size_t
 p_int, p_dbl, p_ll, p_vp = C.POINTER(c_int), C.POINTER(c_dbl), C.POINTER(c_ll), C.POINTER(c_vp)
+c_flt, p_flt = C.c_float, C.POINTER(C.c_float)
 
 STATUS = {0: "ViennaCLSuccess", 1: "ViennaCLGenericFailure", 2: "ViennaCLB200InvalidArgument", 3: "ViennaCLB200CudaError",
           4: "ViennaCLB200NoDevice", 5: "ViennaCLB200OutOfMemory", 6: "ViennaCLB200NotInitialized", 7: "ViennaCLB200CommError"}
@@ -49,6 +51,15 @@ class HybStruct(C.Structure):
 MONITOR = C.CFUNCTYPE(c_int, c_vp, c_dbl, c_vp)
 
 
+MONITOR_S = C.CFUNCTYPE(c_int, c_vp, C.c_float, c_vp)
+
+
+class TagStructS(C.Structure):
+    _fields_ = [("tolerance", c_dbl), ("abs_tolerance", c_dbl), ("max_iterations", c_int), ("krylov_dim", c_int),
+                ("max_iterations_before_restart", c_int), ("precond", c_int), ("monitor", MONITOR_S), ("monitor_user", c_vp),
+                ("iters", c_int), ("error", c_dbl)]
+
+
 class TagStruct(C.Structure):
     _fields_ = [("tolerance", c_dbl), ("abs_tolerance", c_dbl), ("max_iterations", c_int), ("krylov_dim", c_int),
                 ("max_iterations_before_restart", c_int), ("precond", c_int), ("monitor", MONITOR), ("monitor_user", c_vp),
@@ -56,10 +67,13 @@ class TagStruct(C.Structure):
 
 
 def exported_symbols_from_header():
-    """Names of all functions declared in include/vcl_b200.h (used by the CPU-side symbol test)."""
-    txt = open(HEADER).read()
-    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:ViennaCLStatus|const\s+char\s*\*)\s*(ViennaCL[A-Za-z0-9_]+)\s*\(", txt, flags=re.M)))
+    """Names of all functions declared in include/vcl_b200.h and vcl_b200_float.h (used by the CPU-side symbol test)."""
+    names = set()
+    for h in (HEADER, HEADER_FLOAT):
+        txt = open(h).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names |= set(re.findall(r"^\s*(?:ViennaCLStatus|const\s+char\s*\*)\s*(ViennaCL[A-Za-z0-9_]+)\s*\(", txt, flags=re.M))
+    return sorted(names)
 
 
 EXPORTED_SYMBOLS = exported_symbols_from_header()
@@ -95,6 +109,12 @@ def lib():
         f = getattr(L, name)
         f.argtypes = list(args)
         f.restype = res
+        # single-precision twin (vcl_b200_float.h): same argument list with float scalars; the row-partitioned path is double only
+        if name.startswith("ViennaCLCUDAD") and not name.startswith("ViennaCLCUDADdist_"):
+            g = getattr(L, "ViennaCLCUDAS" + name[len("ViennaCLCUDAD"):])
+            swap = {c_dbl: c_flt, p_dbl: p_flt, C.POINTER(TagStruct): C.POINTER(TagStructS)}
+            g.argtypes = [c_flt if a is c_dbl else p_flt if a is p_dbl else swap.get(a, a) for a in args]
+            g.restype = res
 
     sig("ViennaCLBackendCreate", p_vp)
     sig("ViennaCLBackendCreateOnDevice", p_vp, c_int, c_vp)
@@ -173,8 +193,30 @@ def lib():
     return L
 
 
+class _SingleLib:
+    """View of the library in which every ViennaCLCUDAD... name resolves to its single-precision twin ViennaCLCUDAS..."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        if name.startswith("ViennaCLCUDAD") and not name.startswith("ViennaCLCUDADdist_"):
+            name = "ViennaCLCUDAS" + name[len("ViennaCLCUDAD"):]
+        return getattr(self._L, name)
+
+
 class Backend:
     """ViennaCLBackend handle: device + stream (+ communicator)."""
+
+    def lib_for(self, dtype):
+        """The entry points for float64 (D) or float32 (S) data."""
+        if np.dtype(dtype) == np.float64:
+            return self.L
+        if np.dtype(dtype) == np.float32:
+            if not hasattr(self, "_LS"):
+                self._LS = _SingleLib(self.L)
+            return self._LS
+        raise TypeError("only float64 / float32 matrices and vectors exist in the C-ABI")
 
     def __init__(self, device=-1, stream=None):
         self.L = lib()
@@ -308,10 +350,10 @@ class CsrMatrix:
             self.generate_row_block_information()
 
     @classmethod
-    def from_host(cls, backend, rows, cols, rp, ci, va, with_blocks=True):
+    def from_host(cls, backend, rows, cols, rp, ci, va, with_blocks=True, dtype=np.float64):
         drp = backend.array(np.asarray(rp, np.uint32))
         dci = backend.array(np.asarray(ci, np.uint32)) if len(ci) else backend.empty(1, np.uint32)
-        dva = backend.array(np.asarray(va, np.float64)) if len(va) else backend.empty(1, np.float64)
+        dva = backend.array(np.asarray(va, dtype)) if len(va) else backend.empty(1, dtype)
         m = cls.__new__(cls)
         m.b = backend; m.rows, m.cols = int(rows), int(cols); m.rp, m.ci, m.va = drp, dci, dva
         m.nnz = int(len(va)); m.blocks = None; m.nblocks = 0
@@ -320,15 +362,15 @@ class CsrMatrix:
         return m
 
     @classmethod
-    def stencil(cls, backend, nx, ny, nz=1, cx=0.0, cy=0.0, cz=0.0, row_begin=None, row_end=None):
+    def stencil(cls, backend, nx, ny, nz=1, cx=0.0, cy=0.0, cz=0.0, row_begin=None, row_end=None, dtype=np.float64):
         """Device-side generator (tools/matrix_generation.hpp:47-88 generalised)."""
-        L = backend.L
+        L = backend.lib_for(dtype)
         n = nx * ny * nz
         rb = 0 if row_begin is None else row_begin
         re_ = n if row_end is None else row_end
         nnz = c_ll(0)
         backend.check(L.ViennaCLCUDADgenerate_stencil_rows(backend.h, nx, ny, nz, cx, cy, cz, rb, re_, None, None, None, C.byref(nnz)))
-        rp = backend.empty(re_ - rb + 1, np.uint32); ci = backend.empty(max(nnz.value, 1), np.uint32); va = backend.empty(max(nnz.value, 1), np.float64)
+        rp = backend.empty(re_ - rb + 1, np.uint32); ci = backend.empty(max(nnz.value, 1), np.uint32); va = backend.empty(max(nnz.value, 1), dtype)
         backend.check(L.ViennaCLCUDADgenerate_stencil_rows(backend.h, nx, ny, nz, cx, cy, cz, rb, re_, rp.ptr, ci.ptr, va.ptr, C.byref(nnz)))
         m = cls.__new__(cls)
         m.b = backend; m.rows, m.cols = re_ - rb, n; m.rp, m.ci, m.va = rp, ci, va
@@ -352,12 +394,12 @@ class CsrMatrix:
         """y = alpha*A*x + beta*y.  `backend`: another handle (stream) of the same device -- the matrix arrays are only read."""
         blocks = self.blocks.ptr if (use_blocks and self.blocks is not None) else None
         b = backend or self.b
-        b.check(b.L.ViennaCLCUDADcsrmv(b.h, self.rows, self.cols, self.nnz, self.rp.ptr, self.ci.ptr, self.va.ptr,
+        b.check(b.lib_for(self.va.dtype).ViennaCLCUDADcsrmv(b.h, self.rows, self.cols, self.nnz, self.rp.ptr, self.ci.ptr, self.va.ptr,
                                                  blocks, self.nblocks if blocks else 0, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
     def row_info(self, option=3):
-        out = self.b.empty(self.rows)
-        self.b.check(self.b.L.ViennaCLCUDADcsr_row_info(self.b.h, self.rows, self.rp.ptr, self.ci.ptr, self.va.ptr, out.ptr, option))
+        out = self.b.empty(self.rows, self.va.dtype)
+        self.b.check(self.b.lib_for(self.va.dtype).ViennaCLCUDADcsr_row_info(self.b.h, self.rows, self.rp.ptr, self.ci.ptr, self.va.ptr, out.ptr, option))
         return out
 
     def to_sell(self, Cs=32):
@@ -383,9 +425,10 @@ class SellMatrix:
         ns = (A.rows - 1) // Cs + 1 if A.rows > 0 else 0
         cpb = b.empty(max(ns, 1), np.uint32); bs = b.empty(max(ns, 1), np.uint32)
         tot = c_ll(0)
-        b.check(b.L.ViennaCLCUDADcsr2sell(b.h, A.rows, Cs, A.rp.ptr, A.ci.ptr, A.va.ptr, cpb.ptr, bs.ptr, C.byref(tot), None, None))
-        ci = b.empty(max(tot.value, 1), np.uint32); va = b.empty(max(tot.value, 1), np.float64)
-        b.check(b.L.ViennaCLCUDADcsr2sell(b.h, A.rows, Cs, A.rp.ptr, A.ci.ptr, A.va.ptr, cpb.ptr, bs.ptr, C.byref(tot), ci.ptr, va.ptr))
+        L = b.lib_for(A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2sell(b.h, A.rows, Cs, A.rp.ptr, A.ci.ptr, A.va.ptr, cpb.ptr, bs.ptr, C.byref(tot), None, None))
+        ci = b.empty(max(tot.value, 1), np.uint32); va = b.empty(max(tot.value, 1), A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2sell(b.h, A.rows, Cs, A.rp.ptr, A.ci.ptr, A.va.ptr, cpb.ptr, bs.ptr, C.byref(tot), ci.ptr, va.ptr))
         return cls(b, A.rows, A.cols, Cs, cpb, ci, bs, va, tot.value)
 
     @classmethod
@@ -400,7 +443,7 @@ class SellMatrix:
         return SellStruct(self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr, self.va.ptr)
 
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
-        self.b.check(self.b.L.ViennaCLCUDADsellmv(self.b.h, self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr,
+        self.b.check(self.b.lib_for(self.va.dtype).ViennaCLCUDADsellmv(self.b.h, self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr,
                                                   self.va.ptr, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
     def bytes_spmv(self):
@@ -422,24 +465,25 @@ class EllMatrix:
     def from_csr(cls, A):
         b = A.b
         w = c_int(0)
-        b.check(b.L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), None, None))
+        L = b.lib_for(A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), None, None))
         tot = max(A.rows * w.value, 1)
-        co = b.empty(tot, np.uint32); el = b.empty(tot, np.float64)
-        b.check(b.L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), co.ptr, el.ptr))
+        co = b.empty(tot, np.uint32); el = b.empty(tot, A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2ell(b.h, A.rows, A.rp.ptr, A.ci.ptr, A.va.ptr, C.byref(w), co.ptr, el.ptr))
         return cls(b, A.rows, A.cols, A.rows, w.value, co, el)
 
     @classmethod
     def from_host(cls, backend, E):
         pad = lambda a, dt: np.ascontiguousarray(a if a.size else np.zeros(1, dt), dtype=dt)
         return cls(backend, E["rows"], E["cols"], E["internal_rows"], E["width"], backend.array(pad(E["coords"], np.uint32)),
-                   backend.array(pad(E["elements"], np.float64)))
+                   backend.array(pad(E["elements"], np.asarray(E["elements"]).dtype if np.asarray(E["elements"]).dtype == np.float32 else np.float64)))
 
     def struct(self):
         return EllStruct(self.rows, self.cols, self.internal_rows, self.width, self.coords.ptr, self.elements.ptr)
 
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         s = self.struct()
-        self.b.check(self.b.L.ViennaCLCUDADellmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+        self.b.check(self.b.lib_for(self.elements.dtype).ViennaCLCUDADellmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
     def bytes_spmv(self):
         return 12 * self.internal_rows * self.width + 16 * self.rows
@@ -459,12 +503,13 @@ class HybMatrix:
     def from_csr(cls, A, threshold=0.8):
         b = A.b
         w, tn = c_int(0), c_int(0)
-        b.check(b.L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
-                                         None, None, None, None, None))
+        L = b.lib_for(A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
+                                       None, None, None, None, None))
         tot = max(A.rows * w.value, 1)
-        co = b.empty(tot, np.uint32); el = b.empty(tot, np.float64)
-        cr = b.empty(A.rows + 1, np.uint32); cc = b.empty(max(tn.value, 1), np.uint32); ce = b.empty(max(tn.value, 1), np.float64)
-        b.check(b.L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
+        co = b.empty(tot, np.uint32); el = b.empty(tot, A.va.dtype)
+        cr = b.empty(A.rows + 1, np.uint32); cc = b.empty(max(tn.value, 1), np.uint32); ce = b.empty(max(tn.value, 1), A.va.dtype)
+        b.check(L.ViennaCLCUDADcsr2hyb(b.h, A.rows, A.cols, A.rp.ptr, A.ci.ptr, A.va.ptr, threshold, C.byref(w), C.byref(tn),
                                          co.ptr, el.ptr, cr.ptr, cc.ptr, ce.ptr))
         return cls(b, EllMatrix(b, A.rows, A.cols, A.rows, w.value, co, el), cr, cc, ce, tn.value)
 
@@ -473,20 +518,20 @@ class HybMatrix:
 
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         s = self.struct()
-        self.b.check(self.b.L.ViennaCLCUDADhybmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+        self.b.check(self.b.lib_for(self.ell.elements.dtype).ViennaCLCUDADhybmv(self.b.h, C.byref(s), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
 
 class CooMatrix:
     """coordinate_matrix mirror (coordinate_matrix.hpp:186-400): (row, col) pairs + elements, plus the CSR index of the same
     entries that products and solvers run on (ViennaCLCUDAcoo2csr)."""
 
-    def __init__(self, backend, rows, cols, coords_host, elements_host):
+    def __init__(self, backend, rows, cols, coords_host, elements_host, dtype=np.float64):
         self.b = backend
         self.rows, self.cols = int(rows), int(cols)
         self.nnz = int(len(elements_host))
         pad = lambda a, dt, m: np.ascontiguousarray(a if a.size else np.zeros(m, dt), dtype=dt)
         self.coords = backend.array(pad(np.asarray(coords_host), np.uint32, 2))
-        self.elements = backend.array(pad(np.asarray(elements_host), np.float64, 1))
+        self.elements = backend.array(pad(np.asarray(elements_host), dtype, 1))
         rp = backend.empty(self.rows + 1, np.uint32); ci = backend.empty(max(self.nnz, 1), np.uint32)
         backend.check(backend.L.ViennaCLCUDAcoo2csr(backend.h, self.rows, self.nnz, self.coords.ptr, rp.ptr, ci.ptr))
         self.index = CsrMatrix(backend, self.rows, self.cols, rp, ci, self.elements)      # shares the value array
@@ -495,7 +540,7 @@ class CooMatrix:
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
         i = self.index
         blocks = i.blocks.ptr if i.blocks is not None else None
-        self.b.check(self.b.L.ViennaCLCUDADcoomv(self.b.h, i.rows, i.cols, self.nnz, i.rp.ptr, i.ci.ptr, i.va.ptr, blocks,
+        self.b.check(self.b.lib_for(self.elements.dtype).ViennaCLCUDADcoomv(self.b.h, i.rows, i.cols, self.nnz, i.rp.ptr, i.ci.ptr, i.va.ptr, blocks,
                                                  i.nblocks if blocks else 0, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 
 
@@ -507,6 +552,7 @@ class SolverTag:
         self.t.tolerance = tol; self.t.abs_tolerance = abs_tol; self.t.max_iterations = max_iterations
         self.t.krylov_dim = krylov_dim; self.t.max_iterations_before_restart = restart_every; self.t.precond = precond
         self._cb = None
+        self._monitor = monitor
         if monitor is not None:
             self._cb = MONITOR(lambda xptr, est, user: 1 if monitor(xptr, est) else 0)
             self.t.monitor = self._cb
@@ -523,8 +569,21 @@ class SolverTag:
     def solve(self, solver, A, b, x):
         """solver in {'cg','bicgstab','gmres'}; A a CsrMatrix or SellMatrix; b, x DeviceArrays."""
         kind = "csr" if isinstance(A, CsrMatrix) else getattr(A, "kind", "sell")
-        fn = getattr(A.b.L, "ViennaCLCUDAD%s_%s" % (kind, solver))
+        fn = getattr(A.b.lib_for(b.dtype), "ViennaCLCUDAD%s_%s" % (kind, solver))
         s = A.struct()
+        if b.dtype == np.float32:
+            # the single-precision tag has the same layout; its monitor callback receives a float estimate
+            ts = TagStructS()
+            for f, _ in TagStructS._fields_:
+                if f not in ("monitor",):
+                    setattr(ts, f, getattr(self.t, f))
+            cb = None
+            if self._monitor is not None:
+                cb = MONITOR_S(lambda xptr, est, user: 1 if self._monitor(xptr, est) else 0)
+                ts.monitor = cb
+            A.b.check(fn(A.b.h, C.byref(s), b.ptr, x.ptr, C.byref(ts)))
+            self.t.iters, self.t.error = ts.iters, ts.error
+            return self
         A.b.check(fn(A.b.h, C.byref(s), b.ptr, x.ptr, C.byref(self.t)))
         return self
 

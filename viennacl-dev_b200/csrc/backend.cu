@@ -2,7 +2,9 @@
 // Replaces viennacl/backend/cuda.hpp:103-200 and the handle plumbing of backend/mem_handle.hpp:89-245 /
 // backend/memory.hpp:54-367 for the CUDA domain (the C++ facade keeps mem_handle and calls these).
 #include "common.cuh"
+#include "prec.cuh"
 #include "solver_state.cuh"
+using vcl_f64::SolverState;       // the double-precision state is the larger one: both builds fit
 
 ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, const char *file, int line)
 {

@@ -14,7 +14,6 @@ typedef unsigned int u32;
 // Backend handle (the "stream and/or device descriptors" libviennacl left as a TODO,
 // libviennacl/src/viennacl_private.hpp:38-41).  A handle is single-threaded; handles are independent.
 // ------------------------------------------------------------------------------------------------
-struct SolverState;   // solvers.cu
 
 struct ViennaCLBackend_impl
 {
@@ -34,8 +33,8 @@ struct ViennaCLBackend_impl
   unsigned int *tickets = nullptr;             // [16], zero between kernels
   double *dscal = nullptr;                     // 64 device doubles: results of stand-alone reductions etc.
   double *hscal = nullptr;                     // pinned mirror of dscal
-  SolverState *dstate = nullptr;               // device solver state
-  SolverState *hstate = nullptr;               // pinned mirror
+  void *dstate = nullptr;                      // device solver state (SolverState of the build that runs, solver_state.cuh)
+  void *hstate = nullptr;                      // pinned mirror
   void *flush_buf = nullptr; size_t flush_bytes = 0;
 
   // workspace pool for solver temporaries (grown on demand, freed at destroy)
@@ -67,7 +66,8 @@ static inline int vcl_div_up(long long a, long long b) { return (int)((a + b - 1
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-__device__ __forceinline__ double warp_sum(double v)
+template<typename T>
+__device__ __forceinline__ T warp_sum(T v)
 {
   // XOR butterfly: every lane ends with the same, order-deterministic value.
   v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -79,8 +79,8 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // Sum of NQ per-thread values over the block; result valid in thread 0.  smem: NQ * 32 doubles.
-template<int NQ>
-__device__ __forceinline__ void block_sum(double (&v)[NQ], double *smem)
+template<int NQ, typename T>
+__device__ __forceinline__ void block_sum(T (&v)[NQ], T *smem)
 {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
@@ -97,7 +97,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NQ], double *smem)
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
     {
-      double t = (lane < nw) ? smem[q * 32 + lane] : 0.0;
+      T t = (lane < nw) ? smem[q * 32 + lane] : T(0);
       v[q] = warp_sum(t);
     }
   }
@@ -107,11 +107,11 @@ __device__ __forceinline__ void block_sum(double (&v)[NQ], double *smem)
 // result does not depend on which block that is).  Every block calls this with its NQ block-local sums (valid in thread 0
 // after block_sum).  Returns true in ALL threads of the last block, with totals[] valid in thread 0 of that block.
 // partials: [NQ][VCL_MAX_BLOCKS]; ticket: one counter, left at zero on exit.
-template<int NQ>
-__device__ __forceinline__ bool grid_sum_last_block(double (&v)[NQ], double *partials, unsigned int *ticket, double *smem)
+template<int NQ, typename T>
+__device__ __forceinline__ bool grid_sum_last_block(T (&v)[NQ], T *partials, unsigned int *ticket, T *smem)
 {
   __shared__ bool s_last;
-  block_sum<NQ>(v, smem);
+  block_sum<NQ, T>(v, smem);
   if (threadIdx.x == 0)
   {
 #pragma unroll
@@ -123,15 +123,15 @@ __device__ __forceinline__ bool grid_sum_last_block(double (&v)[NQ], double *par
   __syncthreads();
   if (!s_last) return false;
   __threadfence();
-  double acc[NQ];
+  T acc[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
   {
-    acc[q] = 0.0;
+    acc[q] = T(0);
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
       acc[q] += __ldcg(partials + q * VCL_MAX_BLOCKS + i);
   }
-  block_sum<NQ>(acc, smem);
+  block_sum<NQ, T>(acc, smem);
   if (threadIdx.x == 0)
   {
 #pragma unroll

@@ -23,6 +23,11 @@
 #include <cmath>
 #include <algorithm>
 
+#ifdef VCL_F32
+#error "the row-partitioned path is built in double precision only"
+#endif
+using namespace vcl_f64;
+
 struct ViennaCLB200DistCsr_impl
 {
   long long global_rows = 0, rb = 0, re = 0;
@@ -630,13 +635,13 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
   const double alpha = rr / b->hscal[1];
   double beta = std::sqrt(b->hscal[2]); beta = (alpha * alpha * beta * beta - rr) / rr;
 
-  SolverState *h = b->hstate;
+  SolverState *h = VCL_HSTATE(b);
   std::memset(h, 0, sizeof(SolverState));
   h->alpha = alpha; h->beta = beta; h->norm_rhs_sq = norm_rhs_squared; h->norm_rhs = std::sqrt(norm_rhs_squared);
   h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = rr;
   VCL_CUDA(b, cudaMemcpyAsync(b->dstate, h, sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
-  SolverState *st = b->dstate;
+  SolverState *st = VCL_DSTATE(b);
 
   const int grid = (int)std::max(1LL, std::min((n / 2 + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
   const int kBatch = 32;

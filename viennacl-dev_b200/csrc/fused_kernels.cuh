@@ -8,8 +8,12 @@
 // reference drivers (cg.hpp:168, bicgstab.hpp:180).
 #pragma once
 #include "common.cuh"
+#include "prec.cuh"
 #include "solver_state.cuh"
 #include "peer.cuh"
+
+namespace VCL_NS
+{
 
 #define VEC_THREADS 256
 
@@ -19,12 +23,12 @@
 // cg.hpp:170-180.  sums[0] = <r,r>, sums[1] = <Ap,Ap>, sums[2] = <p,Ap>
 __device__ __forceinline__ void cg_advance(SolverState *st)
 {
-  const double rr = st->sums[0], ApAp = st->sums[1], pAp = st->sums[2];
+  const real rr = st->sums[0], ApAp = st->sums[1], pAp = st->sums[2];
   st->iters += 1;
   st->est = sqrt(fabs(rr / st->norm_rhs_sq));
   if (fabs(rr / st->norm_rhs_sq) < st->tol * st->tol || fabs(rr) < st->abs_tol * st->abs_tol) { st->done = VCL_CONVERGED; return; }
   if (st->iters >= st->maxit) { st->done = VCL_MAXIT; return; }
-  const double alpha = rr / pAp;
+  const real alpha = rr / pAp;
   st->alpha = alpha;
   st->beta = (alpha * alpha * ApAp - rr) / rr;
 }
@@ -33,14 +37,14 @@ __device__ __forceinline__ void cg_advance(SolverState *st)
 // is built on, cg.hpp:116-118, extended by the preconditioner; same iterates as the classical PCG of cg.hpp:257-322 up to
 // rounding).  sums[0] = gamma = <r, u> with u = r ./ diag (written by pcg_update_kernel), delta = <w, u> with w = A u.
 // Bookkeeping as in cg.hpp:296-309: iteration counted, estimate sqrt(|gamma / gamma_0|), squared tolerances.
-__device__ __forceinline__ void pcg_advance(SolverState *st, double delta)
+__device__ __forceinline__ void pcg_advance(SolverState *st, real delta)
 {
-  const double gamma = st->sums[0];
+  const real gamma = st->sums[0];
   st->iters += 1;
   st->est = sqrt(fabs(gamma / st->norm_rhs_sq));
   if (fabs(gamma / st->norm_rhs_sq) < st->tol * st->tol || fabs(gamma) < st->abs_tol * st->abs_tol) { st->done = VCL_CONVERGED; return; }
   if (st->iters >= st->maxit) { st->done = VCL_MAXIT; return; }
-  const double beta = gamma / st->ip_rr0;                          // ip_rr0 holds the previous gamma
+  const real beta = gamma / st->ip_rr0;                          // ip_rr0 holds the previous gamma
   st->alpha = gamma / (delta - beta * gamma / st->alpha);
   st->beta = beta;
   st->ip_rr0 = gamma;
@@ -49,13 +53,13 @@ __device__ __forceinline__ void pcg_advance(SolverState *st, double delta)
 // bicgstab.hpp:184-199.  chunks: 0 <r,r0*>, 1 <As,As>, 2 <As,s>, 3 <Ap,r0*>, 4 <As,r0*>, 5 <s,s>
 __device__ __forceinline__ void bicgstab_advance(SolverState *st)
 {
-  const double r_r0 = st->sums[0], As_As = st->sums[1], As_s = st->sums[2], Ap_r0 = st->sums[3], As_r0 = st->sums[4], s_s = st->sums[5];
+  const real r_r0 = st->sums[0], As_As = st->sums[1], As_s = st->sums[2], Ap_r0 = st->sums[3], As_r0 = st->sums[4], s_s = st->sums[5];
   st->iters += 1;
   st->alpha = r_r0 / Ap_r0;
   st->beta = -As_r0 / Ap_r0;
-  const double omega = As_s / As_As;
+  const real omega = As_s / As_As;
   st->omega = omega;
-  const double res = sqrt(s_s - 2.0 * omega * As_s + omega * omega * As_As);
+  const real res = sqrt(s_s - 2.0 * omega * As_s + omega * omega * As_As);
   st->residual_norm = res;
   st->est = fabs(res / st->norm_rhs);
   if (fabs(res / st->norm_rhs) < st->tol || res < st->abs_tol) st->done = VCL_CONVERGED;
@@ -70,23 +74,23 @@ enum { STEP_NONE = 0, STEP_CG = 1, STEP_BICGSTAB = 2, STEP_PBICG_ALPHA = 3, STEP
 template<int STEP, bool USE_R0, bool JACOBI>
 struct EpiFused
 {
-  double *Ap; const double *p; const double *r0; const double *diag;
-  double *partials; unsigned int *ticket;
+  real *Ap; const real *p; const real *r0; const real *diag;
+  real *partials; unsigned int *ticket;
   SolverState *st;                 // NULL in per-op API mode
-  double *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
-  double acc[3];
-  const double *add_from;          // optional: 3 totals of an earlier launch over a disjoint row subset (interior + boundary split)
+  real *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
+  real acc[3];
+  const real *add_from;          // optional: 3 totals of an earlier launch over a disjoint row subset (interior + boundary split)
   // row-partitioned CG over peer memory (peer.cuh): the last CTA all-reduces {*loc_rr, <Ap,Ap>, <p,Ap>} across the ranks
   // and then advances the CG scalars -- identical on every rank.  win == NULL: single-domain behaviour.
-  const PeerWindow *win; unsigned long long red_seq; const double *loc_rr;
+  const PeerWindow *win; unsigned long long red_seq; const real *loc_rr;
   static constexpr int NQ = 3;
   static constexpr bool COO = false;
-  __device__ __forceinline__ double init(double) const { return 0.0; }
-  __device__ __forceinline__ double term_scale() const { return 1.0; }
+  __device__ __forceinline__ real init(real) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
 
   __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
-  __device__ __forceinline__ double pre(u32 r) const { return p[r]; }
-  __device__ __forceinline__ void row(u32 r, double dot, double p_r)
+  __device__ __forceinline__ real pre(u32 r) const { return p[r]; }
+  __device__ __forceinline__ void row(u32 r, real dot, real p_r)
   {
     if (JACOBI) dot = dot / diag[r];
     Ap[r] = dot;
@@ -94,9 +98,10 @@ struct EpiFused
     acc[1] = fma(p_r, dot, acc[1]);
     if (USE_R0) acc[2] = fma(dot, r0[r], acc[2]);
   }
-  __device__ __forceinline__ void finish(double *smem)
+  __device__ __forceinline__ void finish(real *smem)
   {
     if (!grid_sum_last_block<3>(acc, partials, ticket, smem)) return;
+#ifndef VCL_F32          // the row-partitioned path (peer.cuh) exists in double precision only
     if (win != nullptr)
     {
 #ifdef VCL_PEER_DEBUG
@@ -114,6 +119,7 @@ struct EpiFused
       }
       return;
     }
+#endif
     if (threadIdx.x == 0)
     {
       if (add_from) { acc[0] += add_from[0]; acc[1] += add_from[1]; if (USE_R0) acc[2] += add_from[2]; }
@@ -124,7 +130,7 @@ struct EpiFused
       if (STEP == STEP_BICGSTAB) bicgstab_advance(st);
       if (STEP == STEP_PCG) pcg_advance(st, acc[1]);
       if (STEP == STEP_PBICG_ALPHA) st->alpha = st->ip_rr0 / acc[2];                       // bicgstab.hpp:449
-      if (STEP == STEP_PBICG_OMEGA) { const double nt = sqrt(acc[0]); st->omega = acc[1] / (nt * nt); }  // bicgstab.hpp:455-456
+      if (STEP == STEP_PBICG_OMEGA) { const real nt = sqrt(acc[0]); st->omega = acc[1] / (nt * nt); }  // bicgstab.hpp:455-456
     }
   }
 };
@@ -138,26 +144,26 @@ __device__ __forceinline__ bool aligned16(const void *a, const void *b = nullptr
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(d) |
            reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0u;
 }
-__device__ __forceinline__ double2 ld2(const double *p, long long i) { return *reinterpret_cast<const double2*>(p + i); }
-__device__ __forceinline__ void st2(double *p, long long i, double2 v) { *reinterpret_cast<double2*>(p + i) = v; }
+__device__ __forceinline__ real2 ld2(const real *p, long long i) { return *reinterpret_cast<const real2*>(p + i); }
+__device__ __forceinline__ void st2(real *p, long long i, real2 v) { *reinterpret_cast<real2*>(p + i) = v; }
 
 // ------------------------------------------------------------------------------------------------
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(VEC_THREADS)
-cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap, double alpha_v, double beta_v,
-                 SolverState *st, double *partials, unsigned int *ticket, double *out_rr, const PushRanges pr = PushRanges())
+cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
+                 SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges pr = PushRanges())
 {
-  __shared__ double s_red[32];
+  __shared__ real s_red[32];
   if (st != nullptr && st->done != VCL_RUNNING) return;
-  const double alpha = st ? st->alpha : alpha_v;
-  const double beta  = st ? st->beta  : beta_v;
-  double acc[1] = {0.0};
+  const real alpha = st ? st->alpha : alpha_v;
+  const real beta  = st ? st->beta  : beta_v;
+  real acc[1] = {0.0};
   const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
-    double2 vx = ld2(x, k), vp = ld2(p, k), vr = ld2(r, k); const double2 va = ld2(Ap, k);
+    real2 vx = ld2(x, k), vp = ld2(p, k), vr = ld2(r, k); const real2 va = ld2(Ap, k);
     vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
     vr.x = fma(-alpha, va.x, vr.x);      vr.y = fma(-alpha, va.y, vr.y);
     vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
@@ -167,7 +173,7 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    double vp = p[k], vr = r[k];
+    real vp = p[k], vr = r[k];
     x[k] = fma(alpha, vp, x[k]);
     vr = fma(-alpha, Ap[k], vr);
     vp = fma(beta, vp, vr);
@@ -189,19 +195,19 @@ cg_update_kernel(long long n, double *x, double *p, double *r, const double *Ap,
 // (one pass: 7 reads + 5 writes per entry; the reference's generic PCG makes ~10 passes and 2 blocking reductions)
 // ------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(VEC_THREADS)
-pcg_update_kernel(long long n, double *x, double *r, double *u, const double *w, double *p, double *s, const double *diag,
-                  SolverState *st, double *partials, unsigned int *ticket, double *out_gamma)
+pcg_update_kernel(long long n, real *x, real *r, real *u, const real *w, real *p, real *s, const real *diag,
+                  SolverState *st, real *partials, unsigned int *ticket, real *out_gamma)
 {
-  __shared__ double s_red[32];
+  __shared__ real s_red[32];
   if (st->done != VCL_RUNNING) return;
-  const double alpha = st->alpha, beta = st->beta;
-  double acc[1] = {0.0};
+  const real alpha = st->alpha, beta = st->beta;
+  real acc[1] = {0.0};
   const long long npairs = aligned16(x, r, u, w, p, s, diag) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
-    double2 vx = ld2(x, k), vr = ld2(r, k), vu = ld2(u, k), vp = ld2(p, k), vs = ld2(s, k);
-    const double2 vw = ld2(w, k), vd = ld2(diag, k);
+    real2 vx = ld2(x, k), vr = ld2(r, k), vu = ld2(u, k), vp = ld2(p, k), vs = ld2(s, k);
+    const real2 vw = ld2(w, k), vd = ld2(diag, k);
     vp.x = fma(beta, vp.x, vu.x);        vp.y = fma(beta, vp.y, vu.y);
     vs.x = fma(beta, vs.x, vw.x);        vs.y = fma(beta, vs.y, vw.y);
     vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
@@ -212,10 +218,10 @@ pcg_update_kernel(long long n, double *x, double *r, double *u, const double *w,
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const double vp = fma(beta, p[k], u[k]), vs = fma(beta, s[k], w[k]);
+    const real vp = fma(beta, p[k], u[k]), vs = fma(beta, s[k], w[k]);
     x[k] = fma(alpha, vp, x[k]);
-    const double vr = fma(-alpha, vs, r[k]);
-    const double vu = vr / diag[k];
+    const real vr = fma(-alpha, vs, r[k]);
+    const real vu = vr / diag[k];
     acc[0] = fma(vr, vu, acc[0]);
     p[k] = vp; s[k] = vs; r[k] = vr; u[k] = vu;
   }
@@ -224,13 +230,13 @@ pcg_update_kernel(long long n, double *x, double *r, double *u, const double *w,
 
 // u = r ./ diag; <r,u>   (set-up of the Jacobi-PCG)
 static __global__ void __launch_bounds__(VEC_THREADS)
-pcg_init_kernel(long long n, const double *r, double *u, const double *diag, double *partials, unsigned int *ticket, double *out_gamma)
+pcg_init_kernel(long long n, const real *r, real *u, const real *diag, real *partials, unsigned int *ticket, real *out_gamma)
 {
-  __shared__ double s_red[32];
-  double acc[1] = {0.0};
+  __shared__ real s_red[32];
+  real acc[1] = {0.0};
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const double vu = r[k] / diag[k];
+    const real vu = r[k] / diag[k];
     acc[0] = fma(r[k], vu, acc[0]);
     u[k] = vu;
   }
@@ -242,27 +248,27 @@ pcg_init_kernel(long long n, const double *r, double *u, const double *diag, dou
 // (host_based/iterative_operations.hpp:518-563; cuda K9 :733-788 recomputes alpha in every CTA, here it is two loads)
 // ------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(VEC_THREADS)
-bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *Ap,
-                         const double *in_r_r0, const double *in_Ap_r0,
-                         SolverState *st, double *partials, unsigned int *ticket, double *out_ss)
+bicgstab_update_s_kernel(long long n, real *s, const real *r, const real *Ap,
+                         const real *in_r_r0, const real *in_Ap_r0,
+                         SolverState *st, real *partials, unsigned int *ticket, real *out_ss)
 {
-  __shared__ double s_red[32];
+  __shared__ real s_red[32];
   if (st != nullptr && st->done != VCL_RUNNING) return;
-  const double alpha = (*in_r_r0) / (*in_Ap_r0);
-  double acc[1] = {0.0};
+  const real alpha = (*in_r_r0) / (*in_Ap_r0);
+  real acc[1] = {0.0};
   const long long npairs = aligned16(s, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
-    const double2 vr = ld2(r, k), va = ld2(Ap, k);
-    double2 vs;
+    const real2 vr = ld2(r, k), va = ld2(Ap, k);
+    real2 vs;
     vs.x = fma(-alpha, va.x, vr.x); vs.y = fma(-alpha, va.y, vr.y);
     acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
     st2(s, k, vs);
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    const double vs = fma(-alpha, Ap[k], r[k]);
+    const real vs = fma(-alpha, Ap[k], r[k]);
     acc[0] = fma(vs, vs, acc[0]);
     s[k] = vs;
   }
@@ -271,22 +277,22 @@ bicgstab_update_s_kernel(long long n, double *s, const double *r, const double *
 
 // x += alpha p + omega s;  r = s - omega As;  p = r + beta (p - omega Ap);  <r,r0*>     (host_based/iterative_operations.hpp:572-621)
 static __global__ void __launch_bounds__(VEC_THREADS)
-bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double omega_v, const double *s,
-                       double *r, const double *As, double beta_v, const double *Ap, const double *r0,
-                       SolverState *st, double *partials, unsigned int *ticket, double *out_r_r0)
+bicgstab_update_kernel(long long n, real *x, real alpha_v, real *p, real omega_v, const real *s,
+                       real *r, const real *As, real beta_v, const real *Ap, const real *r0,
+                       SolverState *st, real *partials, unsigned int *ticket, real *out_r_r0)
 {
-  __shared__ double s_red[32];
+  __shared__ real s_red[32];
   if (st != nullptr && st->done != VCL_RUNNING) return;
-  const double alpha = st ? st->alpha : alpha_v;
-  const double beta  = st ? st->beta  : beta_v;
-  const double omega = st ? st->omega : omega_v;
-  double acc[1] = {0.0};
+  const real alpha = st ? st->alpha : alpha_v;
+  const real beta  = st ? st->beta  : beta_v;
+  const real omega = st ? st->omega : omega_v;
+  real acc[1] = {0.0};
   const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
     const long long k = i * 2;
-    double2 vx = ld2(x, k), vp = ld2(p, k); const double2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
-    double2 vr;
+    real2 vx = ld2(x, k), vp = ld2(p, k); const real2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
+    real2 vr;
     vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
     vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
     vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
@@ -295,9 +301,9 @@ bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
-    double vp = p[k]; const double vs = s[k];
+    real vp = p[k]; const real vs = s[k];
     x[k] += alpha * vp + omega * vs;
-    const double vr = fma(-omega, As[k], vs);
+    const real vr = fma(-omega, As[k], vs);
     vp = fma(beta, fma(-omega, Ap[k], vp), vr);
     acc[0] = fma(vr, r0[k], acc[0]);
     r[k] = vr; p[k] = vp;
@@ -314,29 +320,29 @@ bicgstab_update_kernel(long long n, double *x, double alpha_v, double *p, double
 // ------------------------------------------------------------------------------------------------
 // s = r - alpha t0                                            (bicgstab.hpp:451)
 static __global__ void __launch_bounds__(VEC_THREADS)
-pbicg_s_kernel(long long n, double *s, const double *r, const double *t0, const SolverState *st)
+pbicg_s_kernel(long long n, real *s, const real *r, const real *t0, const SolverState *st)
 {
   if (st->done != VCL_RUNNING || st->need_restart) return;
-  const double alpha = st->alpha;
+  const real alpha = st->alpha;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s[i] = fma(-alpha, t0[i], r[i]);
 }
 
 // x += alpha p + omega s; r = s - omega t1; ||r||^2, <r,r0*>; then beta / restart bookkeeping   (bicgstab.hpp:458-474)
 static __global__ void __launch_bounds__(VEC_THREADS)
-pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double *r, const double *t1, const double *r0,
-                SolverState *st, double *partials, unsigned int *ticket)
+pbicg_xr_kernel(long long n, real *x, const real *p, const real *s, real *r, const real *t1, const real *r0,
+                SolverState *st, real *partials, unsigned int *ticket)
 {
-  __shared__ double s_red[64];
+  __shared__ real s_red[64];
   if (st->done != VCL_RUNNING || st->need_restart) return;
-  const double alpha = st->alpha, omega = st->omega;
-  double acc[2] = {0.0, 0.0};
+  const real alpha = st->alpha, omega = st->omega;
+  real acc[2] = {0.0, 0.0};
   const long long npairs = aligned16(x, p, s, r, t1, r0) ? (n >> 1) : 0;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
     const long long k = 2 * pi;
-    const double2 vs = ld2(s, k), vp = ld2(p, k), vt = ld2(t1, k), v0 = ld2(r0, k);
-    double2 vx = ld2(x, k), vr;
+    const real2 vs = ld2(s, k), vp = ld2(p, k), vt = ld2(t1, k), v0 = ld2(r0, k);
+    real2 vx = ld2(x, k), vr;
     vx.x += alpha * vp.x + omega * vs.x;   vx.y += alpha * vp.y + omega * vs.y;
     vr.x = fma(-omega, vt.x, vs.x);        vr.y = fma(-omega, vt.y, vs.y);
     acc[0] = fma(vr.x, vr.x, acc[0]);      acc[0] = fma(vr.y, vr.y, acc[0]);
@@ -345,9 +351,9 @@ pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double
   }
   for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
-    const double vs = s[i];
+    const real vs = s[i];
     x[i] += alpha * p[i] + omega * vs;
-    const double vr = fma(-omega, t1[i], vs);
+    const real vr = fma(-omega, t1[i], vs);
     r[i] = vr;
     acc[0] = fma(vr, vr, acc[0]);
     acc[1] = fma(vr, r0[i], acc[1]);
@@ -356,11 +362,11 @@ pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double
   {
     const int i = st->iters;            // index of the iteration just finished
     st->iters = i + 1;
-    const double res = sqrt(acc[0]);
+    const real res = sqrt(acc[0]);
     st->residual_norm = res;
     st->est = fabs(res / st->norm_rhs);
     if (res / st->norm_rhs < st->tol || res < st->abs_tol) { st->done = VCL_CONVERGED; return; }
-    const double new_ip = acc[1];
+    const real new_ip = acc[1];
     st->beta = new_ip / st->ip_rr0 * alpha / omega;
     st->ip_rr0 = new_ip;
     if (new_ip == 0.0 || omega == 0.0 || i - st->last_restart > st->restart_every) st->need_restart = 1;
@@ -370,10 +376,10 @@ pbicg_xr_kernel(long long n, double *x, const double *p, const double *s, double
 
 // p -= omega t0; p = r + beta p                               (bicgstab.hpp:479-480)
 static __global__ void __launch_bounds__(VEC_THREADS)
-pbicg_p_kernel(long long n, double *p, const double *r, const double *t0, const SolverState *st)
+pbicg_p_kernel(long long n, real *p, const real *r, const real *t0, const SolverState *st)
 {
   if (st->done != VCL_RUNNING || st->need_restart) return;
-  const double beta = st->beta, omega = st->omega;
+  const real beta = st->beta, omega = st->omega;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = fma(beta, fma(-omega, t0[i], p[i]), r[i]);
 }
@@ -381,21 +387,21 @@ pbicg_p_kernel(long long n, double *p, const double *r, const double *t0, const 
 // restart: r = (b - r) [/ diag]; p = r; r0 = r; ip_rr0 = ||r||^2     (bicgstab.hpp:430-442; r holds A*x on entry)
 template<bool JACOBI>
 static __global__ void __launch_bounds__(VEC_THREADS)
-pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double *r0, const double *diag,
-                     SolverState *st, double *partials, unsigned int *ticket)
+pbicg_restart_kernel(long long n, const real *b, real *r, real *p, real *r0, const real *diag,
+                     SolverState *st, real *partials, unsigned int *ticket)
 {
-  __shared__ double s_red[32];
-  double acc[1] = {0.0};
+  __shared__ real s_red[32];
+  real acc[1] = {0.0};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
-    double v = b[i] - r[i];
+    real v = b[i] - r[i];
     if (JACOBI) v = v / diag[i];
     r[i] = v; p[i] = v; r0[i] = v;
     acc[0] = fma(v, v, acc[0]);
   }
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0)
   {
-    const double nrm = sqrt(acc[0]);
+    const real nrm = sqrt(acc[0]);
     st->ip_rr0 = nrm * nrm;
     st->need_restart = 0;
     st->last_restart = st->iters;
@@ -414,24 +420,24 @@ pbicg_restart_kernel(long long n, const double *b, double *r, double *p, double 
 // the same time and re-read the same slice of v_k, which L2 serves: DRAM traffic stays (k+1)*8*n bytes.
 #define GS1_COLS 8
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double *out_h, int out_stride,
-                 double *partials, unsigned int *ticket)
+gmres_gs1_kernel(const real *basis, long long n, long long isz, int k, real *out_h, int out_stride,
+                 real *partials, unsigned int *ticket)
 {
-  __shared__ double s_part[8][GS1_COLS];
+  __shared__ real s_part[8][GS1_COLS];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.y * GS1_COLS;
   const int nc = min(GS1_COLS, k - c0);
-  const double *vk = basis + (size_t)k * isz;
-  const double *col = basis + (size_t)c0 * isz;
-  double acc[GS1_COLS];
+  const real *vk = basis + (size_t)k * isz;
+  const real *col = basis + (size_t)c0 * isz;
+  real acc[GS1_COLS];
 #pragma unroll
   for (int q = 0; q < GS1_COLS; ++q) acc[q] = 0.0;
   const long long npairs = n >> 1;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
-    const double2 v = ld2(vk, 2 * pi);
-    double2 a[GS1_COLS];
+    const real2 v = ld2(vk, 2 * pi);
+    real2 a[GS1_COLS];
 #pragma unroll
     for (int q = 0; q < GS1_COLS; ++q)
       if (q < nc) a[q] = ld2(col + (size_t)q * isz, 2 * pi);
@@ -441,7 +447,7 @@ gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double 
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
   {
-    const double v = vk[n - 1];
+    const real v = vk[n - 1];
 #pragma unroll
     for (int q = 0; q < GS1_COLS; ++q)
       if (q < nc) acc[q] = fma(col[(size_t)q * isz + n - 1], v, acc[q]);
@@ -449,13 +455,13 @@ gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double 
 #pragma unroll
   for (int q = 0; q < GS1_COLS; ++q)
   {
-    const double t = warp_sum(acc[q]);
+    const real t = warp_sum(acc[q]);
     if (lane == 0) s_part[w][q] = t;
   }
   __syncthreads();
   if ((int)threadIdx.x < nc)
   {
-    double t = 0.0;
+    real t = 0.0;
     for (int r = 0; r < 8; ++r) t += s_part[r][threadIdx.x];
     partials[(size_t)(c0 + threadIdx.x) * VCL_MAX_BLOCKS + blockIdx.x] = t;
   }
@@ -468,7 +474,7 @@ gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double 
   // last CTA: warp w finishes columns w, w+8, ... in a fixed order
   for (int j = w; j < k; j += 8)
   {
-    double t = 0.0;
+    real t = 0.0;
     for (unsigned int i = lane; i < gridDim.x; i += 32) t += __ldcg(partials + (size_t)j * VCL_MAX_BLOCKS + i);
     t = warp_sum(t);
     if (lane == 0) out_h[(size_t)j * out_stride] = t;
@@ -478,24 +484,24 @@ gmres_gs1_kernel(const double *basis, long long n, long long isz, int k, double 
 
 // stage 2: v_k -= sum_j h_j v_j; R[j + k*m] = h_j; ||v_k||^2       (host_based/iterative_operations.hpp:852-893)
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double *h, int h_stride,
-                 double *R, int krylov_dim, double *out_norm_sq, double *partials, unsigned int *ticket)
+gmres_gs2_kernel(real *basis, long long n, long long isz, int k, const real *h, int h_stride,
+                 real *R, int krylov_dim, real *out_norm_sq, real *partials, unsigned int *ticket)
 {
-  __shared__ double s_red[32];
-  __shared__ double s_h[VCL_GMRES_MAX_KRYLOV];
+  __shared__ real s_red[32];
+  __shared__ real s_h[VCL_GMRES_MAX_KRYLOV];
   for (int j = threadIdx.x; j < k; j += blockDim.x) s_h[j] = h[(size_t)j * h_stride];
   __syncthreads();
-  double *vk = basis + (size_t)k * isz;
-  double acc[1] = {0.0};
+  real *vk = basis + (size_t)k * isz;
+  real acc[1] = {0.0};
   const long long npairs = n >> 1;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
-    double2 v = ld2(vk, 2 * pi);
+    real2 v = ld2(vk, 2 * pi);
     int j = 0;
     for (; j + 4 <= k; j += 4)
     {
-      const double2 a0 = ld2(basis + (size_t)j * isz, 2 * pi), a1 = ld2(basis + (size_t)(j + 1) * isz, 2 * pi);
-      const double2 a2 = ld2(basis + (size_t)(j + 2) * isz, 2 * pi), a3 = ld2(basis + (size_t)(j + 3) * isz, 2 * pi);
+      const real2 a0 = ld2(basis + (size_t)j * isz, 2 * pi), a1 = ld2(basis + (size_t)(j + 1) * isz, 2 * pi);
+      const real2 a2 = ld2(basis + (size_t)(j + 2) * isz, 2 * pi), a3 = ld2(basis + (size_t)(j + 3) * isz, 2 * pi);
       v.x = fma(-s_h[j], a0.x, v.x);     v.y = fma(-s_h[j], a0.y, v.y);
       v.x = fma(-s_h[j + 1], a1.x, v.x); v.y = fma(-s_h[j + 1], a1.y, v.y);
       v.x = fma(-s_h[j + 2], a2.x, v.x); v.y = fma(-s_h[j + 2], a2.y, v.y);
@@ -503,7 +509,7 @@ gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double 
     }
     for (; j < k; ++j)
     {
-      const double2 a0 = ld2(basis + (size_t)j * isz, 2 * pi);
+      const real2 a0 = ld2(basis + (size_t)j * isz, 2 * pi);
       v.x = fma(-s_h[j], a0.x, v.x); v.y = fma(-s_h[j], a0.y, v.y);
     }
     acc[0] = fma(v.x, v.x, acc[0]); acc[0] = fma(v.y, v.y, acc[0]);
@@ -511,7 +517,7 @@ gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double 
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
   {
-    double v = vk[n - 1];
+    real v = vk[n - 1];
     for (int j = 0; j < k; ++j) v = fma(-s_h[j], basis[(size_t)j * isz + n - 1], v);
     acc[0] = fma(v, v, acc[0]);
     vk[n - 1] = v;
@@ -525,25 +531,25 @@ gmres_gs2_kernel(double *basis, long long n, long long isz, int k, const double 
 
 // normalize: R[off] = ||v_k||; v_k /= ||v_k||; xi_k = <r, v_k>      (host_based/iterative_operations.hpp:733-778)
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, int offset_in_R, const double *in_norm_sq,
-                       double *out_r_dot_vk, double *partials, unsigned int *ticket)
+gmres_normalize_kernel(long long n, real *vk, const real *res, real *R, int offset_in_R, const real *in_norm_sq,
+                       real *out_r_dot_vk, real *partials, unsigned int *ticket)
 {
-  __shared__ double s_red[32];
-  const double nrm = sqrt(*in_norm_sq);
+  __shared__ real s_red[32];
+  const real nrm = sqrt(*in_norm_sq);
   if (blockIdx.x == 0 && threadIdx.x == 0) R[offset_in_R] = nrm;
-  double acc[1] = {0.0};
+  real acc[1] = {0.0};
   const bool vec = ((reinterpret_cast<uintptr_t>(vk) | reinterpret_cast<uintptr_t>(res)) & 15u) == 0u;
   const long long npairs = vec ? (n >> 1) : 0;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
-    double2 v = ld2(vk, 2 * pi); const double2 rr = ld2(res, 2 * pi);
+    real2 v = ld2(vk, 2 * pi); const real2 rr = ld2(res, 2 * pi);
     v.x = v.x / nrm; v.y = v.y / nrm;
     acc[0] = fma(rr.x, v.x, acc[0]); acc[0] = fma(rr.y, v.y, acc[0]);
     st2(vk, 2 * pi, v);
   }
   for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
-    const double v = vk[i] / nrm;
+    const real v = vk[i] / nrm;
     acc[0] = fma(res[i], v, acc[0]);
     vk[i] = v;
   }
@@ -552,29 +558,30 @@ gmres_normalize_kernel(long long n, double *vk, const double *res, double *R, in
 
 // x += c_0 r + sum_{j=1}^{k-1} c_j v_{j-1}                         (host_based/iterative_operations.hpp:895-922)
 static __global__ void __launch_bounds__(VEC_THREADS)
-gmres_update_kernel(long long n, double *x, const double *res, const double *basis, long long isz, const double *coef, int k)
+gmres_update_kernel(long long n, real *x, const real *res, const real *basis, long long isz, const real *coef, int k)
 {
-  __shared__ double s_c[VCL_GMRES_MAX_KRYLOV];
+  __shared__ real s_c[VCL_GMRES_MAX_KRYLOV];
   for (int j = threadIdx.x; j < max(k, 1); j += blockDim.x) s_c[j] = coef[j];
   __syncthreads();
   const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(basis)) & 15u) == 0u && (isz & 1) == 0;
   const long long npairs = vec ? (n >> 1) : 0;
   for (long long pi = (long long)blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += (long long)gridDim.x * blockDim.x)
   {
-    double2 v = ld2(x, 2 * pi); const double2 rr = ld2(res, 2 * pi);
+    real2 v = ld2(x, 2 * pi); const real2 rr = ld2(res, 2 * pi);
     v.x = fma(s_c[0], rr.x, v.x); v.y = fma(s_c[0], rr.y, v.y);
     for (int j = 1; j < k; ++j)
     {
-      const double2 a = ld2(basis + (size_t)(j - 1) * isz, 2 * pi);
+      const real2 a = ld2(basis + (size_t)(j - 1) * isz, 2 * pi);
       v.x = fma(s_c[j], a.x, v.x); v.y = fma(s_c[j], a.y, v.y);
     }
     st2(x, 2 * pi, v);
   }
   for (long long i = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
-    double v = x[i];
+    real v = x[i];
     v = fma(s_c[0], res[i], v);
     for (int j = 1; j < k; ++j) v = fma(s_c[j], basis[(size_t)(j - 1) * isz + i], v);
     x[i] = v;
   }
 }
+} // namespace VCL_NS

@@ -5,9 +5,13 @@
 // Conventions (identical to oracle/vcl_oracle.c vclo_gen_stencil*): row = i + nx*(j + ny*l); neighbours outside the grid
 // are dropped; columns ascend within a row; down/south/west = -1-c, diagonal = 2*dim + sum(c), east/north/up = -1.
 #include "common.cuh"
+#include "prec.cuh"
 #include <algorithm>
 
-struct StencilGeom { int nx, ny, nz; double cx, cy, cz; };
+namespace VCL_NS
+{
+
+struct StencilGeom { int nx, ny, nz; real cx, cy, cz; };
 
 // number of stored entries in rows [0, r)
 __device__ __forceinline__ unsigned long long stencil_offset(const StencilGeom &g, long long r)
@@ -30,7 +34,7 @@ __device__ __forceinline__ unsigned long long stencil_offset(const StencilGeom &
 }
 
 __global__ void __launch_bounds__(256)
-stencil_kernel(StencilGeom g, long long row_begin, long long row_end, u32 *rp, u32 *ci, double *va)
+stencil_kernel(StencilGeom g, long long row_begin, long long row_end, u32 *rp, u32 *ci, real *va)
 {
   const long long nxy = (long long)g.nx * g.ny;
   const unsigned long long base = stencil_offset(g, row_begin);
@@ -63,7 +67,7 @@ static unsigned long long host_offset(const StencilGeom &g, long long r)
 }
 
 __global__ void __launch_bounds__(256)
-fill_uniform_kernel(long long n, double *x, unsigned long long seed, long long index_offset, double lo, double hi)
+fill_uniform_kernel(long long n, real *x, unsigned long long seed, long long index_offset, real lo, real hi)
 {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
@@ -71,7 +75,7 @@ fill_uniform_kernel(long long n, double *x, unsigned long long seed, long long i
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     z = z ^ (z >> 31);
-    const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    const real u = (real)(z >> 11) * (1.0 / 9007199254740992.0);
     x[i] = lo + (hi - lo) * u;
   }
 }
@@ -79,8 +83,8 @@ fill_uniform_kernel(long long n, double *x, unsigned long long seed, long long i
 extern "C" {
 
 ViennaCLStatus ViennaCLCUDADgenerate_stencil_rows(ViennaCLBackend b, ViennaCLInt nx, ViennaCLInt ny, ViennaCLInt nz,
-                                                  double cx, double cy, double cz, long long row_begin, long long row_end,
-                                                  unsigned int *row_ptr, unsigned int *col_idx, double *values, long long *nnz)
+                                                  real cx, real cy, real cz, long long row_begin, long long row_end,
+                                                  unsigned int *row_ptr, unsigned int *col_idx, real *values, long long *nnz)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, nx > 0 && ny > 0 && nz > 0, "grid dimensions must be positive");
@@ -100,8 +104,8 @@ ViennaCLStatus ViennaCLCUDADgenerate_stencil_rows(ViennaCLBackend b, ViennaCLInt
 }
 
 ViennaCLStatus ViennaCLCUDADgenerate_stencil(ViennaCLBackend b, ViennaCLInt nx, ViennaCLInt ny, ViennaCLInt nz,
-                                             double cx, double cy, double cz,
-                                             unsigned int *row_ptr, unsigned int *col_idx, double *values,
+                                             real cx, real cy, real cz,
+                                             unsigned int *row_ptr, unsigned int *col_idx, real *values,
                                              long long *rows, long long *nnz)
 {
   VCL_CHECK_BACKEND(b);
@@ -111,8 +115,8 @@ ViennaCLStatus ViennaCLCUDADgenerate_stencil(ViennaCLBackend b, ViennaCLInt nx, 
   return ViennaCLCUDADgenerate_stencil_rows(b, nx, ny, nz, cx, cy, cz, 0, n, row_ptr, col_idx, values, nnz);
 }
 
-ViennaCLStatus ViennaCLCUDADfill_uniform(ViennaCLBackend b, long long n, double *x, unsigned long long seed,
-                                         long long index_offset, double lo, double hi)
+ViennaCLStatus ViennaCLCUDADfill_uniform(ViennaCLBackend b, long long n, real *x, unsigned long long seed,
+                                         long long index_offset, real lo, real hi)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0, "negative size");
@@ -125,3 +129,4 @@ ViennaCLStatus ViennaCLCUDADfill_uniform(ViennaCLBackend b, long long n, double 
 }
 
 } // extern "C"
+} // namespace VCL_NS

@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include "spmv_kernels.cuh"
 
+namespace VCL_NS
+{
+
 // Resident CTAs per SM for a kernel, queried once per instantiation (all B200s of a box are identical).
 template<class K>
 static int vcl_occupancy(K kernel, int threads, int dyn_smem = 0)
@@ -86,3 +89,4 @@ static ViennaCLStatus vcl_launch_ell(ViennaCLBackend b, const ViennaCLCUDADhyb &
   VCL_LAUNCHED(b, "ell_kernel");
   return ViennaCLSuccess;
 }
+} // namespace VCL_NS

@@ -8,6 +8,8 @@
 #include <cmath>
 #include <algorithm>
 
+namespace VCL_NS
+{
 namespace {
 
 struct MatOp
@@ -21,7 +23,7 @@ struct MatOp
 };
 
 template<class Epi>
-ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const double *x, Epi epi)
+ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const real *x, Epi epi)
 {
   XVec xv = make_xvec(x, 0, 1);
   if (A.fmt == 0) return vcl_launch_csr(b, A.csr, xv, epi);
@@ -29,7 +31,7 @@ ViennaCLStatus launch_prod(ViennaCLBackend b, const MatOp &A, const double *x, E
   return vcl_launch_ell(b, A.hyb, xv, epi);
 }
 
-ViennaCLStatus plain_prod(ViennaCLBackend b, const MatOp &A, const double *x, double *y)
+ViennaCLStatus plain_prod(ViennaCLBackend b, const MatOp &A, const real *x, real *y)
 {
   EpiAxpby epi = {y, 0, 1, 1.0, 0.0};
   return launch_prod(b, A, x, epi);
@@ -66,20 +68,20 @@ struct Carver
 {
   char *base; size_t off;
   explicit Carver(void *p) : base((char*)p), off(0) {}
-  double *take(size_t n) { double *p = (double*)(base + off); off += ((n * sizeof(double) + 255) / 256) * 256; return p; }
-  static size_t need(size_t n) { return ((n * sizeof(double) + 255) / 256) * 256; }
+  real *take(size_t n) { real *p = (real*)(base + off); off += ((n * sizeof(real) + 255) / 256) * 256; return p; }
+  static size_t need(size_t n) { return ((n * sizeof(real) + 255) / 256) * 256; }
 };
 
 ViennaCLStatus push_state(ViennaCLBackend b)
 {
-  VCL_CUDA(b, cudaMemcpyAsync(b->dstate, b->hstate, sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(VCL_DSTATE(b), VCL_HSTATE(b), sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));   // hstate is reused as the read-back mirror
   return ViennaCLSuccess;
 }
 
 ViennaCLStatus pull_state(ViennaCLBackend b)
 {
-  VCL_CUDA(b, cudaMemcpyAsync(b->hstate, b->dstate, sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(VCL_HSTATE(b), VCL_DSTATE(b), sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   return ViennaCLSuccess;
 }
@@ -92,35 +94,35 @@ const int kBatch = 32;   // iterations enqueued between two looks at the device 
 // iteration -- pcg_update_kernel (all vector updates, u = r ./ diag, <r,u>) and the fused SpMV w = A u with <w,u>,
 // whose last CTA advances alpha/beta/convergence on the device.  12*nnz + 116*N bytes per iteration.
 // ------------------------------------------------------------------------------------------------
-ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
   Carver cv(b->ws);
-  double *r = cv.take(n), *u = cv.take(n), *w = cv.take(n), *p = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
+  real *r = cv.take(n), *u = cv.take(n), *w = cv.take(n), *p = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
   const int grid = vec_grid(b, n);
 
   VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
-  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemsetAsync(p, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemsetAsync(s, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  pcg_init_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, r, u, diag, b->partials, b->tickets, b->dscal + 0);
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(p, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(s, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  pcg_init_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, r, u, diag, VCL_PARTIALS(b), b->tickets, VCL_DSCAL(b) + 0);
   VCL_LAUNCHED(b, "pcg_init_kernel");
   VCL_TRY(plain_prod(b, A, u, w));
-  VCL_TRY(vcl_dot_async(b, n, w, 0, 1, u, 0, 1, b->dscal + 1));
-  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_TRY(vcl_dot_async(b, n, w, 0, 1, u, 0, 1, VCL_DSCAL(b) + 1));
+  VCL_CUDA(b, cudaMemcpyAsync(VCL_HSCAL(b), VCL_DSCAL(b), 2 * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
-  const double gamma0 = b->hscal[0], delta0 = b->hscal[1];
+  const real gamma0 = VCL_HSCAL(b)[0], delta0 = VCL_HSCAL(b)[1];
   if (std::fabs(gamma0) <= tag->abs_tolerance * tag->abs_tolerance) return ViennaCLSuccess;       // cg.hpp:286-287
 
-  SolverState *h = b->hstate;
+  SolverState *h = VCL_HSTATE(b);
   std::memset(h, 0, sizeof(SolverState));
   h->alpha = gamma0 / delta0; h->beta = 0.0; h->ip_rr0 = gamma0; h->norm_rhs_sq = gamma0; h->norm_rhs = std::sqrt(std::fabs(gamma0));
   h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = gamma0;
   VCL_TRY(push_state(b));
-  SolverState *st = b->dstate;
+  SolverState *st = VCL_DSTATE(b);
 
   const int batch = tag->monitor ? 1 : kBatch;
   int launched = 0;
@@ -129,9 +131,9 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, 
     const int nb = std::min(batch, tag->max_iterations - launched);
     for (int k = 0; k < nb; ++k)
     {
-      pcg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, r, u, w, p, s, diag, st, b->partials, b->tickets, &st->sums[0]);
+      pcg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, r, u, w, p, s, diag, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);
       VCL_LAUNCHED(b, "pcg_update_kernel");
-      EpiFused<STEP_PCG, false, false> epi = {w, u, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_PCG, false, false> epi = {w, u, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, u, epi));
     }
     launched += nb;
@@ -147,7 +149,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, 
 // ------------------------------------------------------------------------------------------------
 // CG  (cg.hpp:128-187)
 // ------------------------------------------------------------------------------------------------
-ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
@@ -161,30 +163,30 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, do
   VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: unknown preconditioner id");
   VCL_TRY(vcl_ws_reserve(b, 3 * Carver::need(n)));
   Carver cv(b->ws);
-  double *r = cv.take(n), *p = cv.take(n), *Ap = cv.take(n);
+  real *r = cv.take(n), *p = cv.take(n), *Ap = cv.take(n);
 
-  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
   VCL_TRY(plain_prod(b, A, p, Ap));
-  VCL_TRY(vcl_dot_async(b, n, r, 0, 1, r, 0, 1, b->dscal + 0));
-  VCL_TRY(vcl_dot_async(b, n, p, 0, 1, Ap, 0, 1, b->dscal + 1));
-  VCL_TRY(vcl_dot_async(b, n, Ap, 0, 1, Ap, 0, 1, b->dscal + 2));
-  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 3 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_TRY(vcl_dot_async(b, n, r, 0, 1, r, 0, 1, VCL_DSCAL(b) + 0));
+  VCL_TRY(vcl_dot_async(b, n, p, 0, 1, Ap, 0, 1, VCL_DSCAL(b) + 1));
+  VCL_TRY(vcl_dot_async(b, n, Ap, 0, 1, Ap, 0, 1, VCL_DSCAL(b) + 2));
+  VCL_CUDA(b, cudaMemcpyAsync(VCL_HSCAL(b), VCL_DSCAL(b), 3 * sizeof(real), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
 
-  double norm_rhs_squared = std::sqrt(b->hscal[0]); norm_rhs_squared *= norm_rhs_squared;          // cg.hpp:147
+  real norm_rhs_squared = std::sqrt(VCL_HSCAL(b)[0]); norm_rhs_squared *= norm_rhs_squared;          // cg.hpp:147
   if (norm_rhs_squared <= tag->abs_tolerance * tag->abs_tolerance) return ViennaCLSuccess;         // cg.hpp:149-150
-  const double rr = norm_rhs_squared;
-  const double alpha = rr / b->hscal[1];
-  double beta = std::sqrt(b->hscal[2]); beta = (alpha * alpha * beta * beta - rr) / rr;            // cg.hpp:153-154
+  const real rr = norm_rhs_squared;
+  const real alpha = rr / VCL_HSCAL(b)[1];
+  real beta = std::sqrt(VCL_HSCAL(b)[2]); beta = (alpha * alpha * beta * beta - rr) / rr;            // cg.hpp:153-154
 
-  SolverState *h = b->hstate;
+  SolverState *h = VCL_HSTATE(b);
   std::memset(h, 0, sizeof(SolverState));
   h->alpha = alpha; h->beta = beta; h->norm_rhs_sq = norm_rhs_squared; h->norm_rhs = std::sqrt(norm_rhs_squared);
   h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = rr;
   VCL_TRY(push_state(b));
-  SolverState *st = b->dstate;
+  SolverState *st = VCL_DSTATE(b);
 
   const int grid = vec_grid(b, n);
   const int batch = tag->monitor ? 1 : kBatch;
@@ -194,9 +196,9 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, do
     const int nb = std::min(batch, tag->max_iterations - launched);
     for (int k = 0; k < nb; ++k)
     {
-      cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, &st->sums[0]);
+      cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);
       VCL_LAUNCHED(b, "cg_update_kernel");
-      EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, epi));
     }
     launched += nb;
@@ -212,29 +214,29 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, do
 // ------------------------------------------------------------------------------------------------
 // Pipelined BiCGStab  (bicgstab.hpp:97-215)
 // ------------------------------------------------------------------------------------------------
-ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
   Carver cv(b->ws);
-  double *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *Ap = cv.take(n), *s = cv.take(n), *As = cv.take(n);
+  real *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *Ap = cv.take(n), *s = cv.take(n), *As = cv.take(n);
 
-  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(r0, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  double ss = 0.0;
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r0, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  real ss = 0.0;
   VCL_TRY(vcl_dot_host(b, n, r, 0, 1, r, 0, 1, &ss));
-  const double norm_rhs = std::sqrt(ss);
+  const real norm_rhs = std::sqrt(ss);
   if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                       // bicgstab.hpp:140-141
 
-  SolverState *h = b->hstate;
+  SolverState *h = VCL_HSTATE(b);
   std::memset(h, 0, sizeof(SolverState));
   h->norm_rhs = norm_rhs; h->norm_rhs_sq = norm_rhs * norm_rhs; h->residual_norm = norm_rhs;
   h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations;
   h->sums[0] = norm_rhs * norm_rhs;                                                 // bicgstab.hpp:131
   VCL_TRY(push_state(b));
-  SolverState *st = b->dstate;
+  SolverState *st = VCL_DSTATE(b);
 
   const int grid = vec_grid(b, n);
   const int batch = tag->monitor ? 1 : kBatch;
@@ -245,11 +247,11 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const doubl
     const int nb = std::min(batch, tag->max_iterations - launched);
     for (int k = 0; k < nb; ++k)
     {
-      EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, VCL_PARTIALS(b), b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, e1));
-      bicgstab_update_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, &st->sums[0], &st->sums[3], st, b->partials, b->tickets, &st->sums[5]);
+      bicgstab_update_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, &st->sums[0], &st->sums[3], st, VCL_PARTIALS(b), b->tickets, &st->sums[5]);
       VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
-      EpiFused<STEP_BICGSTAB, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[4], {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_BICGSTAB, true, false> e2 = {As, s, r0, nullptr, VCL_PARTIALS(b), b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[4], {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, s, e2));
       if (tag->monitor)
       {
@@ -258,7 +260,7 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const doubl
         if (tag->monitor(x, h->est, tag->monitor_user)) { stopped = true; break; }
         if (h->done != VCL_RUNNING) break;
       }
-      bicgstab_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, 0.0, p, 0.0, s, r, As, 0.0, Ap, r0, st, b->partials, b->tickets, &st->sums[0]);
+      bicgstab_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, 0.0, p, 0.0, s, r, As, 0.0, Ap, r0, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);
       VCL_LAUNCHED(b, "bicgstab_update_kernel");
     }
     launched += nb;
@@ -275,29 +277,29 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const doubl
 // Five kernels per iteration instead of the reference's 2 SpMV + 2 element_div + ~12 BLAS-1 launches + ~6 blocking
 // scalar read-backs; the divide by diag(A) is folded into the SpMV epilogue.
 // ------------------------------------------------------------------------------------------------
-ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 7 * Carver::need(n)));
   Carver cv(b->ws);
-  double *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *t0 = cv.take(n), *t1 = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
+  real *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *t0 = cv.take(n), *t1 = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
 
   VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
-  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
-  double ss = 0.0;
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
+  real ss = 0.0;
   VCL_TRY(vcl_dot_host(b, n, rhs, 0, 1, rhs, 0, 1, &ss));
-  const double norm_rhs = std::sqrt(ss);
+  const real norm_rhs = std::sqrt(ss);
   if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                       // bicgstab.hpp:424-425
 
-  SolverState *h = b->hstate;
+  SolverState *h = VCL_HSTATE(b);
   std::memset(h, 0, sizeof(SolverState));
   h->norm_rhs = norm_rhs; h->norm_rhs_sq = norm_rhs * norm_rhs; h->residual_norm = norm_rhs;
   h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations;
   h->restart_every = tag->max_iterations_before_restart;
   h->need_restart = 1;
   VCL_TRY(push_state(b));
-  SolverState *st = b->dstate;
+  SolverState *st = VCL_DSTATE(b);
 
   const int grid = vec_grid(b, n);
   const int batch = tag->monitor ? 1 : kBatch;
@@ -306,7 +308,7 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *
     if (h->need_restart)
     {
       VCL_TRY(plain_prod(b, A, x, r));                                               // residual = A*x
-      pbicg_restart_kernel<true><<<grid, VEC_THREADS, 0, b->stream>>>(n, rhs, r, p, r0, diag, st, b->partials, b->tickets);
+      pbicg_restart_kernel<true><<<grid, VEC_THREADS, 0, b->stream>>>(n, rhs, r, p, r0, diag, st, VCL_PARTIALS(b), b->tickets);
       VCL_LAUNCHED(b, "pbicg_restart_kernel");
       h->need_restart = 0;
     }
@@ -315,13 +317,13 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *
     const int nb = std::min(batch, remaining);
     for (int k = 0; k < nb; ++k)
     {
-      EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, VCL_PARTIALS(b), b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, p, e1));
       pbicg_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, t0, st);
       VCL_LAUNCHED(b, "pbicg_s_kernel");
-      EpiFused<STEP_PBICG_OMEGA, false, true> e2 = {t1, s, nullptr, diag, b->partials, b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
+      EpiFused<STEP_PBICG_OMEGA, false, true> e2 = {t1, s, nullptr, diag, VCL_PARTIALS(b), b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, s, e2));
-      pbicg_xr_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, s, r, t1, r0, st, b->partials, b->tickets);
+      pbicg_xr_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, s, r, t1, r0, st, VCL_PARTIALS(b), b->tickets);
       VCL_LAUNCHED(b, "pbicg_xr_kernel");
       pbicg_p_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, p, r, t0, st);
       VCL_LAUNCHED(b, "pbicg_p_kernel");
@@ -335,7 +337,7 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const double *
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
@@ -352,27 +354,27 @@ ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const double *r
 // GMRES(m), pipelined simpler-GMRES with classical Gram-Schmidt  (gmres.hpp:181-367)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(VEC_THREADS)
-scale_residual_kernel(long long n, double *res, double rho0)
+scale_residual_kernel(long long n, real *res, real rho0)
 {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     res[i] = res[i] / rho0;
 }
 
 __global__ void __launch_bounds__(VEC_THREADS)
-residual_kernel(long long n, double *res, const double *rhs)     // res = rhs - res
+residual_kernel(long long n, real *res, const real *rhs)     // res = rhs - res
 {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     res[i] = rhs[i] - res[i];
 }
 
-ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const double *basis, long long n, long long isz, int k, double *out_h, int stride)
+ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const real *basis, long long n, long long isz, int k, real *out_h, int stride)
 {
   VCL_REQUIRE(b, (isz & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u,
               "Krylov basis must be 16-byte aligned with an even internal size (the reference pads vectors to 128 entries, forwards.h:385)");
   (void)grid;
   const int gy = (k + GS1_COLS - 1) / GS1_COLS;                      // column groups
   const int gx = std::max(1, std::min(vcl_div_up(n / 2, VEC_THREADS), std::min(std::max(b->sm_count * 8 / gy, b->sm_count), VCL_MAX_BLOCKS)));
-  gmres_gs1_kernel<<<dim3(gx, gy), VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, b->partials, b->tickets);
+  gmres_gs1_kernel<<<dim3(gx, gy), VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, VCL_PARTIALS(b), b->tickets);
   VCL_LAUNCHED(b, "gmres_gs1_kernel");
   return ViennaCLSuccess;
 }
@@ -382,7 +384,7 @@ int scalar_grid(ViennaCLBackend b, long long n)
   return (int)std::max(1LL, std::min((n + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
 }
 
-ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
@@ -400,21 +402,21 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs,
   const size_t small = Carver::need((size_t)m * m) + 4 * Carver::need(m);
   VCL_TRY(vcl_ws_reserve(b, Carver::need(n) + Carver::need((size_t)isz * m) + small));
   Carver cv(b->ws);
-  double *res = cv.take(n), *V = cv.take((size_t)isz * m), *R = cv.take((size_t)m * m);
-  double *d_xi = cv.take(m), *d_h = cv.take(m), *d_coef = cv.take(m);
-  double *d_nsq = b->dscal + 8, *d_junk = b->dscal + 9;
+  real *res = cv.take(n), *V = cv.take((size_t)isz * m), *R = cv.take((size_t)m * m);
+  real *d_xi = cv.take(m), *d_h = cv.take(m), *d_coef = cv.take(m);
+  real *d_nsq = VCL_DSCAL(b) + 8, *d_junk = VCL_DSCAL(b) + 9;
 
-  std::vector<double> hR((size_t)m * m), xi(m), eta(m), coef(m, 0.0);
+  std::vector<real> hR((size_t)m * m), xi(m), eta(m), coef(m, 0.0);
 
-  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
-  VCL_CUDA(b, cudaMemcpyAsync(res, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
-  VCL_CUDA(b, cudaMemsetAsync(R, 0, sizeof(double) * m * m, b->stream));
-  VCL_CUDA(b, cudaMemsetAsync(d_xi, 0, sizeof(double) * m, b->stream));
-  VCL_CUDA(b, cudaMemsetAsync(d_coef, 0, sizeof(double) * m, b->stream));
-  double ss = 0.0;
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(res, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(R, 0, sizeof(real) * m * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_xi, 0, sizeof(real) * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_coef, 0, sizeof(real) * m, b->stream));
+  real ss = 0.0;
   VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
-  const double norm_rhs = std::sqrt(ss);
-  double rho_0 = norm_rhs, rho = 1.0;
+  const real norm_rhs = std::sqrt(ss);
+  real rho_0 = norm_rhs, rho = 1.0;
 
   unsigned max_restarts = (unsigned)tag->max_iterations / (unsigned)m;         // gmres.hpp:74-80
   if (max_restarts > 0 && max_restarts * (unsigned)m == (unsigned)tag->max_iterations) max_restarts -= 1;
@@ -439,22 +441,22 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs,
     int k;
     for (k = 0; k < m; ++k)
     {
-      double *vk = V + (size_t)k * isz;
-      const double *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
-      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, b->partials, b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
+      real *vk = V + (size_t)k * isz;
+      const real *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
+      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
       VCL_TRY(launch_prod(b, A, src, e));
       if (k > 0)
       {
         VCL_TRY(launch_gs1(b, grid, V, n, isz, k, d_h, 1));
-        gmres_gs2_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(V, n, isz, k, d_h, 1, R, m, d_nsq, b->partials, b->tickets);
+        gmres_gs2_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(V, n, isz, k, d_h, 1, R, m, d_nsq, VCL_PARTIALS(b), b->tickets);
         VCL_LAUNCHED(b, "gmres_gs2_kernel");
       }
-      gmres_normalize_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, vk, res, R, k * m + k, d_nsq, d_xi + k, b->partials, b->tickets);
+      gmres_normalize_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, vk, res, R, k * m + k, d_nsq, d_xi + k, VCL_PARTIALS(b), b->tickets);
       VCL_LAUNCHED(b, "gmres_normalize_kernel");
     }
 
-    VCL_CUDA(b, cudaMemcpyAsync(xi.data(), d_xi, sizeof(double) * m, cudaMemcpyDeviceToHost, b->stream));
-    VCL_CUDA(b, cudaMemcpyAsync(hR.data(), R, sizeof(double) * m * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(xi.data(), d_xi, sizeof(real) * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(hR.data(), R, sizeof(real) * m * m, cudaMemcpyDeviceToHost, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
 
     size_t kk = (size_t)k;
@@ -478,7 +480,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs,
     }
     for (size_t i = 0; i < kk; ++i) coef[i] = rho_0 * eta[i];                    // gmres.hpp:351-352
 
-    VCL_CUDA(b, cudaMemcpyAsync(d_coef, coef.data(), sizeof(double) * m, cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(d_coef, coef.data(), sizeof(real) * m, cudaMemcpyHostToDevice, b->stream));
     gmres_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, res, V, isz, d_coef, (int)kk);
     VCL_LAUNCHED(b, "gmres_update_kernel");
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));                               // coef (pageable) must outlive the copy
@@ -490,10 +492,10 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const double *rhs,
 }
 
 // sums `chunk` entries starting at in[0] into out[0] (per-op API: tolerate producers that spread partials over a chunk)
-__global__ void chunk_sum_kernel(const double *in, int chunk, double *out)
+__global__ void chunk_sum_kernel(const real *in, int chunk, real *out)
 {
-  __shared__ double s_red[32];
-  double acc[1] = {0.0};
+  __shared__ real s_red[32];
+  real acc[1] = {0.0};
   for (int i = threadIdx.x; i < chunk; i += blockDim.x) acc[0] += in[i];
   block_sum<1>(acc, s_red);
   if (threadIdx.x == 0) out[0] = acc[0];
@@ -504,8 +506,8 @@ MatOp from_sell(const ViennaCLCUDADsell *A) { MatOp m; m.fmt = 1; m.sell = *A; m
 MatOp from_hyb(const ViennaCLCUDADhyb *A) { MatOp m; m.fmt = 2; m.hyb = *A; m.csr = ViennaCLCUDADcsr(); m.sell = ViennaCLCUDADsell(); return m; }
 MatOp from_ell(const ViennaCLCUDADell *A) { ViennaCLCUDADhyb h = ViennaCLCUDADhyb(); h.ell = *A; return from_hyb(&h); }
 
-ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p, double *Ap, const double *r0,
-                              double *out_ApAp, double *out_pAp, double *out_Apr0)
+ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const real *p, real *Ap, const real *r0,
+                              real *out_ApAp, real *out_pAp, real *out_Apr0)
 {
   VCL_CHECK_BACKEND(b);
   VCL_TRY(check_matrix(b, A));
@@ -513,10 +515,10 @@ ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p
   VCL_REQUIRE(b, p && Ap && p != Ap, "bad vectors");
   if (r0)
   {
-    EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}, nullptr};
+    EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}, nullptr};
     return launch_prod(b, A, p, e);
   }
-  EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, nullptr, out_ApAp, out_pAp, nullptr, {0.0, 0.0, 0.0}, nullptr};
+  EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, out_ApAp, out_pAp, nullptr, {0.0, 0.0, 0.0}, nullptr};
   return launch_prod(b, A, p, e);
 }
 
@@ -527,21 +529,21 @@ ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const double *p
 // ================================================================================================
 extern "C" {
 
-ViennaCLStatus ViennaCLCUDADcsr_cg(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADcsr_cg(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return cg_solve(b, from_csr(A), rhs, x, tag); }
-ViennaCLStatus ViennaCLCUDADsell_cg(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADsell_cg(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return cg_solve(b, from_sell(A), rhs, x, tag); }
-ViennaCLStatus ViennaCLCUDADcsr_bicgstab(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADcsr_bicgstab(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return bicgstab_solve(b, from_csr(A), rhs, x, tag); }
-ViennaCLStatus ViennaCLCUDADsell_bicgstab(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADsell_bicgstab(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return bicgstab_solve(b, from_sell(A), rhs, x, tag); }
-ViennaCLStatus ViennaCLCUDADcsr_gmres(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADcsr_gmres(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_csr(A), rhs, x, tag); }
-ViennaCLStatus ViennaCLCUDADsell_gmres(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+ViennaCLStatus ViennaCLCUDADsell_gmres(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return gmres_solve(b, from_sell(A), rhs, x, tag); }
 
 #define VCL_SOLVER_ENTRY(name, type, conv, fn) \
-ViennaCLStatus name(ViennaCLBackend b, const type *A, const double *rhs, double *x, ViennaCLB200SolverTag *tag) \
+ViennaCLStatus name(ViennaCLBackend b, const type *A, const real *rhs, real *x, ViennaCLB200SolverTag *tag) \
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return fn(b, conv(A), rhs, x, tag); }
 VCL_SOLVER_ENTRY(ViennaCLCUDADell_cg, ViennaCLCUDADell, from_ell, cg_solve)
 VCL_SOLVER_ENTRY(ViennaCLCUDADhyb_cg, ViennaCLCUDADhyb, from_hyb, cg_solve)
@@ -551,8 +553,8 @@ VCL_SOLVER_ENTRY(ViennaCLCUDADell_gmres, ViennaCLCUDADell, from_ell, gmres_solve
 VCL_SOLVER_ENTRY(ViennaCLCUDADhyb_gmres, ViennaCLCUDADhyb, from_hyb, gmres_solve)
 
 // plain products for the other formats (linalg/sparse_matrix_operations.hpp:90-121 dispatch)
-static ViennaCLStatus ellhyb_mv(ViennaCLBackend b, const MatOp &A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+static ViennaCLStatus ellhyb_mv(ViennaCLBackend b, const MatOp &A, const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 {
   VCL_TRY(check_matrix_any(b, A));
   if (A.rows() == 0) return ViennaCLSuccess;
@@ -560,123 +562,123 @@ static ViennaCLStatus ellhyb_mv(ViennaCLBackend b, const MatOp &A, const double 
   EpiAxpby epi = {y, offy, incy, alpha, beta};
   return vcl_launch_ell(b, A.hyb, make_xvec(x, offx, incx), epi);
 }
-ViennaCLStatus ViennaCLCUDADellmv(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+ViennaCLStatus ViennaCLCUDADellmv(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                  real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return ellhyb_mv(b, from_ell(A), x, offx, incx, alpha, y, offy, incy, beta); }
-ViennaCLStatus ViennaCLCUDADhybmv(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                  double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+ViennaCLStatus ViennaCLCUDADhybmv(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                  real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A, "null matrix"); return ellhyb_mv(b, from_hyb(A), x, offx, incx, alpha, y, offy, incy, beta); }
 
-ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
   return fused_prod_api(b, from_ell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
-ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
   return fused_prod_api(b, from_hyb(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap,
-                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap,
+                                                        const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
   return fused_prod_api(b, from_ell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap,
-                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap,
+                                                        const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
   return fused_prod_api(b, from_hyb(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { return ViennaCLCUDADpipelined_cg_prod_ell(b, A, p, Ap, buf, buf_size); }
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const double *p, double *Ap, double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { return ViennaCLCUDADpipelined_cg_prod_hyb(b, A, p, Ap, buf, buf_size); }
 
 // ---- per-step entry points (linalg/iterative_operations.hpp) ----
-ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend b, ViennaCLInt n, double *result, double alpha,
-                                                       double *p, double *r, const double *Ap, double beta,
-                                                       double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend b, ViennaCLInt n, real *result, real alpha,
+                                                       real *p, real *r, const real *Ap, real beta,
+                                                       real *buf, ViennaCLInt buf_size)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && buf && buf_size >= 3, "bad arguments");
   if (n == 0) return ViennaCLSuccess;
-  cg_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, p, r, Ap, alpha, beta, nullptr, b->partials, b->tickets, buf);
+  cg_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, p, r, Ap, alpha, beta, nullptr, VCL_PARTIALS(b), b->tickets, buf);
   VCL_LAUNCHED(b, "cg_update_kernel");
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
-                                                  double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *p, real *Ap,
+                                                  real *buf, ViennaCLInt buf_size)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
   const int chunk = buf_size / 3;
   return fused_prod_api(b, from_csr(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
-                                                   double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *p, real *Ap,
+                                                   real *buf, ViennaCLInt buf_size)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
   const int chunk = buf_size / 3;
   return fused_prod_api(b, from_sell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_update_s(ViennaCLBackend b, ViennaCLInt n, double *s, const double *r, const double *Ap,
-                                                        double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_update_s(ViennaCLBackend b, ViennaCLInt n, real *s, const real *r, const real *Ap,
+                                                        real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && buf && chunk >= 1, "bad arguments");
   if (n == 0) return ViennaCLSuccess;
-  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf, chunk, b->dscal + 16);
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf, chunk, VCL_DSCAL(b) + 16);
   VCL_LAUNCHED(b, "chunk_sum_kernel");
-  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + 3 * (size_t)chunk, chunk, b->dscal + 17);
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + 3 * (size_t)chunk, chunk, VCL_DSCAL(b) + 17);
   VCL_LAUNCHED(b, "chunk_sum_kernel");
-  bicgstab_update_s_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, b->dscal + 16, b->dscal + 17, nullptr,
-                                                                        b->partials, b->tickets, buf + chunk_offset);
+  bicgstab_update_s_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, VCL_DSCAL(b) + 16, VCL_DSCAL(b) + 17, nullptr,
+                                                                        VCL_PARTIALS(b), b->tickets, buf + chunk_offset);
   VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_vector_update(ViennaCLBackend b, ViennaCLInt n, double *result, double alpha, double *p,
-                                                             double omega, const double *s, double *residual, const double *As,
-                                                             double beta, const double *Ap, const double *r0star,
-                                                             double *buf, ViennaCLInt chunk)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_vector_update(ViennaCLBackend b, ViennaCLInt n, real *result, real alpha, real *p,
+                                                             real omega, const real *s, real *residual, const real *As,
+                                                             real beta, const real *Ap, const real *r0star,
+                                                             real *buf, ViennaCLInt chunk)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && buf, "bad arguments");
   (void)chunk;
   if (n == 0) return ViennaCLSuccess;
   bicgstab_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, alpha, p, omega, s, residual, As, beta, Ap, r0star,
-                                                                      nullptr, b->partials, b->tickets, buf);
+                                                                      nullptr, VCL_PARTIALS(b), b->tickets, buf);
   VCL_LAUNCHED(b, "bicgstab_update_kernel");
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
-                                                        const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *p, real *Ap,
+                                                        const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
   return fused_prod_api(b, from_csr(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
-                                                         const double *r0star, double *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *p, real *Ap,
+                                                         const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
   return fused_prod_api(b, from_sell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_normalize_vk(ViennaCLBackend b, ViennaCLInt n, double *v_k, const double *residual,
-                                                         double *R, ViennaCLInt offset_in_R, const double *buf,
-                                                         double *r_dot_vk, ViennaCLInt chunk, ViennaCLInt chunk_offset)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_normalize_vk(ViennaCLBackend b, ViennaCLInt n, real *v_k, const real *residual,
+                                                         real *R, ViennaCLInt offset_in_R, const real *buf,
+                                                         real *r_dot_vk, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && v_k && residual && R && buf && r_dot_vk && chunk >= 1, "bad arguments");
   if (n == 0) return ViennaCLSuccess;
-  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + chunk, chunk, b->dscal + 16);      // ||v_k||^2 lives in chunk 1
+  chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + chunk, chunk, VCL_DSCAL(b) + 16);      // ||v_k||^2 lives in chunk 1
   VCL_LAUNCHED(b, "chunk_sum_kernel");
-  gmres_normalize_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, v_k, residual, R, offset_in_R, b->dscal + 16,
-                                                                         r_dot_vk + chunk_offset, b->partials, b->tickets);
+  gmres_normalize_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, v_k, residual, R, offset_in_R, VCL_DSCAL(b) + 16,
+                                                                         r_dot_vk + chunk_offset, VCL_PARTIALS(b), b->tickets);
   VCL_LAUNCHED(b, "gmres_normalize_kernel");
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage1(ViennaCLBackend b, const double *basis, ViennaCLInt n,
-                                                                ViennaCLInt internal_n, ViennaCLInt k, double *vi_in_vk, ViennaCLInt chunk)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage1(ViennaCLBackend b, const real *basis, ViennaCLInt n,
+                                                                ViennaCLInt internal_n, ViennaCLInt k, real *vi_in_vk, ViennaCLInt chunk)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && basis && vi_in_vk && k >= 0 && k < VCL_GMRES_MAX_KRYLOV && chunk >= 1, "bad arguments");
@@ -684,9 +686,9 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage1(ViennaCLBackend 
   return launch_gs1(b, scalar_grid(b, n), basis, n, internal_n, k, vi_in_vk, chunk);
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend b, double *basis, ViennaCLInt n,
-                                                                ViennaCLInt internal_n, ViennaCLInt k, const double *vi_in_vk,
-                                                                double *R, ViennaCLInt krylov_dim, double *buf, ViennaCLInt chunk)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend b, real *basis, ViennaCLInt n,
+                                                                ViennaCLInt internal_n, ViennaCLInt k, const real *vi_in_vk,
+                                                                real *R, ViennaCLInt krylov_dim, real *buf, ViennaCLInt chunk)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && basis && vi_in_vk && R && buf && k >= 0 && k < VCL_GMRES_MAX_KRYLOV && chunk >= 1, "bad arguments");
@@ -694,18 +696,18 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend 
   // second reduction stage of <v_i, v_k>: fold each chunk into its first element (no-op for our own stage 1)
   for (int j = 0; j < k; ++j)
   {
-    chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, b->dscal + 16 + j);
+    chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, VCL_DSCAL(b) + 16 + j);
     VCL_LAUNCHED(b, "chunk_sum_kernel");
   }
   VCL_REQUIRE(b, (internal_n & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u, "Krylov basis must be 16-byte aligned with an even internal size");
-  gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, b->dscal + 16, 1, R, krylov_dim,
-                                                                   buf + chunk, b->partials, b->tickets);
+  gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, VCL_DSCAL(b) + 16, 1, R, krylov_dim,
+                                                                   buf + chunk, VCL_PARTIALS(b), b->tickets);
   VCL_LAUNCHED(b, "gmres_gs2_kernel");
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_update_result(ViennaCLBackend b, ViennaCLInt n, double *result, const double *residual,
-                                                          const double *basis, ViennaCLInt internal_n, const double *coefficients, ViennaCLInt k)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_update_result(ViennaCLBackend b, ViennaCLInt n, real *result, const real *residual,
+                                                          const real *basis, ViennaCLInt internal_n, const real *coefficients, ViennaCLInt k)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && result && residual && coefficients && k >= 0 && k <= VCL_GMRES_MAX_KRYLOV, "bad arguments");
@@ -715,12 +717,13 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_update_result(ViennaCLBackend b, Vie
   return ViennaCLSuccess;
 }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const double *p, double *Ap,
-                                                     double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_csr(ViennaCLBackend b, const ViennaCLCUDADcsr *A, const real *p, real *Ap,
+                                                     real *buf, ViennaCLInt buf_size)
 { return ViennaCLCUDADpipelined_cg_prod_csr(b, A, p, Ap, buf, buf_size); }
 
-ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const double *p, double *Ap,
-                                                      double *buf, ViennaCLInt buf_size)
+ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *p, real *Ap,
+                                                      real *buf, ViennaCLInt buf_size)
 { return ViennaCLCUDADpipelined_cg_prod_sell(b, A, p, Ap, buf, buf_size); }
 
 } // extern "C"
+} // namespace VCL_NS

@@ -3,6 +3,10 @@
 #include "launch.cuh"
 #include <cstdlib>
 
+namespace VCL_NS
+{
+
+#ifndef VCL_F32      // index-only helpers: compiled once (double build)
 // ------------------------------------------------------------------------------------------------
 // Row blocks (compressed_matrix.hpp:1152-1188 analogue).  Greedy over whole rows: a block closes when the next row would
 // exceed VCL_B200_CSR_BLOCK_NNZ staged entries or VCL_B200_CSR_BLOCK_ROWS rows; a longer row gets a block of its own.
@@ -117,14 +121,16 @@ extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCL
   return ViennaCLSuccess;
 }
 
+#endif // !VCL_F32
+
 // ------------------------------------------------------------------------------------------------
 // prod_impl
 // ------------------------------------------------------------------------------------------------
 extern "C" ViennaCLStatus ViennaCLCUDADcsrmv(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
-                                             const unsigned int *row_ptr, const unsigned int *col_idx, const double *values,
+                                             const unsigned int *row_ptr, const unsigned int *col_idx, const real *values,
                                              const unsigned int *row_blocks, ViennaCLInt num_blocks,
-                                             const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                             double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+                                             const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                             real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && cols >= 0 && nnz >= 0, "negative size");
@@ -140,9 +146,9 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsrmv(ViennaCLBackend b, ViennaCLInt rows
 
 extern "C" ViennaCLStatus ViennaCLCUDADsellmv(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt rows_per_block,
                                               const unsigned int *columns_per_block, const unsigned int *col_idx,
-                                              const unsigned int *block_start, const double *values,
-                                              const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                              double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+                                              const unsigned int *block_start, const real *values,
+                                              const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                              real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && cols >= 0 && rows_per_block > 0, "bad size");
@@ -152,6 +158,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADsellmv(ViennaCLBackend b, ViennaCLInt row
   VCL_REQUIRE(b, x != y, "x and y alias");
   ViennaCLCUDADsell A = {rows, cols, rows_per_block, columns_per_block, col_idx, block_start, values};
   EpiAxpby epi = {y, offy, incy, alpha, beta};
+  epi.sell_f32 = sizeof(real) == 4;
   XVec xv = make_xvec(x, offx, incx);
   return vcl_launch_sell(b, A, xv, epi);
 }
@@ -160,11 +167,11 @@ extern "C" ViennaCLStatus ViennaCLCUDADsellmv(ViennaCLBackend b, ViennaCLInt row
 // row_info (cuda/sparse_matrix_operations.hpp:53-119): inf-/1-/2-norm or diagonal of every row
 // ------------------------------------------------------------------------------------------------
 __global__ void csr_row_info_kernel(int rows, const u32 * __restrict__ rp, const u32 * __restrict__ ci,
-                                    const double * __restrict__ va, double *out, int option)
+                                    const real * __restrict__ va, real *out, int option)
 {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
   {
-    double value = 0.0;
+    real value = 0.0;
     const u32 e = rp[r + 1];
     switch (option)
     {
@@ -181,8 +188,8 @@ __global__ void csr_row_info_kernel(int rows, const u32 * __restrict__ rp, const
 }
 
 extern "C" ViennaCLStatus ViennaCLCUDADcsr_row_info(ViennaCLBackend b, ViennaCLInt rows,
-                                                    const unsigned int *row_ptr, const unsigned int *col_idx, const double *values,
-                                                    double *result, ViennaCLInt option)
+                                                    const unsigned int *row_ptr, const unsigned int *col_idx, const real *values,
+                                                    real *result, ViennaCLInt option)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && option >= 0 && option <= 3, "bad arguments");
@@ -210,8 +217,8 @@ __global__ void sell_width_kernel(int rows, int C, const u32 * __restrict__ rp, 
   }
 }
 
-__global__ void sell_fill_kernel(int rows, int C, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const double * __restrict__ cva,
-                                 const u32 * __restrict__ cpb, const u32 * __restrict__ bs, u32 *ci, double *va)
+__global__ void sell_fill_kernel(int rows, int C, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const real * __restrict__ cva,
+                                 const u32 * __restrict__ cpb, const u32 * __restrict__ bs, u32 *ci, real *va)
 {
   // one thread per (row of the padded slice): writes its real entries, then zero/col-0 padding up to the slice width
   const long long padded_rows = ((long long)(rows - 1) / C + 1) * C;
@@ -231,9 +238,9 @@ __global__ void sell_fill_kernel(int rows, int C, const u32 * __restrict__ rp, c
 }
 
 extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt C,
-                                                const unsigned int *row_ptr, const unsigned int *csr_col, const double *csr_val,
+                                                const unsigned int *row_ptr, const unsigned int *csr_col, const real *csr_val,
                                                 unsigned int *columns_per_block, unsigned int *block_start, long long *padded_nnz,
-                                                unsigned int *col_idx, double *values)
+                                                unsigned int *col_idx, real *values)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && C > 0 && padded_nnz, "bad arguments");
@@ -268,8 +275,8 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend b, ViennaCLInt r
 // on the host from a D2H copy of row_ptr (set-up path, like the reference, which builds both formats entirely on the
 // host); the entries are scattered on the device.
 // ------------------------------------------------------------------------------------------------
-__global__ void ell_fill_kernel(int rows, int width, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const double * __restrict__ cva,
-                                u32 *coords, double *elements, const u32 * __restrict__ tail_rows, u32 *tail_cols, double *tail_elements)
+__global__ void ell_fill_kernel(int rows, int width, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const real * __restrict__ cva,
+                                u32 *coords, real *elements, const u32 * __restrict__ tail_rows, u32 *tail_cols, real *tail_elements)
 {
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x)
   {
@@ -296,8 +303,8 @@ static ViennaCLStatus fetch_row_ptr(ViennaCLBackend b, int rows, const u32 *row_
 }
 
 extern "C" ViennaCLStatus ViennaCLCUDADcsr2ell(ViennaCLBackend b, ViennaCLInt rows, const unsigned int *row_ptr,
-                                               const unsigned int *csr_col, const double *csr_val, ViennaCLInt *maxnnz,
-                                               unsigned int *coords, double *elements)
+                                               const unsigned int *csr_col, const real *csr_val, ViennaCLInt *maxnnz,
+                                               unsigned int *coords, real *elements)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && maxnnz, "bad arguments");
@@ -322,10 +329,10 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2ell(ViennaCLBackend b, ViennaCLInt ro
 }
 
 extern "C" ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, const unsigned int *row_ptr,
-                                               const unsigned int *csr_col, const double *csr_val, double csr_threshold,
+                                               const unsigned int *csr_col, const real *csr_val, real csr_threshold,
                                                ViennaCLInt *ell_width, ViennaCLInt *csr_nnz,
-                                               unsigned int *ell_coords, double *ell_elements,
-                                               unsigned int *csr_rows, unsigned int *csr_cols, double *csr_elements)
+                                               unsigned int *ell_coords, real *ell_elements,
+                                               unsigned int *csr_rows, unsigned int *csr_cols, real *csr_elements)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && cols >= 0 && ell_width && csr_nnz, "bad arguments");
@@ -344,7 +351,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend b, ViennaCLInt ro
     for (u32 ind = 0; ind <= maxw; ++ind)
     {
       sum += hist[ind];
-      if ((double)sum >= csr_threshold * (double)rows) { w = ind; break; }
+      if ((real)sum >= csr_threshold * (real)rows) { w = ind; break; }
     }
     unsigned long long tail = 0;
     for (int r = 0; r < rows; ++r) if (rp[r + 1] - rp[r] > w) tail += (rp[r + 1] - rp[r]) - w;
@@ -363,7 +370,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend b, ViennaCLInt ro
   if (t == 0)
   {
     VCL_CUDA(b, cudaMemsetAsync(csr_cols, 0, sizeof(u32), b->stream));
-    VCL_CUDA(b, cudaMemsetAsync(csr_elements, 0, sizeof(double), b->stream));
+    VCL_CUDA(b, cudaMemsetAsync(csr_elements, 0, sizeof(real), b->stream));
   }
   VCL_REQUIRE(b, rp[rows] == 0 || (csr_col && csr_val), "null CSR array");
   ell_fill_kernel<<<std::min(vcl_div_up(rows, 256), b->sm_count * 8), 256, 0, b->stream>>>(rows, (int)w, row_ptr, csr_col, csr_val, ell_coords, ell_elements,
@@ -373,6 +380,7 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2hyb(ViennaCLBackend b, ViennaCLInt ro
   return ViennaCLSuccess;
 }
 
+#ifndef VCL_F32      // index-only helper: compiled once (double build)
 // ------------------------------------------------------------------------------------------------
 // COO -> CSR index (coordinate_matrix.hpp:47-102 stores (row, col) pairs sorted by row).  The reference's CUDA kernel
 // (cuda/sparse_matrix_operations.hpp:1239-1340) runs a segmented reduction over 64 fixed groups; here the entries get a
@@ -406,11 +414,13 @@ extern "C" ViennaCLStatus ViennaCLCUDAcoo2csr(ViennaCLBackend b, ViennaCLInt row
   return ViennaCLSuccess;
 }
 
+#endif // !VCL_F32
+
 extern "C" ViennaCLStatus ViennaCLCUDADcoomv(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
-                                             const unsigned int *row_ptr, const unsigned int *col_idx, const double *elements,
+                                             const unsigned int *row_ptr, const unsigned int *col_idx, const real *elements,
                                              const unsigned int *row_blocks, ViennaCLInt num_blocks,
-                                             const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
-                                             double *y, ViennaCLInt offy, ViennaCLInt incy, double beta)
+                                             const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                             real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, rows >= 0 && cols >= 0 && nnz >= 0, "negative size");
@@ -421,3 +431,5 @@ extern "C" ViennaCLStatus ViennaCLCUDADcoomv(ViennaCLBackend b, ViennaCLInt rows
   EpiCoo epi = {y, offy, incy, alpha, beta};
   return vcl_launch_csr(b, A, make_xvec(x, offx, incx), epi);
 }
+
+} // namespace VCL_NS

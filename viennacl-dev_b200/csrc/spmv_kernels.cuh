@@ -13,8 +13,12 @@
 // gather adjacent x entries, so the gathers of a warp coalesce).
 #pragma once
 #include "common.cuh"
+#include "prec.cuh"
 #include "solver_state.cuh"
 #include "peer.cuh"
+
+namespace VCL_NS
+{
 
 #define CSR_BLOCK_THREADS 256
 #define CSR_CAP (VCL_B200_CSR_BLOCK_NNZ)          // staged non-zeros per row block
@@ -23,7 +27,7 @@
 struct CsrDev
 {
   int rows; u32 nnz;
-  const u32 *rp, *ci; const double *va;
+  const u32 *rp, *ci; const real *va;
   const u32 *blk_start, *blk_end; int nblk;     // row block i covers rows [blk_start[i], blk_end[i]); for a plain plan
                                                 // blk_end == blk_start + 1 (compressed_matrix handle3() layout)
   // peer-memory halo (row-partitioned path, peer.cuh): list positions >= wait_from read halo columns and must first see
@@ -35,40 +39,55 @@ struct CsrDev
 struct SellDev
 {
   int rows; int C;
-  const u32 *cpb, *ci, *bs; const double *va;
+  const u32 *cpb, *ci, *bs; const real *va;
 };
 
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
 // `x` already points at the first entry (start offset folded in); inc8 = stride in BYTES, so an entry address is ONE
 // 32x32+64-bit multiply-add.  Build with make_xvec().
-struct XVec { const double *x; u32 inc8; const double *x2; u32 split; };
+struct XVec { const real *x; u32 inc8; const real *x2; u32 split; };
 
-static inline XVec make_xvec(const double *x, long long off, long long inc, const double *x2 = nullptr, u32 split = 0)
+static inline XVec make_xvec(const real *x, long long off, long long inc, const real *x2 = nullptr, u32 split = 0)
 {
-  XVec v = {x + off, (u32)(inc * 8), x2, split};
+  XVec v = {x + off, (u32)(inc * (long long)sizeof(real)), x2, split};
   return v;
 }
 
 // SPLIT: one load from a selected base (no branch).  Halo entries are written by peer GPUs; reading them through L1 is safe
 // because a CTA touches the halo only after its acquire on the arrival flag (peer.cuh) and L1 does not outlive a launch.
 template<bool SPLIT>
-__device__ __forceinline__ double xload(const XVec &xv, u32 c)
+__device__ __forceinline__ real xload(const XVec &xv, u32 c)
 {
   if (SPLIT)
   {
-    const double *base = (c >= xv.split) ? (xv.x2 - xv.split) : xv.x;
+    const real *base = (c >= xv.split) ? (xv.x2 - xv.split) : xv.x;
     return base[c];
   }
-  return *reinterpret_cast<const double*>(reinterpret_cast<const char*>(xv.x) + (unsigned long long)c * xv.inc8);
+  return *reinterpret_cast<const real*>(reinterpret_cast<const char*>(xv.x) + (unsigned long long)c * xv.inc8);
 }
 
 // In-row CSR accumulation step.  The reference host backend (host_based/sparse_matrix_operations.hpp:167-184), built with
 // g++ -O3 for x86-64-v3, evaluates `dot += a*x` as a rounded multiply followed by a rounded add (GCC does not form FMA
 // chains in reductions under generic tuning); the same two roundings are used here so that CSR results match it bit for bit.
-__device__ __forceinline__ double madd(double a, double x, double acc) { return __dadd_rn(acc, __dmul_rn(a, x)); }
+__device__ __forceinline__ real madd(real a, real x, real acc) { return radd(acc, rmul(a, x)); }
 
-// v != 0.0 without the FP64 pipe (true for NaN, false for +-0.0, like the floating-point comparison)
-__device__ __forceinline__ bool nonzero(double v) { return (__double_as_longlong(v) << 1) != 0; }
+#ifdef VCL_F32
+// The FLOAT instantiation of the same reference loop is compiled differently by that build (pinned empirically,
+// SURVEY 8c / DESIGN.md section 2): for unit-stride x GCC vectorises the gather loop 4 wide with an in-order reduction --
+// rounded products, then adds -- and contracts the scalar remainder loop, i.e. the last (row length mod 4) entries, to
+// fmaf; for strided x nothing is vectorised or contracted.  first_fused() = index of the first contracted entry of a row
+// [s, e); madd_at() applies the matching operation to entry i.
+__device__ __forceinline__ u32 first_fused(u32 s, u32 e, const XVec &xv) { return (xv.inc8 == (u32)sizeof(real)) ? s + ((e - s) & ~3u) : 0xffffffffu; }
+__device__ __forceinline__ real madd_at(real a, real x, real acc, u32 i, u32 ff)
+{
+  const real q = fma(a, x, acc), p = radd(acc, rmul(a, x));
+  return (i >= ff) ? q : p;
+}
+#else
+__device__ __forceinline__ u32 first_fused(u32, u32, const XVec &) { return 0xffffffffu; }
+__device__ __forceinline__ real madd_at(real a, real x, real acc, u32, u32) { return madd(a, x, acc); }
+#endif
+
 
 // The matrix arrays are read exactly once per product: they are streamed with an L2 evict-first policy so that they do not
 // push the gathered x entries (re-used by the rows of the next planes, tens of MB of streamed matrix data later) out of L2.
@@ -92,39 +111,40 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 // y[off + r*inc] = alpha*dot + beta*y   (spmv_alpha_beta semantics, cuda/sparse_matrix_operations.hpp:130: beta == 0 -> y not read)
 struct EpiAxpby
 {
-  double *y; int off, inc; double alpha, beta;
+  real *y; int off, inc; real alpha, beta;
+  bool sell_f32 = false;     // float SELL only: the reference build evaluates fma(alpha, dot, beta*y) there
   static constexpr int NQ = 0;
   static constexpr bool COO = false;
-  __device__ __forceinline__ double init(double) const { return 0.0; }
-  __device__ __forceinline__ double term_scale() const { return 1.0; }
+  __device__ __forceinline__ real init(real) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
   __device__ __forceinline__ bool skip() const { return false; }
   // pre(): the epilogue's own per-row operand, requested BEFORE the row's gather chain so that its latency overlaps
-  __device__ __forceinline__ double pre(u32 r) const
+  __device__ __forceinline__ real pre(u32 r) const
   {
     return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0;
   }
-  __device__ __forceinline__ void row(u32 r, double dot, double y_old)
+  __device__ __forceinline__ void row(u32 r, real dot, real y_old)
   {
     size_t idx = (size_t)r * (size_t)inc + (size_t)off;
     // same operations as the reference host build: t = alpha*dot (rounded), then one fused beta*y + t
-    if (beta != 0.0) y[idx] = fma(beta, y_old, __dmul_rn(alpha, dot));
-    else             y[idx] = __dmul_rn(alpha, dot);
+    if (beta != 0.0) y[idx] = sell_f32 ? fma(alpha, dot, rmul(beta, y_old)) : fma(beta, y_old, rmul(alpha, dot));
+    else             y[idx] = rmul(alpha, dot);
   }
-  __device__ __forceinline__ void finish(double *) {}
+  __device__ __forceinline__ void finish(real *) {}
 };
 
 // coordinate_matrix product on the CSR index of the COO entries: y = (beta*y) + sum_k fma(alpha*a_k, x_k, .) in storage order
 struct EpiCoo
 {
-  double *y; int off, inc; double alpha, beta;
+  real *y; int off, inc; real alpha, beta;
   static constexpr int NQ = 0;
   static constexpr bool COO = true;
   __device__ __forceinline__ bool skip() const { return false; }
-  __device__ __forceinline__ double pre(u32 r) const { return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0; }
-  __device__ __forceinline__ double init(double y_old) const { return (beta != 0.0) ? __dmul_rn(y_old, beta) : 0.0; }
-  __device__ __forceinline__ double term_scale() const { return alpha; }
-  __device__ __forceinline__ void row(u32 r, double dot, double) { y[(size_t)r * (size_t)inc + (size_t)off] = dot; }
-  __device__ __forceinline__ void finish(double *) {}
+  __device__ __forceinline__ real pre(u32 r) const { return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0; }
+  __device__ __forceinline__ real init(real y_old) const { return (beta != 0.0) ? rmul(y_old, beta) : 0.0; }
+  __device__ __forceinline__ real term_scale() const { return alpha; }
+  __device__ __forceinline__ void row(u32 r, real dot, real) { y[(size_t)r * (size_t)inc + (size_t)off] = dot; }
+  __device__ __forceinline__ void finish(real *) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -160,7 +180,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #ifndef CSR_NSTAGE
 #define CSR_NSTAGE 2                                                               // shared-memory ring depth (blocks)
 #endif
-#define CSR_SMEM_BYTES (CSR_NSTAGE * CSR_STAGE * (int)(sizeof(double) + sizeof(u32)))  // dynamic shared memory
+#define CSR_SMEM_BYTES (CSR_NSTAGE * CSR_STAGE * (int)(sizeof(real) + sizeof(u32)))  // dynamic shared memory
 #define CSR_MIN_CTAS (CSR_NSTAGE <= 2 ? 4 : (CSR_NSTAGE == 3 ? 3 : 2))
 
 struct CsrBlockDesc { u32 r0, r1, n0, n1; };
@@ -178,13 +198,14 @@ __device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
 // COO == true: coordinate_matrix semantics (host_based/sparse_matrix_operations.hpp:1233-1246): the chain starts at beta*y
 // and every term is fma(alpha*a, x, .) -- what the reference build does for that format.
 template<bool SPLIT, bool COO>
-__device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv,
-                                              double init = 0.0, double alpha = 1.0)
+__device__ __forceinline__ real csr_row_dot(const real *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv,
+                                              real init = 0.0, real alpha = 1.0)
 {
-  double dot = COO ? init : 0.0;
+  real dot = COO ? init : 0.0;
+  const u32 ff = first_fused(j, e, xv);
   for (; j < e; j += 8)
   {
-    double v[8], xx[8];
+    real v[8], xx[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k)
     {
@@ -195,7 +216,7 @@ __device__ __forceinline__ double csr_row_dot(const double *s_val, const u32 *s_
     // empty slots hold v = x = +0.0: adding +0.0 never changes the bits of `dot` (a round-to-nearest sum that starts at
     // +0.0 cannot be -0.0), so the chain needs no predicates and stays bit-identical to the sequential reference
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dot = COO ? fma(__dmul_rn(alpha, v[k]), xx[k], dot) : madd(v[k], xx[k], dot);
+    for (int k = 0; k < 8; ++k) dot = COO ? fma(rmul(alpha, v[k]), xx[k], dot) : madd_at(v[k], xx[k], dot, j + k, ff);
   }
   return dot;
 }
@@ -207,9 +228,9 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
   constexpr int S = CSR_NSTAGE;
   extern __shared__ __align__(128) unsigned char csr_smem[];
   __shared__ __align__(8) unsigned long long s_bar[S];
-  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
-  double *s_val0 = reinterpret_cast<double*>(csr_smem);
-  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(double));
+  __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  real *s_val0 = reinterpret_cast<real*>(csr_smem);
+  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(real));
 
   if (epi.skip()) return;
   const int tid = threadIdx.x;
@@ -234,8 +255,8 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
     const u32 a0 = d.n0 & ~3u;
     const u32 cnt4 = (d.n1 - a0 + 3u) & ~3u;
     fence_proxy_async();                                   // earlier generic-proxy accesses to this buffer are done (barrier)
-    mbar_expect_tx(&s_bar[buf], cnt4 * 12u);
-    tma_load_1d(s_val0 + buf * CSR_STAGE, A.va + a0, cnt4 * 8u, &s_bar[buf], pol);
+    mbar_expect_tx(&s_bar[buf], cnt4 * (unsigned)(sizeof(real) + sizeof(u32)));
+    tma_load_1d(s_val0 + buf * CSR_STAGE, A.va + a0, cnt4 * (unsigned)sizeof(real), &s_bar[buf], pol);
     tma_load_1d(s_col0 + buf * CSR_STAGE, A.ci + a0, cnt4 * 4u, &s_bar[buf], pol);
   };
 
@@ -294,22 +315,22 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
     if (cls == 1)
     {
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
-      double part[1] = {0.0};
+      real part[1] = {0.0};
       for (u32 k = cur.n0 + tid; k < cur.n1; k += CSR_BLOCK_THREADS)
         part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
-      __shared__ double s_long[32];
+      __shared__ real s_long[32];
       block_sum<1>(part, s_long);
       if (tid == 0)
       {
-        const double pre = epi.pre(cur.r0);
+        const real pre = epi.pre(cur.r0);
         epi.row(cur.r0, Epi::COO ? fma(epi.term_scale(), part[0], epi.init(pre)) : part[0], pre);
       }
     }
     else
     {
-      const double pre = ((u32)tid < nrows) ? epi.pre(cur.r0 + tid) : 0.0;
+      const real pre = ((u32)tid < nrows) ? epi.pre(cur.r0 + tid) : 0.0;
       const u32 a0 = cur.n0 & ~3u;
-      const double *s_val = s_val0 + buf * CSR_STAGE;
+      const real *s_val = s_val0 + buf * CSR_STAGE;
       const u32 *s_col = s_col0 + buf * CSR_STAGE;
       if (cls == 0)
       {
@@ -319,7 +340,7 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
       else
       {
         // guarded staging of the last few entries of the arrays (never reads past nnz)
-        double *wv = s_val0 + buf * CSR_STAGE; u32 *wc = s_col0 + buf * CSR_STAGE;
+        real *wv = s_val0 + buf * CSR_STAGE; u32 *wc = s_col0 + buf * CSR_STAGE;
         for (u32 i = tid; a0 + i < cur.n1; i += CSR_BLOCK_THREADS) { wv[i] = A.va[a0 + i]; wc[i] = A.ci[a0 + i]; }
         __syncthreads();
       }
@@ -344,15 +365,16 @@ template<class Epi>
 __global__ void __launch_bounds__(256)
 csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 {
-  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
   if (epi.skip()) return;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
-    const double pre = epi.pre((u32)r);
-    double dot = Epi::COO ? epi.init(pre) : 0.0;
+    const real pre = epi.pre((u32)r);
+    real dot = Epi::COO ? epi.init(pre) : 0.0;
     const u32 e = A.rp[r + 1];
+    const u32 ff = first_fused(A.rp[r], e, xv);
     for (u32 k = A.rp[r]; k < e; ++k)
-      dot = Epi::COO ? fma(__dmul_rn(epi.term_scale(), A.va[k]), xload<false>(xv, A.ci[k]), dot) : madd(A.va[k], xload<false>(xv, A.ci[k]), dot);
+      dot = Epi::COO ? fma(rmul(epi.term_scale(), A.va[k]), xload<false>(xv, A.ci[k]), dot) : madd_at(A.va[k], xload<false>(xv, A.ci[k]), dot, k, ff);
     epi.row((u32)r, dot, pre);
   }
   epi.finish(s_red);
@@ -375,13 +397,13 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   constexpr int S = CSR_NSTAGE;
   extern __shared__ __align__(128) unsigned char csr_smem[];
   __shared__ __align__(8) unsigned long long s_bar[S];
-  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
-  double *s_val0 = reinterpret_cast<double*>(csr_smem);
-  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(double));
+  __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  real *s_val0 = reinterpret_cast<real*>(csr_smem);
+  u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(real));
   static_assert(CSR_NSTAGE == 2, "sell_kernel is written for a two-stage ring");
 
   if (epi.skip()) return;
-  const double * __restrict__ va = A.va;
+  const real * __restrict__ va = A.va;
   const u32 * __restrict__ ci = A.ci;
   const int tid = threadIdx.x;
   const int step = (int)gridDim.x;
@@ -412,8 +434,8 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   {
     const u32 cnt = end - base;                            // multiple of C, hence of 4; base likewise
     fence_proxy_async();
-    mbar_expect_tx(&s_bar[buf], cnt * 12u);
-    tma_load_1d(s_val0 + buf * CSR_STAGE, va + base, cnt * 8u, &s_bar[buf], pol);
+    mbar_expect_tx(&s_bar[buf], cnt * (unsigned)(sizeof(real) + sizeof(u32)));
+    tma_load_1d(s_val0 + buf * CSR_STAGE, va + base, cnt * (unsigned)sizeof(real), &s_bar[buf], pol);
     tma_load_1d(s_col0 + buf * CSR_STAGE, ci + base, cnt * 4u, &s_bar[buf], pol);
   };
   // this thread's row of pass b: slice width and offset of its first entry
@@ -445,18 +467,18 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       // (s1 - s0) * C <= 256 here: one row per thread
       const long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);
       const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
-      const double pre = active ? epi.pre((u32)r) : 0.0;
-      const double *s_val = s_val0 + buf * CSR_STAGE;
+      const real pre = active ? epi.pre((u32)r) : 0.0;
+      const real *s_val = s_val0 + buf * CSR_STAGE;
       const u32 *s_col = s_col0 + buf * CSR_STAGE;
       mbar_wait(&s_bar[buf], (phase >> buf) & 1u);
       phase ^= 1u << buf;
       if (active)
       {
-        double acc = 0.0;
+        real acc = 0.0;
         u32 idx = first_c - base_c;
         for (u32 j = 0; j < w_c; j += 8, idx += 8 * C)
         {
-          double v[8], xx[8];
+          real v[8], xx[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k)
           {
@@ -480,16 +502,16 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         if (r >= A.rows) continue;
         const u32 w = A.cpb[slice];
         size_t idx = (size_t)A.bs[slice] + (t % C);
-        double acc = 0.0;
+        real acc = 0.0;
         u32 j = 0;
         for (; j + 4 <= w; j += 4, idx += 4 * (size_t)C)
         {
-          const double v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * (size_t)C], v3 = va[idx + 3 * (size_t)C];
+          const real v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * (size_t)C], v3 = va[idx + 3 * (size_t)C];
           const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * (size_t)C], c3 = ci[idx + 3 * (size_t)C];
-          const double x0 = (v0 != 0.0) ? xload<false>(xv, c0) : 0.0;
-          const double x1 = (v1 != 0.0) ? xload<false>(xv, c1) : 0.0;
-          const double x2 = (v2 != 0.0) ? xload<false>(xv, c2) : 0.0;
-          const double x3 = (v3 != 0.0) ? xload<false>(xv, c3) : 0.0;
+          const real x0 = (v0 != 0.0) ? xload<false>(xv, c0) : 0.0;
+          const real x1 = (v1 != 0.0) ? xload<false>(xv, c1) : 0.0;
+          const real x2 = (v2 != 0.0) ? xload<false>(xv, c2) : 0.0;
+          const real x3 = (v3 != 0.0) ? xload<false>(xv, c3) : 0.0;
           if (v0 != 0.0) acc = fma(x0, v0, acc);
           if (v1 != 0.0) acc = fma(x1, v1, acc);
           if (v2 != 0.0) acc = fma(x2, v2, acc);
@@ -497,7 +519,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         }
         for (; j < w; ++j, idx += C)
         {
-          const double v0 = va[idx];
+          const real v0 = va[idx];
           if (v0 != 0.0) acc = fma(xload<false>(xv, ci[idx]), v0, acc);
         }
         epi.row((u32)r, acc, epi.pre((u32)r));
@@ -520,14 +542,14 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
 struct EllDev
 {
   int rows, internal_rows, width;
-  const u32 *coords; const double *elements;
-  const u32 *csr_rows, *csr_cols; const double *csr_elements;      // HYB tail, NULL for plain ELL
+  const u32 *coords; const real *elements;
+  const u32 *csr_rows, *csr_cols; const real *csr_elements;      // HYB tail, NULL for plain ELL
 };
 
-__device__ __forceinline__ double ldg_stream(const double *p, unsigned long long pol)
+__device__ __forceinline__ real ldg_stream(const real *p, unsigned long long pol)
 {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(p), "l"(pol));
+  real v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint." VCL_PTX_REAL " %0, [%1], %2;\n" : "=" VCL_PTX_REG(v) : "l"(p), "l"(pol));
   return v;
 }
 __device__ __forceinline__ u32 ldg_stream(const u32 *p, unsigned long long pol)
@@ -538,27 +560,31 @@ __device__ __forceinline__ u32 ldg_stream(const u32 *p, unsigned long long pol)
 }
 
 #ifndef ELL_ILP
+#ifdef VCL_F32
+#define ELL_ILP 8            // float: half the bytes per slot and half the registers -- twice the slots in flight
+#else
 #define ELL_ILP 4
+#endif
 #endif
 template<class Epi>
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, 6)
 ell_kernel(EllDev A, XVec xv, Epi epi)
 {
-  __shared__ double s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
+  __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
   if (epi.skip()) return;
   const unsigned long long pol = l2_evict_first_policy();
   const size_t IR = (size_t)A.internal_rows;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
-    const double pre = epi.pre((u32)r);
+    const real pre = epi.pre((u32)r);
     u32 t0 = 0, t1 = 0;
     if (A.csr_rows) { t0 = A.csr_rows[r]; t1 = A.csr_rows[r + 1]; }
-    double acc = 0.0;
-    const double *pv = A.elements + r;
+    real acc = 0.0;
+    const real *pv = A.elements + r;
     const u32 *pc = A.coords + r;
     for (int j = 0; j < A.width; j += ELL_ILP, pv += ELL_ILP * IR, pc += ELL_ILP * IR)
     {
-      double v[ELL_ILP], xx[ELL_ILP]; u32 c[ELL_ILP];
+      real v[ELL_ILP], xx[ELL_ILP]; u32 c[ELL_ILP];
 #pragma unroll
       for (int k = 0; k < ELL_ILP; ++k)
       {
@@ -571,8 +597,10 @@ ell_kernel(EllDev A, XVec xv, Epi epi)
 #pragma unroll
       for (int k = 0; k < ELL_ILP; ++k) acc = fma(xx[k], v[k], acc);      // zero slots: +0.0, bits unchanged
     }
-    for (u32 k = t0; k < t1; ++k) acc = madd(A.csr_elements[k], xload<false>(xv, A.csr_cols[k]), acc);
+    const u32 ff = first_fused(t0, t1, xv);     // float build of the reference: same vectorised loop shape as the CSR product
+    for (u32 k = t0; k < t1; ++k) acc = madd_at(A.csr_elements[k], xload<false>(xv, A.csr_cols[k]), acc, k, ff);
     epi.row((u32)r, acc, pre);
   }
   epi.finish(s_red);
 }
+} // namespace VCL_NS

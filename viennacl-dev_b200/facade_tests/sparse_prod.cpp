@@ -21,7 +21,12 @@
 #include "viennacl/linalg/norm_2.hpp"
 #include "viennacl/tools/matrix_generation.hpp"
 
-typedef double NumericT;
+// built twice, like the reference's test (tests/src/sparse.cpp:1098-1140 runs float, eps 1e-4, then double, eps 1e-12):
+// sparse_prod (double) and sparse_prod_float (-DNUMERIC_T=float)
+#ifndef NUMERIC_T
+#define NUMERIC_T double
+#endif
+typedef NUMERIC_T NumericT;
 typedef std::vector< std::map<unsigned int, NumericT> > StlMatrix;
 
 static unsigned long long rng_state = 88172645463325252ULL;
@@ -153,7 +158,7 @@ static int product_tests(const char *name, NumericT epsilon, StlMatrix const & s
 
 int main()
 {
-  const NumericT epsilon = 1e-12;                     // tests/src/sparse.cpp:1113
+  const NumericT epsilon = sizeof(NumericT) == 4 ? NumericT(1e-4) : NumericT(1e-12);   // tests/src/sparse.cpp:1105, :1113
   const std::size_t n = 65025;                        // size of the reference's fixture
 
   StlMatrix std_matrix(n);
@@ -166,15 +171,15 @@ int main()
       long j = long(i) + long(randomNumber() * 600.0) - 300;
       if (j < 0) j = 0;
       if (j >= long(n)) j = long(n) - 1;
-      std_matrix[i][static_cast<unsigned int>(j)] = -0.02 * randomNumber();   // no cancellation in A*x or b - A*x:
+      std_matrix[i][static_cast<unsigned int>(j)] = NumericT(-0.02) * randomNumber();   // no cancellation in A*x or b - A*x:
                                                                                // the metric below is a RELATIVE error per entry
     }
     std_matrix[i][static_cast<unsigned int>(i)] = 0.5;
-    rhs[i] = 1.0 + randomNumber();
+    rhs[i] = NumericT(1.0) + randomNumber();
   }
   std_matrix[n - 1][static_cast<unsigned int>(n - 1)] = 0.5;   // last column populated -> copy() infers a square matrix
   for (std::size_t r = 100; r < n; r += 20000)                  // rows longer than one row block (2048) and than 4 KiB staging
-    for (std::size_t j = 0; j < 5000; ++j) std_matrix[r][static_cast<unsigned int>((j * 13) % n)] = -0.02 * randomNumber();
+    for (std::size_t j = 0; j < 5000; ++j) std_matrix[r][static_cast<unsigned int>((j * 13) % n)] = NumericT(-0.02) * randomNumber();
   std_matrix[7].clear();                                         // an empty row
 
   if (product_tests< viennacl::compressed_matrix<NumericT> >("compressed_matrix", epsilon, std_matrix, rhs) != EXIT_SUCCESS) return EXIT_FAILURE;
@@ -225,8 +230,9 @@ int main()
     viennacl::copy(rhs.begin(), rhs.end(), a.begin());
     b = NumericT(2) * a;
     NumericT ip = viennacl::linalg::inner_prod(a, b), nrm = viennacl::linalg::norm_2(a);
-    NumericT ip_ref = 0; for (std::size_t i = 0; i < n; ++i) ip_ref += rhs[i] * 2 * rhs[i];
-    if (std::fabs(ip - ip_ref) > 1e-10 * ip_ref || std::fabs(nrm * nrm * 2 - ip_ref) > 1e-10 * ip_ref)
+    double ip_ref = 0; for (std::size_t i = 0; i < n; ++i) ip_ref += double(rhs[i]) * 2 * double(rhs[i]);
+    const double blas_eps = sizeof(NumericT) == 4 ? 1e-5 : 1e-10;
+    if (std::fabs(ip - ip_ref) > blas_eps * ip_ref || std::fabs(double(nrm) * nrm * 2 - ip_ref) > blas_eps * ip_ref)
     { std::cout << "# inner_prod / norm_2 mismatch: " << ip << " " << nrm << " vs " << ip_ref << std::endl; return EXIT_FAILURE; }
     viennacl::vector<NumericT> c = a - b;            // c = -a
     c += a;                                          // c = 0

@@ -9,6 +9,7 @@
 #include "viennacl/forwards.h"
 #include "viennacl/context.hpp"
 #include "vcl_b200.h"
+#include "viennacl/backend/abi.hpp"
 
 namespace viennacl
 {

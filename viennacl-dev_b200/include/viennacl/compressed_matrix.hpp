@@ -15,7 +15,6 @@ namespace viennacl
 template<typename NumericT, unsigned int AlignmentV>
 class compressed_matrix
 {
-  typedef typename viennacl::detail::only_double<NumericT>::type numeric_must_be_double;
 public:
   typedef backend::mem_handle handle_type;
   typedef NumericT value_type;
@@ -94,9 +93,9 @@ public:
   viennacl::memory_types memory_context() const { return CUDA_MEMORY; }
 
   /** @brief The raw-array view the C-ABI takes */
-  ViennaCLCUDADcsr abi() const
+  typename viennacl::backend::b200::abi<NumericT>::csr abi() const
   {
-    ViennaCLCUDADcsr a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_), row_buffer_.ptr<unsigned int>(),
+    typename viennacl::backend::b200::abi<NumericT>::csr a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_), row_buffer_.ptr<unsigned int>(),
                           col_buffer_.ptr<unsigned int>(), elements_.ptr<NumericT>(), row_blocks_.ptr<unsigned int>(), ViennaCLInt(row_block_num_)};
     return a;
   }
@@ -106,7 +105,7 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for compressed matrix-vector product"));
     if (rows_ == 0) return;
-    backend::b200::check(ViennaCLCUDADcsrmv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::csrmv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_),
                                             row_buffer_.ptr<unsigned int>(), col_buffer_.ptr<unsigned int>(), elements_.ptr<NumericT>(),
                                             row_blocks_.ptr<unsigned int>(), ViennaCLInt(row_block_num_),
                                             x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
@@ -181,7 +180,7 @@ namespace linalg
     void row_info(compressed_matrix<NumericT, AlignmentV> const & mat, vector_base<NumericT> & vec, row_info_types info_selector)
     {
       assert(vec.size() == mat.size1() && vec.stride() == 1 && bool("row_info needs a contiguous vector of size1() entries"));
-      backend::b200::check(ViennaCLCUDADcsr_row_info(backend::b200::handle(), ViennaCLInt(mat.size1()), mat.handle1().template ptr<unsigned int>(),
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::csr_row_info(backend::b200::handle(), ViennaCLInt(mat.size1()), mat.handle1().template ptr<unsigned int>(),
                                                      mat.handle2().template ptr<unsigned int>(), mat.handle().template ptr<NumericT>(),
                                                      vec.ptr() + vec.start(), ViennaCLInt(info_selector)));
     }

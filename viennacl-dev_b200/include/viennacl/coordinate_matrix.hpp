@@ -17,7 +17,6 @@ namespace viennacl
 template<typename NumericT, unsigned int AlignmentV>
 class coordinate_matrix
 {
-  typedef typename viennacl::detail::only_double<NumericT>::type numeric_must_be_double;
 public:
   typedef backend::mem_handle handle_type;
   typedef NumericT value_type;
@@ -54,9 +53,9 @@ public:
   }
 
   /** @brief The CSR view products and solvers use (values shared with handle()) */
-  ViennaCLCUDADcsr abi() const
+  typename viennacl::backend::b200::abi<NumericT>::csr abi() const
   {
-    ViennaCLCUDADcsr a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_), idx_rows_.ptr<unsigned int>(),
+    typename viennacl::backend::b200::abi<NumericT>::csr a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_), idx_rows_.ptr<unsigned int>(),
                           idx_cols_.ptr<unsigned int>(), elements_.ptr<NumericT>(), idx_blocks_.ptr<unsigned int>(), ViennaCLInt(row_block_num_)};
     return a;
   }
@@ -66,7 +65,7 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for coordinate matrix-vector product"));
     if (rows_ == 0) return;
-    backend::b200::check(ViennaCLCUDADcoomv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::coomv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_),
                                             idx_rows_.ptr<unsigned int>(), idx_cols_.ptr<unsigned int>(), elements_.ptr<NumericT>(),
                                             idx_blocks_.ptr<unsigned int>(), ViennaCLInt(row_block_num_),
                                             x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,

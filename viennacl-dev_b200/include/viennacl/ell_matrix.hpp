@@ -14,7 +14,6 @@ namespace viennacl
 template<typename NumericT, unsigned int AlignmentV>
 class ell_matrix
 {
-  typedef typename viennacl::detail::only_double<NumericT>::type numeric_must_be_double;
 public:
   typedef backend::mem_handle handle_type;
   typedef NumericT value_type;
@@ -40,9 +39,9 @@ public:
 
   void clear() { maxnnz_ = 0; coords_ = handle_type(); elements_ = handle_type(); }
 
-  ViennaCLCUDADell abi() const
+  typename viennacl::backend::b200::abi<NumericT>::ell abi() const
   {
-    ViennaCLCUDADell a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_), ViennaCLInt(maxnnz_),
+    typename viennacl::backend::b200::abi<NumericT>::ell a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_), ViennaCLInt(maxnnz_),
                           coords_.ptr<unsigned int>(), elements_.ptr<NumericT>()};
     return a;
   }
@@ -52,8 +51,8 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for ELL matrix-vector product"));
     if (rows_ == 0) return;
-    ViennaCLCUDADell a = abi();
-    backend::b200::check(ViennaCLCUDADellmv(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
+    typename viennacl::backend::b200::abi<NumericT>::ell a = abi();
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::ellmv(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
                                             y.ptr(), ViennaCLInt(y.start()), ViennaCLInt(y.stride()), beta));
   }
 
@@ -65,13 +64,13 @@ public:
     if (rows_ == 0) return;
     ViennaCLBackend b = backend::b200::handle();
     ViennaCLInt w = 0;
-    backend::b200::check(ViennaCLCUDADcsr2ell(b, ViennaCLInt(rows_), A.handle1().template ptr<unsigned int>(), A.handle2().template ptr<unsigned int>(),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::csr2ell(b, ViennaCLInt(rows_), A.handle1().template ptr<unsigned int>(), A.handle2().template ptr<unsigned int>(),
                                               A.handle().template ptr<NumericT>(), &w, NULL, NULL));
     maxnnz_ = vcl_size_t(w);
     const vcl_size_t tot = (rows_ * maxnnz_ > 0) ? rows_ * maxnnz_ : 1;
     coords_.create(sizeof(unsigned int) * tot);
     elements_.create(sizeof(NumericT) * tot);
-    backend::b200::check(ViennaCLCUDADcsr2ell(b, ViennaCLInt(rows_), A.handle1().template ptr<unsigned int>(), A.handle2().template ptr<unsigned int>(),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::csr2ell(b, ViennaCLInt(rows_), A.handle1().template ptr<unsigned int>(), A.handle2().template ptr<unsigned int>(),
                                               A.handle().template ptr<NumericT>(), &w, coords_.ptr<unsigned int>(), elements_.ptr<NumericT>()));
   }
 

@@ -65,10 +65,5 @@ namespace linalg
   };
 }
 
-namespace detail
-{
-  template<typename T> struct only_double;
-  template<> struct only_double<double> { typedef double type; };
-}
 } // namespace viennacl
 #endif

@@ -15,7 +15,6 @@ namespace viennacl
 template<typename NumericT, unsigned int AlignmentV>
 class hyb_matrix
 {
-  typedef typename viennacl::detail::only_double<NumericT>::type numeric_must_be_double;
 public:
   typedef backend::mem_handle handle_type;
   typedef NumericT value_type;
@@ -48,9 +47,9 @@ public:
     ell_coords_ = handle_type(); ell_elements_ = handle_type(); csr_rows_ = handle_type(); csr_cols_ = handle_type(); csr_elements_ = handle_type();
   }
 
-  ViennaCLCUDADhyb abi() const
+  typename viennacl::backend::b200::abi<NumericT>::hyb abi() const
   {
-    ViennaCLCUDADhyb a;
+    typename viennacl::backend::b200::abi<NumericT>::hyb a;
     a.ell.rows = ViennaCLInt(rows_); a.ell.cols = ViennaCLInt(cols_); a.ell.internal_rows = ViennaCLInt(rows_); a.ell.maxnnz = ViennaCLInt(ellnnz_);
     a.ell.coords = ell_coords_.ptr<unsigned int>(); a.ell.elements = ell_elements_.ptr<NumericT>();
     a.csr_rows = csr_rows_.ptr<unsigned int>(); a.csr_cols = csr_cols_.ptr<unsigned int>(); a.csr_elements = csr_elements_.ptr<NumericT>();
@@ -63,8 +62,8 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for HYB matrix-vector product"));
     if (rows_ == 0) return;
-    ViennaCLCUDADhyb a = abi();
-    backend::b200::check(ViennaCLCUDADhybmv(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
+    typename viennacl::backend::b200::abi<NumericT>::hyb a = abi();
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::hybmv(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
                                             y.ptr(), ViennaCLInt(y.start()), ViennaCLInt(y.stride()), beta));
   }
 
@@ -78,7 +77,7 @@ public:
     ViennaCLInt w = 0, tn = 0;
     const unsigned int *rp = A.handle1().template ptr<unsigned int>(), *ci = A.handle2().template ptr<unsigned int>();
     const NumericT *va = A.handle().template ptr<NumericT>();
-    backend::b200::check(ViennaCLCUDADcsr2hyb(b, ViennaCLInt(rows_), ViennaCLInt(cols_), rp, ci, va, double(csr_threshold_), &w, &tn,
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::csr2hyb(b, ViennaCLInt(rows_), ViennaCLInt(cols_), rp, ci, va, NumericT(csr_threshold_), &w, &tn,
                                               NULL, NULL, NULL, NULL, NULL));
     ellnnz_ = vcl_size_t(w); csrnnz_ = vcl_size_t(tn);
     const vcl_size_t tot = (rows_ * ellnnz_ > 0) ? rows_ * ellnnz_ : 1;
@@ -87,7 +86,7 @@ public:
     csr_rows_.create(sizeof(unsigned int) * (rows_ + 1));
     csr_cols_.create(sizeof(unsigned int) * (csrnnz_ ? csrnnz_ : 1));
     csr_elements_.create(sizeof(NumericT) * (csrnnz_ ? csrnnz_ : 1));
-    backend::b200::check(ViennaCLCUDADcsr2hyb(b, ViennaCLInt(rows_), ViennaCLInt(cols_), rp, ci, va, double(csr_threshold_), &w, &tn,
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::csr2hyb(b, ViennaCLInt(rows_), ViennaCLInt(cols_), rp, ci, va, NumericT(csr_threshold_), &w, &tn,
                                               ell_coords_.ptr<unsigned int>(), ell_elements_.ptr<NumericT>(), csr_rows_.ptr<unsigned int>(),
                                               csr_cols_.ptr<unsigned int>(), csr_elements_.ptr<NumericT>()));
   }

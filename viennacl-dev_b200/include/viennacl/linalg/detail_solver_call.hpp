@@ -1,6 +1,7 @@
 // viennacl/linalg/detail_solver_call.hpp -- shared glue between the solver tags and the whole-solve entry points of the C-ABI.
 #ifndef VIENNACL_B200_LINALG_DETAIL_SOLVER_CALL_HPP
 #define VIENNACL_B200_LINALG_DETAIL_SOLVER_CALL_HPP
+#include "viennacl/backend/abi.hpp"
 #include "viennacl/vector.hpp"
 #include "viennacl/compressed_matrix.hpp"
 #include "viennacl/sliced_ell_matrix.hpp"
@@ -24,7 +25,7 @@ namespace detail
     bool (*fun)(viennacl::vector<NumericT> const &, NumericT, void*);
     void *user;
     vcl_size_t size;
-    static ViennaCLInt trampoline(const double *x_dev, double est, void *self_)
+    static ViennaCLInt trampoline(const NumericT *x_dev, NumericT est, void *self_)
     {
       monitor_bridge *self = static_cast<monitor_bridge*>(self_);
       viennacl::vector<NumericT> view(const_cast<NumericT*>(x_dev), CUDA_MEMORY, self->size);
@@ -32,35 +33,41 @@ namespace detail
     }
   };
 
-  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADcsr const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
+  /** @brief Whole-solve entry points of one precision (abi<NumericT>), selected by the matrix struct type */
+  template<typename NumericT>
+  struct solver_calls
   {
-    ViennaCLBackend h = backend::b200::handle();
-    if (k == SOLVER_CG) return ViennaCLCUDADcsr_cg(h, &A, b, x, t);
-    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADcsr_bicgstab(h, &A, b, x, t);
-    return ViennaCLCUDADcsr_gmres(h, &A, b, x, t);
-  }
-  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADsell const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
-  {
-    ViennaCLBackend h = backend::b200::handle();
-    if (k == SOLVER_CG) return ViennaCLCUDADsell_cg(h, &A, b, x, t);
-    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADsell_bicgstab(h, &A, b, x, t);
-    return ViennaCLCUDADsell_gmres(h, &A, b, x, t);
-  }
-
-  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADell const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
-  {
-    ViennaCLBackend h = backend::b200::handle();
-    if (k == SOLVER_CG) return ViennaCLCUDADell_cg(h, &A, b, x, t);
-    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADell_bicgstab(h, &A, b, x, t);
-    return ViennaCLCUDADell_gmres(h, &A, b, x, t);
-  }
-  inline ViennaCLStatus call(solver_kind k, ViennaCLCUDADhyb const & A, const double *b, double *x, ViennaCLB200SolverTag *t)
-  {
-    ViennaCLBackend h = backend::b200::handle();
-    if (k == SOLVER_CG) return ViennaCLCUDADhyb_cg(h, &A, b, x, t);
-    if (k == SOLVER_BICGSTAB) return ViennaCLCUDADhyb_bicgstab(h, &A, b, x, t);
-    return ViennaCLCUDADhyb_gmres(h, &A, b, x, t);
-  }
+    typedef viennacl::backend::b200::abi<NumericT> abi;
+    typedef typename abi::solver_tag tag_type;
+    static ViennaCLStatus call(solver_kind k, typename abi::csr const & A, const NumericT *b, NumericT *x, tag_type *t)
+    {
+      ViennaCLBackend h = backend::b200::handle();
+      if (k == SOLVER_CG) return abi::csr_cg(h, &A, b, x, t);
+      if (k == SOLVER_BICGSTAB) return abi::csr_bicgstab(h, &A, b, x, t);
+      return abi::csr_gmres(h, &A, b, x, t);
+    }
+    static ViennaCLStatus call(solver_kind k, typename abi::sell const & A, const NumericT *b, NumericT *x, tag_type *t)
+    {
+      ViennaCLBackend h = backend::b200::handle();
+      if (k == SOLVER_CG) return abi::sell_cg(h, &A, b, x, t);
+      if (k == SOLVER_BICGSTAB) return abi::sell_bicgstab(h, &A, b, x, t);
+      return abi::sell_gmres(h, &A, b, x, t);
+    }
+    static ViennaCLStatus call(solver_kind k, typename abi::ell const & A, const NumericT *b, NumericT *x, tag_type *t)
+    {
+      ViennaCLBackend h = backend::b200::handle();
+      if (k == SOLVER_CG) return abi::ell_cg(h, &A, b, x, t);
+      if (k == SOLVER_BICGSTAB) return abi::ell_bicgstab(h, &A, b, x, t);
+      return abi::ell_gmres(h, &A, b, x, t);
+    }
+    static ViennaCLStatus call(solver_kind k, typename abi::hyb const & A, const NumericT *b, NumericT *x, tag_type *t)
+    {
+      ViennaCLBackend h = backend::b200::handle();
+      if (k == SOLVER_CG) return abi::hyb_cg(h, &A, b, x, t);
+      if (k == SOLVER_BICGSTAB) return abi::hyb_bicgstab(h, &A, b, x, t);
+      return abi::hyb_gmres(h, &A, b, x, t);
+    }
+  };
 
   /** @brief Runs one solve on the device; rhs may be a strided view (it is compacted first). */
   template<typename MatrixT, typename NumericT>
@@ -73,9 +80,14 @@ namespace detail
     const vector_base<NumericT> *b = &rhs;
     if (rhs.stride() != 1) { compact = rhs; b = &compact; }
     monitor_bridge<NumericT> bridge = {monitor, monitor_data, rhs.size()};
-    if (monitor) { t.monitor = &monitor_bridge<NumericT>::trampoline; t.monitor_user = &bridge; }
-    else { t.monitor = NULL; t.monitor_user = NULL; }
-    backend::b200::check(call(kind, A.abi(), b->ptr() + b->start(), result.ptr(), &t));
+    // the tag of this precision: same fields, tolerances and results in double, monitor estimate in NumericT
+    typename solver_calls<NumericT>::tag_type tn;
+    tn.tolerance = t.tolerance; tn.abs_tolerance = t.abs_tolerance; tn.max_iterations = t.max_iterations; tn.krylov_dim = t.krylov_dim;
+    tn.max_iterations_before_restart = t.max_iterations_before_restart; tn.precond = t.precond; tn.iters = 0; tn.error = 0;
+    if (monitor) { tn.monitor = &monitor_bridge<NumericT>::trampoline; tn.monitor_user = &bridge; }
+    else { tn.monitor = NULL; tn.monitor_user = NULL; }
+    backend::b200::check(solver_calls<NumericT>::call(kind, A.abi(), b->ptr() + b->start(), result.ptr(), &tn));
+    t.iters = tn.iters; t.error = tn.error;
     return result;
   }
 }

@@ -11,7 +11,7 @@ namespace linalg
   {
     assert(x.size() == y.size() && bool("Incompatible vector sizes!"));
     NumericT r = 0;
-    backend::b200::check(ViennaCLCUDADdot(backend::b200::handle(), ViennaCLInt(x.size()), &r, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::dot(backend::b200::handle(), ViennaCLInt(x.size()), &r, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()),
                                           y.ptr(), ViennaCLInt(y.start()), ViennaCLInt(y.stride())));
     return viennacl::host_scalar<NumericT>(r);
   }

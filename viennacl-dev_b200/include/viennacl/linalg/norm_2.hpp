@@ -10,7 +10,7 @@ namespace linalg
   viennacl::host_scalar<NumericT> norm_2(vector_base<NumericT> const & x)
   {
     NumericT r = 0;
-    backend::b200::check(ViennaCLCUDADnrm2(backend::b200::handle(), ViennaCLInt(x.size()), &r, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride())));
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::nrm2(backend::b200::handle(), ViennaCLInt(x.size()), &r, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride())));
     return viennacl::host_scalar<NumericT>(r);
   }
 }

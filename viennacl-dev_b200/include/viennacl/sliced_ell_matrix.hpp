@@ -45,9 +45,9 @@ public:
     columns_per_block_ = handle_type(); column_indices_ = handle_type(); block_start_ = handle_type(); elements_ = handle_type();
   }
 
-  ViennaCLCUDADsell abi() const
+  typename viennacl::backend::b200::abi<ScalarT>::sell abi() const
   {
-    ViennaCLCUDADsell a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_), columns_per_block_.ptr<unsigned int>(),
+    typename viennacl::backend::b200::abi<ScalarT>::sell a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_), columns_per_block_.ptr<unsigned int>(),
                            column_indices_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), elements_.ptr<ScalarT>()};
     return a;
   }
@@ -57,7 +57,7 @@ public:
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for sliced ELL matrix-vector product"));
     if (rows_ == 0) return;
     if (!columns_per_block_.get()) throw memory_exception("not initialised!");
-    backend::b200::check(ViennaCLCUDADsellmv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_),
+    backend::b200::check(viennacl::backend::b200::abi<ScalarT>::sellmv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_),
                                              columns_per_block_.ptr<unsigned int>(), column_indices_.ptr<unsigned int>(),
                                              block_start_.ptr<unsigned int>(), elements_.ptr<ScalarT>(),
                                              x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
@@ -76,12 +76,12 @@ public:
     block_start_.create(sizeof(unsigned int) * slices);
     long long padded = 0;
     ViennaCLBackend b = backend::b200::handle();
-    backend::b200::check(ViennaCLCUDADcsr2sell(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), A.handle1().template ptr<unsigned int>(),
+    backend::b200::check(viennacl::backend::b200::abi<ScalarT>::csr2sell(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), A.handle1().template ptr<unsigned int>(),
                                                A.handle2().template ptr<unsigned int>(), A.handle().template ptr<ScalarT>(),
                                                columns_per_block_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), &padded, NULL, NULL));
     column_indices_.create(sizeof(unsigned int) * vcl_size_t(padded ? padded : 1));
     elements_.create(sizeof(ScalarT) * vcl_size_t(padded ? padded : 1));
-    backend::b200::check(ViennaCLCUDADcsr2sell(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), A.handle1().template ptr<unsigned int>(),
+    backend::b200::check(viennacl::backend::b200::abi<ScalarT>::csr2sell(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), A.handle1().template ptr<unsigned int>(),
                                                A.handle2().template ptr<unsigned int>(), A.handle().template ptr<ScalarT>(),
                                                columns_per_block_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), &padded,
                                                column_indices_.ptr<unsigned int>(), elements_.ptr<ScalarT>()));

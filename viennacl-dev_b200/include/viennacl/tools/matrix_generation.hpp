@@ -10,14 +10,15 @@ namespace tools
   /** @brief 5-/7-point stencil with first-order upwind convection c (c = 0: Laplacian); points_z == 1 selects 2-D */
   template<typename NumericT, unsigned int AlignmentV>
   void generate_fdm_stencil(viennacl::compressed_matrix<NumericT, AlignmentV> & A, vcl_size_t points_x, vcl_size_t points_y, vcl_size_t points_z = 1,
-                            NumericT cx = 0, NumericT cy = 0, NumericT cz = 0)
+                            double cx_ = 0, double cy_ = 0, double cz_ = 0)
   {
+    const NumericT cx = NumericT(cx_), cy = NumericT(cy_), cz = NumericT(cz_);
     ViennaCLBackend b = viennacl::backend::b200::handle();
     long long rows = 0, nnz = 0;
-    viennacl::backend::b200::check(ViennaCLCUDADgenerate_stencil(b, ViennaCLInt(points_x), ViennaCLInt(points_y), ViennaCLInt(points_z), cx, cy, cz,
+    viennacl::backend::b200::check(viennacl::backend::b200::abi<NumericT>::generate_stencil(b, ViennaCLInt(points_x), ViennaCLInt(points_y), ViennaCLInt(points_z), cx, cy, cz,
                                                                  NULL, NULL, NULL, &rows, &nnz));
     A = viennacl::compressed_matrix<NumericT, AlignmentV>(vcl_size_t(rows), vcl_size_t(rows), vcl_size_t(nnz));
-    viennacl::backend::b200::check(ViennaCLCUDADgenerate_stencil(b, ViennaCLInt(points_x), ViennaCLInt(points_y), ViennaCLInt(points_z), cx, cy, cz,
+    viennacl::backend::b200::check(viennacl::backend::b200::abi<NumericT>::generate_stencil(b, ViennaCLInt(points_x), ViennaCLInt(points_y), ViennaCLInt(points_z), cx, cy, cz,
                                                                  A.handle1().template ptr<unsigned int>(), A.handle2().template ptr<unsigned int>(),
                                                                  A.handle().template ptr<NumericT>(), &rows, &nnz));
     A.generate_row_block_information();

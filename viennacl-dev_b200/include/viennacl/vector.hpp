@@ -168,7 +168,6 @@ namespace detail
 template<typename NumericT>
 class vector_base
 {
-  typedef typename viennacl::detail::only_double<NumericT>::type numeric_must_be_double;   // float: next row
 public:
   typedef NumericT value_type;
   typedef NumericT cpu_value_type;
@@ -215,14 +214,14 @@ public:
   {
     // v / s, not v * (1/s): the reference divides (vector_operations.hpp av with reciprocal flag), and so does the oracle
     backend::mem_handle den; den.create(sizeof(NumericT), &s);
-    backend::b200::check(ViennaCLCUDADelement_div(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::element_div(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
                                                   ptr(), int(start_), int(stride_), den.ptr<NumericT>(), 0, 0));
     return *this;
   }
   vector_base & operator=(detail::element_div_expr<NumericT> const & e)
   {
     ensure_size(e.num->size());
-    backend::b200::check(ViennaCLCUDADelement_div(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::element_div(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
                                                   e.num->ptr(), int(e.num->start()), int(e.num->stride()),
                                                   e.den->ptr(), int(e.den->start()), int(e.den->stride())));
     return *this;
@@ -251,7 +250,7 @@ public:
   vector_base & operator=(scalar_vector<NumericT> const & v)
   {
     ensure_size(v.size());
-    backend::b200::check(ViennaCLCUDADassign(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_), v.value()));
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::assign(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_), v.value()));
     return *this;
   }
 
@@ -280,7 +279,7 @@ public:
   void clear()
   {
     if (size_ == 0) return;
-    backend::b200::check(ViennaCLCUDADassign(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_), NumericT(0)));
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::assign(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_), NumericT(0)));
   }
 
   void resize(size_type new_size, bool preserve = true)
@@ -290,7 +289,7 @@ public:
     if (preserve && size_ > 0 && new_size > 0)
     {
       size_type m = new_size < size_ ? new_size : size_;
-      backend::b200::check(ViennaCLCUDADav(backend::b200::handle(), int(m), fresh.ptr(), 0, 1, ptr(), int(start_), int(stride_), NumericT(1)));
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::av(backend::b200::handle(), int(m), fresh.ptr(), 0, 1, ptr(), int(start_), int(stride_), NumericT(1)));
     }
     swap(fresh);
   }
@@ -320,7 +319,7 @@ protected:
   {
     if (&other == this || other.size() == 0) return;
     ensure_size(other.size());
-    backend::b200::check(ViennaCLCUDADav(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::av(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_),
                                          other.ptr(), int(other.start()), int(other.stride()), NumericT(1)));
   }
   template<typename MatrixT>
@@ -345,17 +344,17 @@ protected:
     const vector_base *a = e.v[0], *c = e.terms > 1 ? e.v[1] : e.v[0];
     const NumericT ca = e.c[0], cc = e.terms > 1 ? e.c[1] : NumericT(0);
     if (!accumulate && e.terms == 1)
-      backend::b200::check(ViennaCLCUDADav(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca));
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::av(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca));
     else if (!accumulate)
-      backend::b200::check(ViennaCLCUDADavbv(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca,
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::avbv(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca,
                                              c->ptr(), int(c->start()), int(c->stride()), cc));
     else
-      backend::b200::check(ViennaCLCUDADavbv_v(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca,
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::avbv_v(b, int(size_), ptr(), int(start_), int(stride_), a->ptr(), int(a->start()), int(a->stride()), ca,
                                                c->ptr(), int(c->start()), int(c->stride()), cc));
     if (e.terms == 3)
     {
       const vector_base *d = e.v[2];
-      backend::b200::check(ViennaCLCUDADavbv_v(b, int(size_), ptr(), int(start_), int(stride_), d->ptr(), int(d->start()), int(d->stride()), e.c[2],
+      backend::b200::check(viennacl::backend::b200::abi<NumericT>::avbv_v(b, int(size_), ptr(), int(start_), int(stride_), d->ptr(), int(d->start()), int(d->stride()), e.c[2],
                                                d->ptr(), int(d->start()), int(d->stride()), NumericT(0)));
     }
   }
