@@ -310,6 +310,19 @@ ViennaCLStatus ViennaCLCUDADhyb_bicgstab(ViennaCLBackend backend, const ViennaCL
 ViennaCLStatus ViennaCLCUDADell_gmres(ViennaCLBackend backend, const ViennaCLCUDADell *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
 ViennaCLStatus ViennaCLCUDADhyb_gmres(ViennaCLBackend backend, const ViennaCLCUDADhyb *A, const double *b, double *x, ViennaCLB200SolverTag *tag);
 
+/* ---------------------------------------------------------------- mixed precision (double outside, float inside) ------------------------- */
+/* linalg/mixed_precision_cg.hpp:95-186: CG on a compressed_matrix<double> whose inner iterations run on a float copy of the
+ * matrix (8 instead of 12 bytes per entry); whenever the float residual has dropped by `inner_tolerance` (a ratio of SQUARED
+ * norms, :160) the iterate is folded into the double result, the residual is recomputed in double (:165-166) and the float
+ * iteration restarts from it.  tag: tolerance, max_iterations (total inner iterations), iters/error as in the reference
+ * (:151, :182).  Here the inner iterations are the fused single-precision pipelined CG (ViennaCLCUDAScsr_cg).
+ * values_float: the float copy of A's values if the caller keeps one (compressed_matrix<float> sharing A's index arrays),
+ * or NULL: converted into backend workspace on every call. */
+ViennaCLStatus ViennaCLCUDAconvert_DtoS(ViennaCLBackend backend, long long n, const double *x, float *y);        /* y = (float) x */
+ViennaCLStatus ViennaCLCUDAconvert_StoD(ViennaCLBackend backend, long long n, const float *x, double *y);        /* y = (double) x */
+ViennaCLStatus ViennaCLCUDADcsr_mixed_precision_cg(ViennaCLBackend backend, const ViennaCLCUDADcsr *A, const float *values_float,
+                                                   const double *b, double *x, float inner_tolerance, ViennaCLB200SolverTag *tag);
+
 /* ---------------------------------------------------------------- row-partitioned (multi-GPU) CG ------------------------------------------ */
 /* New (no reference counterpart).  Rank g owns a contiguous block of rows of a square matrix; `A_local` holds those rows with
  * GLOBAL column indices.  DistCreate analyses the halo (columns outside the owned range, assumed to belong to the two

@@ -37,6 +37,9 @@
 #include "viennacl/linalg/bicgstab.hpp"
 #include "viennacl/linalg/gmres.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
+#ifndef VCLREF_F32
+#include "viennacl/linalg/mixed_precision_cg.hpp"
+#endif
 
 typedef unsigned int u32;
 // element type: built twice, as it is (double -> libvcl_ref.so) and with -DVCLREF_F32 (float -> libvcl_ref_f32.so)
@@ -414,6 +417,21 @@ int vclref_solve(int solver, int precond, int format,
   if (rc == 0) viennacl::fast_copy(vx.begin(), vx.end(), x);
   return rc;
 }
+
+#ifndef VCLREF_F32
+// mixed_precision_cg.hpp:95-186 on the host backend (double system, float inner iterations)
+int vclref_mixed_cg(int rows, int nnz, const u32 *rp, const u32 *ci, const double *v, const double *b, double *x,
+                    double tol, int maxit, float inner_tol, int *iters, double *err)
+{
+  csr_t A(const_cast<u32*>(rp), const_cast<u32*>(ci), const_cast<double*>(v), viennacl::MAIN_MEMORY, rows, rows, nnz);
+  vec_t vb(const_cast<double*>(b), viennacl::MAIN_MEMORY, std::size_t(rows));
+  viennacl::linalg::mixed_precision_cg_tag tag(tol, maxit, inner_tol);
+  vec_t vx = viennacl::linalg::solve(A, vb, tag);
+  *iters = int(tag.iters()); *err = tag.error();
+  viennacl::fast_copy(vx.begin(), vx.end(), x);
+  return 0;
+}
+#endif
 
 // Times `reps` plain y = A*x products the way examples/benchmarks/sparse.cpp:123-130 does (one warm-up first).
 double vclref_time_csr_spmv(int rows, int cols, int nnz, const u32 *rp, const u32 *ci, const real_t *v,

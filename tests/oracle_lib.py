@@ -90,6 +90,8 @@ class _Oracle:
         lib.vclo_gmres.argtypes = [c_int, u32p, u32p, fp, fp, fp, c_dbl, c_dbl, c_int, c_int, ip, dp, C.c_void_p, c_int, ip]
         lib.vclo_max_threads.restype = c_int
         lib.vclo_set_threads.argtypes = [c_int]
+        if not single:
+            lib.vclo_mixed_cg.argtypes = [c_int, u32p, u32p, fp, fp, fp, c_dbl, c_int, C.c_float, ip, dp, ip]
 
     # -- generators --------------------------------------------------------------------------
     def stencil2d(self, nx, ny, cx=0.0, cy=0.0):
@@ -222,6 +224,13 @@ class _Oracle:
                                        C.byref(it), C.byref(err), hist.ctypes.data, hist_cap, C.byref(hl))
         return dict(x=x, iters=it.value, error=err.value, history=hist[:min(hl.value, hist_cap)].copy())
 
+    def mixed_cg(self, A, b, tol=1e-8, maxit=300, inner_tol=1e-2):
+        """mixed_precision_cg.hpp:95-186 (double system, float inner iterations); double oracle only."""
+        x = np.zeros(A.rows, np.float64)
+        it, err, up = c_int(0), c_dbl(0), c_int(0)
+        self.lib.vclo_mixed_cg(A.rows, A.rp, A.ci, A.v, b, x, tol, maxit, inner_tol, C.byref(it), C.byref(err), C.byref(up))
+        return dict(x=x, iters=it.value, error=err.value, outer_updates=up.value)
+
     def gmres(self, A, b, tol=1e-10, maxit=300, krylov=20, abs_tol=0.0, hist_cap=0):
         return self._run(self.lib.vclo_gmres, A, b, lambda b, x: (b, x, tol, abs_tol, maxit, krylov), hist_cap)
 
@@ -266,6 +275,8 @@ class _Ref:
         lib.vclref_inner_prod.argtypes = [fp, fp, c_int]
         lib.vclref_solve.argtypes = [c_int, c_int, c_int, c_int, c_int, u32p, u32p, fp, fp, fp,
                                      c_dbl, c_dbl, c_int, c_int, c_int, ip, dp, C.c_void_p, c_int, ip, dp]
+        if not single and hasattr(lib, "vclref_mixed_cg"):
+            lib.vclref_mixed_cg.argtypes = [c_int, c_int, u32p, u32p, fp, fp, fp, c_dbl, c_int, C.c_float, ip, dp]
         lib.vclref_time_csr_spmv.restype = c_dbl
         lib.vclref_time_csr_spmv.argtypes = [c_int, c_int, c_int, u32p, u32p, fp, fp, fp, c_int]
 
@@ -389,6 +400,13 @@ class _Ref:
         if rc != 0:
             raise RuntimeError("vclref_solve rc=%d" % rc)
         return dict(x=x, iters=it.value, error=err.value, history=hist[:min(hl.value, hist_cap)].copy(), seconds=sec.value)
+
+    def mixed_cg(self, A, b, tol=1e-8, maxit=300, inner_tol=1e-2):
+        x = np.zeros(A.rows, np.float64)
+        it, err = c_int(0), c_dbl(0)
+        rc = self.lib.vclref_mixed_cg(A.rows, A.nnz, A.rp, A.ci, A.v, b, x, tol, maxit, inner_tol, C.byref(it), C.byref(err))
+        assert rc == 0
+        return dict(x=x, iters=it.value, error=err.value)
 
     def time_csr_spmv(self, A, x, reps):
         y = np.zeros(A.rows, self.dt)

@@ -195,3 +195,23 @@ def test_coo_layout_and_spmv_bitexact(golden, golden_formats, orc, name):
     x, y0 = golden[name + "/x"], golden[name + "/y0"]
     assert np.array_equal(orc.coo_spmv(M, x), gf[name + "/coo/y"])
     assert np.array_equal(orc.coo_spmv(M, x, y0.copy(), 1.5, -0.25), gf[name + "/coo/y_ab"])
+
+
+# ----------------------------------------------------------------------------------------------- mixed-precision CG
+def _mixed_cases():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mixed_precision_cg.json")))
+
+
+@pytest.mark.parametrize("case", _mixed_cases(), ids=lambda c: "%s-%g-%d" % (c["name"], c["tol"], c["maxit"]))
+def test_mixed_precision_cg_restatement(orc, case):
+    """oracle/vcl_oracle_mixed.c vs the reference's mixed_precision_cg.hpp (golden counts from the reference build)."""
+    nx, ny, nz = case["grid"]
+    A = orc.stencil3d(nx, ny, nz) if nz > 1 else orc.stencil2d(nx, ny)
+    b = np.ones(A.rows)
+    res = orc.mixed_cg(A, b, case["tol"], case["maxit"], case["inner_tol"])
+    assert abs(res["iters"] - case["iters"]) <= max(2, case["iters"] // 30), (res["iters"], case["iters"])
+    true = np.linalg.norm(b - A.to_scipy() @ res["x"]) / np.linalg.norm(b)
+    if case["iters"] < case["maxit"]:
+        assert res["error"] < case["tol"] and abs(true - res["error"]) <= 1e-3 * case["tol"] + 1e-12
+    assert abs(np.linalg.norm(res["x"]) - case["x_norm"]) <= 1e-4 * case["x_norm"]

@@ -9,5 +9,5 @@ Load it with `import __graft_entry__; pkg = __graft_entry__.load_package()` (the
 """
 from .capi import (  # noqa: F401
     LIB_PATH, VclError, Backend, DeviceArray, CsrMatrix, SellMatrix, SolverTag, build_library, library_available, lib,
-    EXPORTED_SYMBOLS, DistCsr, EllMatrix, HybMatrix, CooMatrix,
+    EXPORTED_SYMBOLS, DistCsr, EllMatrix, HybMatrix, CooMatrix, mixed_precision_cg,
 )

@@ -105,12 +105,12 @@ def lib():
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     S = c_int  # status
 
-    def sig(name, *args, res=S):
+    def sig(name, *args, res=S, twin=True):
         f = getattr(L, name)
         f.argtypes = list(args)
         f.restype = res
         # single-precision twin (vcl_b200_float.h): same argument list with float scalars; the row-partitioned path is double only
-        if name.startswith("ViennaCLCUDAD") and not name.startswith("ViennaCLCUDADdist_"):
+        if name.startswith("ViennaCLCUDAD") and not name.startswith("ViennaCLCUDADdist_") and twin:
             g = getattr(L, "ViennaCLCUDAS" + name[len("ViennaCLCUDAD"):])
             swap = {c_dbl: c_flt, p_dbl: p_flt, C.POINTER(TagStruct): C.POINTER(TagStructS)}
             g.argtypes = [c_flt if a is c_dbl else p_flt if a is p_dbl else swap.get(a, a) for a in args]
@@ -184,6 +184,9 @@ def lib():
         sig("ViennaCLCUDADsell_" + nm, c_vp, ps, c_vp, c_vp, pt)
         sig("ViennaCLCUDADell_" + nm, c_vp, pe, c_vp, c_vp, pt)
         sig("ViennaCLCUDADhyb_" + nm, c_vp, ph, c_vp, c_vp, pt)
+    sig("ViennaCLCUDAconvert_DtoS", c_vp, c_ll, c_vp, c_vp)
+    sig("ViennaCLCUDAconvert_StoD", c_vp, c_ll, c_vp, c_vp)
+    sig("ViennaCLCUDADcsr_mixed_precision_cg", c_vp, pc, c_vp, c_vp, c_vp, c_flt, pt, twin=False)
     sig("ViennaCLCUDADdist_csr_create", c_vp, c_ll, c_ll, c_ll, c_int, c_vp, c_vp, c_vp, p_vp)
     sig("ViennaCLCUDADdist_csr_destroy", c_vp, p_vp)
     sig("ViennaCLCUDADdist_csrmv", c_vp, c_vp, c_vp, c_vp)
@@ -586,6 +589,15 @@ class SolverTag:
             return self
         A.b.check(fn(A.b.h, C.byref(s), b.ptr, x.ptr, C.byref(self.t)))
         return self
+
+
+def mixed_precision_cg(A, b, x, tol=1e-8, max_iterations=300, inner_tol=1e-2, values_float=None):
+    """solve(A, b, mixed_precision_cg_tag(tol, max_iterations, inner_tol)) -- mixed_precision_cg.hpp:95-186.  A: CsrMatrix (float64)."""
+    tag = SolverTag(tol=tol, max_iterations=max_iterations)
+    s = A.struct()
+    A.b.check(A.b.L.ViennaCLCUDADcsr_mixed_precision_cg(A.b.h, C.byref(s), values_float.ptr if values_float is not None else None,
+                                                        b.ptr, x.ptr, inner_tol, C.byref(tag.t)))
+    return tag
 
 
 class DistCsr:

@@ -20,6 +20,7 @@
 #include "viennacl/linalg/cg.hpp"
 #include "viennacl/linalg/bicgstab.hpp"
 #include "viennacl/linalg/gmres.hpp"
+#include "viennacl/linalg/mixed_precision_cg.hpp"
 #include "viennacl/tools/matrix_generation.hpp"
 
 // built twice: iterative (double) and iterative_float (-DNUMERIC_T=float; the reference's tutorials run with either)
@@ -104,6 +105,22 @@ int main()
     expect(few.iters() == 20 && few.error() > TOL, "cg_tag(TOL, 20) stops at max_iterations and reports the estimate");
     x = viennacl::linalg::solve(A, b, viennacl::linalg::cg_tag(), viennacl::linalg::no_precond());
     expect(x.size() == b.size(), "solve(A, b, cg_tag(), no_precond())");
+  }
+
+  std::cout << "----- mixed-precision CG (mixed_precision_cg.hpp) -----" << std::endl;
+  if (!SINGLE)
+  {
+    viennacl::compressed_matrix<double> Ad;
+    viennacl::tools::generate_fdm_laplace(Ad, 96, 80);
+    viennacl::vector<double> bd = viennacl::scalar_vector<double>(Ad.size1(), 1.0);
+    viennacl::linalg::mixed_precision_cg_tag mtag(1e-8, 2000, 1e-2f);
+    viennacl::vector<double> xm = viennacl::linalg::solve(Ad, bd, mtag);
+    viennacl::vector<double> rm = viennacl::linalg::prod(Ad, xm);
+    rm = bd - rm;
+    const double true_res = viennacl::linalg::norm_2(rm) / viennacl::linalg::norm_2(bd);
+    std::cout << "  mixed CG : " << mtag.iters() << " iterations, error " << mtag.error() << ", true " << true_res << std::endl;
+    expect(mtag.iters() > 10 && mtag.iters() < 2000 && mtag.error() < 1e-8 && true_res < 1e-8 && std::fabs(true_res - mtag.error()) < 1e-9,
+           "solve(compressed_matrix<double>, b, mixed_precision_cg_tag): double-accurate result from float inner iterations");
   }
 
   std::cout << "----- BiCGStab Method -----" << std::endl;
