@@ -474,7 +474,9 @@ def test_solver_edge_cases(pkg, be, orc):
     assert tag.iters == ref["iters"] and np.allclose(dx.download(), ref["x"], rtol=1e-8, atol=1e-12)
     # unsupported combinations fail loudly instead of silently taking another path
     with pytest.raises(pkg.VclError):
-        pkg.SolverTag(precond=1, krylov_dim=10).solve("gmres", dA, db, dx)     # GMRES + Jacobi: facade's generic path only
+        pkg.SolverTag(precond=1, krylov_dim=10).solve("gmres", dA.to_sell(32), db, dx)   # Jacobi needs the CSR matrix (row_info)
+    with pytest.raises(pkg.VclError):
+        pkg.SolverTag(precond=7).solve("gmres", dA, db, dx)                    # unknown preconditioner id
     with pytest.raises(pkg.VclError):
         pkg.SolverTag(precond=1).solve("cg", dA.to_sell(32), db, dx)           # Jacobi needs the CSR matrix (row_info)
 
@@ -495,3 +497,32 @@ def test_config1_cg_parity_1024(pkg, be, orc):
     assert _true_res(A, b, x) <= _true_res(A, b, ref["x"]) * (1 + 1e-6) + 1e-8
     tag2 = pkg.SolverTag(tol=1e-8, max_iterations=5000).solve("cg", dA.to_sell(32), db, dx)
     assert abs(tag2.iters - ref["iters"]) <= 2
+
+
+# ----------------------------------------------------------------------------------------------- GMRES + Jacobi (fused)
+def _gmres_jacobi_cases():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmres_jacobi.json")))
+
+
+@pytest.mark.parametrize("case", _gmres_jacobi_cases(), ids=lambda c: "%s-m%d-%d" % (c["name"], c["krylov"], c["maxit"]))
+def test_gmres_jacobi_fused_vs_reference(pkg, be, orc, case):
+    """solve(A, b, gmres_tag, jacobi_precond) on the fused path (pipelined cycle on D^-1 A, per-iteration stopping rule) against
+    the reference's Householder path (gmres.hpp:449-631): same iteration count (+-2), estimate and solution."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_gmres_jacobi import vardiag
+    nx, ny, nz = case["grid"]; c = case["c"]
+    A = vardiag(orc.stencil3d(nx, ny, nz, *c) if nz > 1 else orc.stencil2d(nx, ny, c[0], c[1]))
+    b = np.ones(A.rows)
+    dA = dev_csr(pkg, be, A)
+    db, dx = be.array(b), be.array(np.full(A.rows, 2.0))
+    tag = pkg.SolverTag(tol=case["tol"], max_iterations=case["maxit"], krylov_dim=case["krylov"], precond=1).solve("gmres", dA, db, dx)
+    assert abs(tag.iters - case["iters"]) <= 2, (tag.iters, case["iters"])
+    x = dx.download()
+    assert abs(np.linalg.norm(x) - case["x_norm"]) <= 1e-5 * case["x_norm"]
+    if case["error"] < case["tol"]:
+        assert tag.error < case["tol"]
+        assert _true_res(A, b, x) <= case["true_residual"] * 1.5 + 1e-9
+    else:
+        assert abs(tag.error - case["error"]) <= 0.05 * case["error"]

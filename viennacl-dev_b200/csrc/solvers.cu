@@ -389,7 +389,12 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
   VCL_TRY(check_matrix(b, A));
-  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "GMRES: only the unpreconditioned pipelined path is provided (DESIGN.md, next rows)");
+  // Jacobi: the pipelined cycle runs on D^-1 A (the divide is folded into the SpMV epilogue) and -- like the reference's
+  // preconditioned path (gmres.hpp:449-631) -- the estimate is tested after EVERY inner iteration: the host walks the
+  // cycle's xi values, stops counting at the first iteration that meets the tolerance and truncates the update to it.
+  const bool jac = tag->precond == ViennaCLB200PrecondJacobi;
+  VCL_REQUIRE(b, jac || tag->precond == ViennaCLB200PrecondNone, "GMRES: unknown preconditioner id");
+  VCL_REQUIRE(b, !jac || A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   VCL_REQUIRE(b, tag->krylov_dim >= 1 && tag->krylov_dim <= VCL_GMRES_MAX_KRYLOV, "krylov_dim must be in [1, 64]");
   const long long n = A.rows();
   tag->iters = 0; tag->error = 0.0;
@@ -400,10 +405,11 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   const int m = tag->krylov_dim;
   const long long isz = (n + 127) / 128 * 128;                      // internal_size(): padded to 128 (forwards.h:385, gmres.hpp:192)
   const size_t small = Carver::need((size_t)m * m) + 4 * Carver::need(m);
-  VCL_TRY(vcl_ws_reserve(b, Carver::need(n) + Carver::need((size_t)isz * m) + small));
+  VCL_TRY(vcl_ws_reserve(b, (jac ? 2 : 1) * Carver::need(n) + Carver::need((size_t)isz * m) + small));
   Carver cv(b->ws);
   real *res = cv.take(n), *V = cv.take((size_t)isz * m), *R = cv.take((size_t)m * m);
   real *d_xi = cv.take(m), *d_h = cv.take(m), *d_coef = cv.take(m);
+  real *diag = jac ? cv.take(n) : nullptr;
   real *d_nsq = VCL_DSCAL(b) + 8, *d_junk = VCL_DSCAL(b) + 9;
 
   std::vector<real> hR((size_t)m * m), xi(m), eta(m), coef(m, 0.0);
@@ -415,8 +421,16 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   VCL_CUDA(b, cudaMemsetAsync(d_coef, 0, sizeof(real) * m, b->stream));
   real ss = 0.0;
   VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
-  const real norm_rhs = std::sqrt(ss);
+  const real norm_rhs = std::sqrt(ss);                                           // of the UNpreconditioned rhs (gmres.hpp:478)
   real rho_0 = norm_rhs, rho = 1.0;
+  if (jac)
+  {
+    if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                  // gmres.hpp:480-481
+    VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+    VCL_TRY(ViennaCLCUDADelement_div(b, (int)n, res, 0, 1, res, 0, 1, diag, 0, 1));   // precond.apply(res), gmres.hpp:492
+    VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
+    rho_0 = std::sqrt(ss);
+  }
 
   unsigned max_restarts = (unsigned)tag->max_iterations / (unsigned)m;         // gmres.hpp:74-80
   if (max_restarts > 0 && max_restarts * (unsigned)m == (unsigned)tag->max_iterations) max_restarts -= 1;
@@ -429,6 +443,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
       VCL_TRY(plain_prod(b, A, x, res));
       residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rhs);
       VCL_LAUNCHED(b, "residual_kernel");
+      if (jac) VCL_TRY(ViennaCLCUDADelement_div(b, (int)n, res, 0, 1, res, 0, 1, diag, 0, 1));
       VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
       rho_0 = std::sqrt(ss);
     }
@@ -436,15 +451,27 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
     scale_residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rho_0);
     VCL_LAUNCHED(b, "scale_residual_kernel");
     rho = 1.0;
-    if (rho_0 / norm_rhs < tag->tolerance || rho_0 < tag->abs_tolerance) break; // gmres.hpp:234-235
+    if (rho_0 / norm_rhs < tag->tolerance || rho_0 < tag->abs_tolerance)        // gmres.hpp:234-235 / :499-503
+    {
+      if (jac) tag->error = rho_0 / norm_rhs;
+      break;
+    }
 
     int k;
     for (k = 0; k < m; ++k)
     {
       real *vk = V + (size_t)k * isz;
       const real *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
-      EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
-      VCL_TRY(launch_prod(b, A, src, e));
+      if (jac)
+      {
+        EpiFused<STEP_NONE, false, true> e = {vk, src, nullptr, diag, VCL_PARTIALS(b), b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
+        VCL_TRY(launch_prod(b, A, src, e));
+      }
+      else
+      {
+        EpiFused<STEP_NONE, false, false> e = {vk, src, nullptr, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, d_nsq, d_junk, nullptr, {0.0, 0.0, 0.0}, nullptr};
+        VCL_TRY(launch_prod(b, A, src, e));
+      }
       if (k > 0)
       {
         VCL_TRY(launch_gs1(b, grid, V, n, isz, k, d_h, 1));
@@ -464,11 +491,13 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
     for (size_t i = 0; i < kk; ++i)
       if (std::fabs(hR[i + i * kk]) < tag->tolerance * hR[0]) { kk = i; break; }
 
+    bool converged = false;
     for (size_t i = 0; i < kk; ++i)                                              // gmres.hpp:318-331
     {
       tag->iters += 1;
       if (xi[i] >= rho || xi[i] <= -rho) { kk = i; break; }
       rho *= std::sin(std::acos(xi[i] / rho));
+      if (jac && std::fabs(rho * rho_0 / norm_rhs) < tag->tolerance) { kk = i + 1; converged = true; break; }   // gmres.hpp:579-584
     }
 
     eta = xi;                                                                    // gmres.hpp:336-345
@@ -487,6 +516,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
 
     tag->error = std::fabs(rho * rho_0 / norm_rhs);                              // gmres.hpp:360
     if (tag->monitor && tag->monitor(x, std::fabs(rho * rho_0 / norm_rhs), tag->monitor_user)) break;
+    if (converged) break;                                                        // gmres.hpp:627-628
   }
   return ViennaCLSuccess;
 }

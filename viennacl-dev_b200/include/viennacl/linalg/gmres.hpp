@@ -58,9 +58,11 @@ namespace detail
   /** @brief Pipelined GMRES(m) on the device (gmres.hpp:181-367): compressed_matrix / sliced_ell_matrix without preconditioner */
   template<typename MatrixT, typename NumericT>
   viennacl::vector<NumericT> fused_gmres(MatrixT const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
-                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data)
+                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*), void *monitor_data,
+                                         ViennaCLB200Precond pc = ViennaCLB200PrecondNone)
   {
     ViennaCLB200SolverTag t = to_abi(tag);
+    t.precond = pc;
     viennacl::vector<NumericT> x = run(SOLVER_GMRES, A, rhs, t, monitor, monitor_data);
     tag.iters(static_cast<unsigned int>(t.iters)); tag.error(t.error);
     return x;
@@ -90,6 +92,16 @@ namespace detail
                                         viennacl::linalg::no_precond,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_gmres(A, rhs, tag, monitor, monitor_data); }
+
+  /** @brief GMRES(m) with the Jacobi preconditioner on a compressed_matrix: the pipelined cycle on D^-1 A (divide folded into
+   *  the SpMV epilogue) with the reference's per-iteration stopping rule (gmres.hpp:579-584) applied to the cycle's
+   *  projections -- same iterate and iteration count as the reference's Householder path (:449-631), no blocking reduction
+   *  per inner product. */
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                        jacobi_precond< compressed_matrix<NumericT, AlignmentV> > const &,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_gmres(A, rhs, tag, monitor, monitor_data, ViennaCLB200PrecondJacobi); }
 
   /** @brief Left-preconditioned restarted GMRES(m) for ANY operator and ANY preconditioner with `apply(v)`.
    *  Same problem statement, stopping rule and bookkeeping as the reference's generic path (gmres.hpp:449-631): the residual
