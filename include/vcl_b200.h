@@ -279,7 +279,10 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend backend, co
  * residual estimate, once per iteration (GMRES: once per restart); returning non-zero stops the solver. */
 typedef ViennaCLInt (*ViennaCLMonitorD)(const double *x_dev, double rel_residual_estimate, void *user);
 
-typedef enum { ViennaCLB200PrecondNone = 0, ViennaCLB200PrecondJacobi = 1 } ViennaCLB200Precond;
+/* Diagonal preconditioners that the drivers fold into their kernels (CSR matrices): Jacobi (jacobi_precond.hpp:103-130,
+ * divide by diag(A)) and row scaling (row_scaling.hpp:150-190, divide by the inf-/1-/2-norm of the row). */
+typedef enum { ViennaCLB200PrecondNone = 0, ViennaCLB200PrecondJacobi = 1, ViennaCLB200PrecondRowScalingInf = 2,
+               ViennaCLB200PrecondRowScaling1 = 3, ViennaCLB200PrecondRowScaling2 = 4 } ViennaCLB200Precond;
 
 typedef struct
 {

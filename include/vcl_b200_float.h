@@ -207,6 +207,8 @@ ViennaCLStatus ViennaCLCUDASpipelined_gmres_prod_hyb(ViennaCLBackend backend, co
  * residual estimate, once per iteration (GMRES: once per restart); returning non-zero stops the solver. */
 typedef ViennaCLInt (*ViennaCLMonitorS)(const float *x_dev, float rel_residual_estimate, void *user);
 
+/* Diagonal preconditioners that the drivers fold into their kernels (CSR matrices): Jacobi (jacobi_precond.hpp:103-130,
+ * divide by diag(A)) and row scaling (row_scaling.hpp:150-190, divide by the inf-/1-/2-norm of the row). */
 
 typedef struct
 {

@@ -9,6 +9,7 @@
 #include "viennacl/compressed_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
+#include "viennacl/linalg/row_scaling.hpp"
 #include "viennacl/linalg/cg.hpp"
 #include "viennacl/linalg/bicgstab.hpp"
 #include "viennacl/linalg/gmres.hpp"
@@ -66,7 +67,9 @@ int main()
     viennacl::linalg::jacobi_precond< viennacl::compressed_matrix<T> > jac(A, viennacl::linalg::jacobi_tag());
     viennacl::linalg::cg_tag t0(1e-10, 2000); viennacl::vector<T> x0 = viennacl::linalg::solve(A, b, t0);
     viennacl::linalg::cg_tag t1(1e-10, 2000); viennacl::vector<T> x1 = viennacl::linalg::solve(A, b, t1, jac);
-    printf(" \"vardiag_cg\": %u, \"vardiag_cg_jacobi\": %u,\n", t0.iters(), t1.iters());
+    viennacl::linalg::row_scaling< viennacl::compressed_matrix<T> > rs2(A, viennacl::linalg::row_scaling_tag(2));
+    viennacl::linalg::cg_tag t2(1e-10, 2000); viennacl::vector<T> x2 = viennacl::linalg::solve(A, b, t2, rs2);
+    printf(" \"vardiag_cg\": %u, \"vardiag_cg_jacobi\": %u, \"vardiag_cg_rowscaling2\": %u,\n", t0.iters(), t1.iters(), t2.iters());
   }
   {
     Stl sC = stencil(20, 18, 16, 0.5, 0.25, 0.125);
@@ -78,7 +81,12 @@ int main()
     viennacl::linalg::gmres_tag t2(1e-9, 600, 20); viennacl::vector<T> x2 = viennacl::linalg::solve(C, c, t2, jac);
     struct ident { void apply(viennacl::vector<T> &) const {} } id;
     viennacl::linalg::gmres_tag t3(1e-9, 600, 20); viennacl::vector<T> x3 = viennacl::linalg::solve(C, c, t3, id);   // Householder path, no preconditioning
-    printf(" \"cd3d_bicgstab_jacobi\": %u, \"cd3d_gmres20_jacobi\": %u, \"cd3d_gmres20_householder\": %u\n", t1.iters(), t2.iters(), t3.iters());
+    viennacl::linalg::row_scaling< viennacl::compressed_matrix<T> > rs1(C, viennacl::linalg::row_scaling_tag(1));
+    viennacl::linalg::row_scaling< viennacl::compressed_matrix<T> > rs0(C, viennacl::linalg::row_scaling_tag(0));
+    viennacl::linalg::bicgstab_tag t4(1e-9, 1000); viennacl::vector<T> x4 = viennacl::linalg::solve(C, c, t4, rs1);
+    viennacl::linalg::gmres_tag t5(1e-9, 600, 20); viennacl::vector<T> x5 = viennacl::linalg::solve(C, c, t5, rs0);
+    printf(" \"cd3d_bicgstab_jacobi\": %u, \"cd3d_gmres20_jacobi\": %u, \"cd3d_gmres20_householder\": %u,\n", t1.iters(), t2.iters(), t3.iters());
+    printf(" \"cd3d_bicgstab_rowscaling1\": %u, \"cd3d_gmres20_rowscaling0\": %u\n", (unsigned)t4.iters(), (unsigned)t5.iters());
   }
   printf("}\n");
   return 0;

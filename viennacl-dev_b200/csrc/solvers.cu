@@ -86,6 +86,20 @@ ViennaCLStatus pull_state(ViennaCLBackend b)
   return ViennaCLSuccess;
 }
 
+// diagonal preconditioners: which row_info option yields the scaling vector (cuda/sparse_matrix_operations.hpp:53-119:
+// 0 inf-norm, 1 1-norm, 2 2-norm, 3 diagonal); -1: not a diagonal preconditioner
+static inline int diag_precond_option(int precond)
+{
+  switch (precond)
+  {
+  case ViennaCLB200PrecondJacobi: return 3;
+  case ViennaCLB200PrecondRowScalingInf: return 0;
+  case ViennaCLB200PrecondRowScaling1: return 1;
+  case ViennaCLB200PrecondRowScaling2: return 2;
+  default: return -1;
+  }
+}
+
 const int kBatch = 32;   // iterations enqueued between two looks at the device state
 
 // ------------------------------------------------------------------------------------------------
@@ -103,7 +117,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
   real *r = cv.take(n), *u = cv.take(n), *w = cv.take(n), *p = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
   const int grid = vec_grid(b, n);
 
-  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, diag_precond_option(tag->precond)));
   VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
   VCL_CUDA(b, cudaMemsetAsync(p, 0, sizeof(real) * n, b->stream));
   VCL_CUDA(b, cudaMemsetAsync(s, 0, sizeof(real) * n, b->stream));
@@ -159,7 +173,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
   if (n == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, rhs && x, "null vector");
   VCL_CUDA(b, cudaSetDevice(b->device));
-  if (tag->precond == ViennaCLB200PrecondJacobi) return pcg_jacobi(b, A, rhs, x, tag);
+  if (diag_precond_option(tag->precond) >= 0) return pcg_jacobi(b, A, rhs, x, tag);
   VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: unknown preconditioner id");
   VCL_TRY(vcl_ws_reserve(b, 3 * Carver::need(n)));
   Carver cv(b->ws);
@@ -285,7 +299,7 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const real *rh
   Carver cv(b->ws);
   real *r = cv.take(n), *p = cv.take(n), *r0 = cv.take(n), *t0 = cv.take(n), *t1 = cv.take(n), *s = cv.take(n), *diag = cv.take(n);
 
-  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+  VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, diag_precond_option(tag->precond)));
   VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
   real ss = 0.0;
   VCL_TRY(vcl_dot_host(b, n, rhs, 0, 1, rhs, 0, 1, &ss));
@@ -346,7 +360,7 @@ ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const real *rhs
   if (A.rows() == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, rhs && x, "null vector");
   VCL_CUDA(b, cudaSetDevice(b->device));
-  if (tag->precond == ViennaCLB200PrecondJacobi) return bicgstab_jacobi(b, A, rhs, x, tag);
+  if (diag_precond_option(tag->precond) >= 0) return bicgstab_jacobi(b, A, rhs, x, tag);
   return bicgstab_pipelined(b, A, rhs, x, tag);
 }
 
@@ -392,7 +406,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   // Jacobi: the pipelined cycle runs on D^-1 A (the divide is folded into the SpMV epilogue) and -- like the reference's
   // preconditioned path (gmres.hpp:449-631) -- the estimate is tested after EVERY inner iteration: the host walks the
   // cycle's xi values, stops counting at the first iteration that meets the tolerance and truncates the update to it.
-  const bool jac = tag->precond == ViennaCLB200PrecondJacobi;
+  const bool jac = diag_precond_option(tag->precond) >= 0;              // Jacobi or row scaling
   VCL_REQUIRE(b, jac || tag->precond == ViennaCLB200PrecondNone, "GMRES: unknown preconditioner id");
   VCL_REQUIRE(b, !jac || A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   VCL_REQUIRE(b, tag->krylov_dim >= 1 && tag->krylov_dim <= VCL_GMRES_MAX_KRYLOV, "krylov_dim must be in [1, 64]");
@@ -426,7 +440,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   if (jac)
   {
     if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                  // gmres.hpp:480-481
-    VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, 3));
+    VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A.csr.row_ptr, A.csr.col_idx, A.csr.values, diag, diag_precond_option(tag->precond)));
     VCL_TRY(ViennaCLCUDADelement_div(b, (int)n, res, 0, 1, res, 0, 1, diag, 0, 1));   // precond.apply(res), gmres.hpp:492
     VCL_TRY(vcl_dot_host(b, n, res, 0, 1, res, 0, 1, &ss));
     rho_0 = std::sqrt(ss);

@@ -13,6 +13,7 @@
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/norm_2.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
+#include "viennacl/linalg/row_scaling.hpp"
 #include "viennacl/linalg/cg.hpp"
 #include "viennacl/linalg/bicgstab.hpp"
 #include "viennacl/linalg/gmres.hpp"
@@ -57,7 +58,8 @@ static ScalarType true_residual(OpT const & A, VectorT const & x, VectorT const 
 // Iteration counts of the UNMODIFIED reference (host backend, generic solver paths) on exactly these systems:
 // tests/golden/generic_solver_counts.json, produced by oracle/ref_generic_counts.cpp (make -C oracle generic_counts).
 static const int REF_OP_CG = 54, REF_OP_BICGSTAB = 40, REF_OP_GMRES30 = 56, REF_VARDIAG_CG = 154, REF_VARDIAG_CG_JACOBI = 7,
-                 REF_CD3D_BICGSTAB_JACOBI = 49, REF_CD3D_GMRES20_JACOBI = 114, REF_CD3D_GMRES20_HOUSEHOLDER = 122;
+                 REF_CD3D_BICGSTAB_JACOBI = 49, REF_CD3D_GMRES20_JACOBI = 114, REF_CD3D_GMRES20_HOUSEHOLDER = 122,
+                 REF_VARDIAG_CG_ROWSCALING2 = 7, REF_CD3D_BICGSTAB_ROWSCALING1 = 49, REF_CD3D_GMRES20_ROWSCALING0 = 114;
 static bool within(unsigned int got, int ref, int tol) { return std::abs(int(got) - ref) <= tol; }
 
 static int failures = 0;
@@ -130,6 +132,11 @@ int main()
            "generic PCG with a user preconditioner equal to Jacobi: the reference's count; fused Jacobi-PCG within 1 of it");
     VectorT diff = x0 - x1;
     expect(ScalarType(viennacl::linalg::norm_2(diff)) < 1e-7 * ScalarType(viennacl::linalg::norm_2(x0)), "same solution with and without preconditioner");
+    viennacl::linalg::row_scaling<MatrixT> rs2(A, viennacl::linalg::row_scaling_tag(2));        // fused path, scaling = row 2-norms
+    viennacl::linalg::cg_tag rs_tag(1e-10, 2000);
+    VectorT x4 = viennacl::linalg::solve(A, b, rs_tag, rs2);
+    expect(true_residual(A, x4, b) < 1e-8 && within(rs_tag.iters(), REF_VARDIAG_CG_ROWSCALING2, 2),
+           "solve(A, b, cg_tag, row_scaling(2)): iterations within +-2 of the reference");
     viennacl::linalg::cg_tag few(1e-6, 20);                 // iterative.cpp:222 -- cg_tag(1e-6, 20) with a preconditioner
     VectorT x3 = viennacl::linalg::solve(A, b, few, vcl_jacobi);
     expect(few.iters() <= 20 && x3.size() == n, "cg_tag(1e-6, 20) with Jacobi respects the iteration budget");
@@ -155,6 +162,18 @@ int main()
     VectorT y1 = viennacl::linalg::solve(C, c, g1, jacobi_C);
     std::cout << "  GMRES(20): none " << g0.iters() << " iterations, Jacobi " << g1.iters() << std::endl;
     expect(true_residual(C, y1, c) < 1e-7 && within(g1.iters(), REF_CD3D_GMRES20_JACOBI, 2), "solve(A, b, gmres_tag, jacobi_precond): iterations within +-2 of the reference");
+    viennacl::linalg::row_scaling<MatrixT> rs1(C, viennacl::linalg::row_scaling_tag(1)), rs0(C, viennacl::linalg::row_scaling_tag(0));
+    viennacl::linalg::bicgstab_tag b_rs(1e-9, 1000);
+    viennacl::linalg::gmres_tag g_rs(1e-9, 600, 20);
+    VectorT z1 = viennacl::linalg::solve(C, c, b_rs, rs1);
+    VectorT z2 = viennacl::linalg::solve(C, c, g_rs, rs0);
+    std::cout << "  row_scaling: BiCGStab(p=1) " << b_rs.iters() << ", GMRES(20)(p=0) " << g_rs.iters() << " iterations" << std::endl;
+    expect(true_residual(C, z1, c) < 1e-7 && within(b_rs.iters(), REF_CD3D_BICGSTAB_ROWSCALING1, 4) &&
+           true_residual(C, z2, c) < 1e-7 && within(g_rs.iters(), REF_CD3D_GMRES20_ROWSCALING0, 2),
+           "solve(A, b, bicgstab_tag / gmres_tag, row_scaling): iterations within +-4 / +-2 of the reference");
+    VectorT probe = viennacl::scalar_vector<ScalarType>(C.size1(), 1.0);
+    rs0.apply(probe);                                         // interior row: sup-norm = diagonal 6 + 0.5 + 0.25 + 0.125
+    expect(std::fabs(ScalarType(probe[C.size1() / 2 + 7]) - 1.0 / 6.875) < 1e-15, "row_scaling::apply divides by the row norm");
     expect(int(g0.iters()) == ((REF_CD3D_GMRES20_HOUSEHOLDER + 19) / 20) * 20,
            "pipelined GMRES(20) stops at the restart boundary after the reference's Householder count (gmres.hpp:234)");
   }

@@ -144,6 +144,13 @@ namespace detail
                                         jacobi_precond< compressed_matrix<NumericT, AlignmentV> > const &,
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_bicgstab(A, rhs, tag, ViennaCLB200PrecondJacobi, monitor, monitor_data); }
+
+  /** @brief Left-preconditioned BiCGStab with a row_scaling preconditioner (row_scaling.hpp:150-190): same fused path */
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, bicgstab_tag const & tag,
+                                        row_scaling< compressed_matrix<NumericT, AlignmentV> > const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_bicgstab(A, rhs, tag, precond.abi_id(), monitor, monitor_data); }
 }
 
 /** @brief x = solve(A, b, bicgstab_tag(...)) for compressed_matrix / sliced_ell_matrix (bicgstab.hpp:495-533) */

@@ -92,6 +92,14 @@ namespace detail
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_cg(A, rhs, tag, monitor, monitor_data, ViennaCLB200PrecondJacobi); }
 
+  /** @brief CG with a row_scaling preconditioner (row_scaling.hpp:150-190) on a compressed_matrix: same fused path, the scaling
+   *  vector holds row norms instead of the diagonal */
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, cg_tag const & tag,
+                                        row_scaling< compressed_matrix<NumericT, AlignmentV> > const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_cg(A, rhs, tag, monitor, monitor_data, precond.abi_id()); }
+
   /** @brief Preconditioned CG for ANY operator (matrix-free `apply()`) and ANY preconditioner with `apply(v)`:
    *  the reference's generic path (cg.hpp:257-322; Saad, Alg. 9.1), built from prod / inner_prod / vector expressions.
    *  One blocking reduction per inner product, exactly like the reference -- the fused paths above avoid that. */

@@ -10,6 +10,7 @@
 #include "viennacl/coordinate_matrix.hpp"
 #include "viennacl/linalg/prod.hpp"
 #include "viennacl/linalg/jacobi_precond.hpp"
+#include "viennacl/linalg/row_scaling.hpp"
 namespace viennacl
 {
 namespace linalg

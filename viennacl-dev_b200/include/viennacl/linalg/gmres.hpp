@@ -103,6 +103,13 @@ namespace detail
                                         bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
   { return fused_gmres(A, rhs, tag, monitor, monitor_data, ViennaCLB200PrecondJacobi); }
 
+  /** @brief GMRES(m) with a row_scaling preconditioner (row_scaling.hpp:150-190): same fused path */
+  template<typename NumericT, unsigned int AlignmentV>
+  viennacl::vector<NumericT> solve_impl(compressed_matrix<NumericT, AlignmentV> const & A, vector_base<NumericT> const & rhs, gmres_tag const & tag,
+                                        row_scaling< compressed_matrix<NumericT, AlignmentV> > const & precond,
+                                        bool (*monitor)(viennacl::vector<NumericT> const &, NumericT, void*) = NULL, void *monitor_data = NULL)
+  { return fused_gmres(A, rhs, tag, monitor, monitor_data, precond.abi_id()); }
+
   /** @brief Left-preconditioned restarted GMRES(m) for ANY operator and ANY preconditioner with `apply(v)`.
    *  Same problem statement, stopping rule and bookkeeping as the reference's generic path (gmres.hpp:449-631): the residual
    *  M^-1 (b - A x) is minimised over the Krylov space of M^-1 A, the estimate |rho * rho_0| / ||b|| is tested after every
