@@ -168,6 +168,30 @@ def cpu_baseline_spmv(n1, reps=10):
             "ms_per_step": sec / reps * 1e3}
 
 
+def cpu_baseline_cg(n1=1024, iters=200):
+    """BASELINE configs[0] on the host: the reference's pipelined CG (cg.hpp:128-187, OpenMP host backend) on the 2-D 5-point
+    Laplacian n1 x n1, fixed iteration budget, all host cores -- the CPU arm of the 'CG iterations/sec' half of the metric."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    o = ol.oracle()
+    cores = o.max_threads()
+    o.set_threads(cores)
+    A = o.stencil2d(n1, n1)
+    b = np.ones(A.rows)
+    if ol.have_ref():
+        r = ol.ref(); r.set_threads(cores)
+        r.solve("cg", A, b, tol=1e-300, maxit=10)
+        res = r.solve("cg", A, b, tol=1e-300, maxit=iters)
+        sec, its, kind = res["seconds"], res["iters"], "reference"
+    else:
+        o.cg(A, b, tol=1e-300, maxit=10)
+        t0 = time.perf_counter()
+        res = o.cg(A, b, tol=1e-300, maxit=iters)
+        sec, its, kind = time.perf_counter() - t0, res["iters"], "port"
+    return {"iterations_per_sec": its / sec, "iterations": its, "cores": cores, "kind": kind,
+            "sample": "%d pipelined CG iterations on the %dx%d Laplacian (reference cg.hpp, OpenMP host backend)" % (its, n1, n1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,6 +255,8 @@ def main():
                 line["cg"] = cg
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_spmv(n1)
+            if not args.no_extras and line.get("cg") and "lap2d_1024" in line["cg"]:
+                line["cg"]["lap2d_1024"]["cpu_baseline"] = cpu_baseline_cg()
     else:
         import bench_workloads as bw
         line = bw.cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler, peak, peak_src)

@@ -1,0 +1,12 @@
+import sys, numpy as np
+sys.path.insert(0, ".")
+import __graft_entry__ as ge
+pkg = ge.load_package(); be = pkg.Backend(0)
+for (nx,ny,nz) in ((63,65,1),(256,256,1),(512,512,1),(1024,1024,1),(128,128,128),(2048,2048,1)):
+    A = pkg.CsrMatrix.stencil(be, nx, ny, nz); n=A.rows
+    b = be.array(np.ones(n)); x = be.zeros(n)
+    t=pkg.SolverTag(tol=1e-8, max_iterations=5000).solve("cg", A, b, x)
+    xs = x.download()
+    pkg.SolverTag(tol=0.0, max_iterations=64).solve("cg", A, b, x)
+    be.sync(); be.timer_begin(); t2=pkg.SolverTag(tol=0.0, max_iterations=1000).solve("cg", A, b, x); ms=be.timer_end()
+    print((nx,ny,nz), "iters", t.iters, "err %.2e" % t.error, "xnorm %.10e" % np.linalg.norm(xs), "%.1f us/iter" % (ms*1e3/t2.iters), "%.0f GB/s" % ((12*A.nnz+76*n)*t2.iters/ms/1e6), flush=True)

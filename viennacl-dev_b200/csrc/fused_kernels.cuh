@@ -150,9 +150,8 @@ __device__ __forceinline__ void st2(real *p, long long i, real2 v) { *reinterpre
 // ------------------------------------------------------------------------------------------------
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(VEC_THREADS)
-cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
-                 SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges pr = PushRanges())
+__device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
+                                               SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges &pr)
 {
   __shared__ real s_red[32];
   if (st != nullptr && st->done != VCL_RUNNING) return;
@@ -188,6 +187,13 @@ cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real al
     // every CTA has fenced its pushes: publish the sequence number to the destinations
     if ((int)threadIdx.x < pr.n) { __threadfence_system(); st_release_sys(pr.flag[threadIdx.x], pr.seq); }
   }
+}
+
+static __global__ void __launch_bounds__(VEC_THREADS)
+cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
+                 SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges pr = PushRanges())
+{
+  cg_update_body(n, x, p, r, Ap, alpha_v, beta_v, st, partials, ticket, out_rr, pr);
 }
 
 // ------------------------------------------------------------------------------------------------

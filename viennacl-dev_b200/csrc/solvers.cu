@@ -4,6 +4,7 @@
 // at the state once per batch (with a monitor callback installed: once per iteration, as the reference's contract demands).
 #include "fused_kernels.cuh"
 #include "launch.cuh"
+#include "persistent.cuh"
 #include "blas1.cuh"
 #include <cmath>
 #include <algorithm>
@@ -163,6 +164,18 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
 // ------------------------------------------------------------------------------------------------
 // CG  (cg.hpp:128-187)
 // ------------------------------------------------------------------------------------------------
+// Use the persistent cooperative kernel?  CSR with a row-block plan and 16-byte aligned arrays (the TMA path), a device that
+// supports cooperative launches, and a system small enough that fixed latencies matter (VCL_B200_PERSISTENT_ROWS, default
+// 2.5M rows -- measured cross-over between 128^3 and 2048^2; 0 disables).
+static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n)
+{
+  static long long max_rows = -1;
+  static int coop = -1;
+  if (max_rows < 0) { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); max_rows = e ? atoll(e) : 2500000LL; }
+  if (coop < 0) { int v = 0; coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, b->device) == cudaSuccess && v) ? 1 : 0; }
+  return coop == 1 && n <= max_rows && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
+}
+
 ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_CHECK_BACKEND(b);
@@ -204,10 +217,31 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
 
   const int grid = vec_grid(b, n);
   const int batch = tag->monitor ? 1 : kBatch;
+  // Small and medium CSR systems: whole iterations inside one cooperative kernel (persistent.cuh) -- the per-iteration cost
+  // of two launches, two ramps and two reduction tails (~16 us) shrinks to two grid barriers.  Large systems are bound by
+  // HBM and keep the two-kernel form (8 CTAs of the update kernel per SM instead of 4).
+  int coop_grid = 0;
+  if (A.fmt == 0 && persistent_cg_wanted(b, A.csr, n))
+  {
+    const int occ = vcl_occupancy(cg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
+  }
   int launched = 0;
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    if (coop_grid > 0)
+    {
+      CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      XVec xv = make_xvec(p, 0, 1);
+      long long nn = n; int iters_arg = nb;
+      real *partials = VCL_PARTIALS(b); unsigned int *tickets = b->tickets;
+      void *args[] = {&d, &xv, &nn, &x, &p, &r, &Ap, &st, &partials, &tickets, &iters_arg};
+      VCL_CUDA(b, cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
+                                              (size_t)CSR_SMEM_BYTES, b->stream));
+      VCL_LAUNCHED(b, "cg_persistent_kernel");
+    }
+    else
     for (int k = 0; k < nb; ++k)
     {
       cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);

@@ -221,9 +221,10 @@ __device__ __forceinline__ real csr_row_dot(const real *s_val, const u32 *s_col,
   return dot;
 }
 
-template<class Epi, bool SPLIT>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
-csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
+// The kernel body is a device function so that the persistent solver kernels (persistent.cuh) can run the same product
+// between two grid-wide barriers; REPEATED: the mbarriers are invalidated on exit because the body will run again.
+template<class Epi, bool SPLIT, bool REPEATED>
+__device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv, Epi &epi)
 {
   constexpr int S = CSR_NSTAGE;
   extern __shared__ __align__(128) unsigned char csr_smem[];
@@ -357,7 +358,25 @@ csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
     buf = (buf + 1 == S) ? 0 : buf + 1;
   }
   epi.finish(s_red);
+  if (REPEATED)
+  {
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < S; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&s_bar[i])) : "memory");
+    }
+    __syncthreads();
+  }
 }
+
+template<class Epi, bool SPLIT>
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
+{
+  csr_stream_body<Epi, SPLIT, false>(A, xv, epi);
+}
+
 
 // Plan-free CSR kernel: one thread per row, sequential order (used when no row blocks are supplied or the
 // arrays are not 16-byte aligned, e.g. oddly offset user-wrapped buffers).
