@@ -3,10 +3,16 @@
 // For systems up to a few million rows a CG iteration is not bound by HBM but by fixed latencies: two dependent launches,
 // two kernel ramps and two last-CTA reduction tails cost ~16 us per iteration whatever the size (measured on B200: 256^2
 // 16.0 us, 1024^2 35.4 us per iteration).  Here one cooperative launch (one CTA set resident on every SM) runs up to
-// `iterations` iterations: the same two bodies as the stand-alone kernels -- cg_update_body, then the CSR row-block
-// product with the fused inner products whose last CTA advances alpha / beta / the convergence test in device memory --
-// separated by grid-wide barriers instead of kernel boundaries.  Arithmetic, reduction order within a CTA and the
-// stopping rule are those of the two-kernel path; only the number of CTAs that share the vector update differs.
+// `iterations` iterations.  Per iteration:
+//     vector update (x += alpha p; r -= alpha Ap; p = r + beta p)        -> one partial <r,r> per CTA
+//     grid barrier
+//     CSR row-block product Ap = A p (csr_stream_body, the stand-alone kernel's body) -> partial <Ap,Ap>, <p,Ap> per CTA
+//     grid barrier
+// and after each barrier EVERY CTA sums the per-CTA partials itself, in the same fixed order, and advances its own copy of
+// the solver scalars (shared memory) -- no ticket, no "last CTA" tail, no second pass through global memory for alpha and
+// beta; all CTAs take identical decisions because they perform identical arithmetic on identical data.  CTA 0 writes the
+// state back for the host when the launch ends.  Arithmetic per entry and the stopping rule are those of the two-kernel
+// path (cg.hpp:128-187); only the grouping of the partial sums differs.
 #pragma once
 #include <cooperative_groups.h>
 #include "fused_kernels.cuh"
@@ -16,21 +22,102 @@ namespace VCL_NS
 {
 namespace cgrp = cooperative_groups;
 
+// epilogue of the product inside the persistent kernel: same per-row work as EpiFused<STEP_CG>, per-CTA partials only
+struct EpiCgPartial
+{
+  real *Ap; const real *p; real *partials;
+  real acc[2];
+  static constexpr int NQ = 2;
+  static constexpr bool COO = false;
+  __device__ __forceinline__ real init(real) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ real pre(u32 r) const { return p[r]; }
+  __device__ __forceinline__ void row(u32 r, real dot, real p_r)
+  {
+    Ap[r] = dot;
+    acc[0] = fma(dot, dot, acc[0]);
+    acc[1] = fma(p_r, dot, acc[1]);
+  }
+  __device__ __forceinline__ void finish(real *smem)
+  {
+    block_sum<2>(acc, smem);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = acc[0]; partials[VCL_MAX_BLOCKS + blockIdx.x] = acc[1]; }
+  }
+};
+
+// totals of NQ partial arrays (stride VCL_MAX_BLOCKS), summed by this CTA in a fixed order; valid in thread 0
+template<int NQ>
+__device__ __forceinline__ void sum_partials(const real *partials, real (&tot)[NQ], real *smem)
+{
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+  {
+    tot[q] = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot[q] += __ldcg(partials + q * VCL_MAX_BLOCKS + i);
+  }
+  block_sum<NQ>(tot, smem);
+}
+
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, real *Ap,
-                     SolverState *st, real *partials, unsigned int *ticket, int iterations)
+                     SolverState *st, real *partials, int iterations)
 {
   cgrp::grid_group grid = cgrp::this_grid();
-  const PushRanges no_push = PushRanges();
+  __shared__ SolverState s_st;                             // this CTA's copy of the scalars
+  __shared__ real s_sum[3 * 32];
+  if (threadIdx.x == 0) s_st = *st;
+  __syncthreads();
+
   for (int it = 0; it < iterations; ++it)
   {
-    // st->done is written by ONE thread of the grid before the barrier that ends an iteration: uniform for all CTAs
-    if (*reinterpret_cast<volatile int*>(&st->done) != VCL_RUNNING) break;
-    cg_update_body(n, x, p, r, Ap, 0.0, 0.0, st, partials, ticket, &st->sums[0], no_push);
-    grid.sync();                                           // new p (and <r,r>) visible to every CTA
-    EpiFused<STEP_CG, false, false> epi = {Ap, p, nullptr, nullptr, partials, ticket, st, &st->sums[1], &st->sums[2], nullptr, {0.0, 0.0, 0.0}, nullptr};
-    csr_stream_body<EpiFused<STEP_CG, false, false>, false, true>(A, xv, epi);
-    grid.sync();                                           // Ap, alpha, beta, done visible
+    if (s_st.done != VCL_RUNNING) break;                   // identical in every CTA
+    // partial arrays: [0]: <Ap,Ap>, [1]: <p,Ap>, [2] / [3]: <r,r> of even / odd iterations.  <r,r> is double-buffered because
+    // it is written before the first barrier of an iteration but read after the second one: a CTA that is already in
+    // the next iteration's update must not overwrite what a slower CTA is still summing.
+    real *part_rr = partials + (2 + (it & 1)) * VCL_MAX_BLOCKS;
+    // ---- vector update with this CTA's share of the entries (cg_update_kernel's arithmetic) ----
+    {
+      const real alpha = s_st.alpha, beta = s_st.beta;
+      real acc[1] = {0.0};
+      const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+      {
+        const long long k = i * 2;
+        real2 vx = ld2(x, k), vp = ld2(p, k), vr = ld2(r, k); const real2 va = ld2(Ap, k);
+        vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
+        vr.x = fma(-alpha, va.x, vr.x);      vr.y = fma(-alpha, va.y, vr.y);
+        vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
+        acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
+        st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+      }
+      for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+      {
+        real vp = p[k], vr = r[k];
+        x[k] = fma(alpha, vp, x[k]);
+        vr = fma(-alpha, Ap[k], vr);
+        vp = fma(beta, vp, vr);
+        acc[0] = fma(vr, vr, acc[0]);
+        p[k] = vp; r[k] = vr;
+      }
+      block_sum<1>(acc, s_sum);
+      if (threadIdx.x == 0) part_rr[blockIdx.x] = acc[0];
+    }
+    grid.sync();                                           // new p and all <r,r> partials visible
+    // ---- Ap = A p with the fused inner products ----
+    EpiCgPartial epi = {Ap, p, partials, {0.0, 0.0}};
+    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi);
+    grid.sync();                                           // Ap and all partials visible
+    real tot[2], rr[1];
+    sum_partials<2>(partials, tot, s_sum);                 // <Ap,Ap>, <p,Ap>
+    sum_partials<1>(part_rr, rr, s_sum);                   // <r,r>
+    if (threadIdx.x == 0)
+    {
+      s_st.sums[0] = rr[0]; s_st.sums[1] = tot[0]; s_st.sums[2] = tot[1];
+      cg_advance(&s_st);                                   // cg.hpp:170-180
+    }
+    __syncthreads();
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
 }
 }
