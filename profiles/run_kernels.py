@@ -3,7 +3,8 @@
     ncu --set full --clock-control none --import-source on -k regex:<name> -s 1 -c 2 -o gpurun_out/prof_<name> \
         python profiles/run_kernels.py <what>
 
-what: spmv (CSR + SELL, 256^3) | cg (3 iterations at 256^3, CSR) | cg_sell | bicgstab | bicgstab_jacobi | gmres | cg1024
+what: spmv (CSR + SELL, 256^3) | cg (3 iterations at 256^3, CSR) | cg_sell | bicgstab | bicgstab_jacobi | gmres | gmres_jacobi |
+      cg1024 (persistent cooperative kernel) | spmv_f32 (float CSR / SELL / ELL, 256^3)
 """
 import os
 import sys
@@ -22,14 +23,24 @@ n1 = 256
 if what == "cg1024":
     A = pkg.CsrMatrix.stencil(be, 1024, 1024, 1)
 else:
-    c = (0.5, 0.25, 0.125) if what.startswith("bicgstab") or what == "gmres" else (0.0, 0.0, 0.0)
+    c = (0.5, 0.25, 0.125) if what.startswith("bicgstab") or what.startswith("gmres") else (0.0, 0.0, 0.0)
     A = pkg.CsrMatrix.stencil(be, n1, n1, n1, *c)
 n = A.rows
 x, y = be.empty(n), be.zeros(n)
 be.check(be.L.ViennaCLCUDADfill_uniform(be.h, n, x.ptr, 1, 0, 1.0, 2.0))
 b = be.array(np.ones(n))
 
-if what == "spmv":
+if what == "spmv_f32":
+    F = np.float32
+    Af = pkg.CsrMatrix.stencil(be, n1, n1, n1, dtype=F)
+    xf, yf = be.empty(n, F), be.zeros(n, F)
+    be.check(be.lib_for(F).ViennaCLCUDADfill_uniform(be.h, n, xf.ptr, 1, 0, 1.0, 2.0))
+    Sf = Af.to_sell(32); Ef = pkg.EllMatrix.from_csr(Af)
+    for _ in range(3):
+        Af.spmv(xf, yf); Sf.spmv(xf, yf); Ef.spmv(xf, yf)
+elif what == "gmres_jacobi":
+    pkg.SolverTag(tol=0.0, max_iterations=30, krylov_dim=30, precond=1).solve("gmres", A, b, y)
+elif what == "spmv":
     S = A.to_sell(32)
     for _ in range(3):
         A.spmv(x, y)

@@ -85,18 +85,27 @@ struct EpiFused
   const PeerWindow *win; unsigned long long red_seq; const real *loc_rr;
   static constexpr int NQ = 3;
   static constexpr bool COO = false;
-  __device__ __forceinline__ real init(real) const { return 0.0; }
+  // the epilogue's own per-row operands, all requested BEFORE the row's gather chain so that their latency overlaps with it
+  struct Pre { real p, d, r0; };
+  __device__ __forceinline__ real init(const Pre &) const { return 0.0; }
   __device__ __forceinline__ real term_scale() const { return 1.0; }
 
   __device__ __forceinline__ bool skip() const { return st != nullptr && (st->done != VCL_RUNNING || st->need_restart != 0); }
-  __device__ __forceinline__ real pre(u32 r) const { return p[r]; }
-  __device__ __forceinline__ void row(u32 r, real dot, real p_r)
+  __device__ __forceinline__ Pre pre(u32 r) const
   {
-    if (JACOBI) dot = dot / diag[r];
+    Pre q;
+    q.p = p[r];
+    q.d = JACOBI ? diag[r] : real(1);
+    q.r0 = USE_R0 ? r0[r] : real(0);
+    return q;
+  }
+  __device__ __forceinline__ void row(u32 r, real dot, const Pre &q)
+  {
+    if (JACOBI) dot = dot / q.d;
     Ap[r] = dot;
     acc[0] = fma(dot, dot, acc[0]);
-    acc[1] = fma(p_r, dot, acc[1]);
-    if (USE_R0) acc[2] = fma(dot, r0[r], acc[2]);
+    acc[1] = fma(q.p, dot, acc[1]);
+    if (USE_R0) acc[2] = fma(dot, q.r0, acc[2]);
   }
   __device__ __forceinline__ void finish(real *smem)
   {

@@ -29,6 +29,7 @@ struct EpiCgPartial
   real acc[2];
   static constexpr int NQ = 2;
   static constexpr bool COO = false;
+  typedef real Pre;
   __device__ __forceinline__ real init(real) const { return 0.0; }
   __device__ __forceinline__ real term_scale() const { return 1.0; }
   __device__ __forceinline__ bool skip() const { return false; }

@@ -112,6 +112,7 @@ template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("
 struct EpiAxpby
 {
   real *y; int off, inc; real alpha, beta;
+  typedef real Pre;
   bool sell_f32 = false;     // float SELL only: the reference build evaluates fma(alpha, dot, beta*y) there
   static constexpr int NQ = 0;
   static constexpr bool COO = false;
@@ -139,6 +140,7 @@ struct EpiCoo
   real *y; int off, inc; real alpha, beta;
   static constexpr int NQ = 0;
   static constexpr bool COO = true;
+  typedef real Pre;
   __device__ __forceinline__ bool skip() const { return false; }
   __device__ __forceinline__ real pre(u32 r) const { return (beta != 0.0) ? y[(size_t)r * (size_t)inc + (size_t)off] : 0.0; }
   __device__ __forceinline__ real init(real y_old) const { return (beta != 0.0) ? rmul(y_old, beta) : 0.0; }
@@ -323,13 +325,14 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
       block_sum<1>(part, s_long);
       if (tid == 0)
       {
-        const real pre = epi.pre(cur.r0);
+        const typename Epi::Pre pre = epi.pre(cur.r0);
         epi.row(cur.r0, Epi::COO ? fma(epi.term_scale(), part[0], epi.init(pre)) : part[0], pre);
       }
     }
     else
     {
-      const real pre = ((u32)tid < nrows) ? epi.pre(cur.r0 + tid) : 0.0;
+      typename Epi::Pre pre = typename Epi::Pre();
+      if ((u32)tid < nrows) pre = epi.pre(cur.r0 + tid);
       const u32 a0 = cur.n0 & ~3u;
       const real *s_val = s_val0 + buf * CSR_STAGE;
       const u32 *s_col = s_col0 + buf * CSR_STAGE;
@@ -388,7 +391,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
   if (epi.skip()) return;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
-    const real pre = epi.pre((u32)r);
+    const typename Epi::Pre pre = epi.pre((u32)r);
     real dot = Epi::COO ? epi.init(pre) : 0.0;
     const u32 e = A.rp[r + 1];
     const u32 ff = first_fused(A.rp[r], e, xv);
@@ -486,7 +489,8 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       // (s1 - s0) * C <= 256 here: one row per thread
       const long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);
       const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
-      const real pre = active ? epi.pre((u32)r) : 0.0;
+      typename Epi::Pre pre = typename Epi::Pre();
+      if (active) pre = epi.pre((u32)r);
       const real *s_val = s_val0 + buf * CSR_STAGE;
       const u32 *s_col = s_col0 + buf * CSR_STAGE;
       mbar_wait(&s_bar[buf], (phase >> buf) & 1u);
@@ -585,8 +589,11 @@ __device__ __forceinline__ u32 ldg_stream(const u32 *p, unsigned long long pol)
 #define ELL_ILP 4
 #endif
 #endif
+#ifndef ELL_FUSED_CTAS
+#define ELL_FUSED_CTAS 4      // fused solver epilogues (3 accumulators + prefetched operands) spill under the 42-register cap of 6 CTAs/SM
+#endif
 template<class Epi>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, 6)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, (Epi::NQ > 0 ? ELL_FUSED_CTAS : 6))
 ell_kernel(EllDev A, XVec xv, Epi epi)
 {
   __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
@@ -595,7 +602,7 @@ ell_kernel(EllDev A, XVec xv, Epi epi)
   const size_t IR = (size_t)A.internal_rows;
   for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (long long)gridDim.x * blockDim.x)
   {
-    const real pre = epi.pre((u32)r);
+    const typename Epi::Pre pre = epi.pre((u32)r);
     u32 t0 = 0, t1 = 0;
     if (A.csr_rows) { t0 = A.csr_rows[r]; t1 = A.csr_rows[r + 1]; }
     real acc = 0.0;
