@@ -558,3 +558,35 @@ def test_row_scaling_fused_paths(pkg, be, orc, precond):
     norms = {2: abs(M).max(axis=1).toarray().ravel(), 3: np.asarray(abs(M).sum(axis=1)).ravel(), 4: np.sqrt(np.asarray(M.multiply(M).sum(axis=1)).ravel())}
     dA = dev_csr(pkg, be, A)
     assert np.allclose(dA.row_info(precond - 2).download(), norms[precond], rtol=1e-14)
+
+
+def test_cg_persistent_kernel_on_ragged_spd_system(pkg, be, orc):
+    """The persistent cooperative CG kernel (small systems) on a matrix that is nothing like a stencil: odd size, empty-ish and
+    very long rows (whole-CTA row path), fewer row blocks than CTAs.  Same iteration count (+-2) and solution as the oracle's
+    pipelined CG; a monitor (one iteration per launch) must see the same sequence of estimates."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(21)
+    n = 6001
+    lens = rng.integers(0, 12, n); lens[17] = 3000; lens[4000] = 2500
+    rows = np.repeat(np.arange(n), lens)
+    cols = np.concatenate([rng.choice(n, l, replace=False) for l in lens])
+    P = sp.coo_matrix((rng.uniform(-1, 0, rows.size), (rows, cols)), shape=(n, n)).tocsr()
+    S = P + P.T
+    S = (S + sp.diags(np.asarray(abs(S).sum(axis=1)).ravel() + 1.0)).tocsr()
+    S.sum_duplicates(); S.sort_indices()
+    A = ol.CSR(n, n, S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data)
+    b = orc.uniform(n, 3, -1.0, 1.0)
+    ref = orc.cg(A, b, tol=1e-10, maxit=500, hist_cap=500)
+    dA = dev_csr(pkg, be, A)
+    db, dx = be.array(b), be.zeros(n)
+    tag = pkg.SolverTag(tol=1e-10, max_iterations=500).solve("cg", dA, db, dx)
+    assert abs(tag.iters - ref["iters"]) <= 2, (tag.iters, ref["iters"])
+    assert np.linalg.norm(dx.download() - ref["x"]) <= 1e-8 * np.linalg.norm(ref["x"])
+    assert _true_res(A, b, dx.download()) < 1e-9
+    hist = []
+    tag2 = pkg.SolverTag(tol=1e-10, max_iterations=500, monitor=lambda xp, est: hist.append(est) or False).solve("cg", dA, db, dx)
+    assert tag2.iters == tag.iters and len(hist) == tag.iters
+    m = min(len(hist), len(ref["history"])) * 2 // 3                     # rounding differences grow along the iteration
+    assert np.allclose(hist[:m], ref["history"][:m], rtol=1e-5, atol=0.0)
+    few = pkg.SolverTag(tol=1e-30, max_iterations=37).solve("cg", dA, db, dx)          # budget not a multiple of the batch
+    assert few.iters == 37

@@ -69,6 +69,7 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
   __shared__ real s_sum[3 * 32];
   if (threadIdx.x == 0) s_st = *st;
   __syncthreads();
+  CsrCarry carry = {0u, 0};                                // descriptors / barriers / first copy of the product carried between iterations
 
   for (int it = 0; it < iterations; ++it)
   {
@@ -107,7 +108,7 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
     grid.sync();                                           // new p and all <r,r> partials visible
     // ---- Ap = A p with the fused inner products ----
     EpiCgPartial epi = {Ap, p, partials, {0.0, 0.0}};
-    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi);
+    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry);
     grid.sync();                                           // Ap and all partials visible
     real tot[2], rr[1];
     sum_partials<2>(partials, tot, s_sum);                 // <Ap,Ap>, <p,Ap>
@@ -118,6 +119,10 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
       cg_advance(&s_st);                                   // cg.hpp:170-180
     }
     __syncthreads();
+  }
+  {
+    EpiCgPartial epi = {Ap, p, partials, {0.0, 0.0}};
+    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry, true);        // wait for the copy issued ahead, if any
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
 }

@@ -237,11 +237,20 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
       long long nn = n; int iters_arg = nb;
       real *partials = VCL_PARTIALS(b);
       void *args[] = {&d, &xv, &nn, &x, &p, &r, &Ap, &st, &partials, &iters_arg};
-      VCL_CUDA(b, cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
-                                              (size_t)CSR_SMEM_BYTES, b->stream));
-      VCL_LAUNCHED(b, "cg_persistent_kernel");
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
+                                                         (size_t)CSR_SMEM_BYTES, b->stream);
+      if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources)
+      {
+        (void)cudaGetLastError();                          // the SMs are shared with another client (MPS, a second stream): two-kernel form
+        coop_grid = 0;
+      }
+      else
+      {
+        VCL_CUDA(b, ce);
+        VCL_LAUNCHED(b, "cg_persistent_kernel");
+      }
     }
-    else
+    if (coop_grid == 0)
     for (int k = 0; k < nb; ++k)
     {
       cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);

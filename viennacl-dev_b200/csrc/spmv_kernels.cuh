@@ -225,10 +225,19 @@ __device__ __forceinline__ real csr_row_dot(const real *s_val, const u32 *s_col,
 
 // The kernel body is a device function so that the persistent solver kernels (persistent.cuh) can run the same product
 // between two grid-wide barriers; REPEATED: the mbarriers are invalidated on exit because the body will run again.
+// REPEATED (persistent kernels): the matrix does not change between calls, so (i) the block descriptors of the prologue are
+// computed once and parked in shared memory, (ii) the mbarriers live on (their phase bits travel in `carry`), and (iii) the
+// copy of this CTA's first block for the NEXT call is issued at the end of the current one -- it is in flight while the
+// kernel does its vector update and waits at the grid barrier.
+struct CsrCarry { unsigned phase; int primed; };
+
 template<class Epi, bool SPLIT, bool REPEATED>
-__device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv, Epi &epi)
+__device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv, Epi &epi, CsrCarry *carry = nullptr, bool drain = false)
 {
   constexpr int S = CSR_NSTAGE;
+  __shared__ CsrBlockDesc s_keepD[REPEATED ? S : 1];
+  __shared__ u32 s_keepR[2];
+  __shared__ u32 s_keepMy[REPEATED ? 2 * CSR_BLOCK_THREADS : 1];
   extern __shared__ __align__(128) unsigned char csr_smem[];
   __shared__ __align__(8) unsigned long long s_bar[S];
   __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
@@ -244,13 +253,28 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
 #endif
   bool halo_ready = !(SPLIT && A.wait_mask != 0u);
 
-  if (tid == 0)
+  const bool resume = REPEATED && carry->primed != 0;     // uniform over the CTA
+  if (REPEATED && drain)
   {
+    // last call of a persistent kernel: a CTA must not exit while a bulk copy into its shared memory is in flight
+    if (resume)
+    {
 #pragma unroll
-    for (int i = 0; i < S; ++i) mbar_init(&s_bar[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      for (int i = 0; i < S - 1; ++i)
+        if ((int)blockIdx.x + i * (int)gridDim.x < A.nblk && csr_block_class(s_keepD[i], A.nnz) == 0) mbar_wait(&s_bar[i], (carry->phase >> i) & 1u);
+    }
+    return;
   }
-  __syncthreads();
+  if (!resume)
+  {
+    if (tid == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < S; ++i) mbar_init(&s_bar[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   // elected thread: bring block `d` into buffer `buf`
   auto issue = [&](const CsrBlockDesc &d, int buf)
@@ -266,26 +290,48 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
   // ---- prologue: D[i] = descriptor of this CTA's i-th block, (r0_S, r1_S) = row range of the S-th ----
   int bi = blockIdx.x;
   CsrBlockDesc D[S];
-#pragma unroll
-  for (int i = 0; i < S; ++i)
-  {
-    D[i].r0 = D[i].r1 = D[i].n0 = D[i].n1 = 0;
-    if (bi + i * step < A.nblk) { D[i].r0 = A.blk_start[bi + i * step]; D[i].r1 = A.blk_end[bi + i * step]; }
-  }
   u32 r0_S = 0, r1_S = 0;
-  if (bi + S * step < A.nblk) { r0_S = A.blk_start[bi + S * step]; r1_S = A.blk_end[bi + S * step]; }
-#pragma unroll
-  for (int i = 0; i < S; ++i)
-    if (bi + i * step < A.nblk) { D[i].n0 = A.rp[D[i].r0]; D[i].n1 = A.rp[D[i].r1]; }
   u32 my_s = 0, my_e = 0;                                  // this thread's row of the current block
-  if (bi < A.nblk && (u32)tid < D[0].r1 - D[0].r0) { my_s = A.rp[D[0].r0 + tid]; my_e = A.rp[D[0].r0 + tid + 1]; }
-  if (tid == 0)
+  unsigned phase = 0;                                      // bit b: parity to wait for on buffer b
+  if (resume)
+  {
+    // descriptors from the first call; the copy of the first block(s) was issued when the previous call ended
+#pragma unroll
+    for (int i = 0; i < S; ++i) D[i] = s_keepD[i];
+    r0_S = s_keepR[0]; r1_S = s_keepR[1];
+    my_s = s_keepMy[tid]; my_e = s_keepMy[CSR_BLOCK_THREADS + tid];
+    phase = carry->phase;
+  }
+  else
   {
 #pragma unroll
-    for (int i = 0; i < S - 1; ++i)
-      if (bi + i * step < A.nblk && csr_block_class(D[i], A.nnz) == 0) issue(D[i], i);
+    for (int i = 0; i < S; ++i)
+    {
+      D[i].r0 = D[i].r1 = D[i].n0 = D[i].n1 = 0;
+      if (bi + i * step < A.nblk) { D[i].r0 = A.blk_start[bi + i * step]; D[i].r1 = A.blk_end[bi + i * step]; }
+    }
+    if (bi + S * step < A.nblk) { r0_S = A.blk_start[bi + S * step]; r1_S = A.blk_end[bi + S * step]; }
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+      if (bi + i * step < A.nblk) { D[i].n0 = A.rp[D[i].r0]; D[i].n1 = A.rp[D[i].r1]; }
+    if (bi < A.nblk && (u32)tid < D[0].r1 - D[0].r0) { my_s = A.rp[D[0].r0 + tid]; my_e = A.rp[D[0].r0 + tid + 1]; }
+    if (REPEATED)
+    {
+      if (tid == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < S; ++i) s_keepD[i] = D[i];
+        s_keepR[0] = r0_S; s_keepR[1] = r1_S;
+      }
+      s_keepMy[tid] = my_s; s_keepMy[CSR_BLOCK_THREADS + tid] = my_e;
+    }
+    if (tid == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < S - 1; ++i)
+        if (bi + i * step < A.nblk && csr_block_class(D[i], A.nnz) == 0) issue(D[i], i);
+    }
   }
-  unsigned phase = 0;                                      // bit b: parity to wait for on buffer b
   int buf = 0;                                             // buffer of the current block
 
   for (; bi < A.nblk; bi += step)
@@ -363,13 +409,15 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
   epi.finish(s_red);
   if (REPEATED)
   {
-    __syncthreads();
-    if (threadIdx.x == 0)
+    __syncthreads();                                       // every buffer is free, s_keep* is complete
+    if (tid == 0)
     {
 #pragma unroll
-      for (int i = 0; i < S; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" :: "r"(smem_u32(&s_bar[i])) : "memory");
+      for (int i = 0; i < S - 1; ++i)
+        if ((int)blockIdx.x + i * step < A.nblk && csr_block_class(s_keepD[i], A.nnz) == 0) issue(s_keepD[i], i);
     }
-    __syncthreads();
+    carry->phase = phase;
+    carry->primed = 1;
   }
 }
 
