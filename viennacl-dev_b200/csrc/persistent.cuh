@@ -126,4 +126,73 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
 }
+// ------------------------------------------------------------------------------------------------
+// Jacobi / row-scaling preconditioned CG (single-reduction form, see pcg_update_kernel) in the same persistent form:
+//     p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = r ./ diag    -> partial gamma = <r,u>
+//     grid barrier;   w = A u (csr_stream_body)                                      -> partial delta = <w,u>
+//     grid barrier;   every CTA sums the partials and advances alpha / beta / the convergence test (pcg_advance)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+pcg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *r, real *u, real *w, real *p, real *s, const real *diag,
+                      SolverState *st, real *partials, int iterations)
+{
+  cgrp::grid_group grid = cgrp::this_grid();
+  __shared__ SolverState s_st;
+  __shared__ real s_sum[2 * 32];
+  if (threadIdx.x == 0) s_st = *st;
+  __syncthreads();
+  CsrCarry carry = {0u, 0};
+  for (int it = 0; it < iterations; ++it)
+  {
+    if (s_st.done != VCL_RUNNING) break;
+    real *part_gamma = partials + (2 + (it & 1)) * VCL_MAX_BLOCKS;     // double-buffered like <r,r> in cg_persistent_kernel
+    {
+      const real alpha = s_st.alpha, beta = s_st.beta;
+      real acc[1] = {0.0};
+      const long long npairs = aligned16(x, r, u, w, p, s, diag) ? (n >> 1) : 0;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+      {
+        const long long k = i * 2;
+        real2 vx = ld2(x, k), vr = ld2(r, k), vu = ld2(u, k), vp = ld2(p, k), vs = ld2(s, k);
+        const real2 vw = ld2(w, k), vd = ld2(diag, k);
+        vp.x = fma(beta, vp.x, vu.x);        vp.y = fma(beta, vp.y, vu.y);
+        vs.x = fma(beta, vs.x, vw.x);        vs.y = fma(beta, vs.y, vw.y);
+        vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
+        vr.x = fma(-alpha, vs.x, vr.x);      vr.y = fma(-alpha, vs.y, vr.y);
+        vu.x = vr.x / vd.x;                  vu.y = vr.y / vd.y;
+        acc[0] = fma(vr.x, vu.x, acc[0]);    acc[0] = fma(vr.y, vu.y, acc[0]);
+        st2(p, k, vp); st2(s, k, vs); st2(x, k, vx); st2(r, k, vr); st2(u, k, vu);
+      }
+      for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+      {
+        const real vp = fma(beta, p[k], u[k]), vs = fma(beta, s[k], w[k]);
+        x[k] = fma(alpha, vp, x[k]);
+        const real vr = fma(-alpha, vs, r[k]);
+        const real vu = vr / diag[k];
+        acc[0] = fma(vr, vu, acc[0]);
+        p[k] = vp; s[k] = vs; r[k] = vr; u[k] = vu;
+      }
+      block_sum<1>(acc, s_sum);
+      if (threadIdx.x == 0) part_gamma[blockIdx.x] = acc[0];
+    }
+    grid.sync();
+    EpiCgPartial epi = {w, u, partials, {0.0, 0.0}};       // partial arrays [0]: <w,w> (unused), [1]: <u,w>
+    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry);
+    grid.sync();
+    real delta[1], gamma[1];
+    sum_partials<1>(partials + VCL_MAX_BLOCKS, delta, s_sum);
+    sum_partials<1>(part_gamma, gamma, s_sum);
+    if (threadIdx.x == 0)
+    {
+      s_st.sums[0] = gamma[0];
+      pcg_advance(&s_st, delta[0]);
+    }
+    __syncthreads();
+  }
+  {
+    EpiCgPartial epi = {w, u, partials, {0.0, 0.0}};
+    csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry, true);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
+}
 }

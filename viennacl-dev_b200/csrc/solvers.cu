@@ -103,6 +103,18 @@ static inline int diag_precond_option(int precond)
 
 const int kBatch = 32;   // iterations enqueued between two looks at the device state
 
+// Use the persistent cooperative kernel?  CSR with a row-block plan and 16-byte aligned arrays (the TMA path), a device that
+// supports cooperative launches, and a system small enough that fixed latencies matter (VCL_B200_PERSISTENT_ROWS, default
+// 10M rows -- measured: ahead up to 200^3, level at 256^3; 0 disables).
+static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n)
+{
+  static long long max_rows = -1;
+  static int coop = -1;
+  if (max_rows < 0) { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); max_rows = e ? atoll(e) : 10000000LL; }
+  if (coop < 0) { int v = 0; coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, b->device) == cudaSuccess && v) ? 1 : 0; }
+  return coop == 1 && n <= max_rows && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
+}
+
 // ------------------------------------------------------------------------------------------------
 // CG with Jacobi preconditioner: the reference runs its generic PCG (cg.hpp:257-322: SpMV + element_div + ~6 BLAS-1
 // launches + 2 blocking reductions per iteration).  Here: single-reduction (Chronopoulos/Gear) PCG, 2 kernels per
@@ -140,10 +152,30 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
   SolverState *st = VCL_DSTATE(b);
 
   const int batch = tag->monitor ? 1 : kBatch;
+  int coop_grid = 0;                                       // persistent form for small / medium systems, see cg_solve
+  if (persistent_cg_wanted(b, A.csr, n))
+  {
+    const int occ = vcl_occupancy(pcg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
+  }
   int launched = 0;
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    if (coop_grid > 0)
+    {
+      CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      XVec xv = make_xvec(u, 0, 1);
+      long long nn = n; int iters_arg = nb;
+      real *partials = VCL_PARTIALS(b);
+      const real *cdiag = diag;
+      void *args[] = {&d, &xv, &nn, &x, &r, &u, &w, &p, &s, &cdiag, &st, &partials, &iters_arg};
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)pcg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
+                                                         (size_t)CSR_SMEM_BYTES, b->stream);
+      if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); coop_grid = 0; }
+      else { VCL_CUDA(b, ce); VCL_LAUNCHED(b, "pcg_persistent_kernel"); }
+    }
+    if (coop_grid == 0)
     for (int k = 0; k < nb; ++k)
     {
       pcg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, r, u, w, p, s, diag, st, VCL_PARTIALS(b), b->tickets, &st->sums[0]);
@@ -164,18 +196,6 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
 // ------------------------------------------------------------------------------------------------
 // CG  (cg.hpp:128-187)
 // ------------------------------------------------------------------------------------------------
-// Use the persistent cooperative kernel?  CSR with a row-block plan and 16-byte aligned arrays (the TMA path), a device that
-// supports cooperative launches, and a system small enough that fixed latencies matter (VCL_B200_PERSISTENT_ROWS, default
-// 10M rows -- measured: ahead up to 200^3, level at 256^3; 0 disables).
-static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n)
-{
-  static long long max_rows = -1;
-  static int coop = -1;
-  if (max_rows < 0) { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); max_rows = e ? atoll(e) : 10000000LL; }
-  if (coop < 0) { int v = 0; coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, b->device) == cudaSuccess && v) ? 1 : 0; }
-  return coop == 1 && n <= max_rows && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
-}
-
 ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_CHECK_BACKEND(b);
