@@ -195,4 +195,160 @@ pcg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *r, real *u,
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
 }
+// ------------------------------------------------------------------------------------------------
+// Pipelined BiCGStab (bicgstab.hpp:97-215) in the persistent form.  Per iteration, four phases and four grid barriers:
+//     Ap = A p                          -> partials <Ap,r0*>                    | barrier | alpha = <r,r0*> / <Ap,r0*>
+//     s = r - alpha Ap                  -> partial  <s,s>                       | barrier |
+//     As = A s                          -> partials <As,As>, <As,s>, <As,r0*>   | barrier | beta, omega, residual, convergence test
+//     x += alpha p + omega s; r = s - omega As; p = r + beta (p - omega Ap)  -> partial <r,r0*> | barrier |
+// (the stand-alone form needs four launches for the same work).  On convergence the loop leaves BEFORE the last vector
+// update, like the reference (bicgstab.hpp:196-206).  Both products go through the same csr_stream_body instantiation, so
+// the descriptors and the copy issued ahead are shared between them.
+// ------------------------------------------------------------------------------------------------
+struct EpiDot3Partial
+{
+  real *out; const real *in; const real *r0; real *partials;
+  real acc[3];
+  static constexpr int NQ = 3;
+  static constexpr bool COO = false;
+  struct Pre { real v, r0; };
+  __device__ __forceinline__ real init(const Pre &) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ Pre pre(u32 r) const { Pre q; q.v = in[r]; q.r0 = r0[r]; return q; }
+  __device__ __forceinline__ void row(u32 r, real dot, const Pre &q)
+  {
+    out[r] = dot;
+    acc[0] = fma(dot, dot, acc[0]);
+    acc[1] = fma(q.v, dot, acc[1]);
+    acc[2] = fma(dot, q.r0, acc[2]);
+  }
+  __device__ __forceinline__ void finish(real *smem)
+  {
+    block_sum<3>(acc, smem);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) partials[q * VCL_MAX_BLOCKS + blockIdx.x] = acc[q];
+    }
+  }
+};
+
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, const real *r0, real *Ap, real *s, real *As,
+                           SolverState *st, real *partials, int iterations)
+{
+  cgrp::grid_group grid = cgrp::this_grid();
+  __shared__ SolverState s_st;
+  __shared__ real s_sum[3 * 32];
+  if (threadIdx.x == 0) s_st = *st;
+  __syncthreads();
+  CsrCarry carry = {0u, 0};
+  real *part_ss = partials + 3 * VCL_MAX_BLOCKS, *part_rr0 = partials + 4 * VCL_MAX_BLOCKS;
+  const XVec xv_p = {p, (u32)sizeof(real), nullptr, 0u}, xv_s = {s, (u32)sizeof(real), nullptr, 0u};
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+
+  for (int it = 0; it < iterations; ++it)
+  {
+    if (s_st.done != VCL_RUNNING) break;
+    // ---- Ap = A p ----
+    {
+      EpiDot3Partial e = {Ap, p, r0, partials, {0.0, 0.0, 0.0}};
+      csr_stream_body<EpiDot3Partial, false, true>(A, xv_p, e, &carry);
+    }
+    grid.sync();
+    {
+      real t[1];
+      sum_partials<1>(partials + 2 * VCL_MAX_BLOCKS, t, s_sum);
+      if (threadIdx.x == 0) s_st.sums[3] = t[0];                                   // <Ap,r0*>
+      __syncthreads();
+    }
+    // ---- s = r - alpha Ap, <s,s> ----
+    {
+      const real alpha = s_st.sums[0] / s_st.sums[3];
+      real acc[1] = {0.0};
+      const long long npairs = aligned16(s, r, Ap) ? (n >> 1) : 0;
+      for (long long i = tid0; i < npairs; i += nthr)
+      {
+        const long long k = i * 2;
+        const real2 vr = ld2(r, k), va = ld2(Ap, k);
+        real2 vs;
+        vs.x = fma(-alpha, va.x, vr.x); vs.y = fma(-alpha, va.y, vr.y);
+        acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
+        st2(s, k, vs);
+      }
+      for (long long k = 2 * npairs + tid0; k < n; k += nthr)
+      {
+        const real vs = fma(-alpha, Ap[k], r[k]);
+        acc[0] = fma(vs, vs, acc[0]);
+        s[k] = vs;
+      }
+      block_sum<1>(acc, s_sum);
+      if (threadIdx.x == 0) part_ss[blockIdx.x] = acc[0];
+    }
+    grid.sync();
+    // ---- As = A s ----
+    {
+      EpiDot3Partial e = {As, s, r0, partials, {0.0, 0.0, 0.0}};
+      csr_stream_body<EpiDot3Partial, false, true>(A, xv_s, e, &carry);
+    }
+    grid.sync();
+    {
+      real t[3], ss[1];
+      sum_partials<3>(partials, t, s_sum);
+      sum_partials<1>(part_ss, ss, s_sum);
+      if (threadIdx.x == 0)
+      {
+        s_st.sums[1] = t[0]; s_st.sums[2] = t[1]; s_st.sums[4] = t[2]; s_st.sums[5] = ss[0];
+        bicgstab_advance(&s_st);                                                   // bicgstab.hpp:184-199
+      }
+      __syncthreads();
+    }
+    if (s_st.done != VCL_RUNNING) break;                                           // converged: the iterate before this update is returned
+    // ---- x += alpha p + omega s; r = s - omega As; p = r + beta (p - omega Ap); <r,r0*> ----
+    {
+      const real alpha = s_st.alpha, beta = s_st.beta, omega = s_st.omega;
+      real acc[1] = {0.0};
+      const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
+      for (long long i = tid0; i < npairs; i += nthr)
+      {
+        const long long k = i * 2;
+        real2 vx = ld2(x, k), vp = ld2(p, k); const real2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
+        real2 vr;
+        vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
+        vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
+        vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
+        acc[0] = fma(vr.x, v0.x, acc[0]);                acc[0] = fma(vr.y, v0.y, acc[0]);
+        st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+      }
+      for (long long k = 2 * npairs + tid0; k < n; k += nthr)
+      {
+        real vp = p[k]; const real vs = s[k];
+        x[k] += alpha * vp + omega * vs;
+        const real vr = fma(-omega, As[k], vs);
+        vp = fma(beta, fma(-omega, Ap[k], vp), vr);
+        acc[0] = fma(vr, r0[k], acc[0]);
+        r[k] = vr; p[k] = vp;
+      }
+      block_sum<1>(acc, s_sum);
+      if (threadIdx.x == 0) part_rr0[blockIdx.x] = acc[0];
+    }
+    grid.sync();
+    {
+      real t[1];
+      sum_partials<1>(part_rr0, t, s_sum);
+      if (threadIdx.x == 0)
+      {
+        s_st.sums[0] = t[0];                                                       // <r,r0*>
+        if (s_st.iters >= s_st.maxit) s_st.done = VCL_MAXIT;
+      }
+      __syncthreads();
+    }
+  }
+  {
+    EpiDot3Partial e = {As, s, r0, partials, {0.0, 0.0, 0.0}};
+    csr_stream_body<EpiDot3Partial, false, true>(A, xv_s, e, &carry, true);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
+}
 }

@@ -319,9 +319,28 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real 
   const int batch = tag->monitor ? 1 : kBatch;
   int launched = 0;
   bool stopped = false;
+  int coop_grid = 0;                                       // persistent form for small / medium CSR systems, see cg_solve
+  if (A.fmt == 0 && !tag->monitor && persistent_cg_wanted(b, A.csr, n))
+  {
+    const int occ = vcl_occupancy(bicgstab_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
+  }
   while (launched < tag->max_iterations && !stopped)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    if (coop_grid > 0)
+    {
+      CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      long long nn = n; int iters_arg = nb;
+      real *partials = VCL_PARTIALS(b);
+      const real *cr0 = r0;
+      void *args[] = {&d, &nn, &x, &r, &p, &cr0, &Ap, &s, &As, &st, &partials, &iters_arg};
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)bicgstab_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
+                                                         (size_t)CSR_SMEM_BYTES, b->stream);
+      if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); coop_grid = 0; }
+      else { VCL_CUDA(b, ce); VCL_LAUNCHED(b, "bicgstab_persistent_kernel"); }
+    }
+    if (coop_grid == 0)
     for (int k = 0; k < nb; ++k)
     {
       EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, VCL_PARTIALS(b), b->tickets, st, &st->sums[1], &st->sums[2], &st->sums[3], {0.0, 0.0, 0.0}, nullptr};
