@@ -106,13 +106,13 @@ const int kBatch = 32;   // iterations enqueued between two looks at the device 
 // Use the persistent cooperative kernel?  CSR with a row-block plan and 16-byte aligned arrays (the TMA path), a device that
 // supports cooperative launches, and a system small enough that fixed latencies matter (VCL_B200_PERSISTENT_ROWS, default
 // 10M rows -- measured: ahead up to 200^3, level at 256^3; 0 disables).
-static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n)
+static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n, int row_limit_divisor = 1)
 {
   static long long max_rows = -1;
   static int coop = -1;
   if (max_rows < 0) { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); max_rows = e ? atoll(e) : 10000000LL; }
   if (coop < 0) { int v = 0; coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, b->device) == cudaSuccess && v) ? 1 : 0; }
-  return coop == 1 && n <= max_rows && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
+  return coop == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -153,7 +153,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
 
   const int batch = tag->monitor ? 1 : kBatch;
   int coop_grid = 0;                                       // persistent form for small / medium systems, see cg_solve
-  if (persistent_cg_wanted(b, A.csr, n))
+  if (persistent_cg_wanted(b, A.csr, n, 3))                // 7 streamed vectors per update: level with two kernels from ~2M rows (128^3), behind at 256^3
   {
     const int occ = vcl_occupancy(pcg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
