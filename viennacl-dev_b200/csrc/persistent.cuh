@@ -351,4 +351,188 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
 }
+// ------------------------------------------------------------------------------------------------
+// One restart cycle of the pipelined GMRES (gmres.hpp:241-300: product, classical Gram-Schmidt in two stages, normalisation)
+// in the persistent form.  Inner iteration k (v_k = column k of the basis, src = the residual for k = 0, else v_{k-1}):
+//     v_k = A src [./ diag]                         -> partial ||v_k||^2 (used for k = 0)                  | barrier
+//     k > 0: partial h_j = <v_j, v_k>, j < k        (4 columns per pass over this CTA's row share)          | barrier
+//            CTA c sums the partials of column c    -> h[c], R[c + k m]                                    | barrier
+//            v_k -= sum_j h_j v_j                   -> partial ||v_k||^2                                   | barrier
+//     R[k + k m] = ||v_k||; v_k /= ||v_k||          -> partial xi_k = <res, v_k> (summed by CTA 0)         | barrier
+// The stand-alone form launches four kernels per inner iteration.  Scratch arrays of the backend: partials[j] for the
+// h_j (j <= 59), partials[60] for ||v_k||^2, partials[61] for xi_k -- hence krylov_dim <= 60 on this path.
+// ------------------------------------------------------------------------------------------------
+#define GMRES_PERSISTENT_MAX_KRYLOV 60
+struct EpiNsqPartial
+{
+  real *out; const real *diag; real *partials;
+  real acc[1];
+  static constexpr int NQ = 1;
+  static constexpr bool COO = false;
+  typedef real Pre;
+  __device__ __forceinline__ real init(real) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ real pre(u32 r) const { return diag ? diag[r] : real(1); }
+  __device__ __forceinline__ void row(u32 r, real dot, real d)
+  {
+    if (diag) dot = dot / d;
+    out[r] = dot;
+    acc[0] = fma(dot, dot, acc[0]);
+  }
+  __device__ __forceinline__ void finish(real *smem)
+  {
+    block_sum<1>(acc, smem);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+  }
+};
+
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+gmres_persistent_kernel(CsrDev A, long long n, long long isz, int m, const real *res, real *V, const real *diag,
+                        real *R, real *d_h, real *d_xi, real *partials)
+{
+  cgrp::grid_group grid = cgrp::this_grid();
+  __shared__ real s_sum[8 * 32];
+  __shared__ real s_h[VCL_GMRES_MAX_KRYLOV];
+  __shared__ real s_nsq;
+  CsrCarry carry = {0u, 0};
+  real *part_nsq = partials + 60 * VCL_MAX_BLOCKS, *part_xi = partials + 61 * VCL_MAX_BLOCKS;
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  const long long npairs = n >> 1;                         // the basis is 16-byte aligned with an even internal size (checked by the host)
+  const bool res_vec = (reinterpret_cast<uintptr_t>(res) & 15u) == 0u;
+
+  for (int k = 0; k < m; ++k)
+  {
+    real *vk = V + (size_t)k * isz;
+    const real *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
+    {
+      const XVec xv = {src, (u32)sizeof(real), nullptr, 0u};
+      EpiNsqPartial e = {vk, diag, part_nsq, {0.0}};
+      csr_stream_body<EpiNsqPartial, false, true>(A, xv, e, &carry);
+    }
+    grid.sync();
+    if (k > 0)
+    {
+      // ---- stage 1: partial h_j = <v_j, v_k> over this CTA's rows, GS columns per pass (4: the 64-register budget of 4 CTAs/SM) ----
+      constexpr int GS = 4;
+      for (int c0 = 0; c0 < k; c0 += GS)
+      {
+        const int nc = min(GS, k - c0);
+        const real *col = V + (size_t)c0 * isz;
+        real acc[GS];
+#pragma unroll
+        for (int q = 0; q < GS; ++q) acc[q] = 0.0;
+        for (long long pi = tid0; pi < npairs; pi += nthr)
+        {
+          const real2 v = ld2(vk, 2 * pi);
+          real2 a[GS];
+#pragma unroll
+          for (int q = 0; q < GS; ++q)
+            if (q < nc) a[q] = ld2(col + (size_t)q * isz, 2 * pi);
+#pragma unroll
+          for (int q = 0; q < GS; ++q)
+            if (q < nc) { acc[q] = fma(a[q].x, v.x, acc[q]); acc[q] = fma(a[q].y, v.y, acc[q]); }
+        }
+        if ((n & 1) && tid0 == 0)
+        {
+          const real v = vk[n - 1];
+#pragma unroll
+          for (int q = 0; q < GS; ++q)
+            if (q < nc) acc[q] = fma(col[(size_t)q * isz + n - 1], v, acc[q]);
+        }
+        block_sum<GS>(acc, s_sum);
+        if (threadIdx.x == 0)
+        {
+#pragma unroll
+          for (int q = 0; q < GS; ++q)
+            if (q < nc) partials[(size_t)(c0 + q) * VCL_MAX_BLOCKS + blockIdx.x] = acc[q];
+        }
+      }
+      grid.sync();
+      // ---- column c is summed by CTA c (c, c + grid, ...) ----
+      for (int c = blockIdx.x; c < k; c += gridDim.x)
+      {
+        real t[1];
+        sum_partials<1>(partials + (size_t)c * VCL_MAX_BLOCKS, t, s_sum);
+        if (threadIdx.x == 0) { d_h[c] = t[0]; R[(size_t)c + (size_t)k * m] = t[0]; }
+      }
+      grid.sync();
+      for (int j = threadIdx.x; j < k; j += blockDim.x) s_h[j] = __ldcg(d_h + j);
+      __syncthreads();
+      // ---- stage 2: v_k -= sum_j h_j v_j, partial ||v_k||^2 ----
+      {
+        real acc[1] = {0.0};
+        for (long long pi = tid0; pi < npairs; pi += nthr)
+        {
+          real2 v = ld2(vk, 2 * pi);
+          int j = 0;
+          for (; j + 4 <= k; j += 4)
+          {
+            const real2 a0 = ld2(V + (size_t)j * isz, 2 * pi), a1 = ld2(V + (size_t)(j + 1) * isz, 2 * pi);
+            const real2 a2 = ld2(V + (size_t)(j + 2) * isz, 2 * pi), a3 = ld2(V + (size_t)(j + 3) * isz, 2 * pi);
+            v.x = fma(-s_h[j], a0.x, v.x);     v.y = fma(-s_h[j], a0.y, v.y);
+            v.x = fma(-s_h[j + 1], a1.x, v.x); v.y = fma(-s_h[j + 1], a1.y, v.y);
+            v.x = fma(-s_h[j + 2], a2.x, v.x); v.y = fma(-s_h[j + 2], a2.y, v.y);
+            v.x = fma(-s_h[j + 3], a3.x, v.x); v.y = fma(-s_h[j + 3], a3.y, v.y);
+          }
+          for (; j < k; ++j)
+          {
+            const real2 a0 = ld2(V + (size_t)j * isz, 2 * pi);
+            v.x = fma(-s_h[j], a0.x, v.x); v.y = fma(-s_h[j], a0.y, v.y);
+          }
+          acc[0] = fma(v.x, v.x, acc[0]); acc[0] = fma(v.y, v.y, acc[0]);
+          st2(vk, 2 * pi, v);
+        }
+        if ((n & 1) && tid0 == 0)
+        {
+          real v = vk[n - 1];
+          for (int j = 0; j < k; ++j) v = fma(-s_h[j], V[(size_t)j * isz + n - 1], v);
+          acc[0] = fma(v, v, acc[0]);
+          vk[n - 1] = v;
+        }
+        block_sum<1>(acc, s_sum);
+        if (threadIdx.x == 0) part_nsq[blockIdx.x] = acc[0];
+      }
+      grid.sync();
+    }
+    // ---- ||v_k|| (every CTA), normalisation, partial xi_k = <res, v_k> ----
+    {
+      real t[1];
+      sum_partials<1>(part_nsq, t, s_sum);
+      if (threadIdx.x == 0) s_nsq = t[0];
+      __syncthreads();
+      const real nrm = sqrt(s_nsq);
+      if (tid0 == 0) R[(size_t)k * m + k] = nrm;
+      real acc[1] = {0.0};
+      const long long np2 = res_vec ? npairs : 0;
+      for (long long pi = tid0; pi < np2; pi += nthr)
+      {
+        real2 v = ld2(vk, 2 * pi); const real2 rr = ld2(res, 2 * pi);
+        v.x = v.x / nrm; v.y = v.y / nrm;
+        acc[0] = fma(rr.x, v.x, acc[0]); acc[0] = fma(rr.y, v.y, acc[0]);
+        st2(vk, 2 * pi, v);
+      }
+      for (long long i = 2 * np2 + tid0; i < n; i += nthr)
+      {
+        const real v = vk[i] / nrm;
+        acc[0] = fma(res[i], v, acc[0]);
+        vk[i] = v;
+      }
+      block_sum<1>(acc, s_sum);
+      if (threadIdx.x == 0) part_xi[blockIdx.x] = acc[0];
+    }
+    grid.sync();
+    if (blockIdx.x == 0)
+    {
+      real t[1];
+      sum_partials<1>(part_xi, t, s_sum);
+      if (threadIdx.x == 0) d_xi[k] = t[0];
+    }
+  }
+  {
+    const XVec xv = {res, (u32)sizeof(real), nullptr, 0u};
+    EpiNsqPartial e = {V, diag, part_nsq, {0.0}};
+    csr_stream_body<EpiNsqPartial, false, true>(A, xv, e, &carry, true);
+  }
+}
 }

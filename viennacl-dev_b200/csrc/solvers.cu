@@ -532,6 +532,12 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   if (max_restarts > 0 && max_restarts * (unsigned)m == (unsigned)tag->max_iterations) max_restarts -= 1;
 
   const int grid = scalar_grid(b, n);
+  int coop_grid = 0;
+  if (A.fmt == 0 && m <= GMRES_PERSISTENT_MAX_KRYLOV && persistent_cg_wanted(b, A.csr, n, 16))      // ahead up to 512^2, behind from 1024^2 (measured)
+  {
+    const int occ = vcl_occupancy(gmres_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
+  }
   for (unsigned restart = 0; restart <= max_restarts; ++restart)
   {
     if (restart > 0)
@@ -553,7 +559,21 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
       break;
     }
 
-    int k;
+    int k = 0;
+    if (coop_grid > 0)
+    {
+      // small / medium CSR systems: the whole cycle in one cooperative kernel (persistent.cuh)
+      CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      long long nn = n, iszz = isz; int mm = m;
+      real *partials = VCL_PARTIALS(b);
+      const real *cres = res, *cdiag = diag;
+      void *args[] = {&d, &nn, &iszz, &mm, &cres, &V, &cdiag, &R, &d_h, &d_xi, &partials};
+      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)gmres_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
+                                                         (size_t)CSR_SMEM_BYTES, b->stream);
+      if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); coop_grid = 0; }
+      else { VCL_CUDA(b, ce); VCL_LAUNCHED(b, "gmres_persistent_kernel"); k = m; }
+    }
+    if (coop_grid == 0)
     for (k = 0; k < m; ++k)
     {
       real *vk = V + (size_t)k * isz;
