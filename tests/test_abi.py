@@ -41,3 +41,28 @@ def test_product_does_not_touch_the_oracle():
                     if "oracle_lib" in txt or "libvcl_oracle" in txt or "libvcl_ref" in txt or "vclo_" in txt.replace("vclo_gen_stencil*", ""):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_generated_float_half_is_up_to_date():
+    """include/vcl_b200_float.h, csrc/prec_names_f32.h and viennacl/backend/abi.hpp are generated from include/vcl_b200.h
+    (tools/gen_float_header.py): the committed copies must equal a fresh generation, and every D entry point of the
+    precision-dependent part must have its S twin."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_float_header", os.path.join(root, "tools", "gen_float_header.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    h, m, a = gen.generate()
+    assert open(gen.OUT_H).read() == h
+    assert open(gen.OUT_MAP).read() == m
+    assert open(gen.OUT_ABI).read() == a
+    d_names = set(re.findall(r"\bViennaCLCUDAD(\w+)\s*\(", h.replace("ViennaCLCUDAS", "ViennaCLCUDAD")))
+    s_names = set(re.findall(r"\bViennaCLCUDAS(\w+)\s*\(", h))
+    assert d_names == s_names and len(s_names) >= 45
+
+
+def test_float_entry_points_refuse_null_backend(pkg):
+    L = pkg.lib()
+    assert L.ViennaCLCUDAScsrmv(None, 1, 1, 1, None, None, None, None, 0, None, 0, 1, 1.0, None, 0, 1, 0.0) != 0
+    assert L.ViennaCLCUDADcsr_mixed_precision_cg(None, None, None, None, None, 0.01, None) != 0
