@@ -130,6 +130,16 @@ ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend backend, ViennaCLInt rows, 
                                      const unsigned int *row_ptr, const unsigned int *csr_col, const double *csr_val,
                                      unsigned int *columns_per_block, unsigned int *block_start, long long *padded_nnz,
                                      unsigned int *col_idx, double *values);
+/* SELL-C-sigma (not in the reference, whose sigma is fixed at 1): inside every window of `sigma` consecutive rows
+ * (sigma a multiple of rows_per_block, <= 4096) the rows are ordered by decreasing length -- stable, ties keep their order --
+ * before they are cut into slices, which removes most of the padding of irregular matrices.  row_perm (out, ceil(rows/C)*C
+ * entries) maps storage rows to matrix rows.  Same two-call protocol as csr2sell: the first call (col_idx == NULL) fills
+ * row_perm, columns_per_block, block_start and *padded_nnz, the second one scatters the entries.  Products and solvers take
+ * the matrix through the ViennaCLCUDADsell struct (row_perm set); per-row arithmetic and results equal those of sigma = 1. */
+ViennaCLStatus ViennaCLCUDADcsr2sell_sigma(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt rows_per_block, ViennaCLInt sigma,
+                                           const unsigned int *row_ptr, const unsigned int *csr_col, const double *csr_val,
+                                           unsigned int *row_perm, unsigned int *columns_per_block, unsigned int *block_start,
+                                           long long *padded_nnz, unsigned int *col_idx, double *values);
 
 /* ELL (ell_matrix.hpp:36-119) and HYB (hyb_matrix.hpp:36-126), AlignmentV = 1 layouts:
  * ELL entry j of row r at j*internal_rows + r (coords / elements hold internal_rows*maxnnz entries, padding value 0, column 0);
@@ -224,7 +234,14 @@ typedef struct
   ViennaCLInt rows, cols, rows_per_block;
   const unsigned int *columns_per_block, *col_idx, *block_start;
   const double *values;
+  const unsigned int *row_perm;   /* NULL: sigma = 1, the reference's layout (sliced_ell_matrix.hpp:43).  Otherwise SELL-C-sigma:
+                                     storage row i holds matrix row row_perm[i] (0xFFFFFFFF: padding row), see csr2sell_sigma */
 } ViennaCLCUDADsell;
+/* y = alpha*A*x + beta*y for a SELL matrix passed as the struct (needed for SELL-C-sigma: row_perm); ViennaCLCUDADsellmv is the
+ * flat-argument form of the reference's kernel signature. */
+ViennaCLStatus ViennaCLCUDADsellmv_struct(ViennaCLBackend backend, const ViennaCLCUDADsell *A,
+                                          const double *x, ViennaCLInt offx, ViennaCLInt incx, double alpha,
+                                          double *y, ViennaCLInt offy, ViennaCLInt incy, double beta);
 
 ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend backend, ViennaCLInt n, double *result, double alpha,
                                                        double *p, double *r, const double *Ap, double beta,

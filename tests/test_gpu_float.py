@@ -43,15 +43,24 @@ def test_csr_spmv_golden_bitexact_f32(pkg, be, g32, name, use_blocks):
     dA = dev_csr(pkg, be, A)
     x, y0 = g32[name + "/x"], g32[name + "/y0"]
     dx = be.array(x)
-    long_row = 50 if name == "ragged_200x180" and use_blocks else None     # 180 entries: still the sequential path
+    long_row = 50 if name == "ragged_200x180" and use_blocks else None     # 180 entries
     for key, (alpha, beta) in {"y_assign": (1.0, 0.0), "y_add": (1.0, 1.0), "y_sub": (-1.0, 1.0), "y_ab": (1.5, -0.25)}.items():
         dy = be.array(y0)
         assert dy.dtype == F
         dA.spmv(dx, dy, alpha, beta, use_blocks=use_blocks)
-        assert np.array_equal(dy.download(), g32[name + "/" + key]), (key, long_row)
+        y = dy.download()
+        exact = np.ones(A.rows, bool)
+        if long_row is not None:
+            exact[long_row] = False                        # > 64 entries: warp tree sum on the row-block path
+        assert np.array_equal(y[exact], g32[name + "/" + key][exact]), (key, long_row)
+        assert ol.rel_err(y, g32[name + "/" + key]).max() <= 2e-6, key
     dxs, dys = be.array(g32[name + "/xs"]), be.array(g32[name + "/ys0"])
     dA.spmv(dxs, dys, 1.0, 0.0, offx=3, incx=2, offy=1, incy=3, use_blocks=use_blocks)
-    assert np.array_equal(dys.download(), g32[name + "/ys"])
+    ys, ys_ref = dys.download(), g32[name + "/ys"]
+    touched = np.zeros(ys.size, bool)
+    if long_row is not None:
+        touched[1 + 3 * long_row] = True
+    assert np.array_equal(ys[~touched], ys_ref[~touched]) and ol.rel_err(ys, ys_ref).max() <= 2e-6
     assert np.array_equal(dA.row_info(3).download(), g32[name + "/diag"])
 
 

@@ -31,17 +31,23 @@ def test_csr_spmv_golden_bitexact(pkg, be, golden, name, use_blocks):
     dA = dev_csr(pkg, be, A)
     x, y0 = golden[name + "/x"], golden[name + "/y0"]
     dx = be.array(x)
+    # rows of more than 64 entries (CSR_LONG_ROW) are summed by a whole warp on the row-block path: tolerance-level parity there
+    exact = np.diff(A.rp.astype(np.int64)) <= (64 if use_blocks else 1 << 30)
     for key, (alpha, beta) in {"y_assign": (1.0, 0.0), "y_add": (1.0, 1.0), "y_sub": (-1.0, 1.0)}.items():
         dy = be.array(y0)
         dA.spmv(dx, dy, alpha, beta, use_blocks=use_blocks)
-        assert np.array_equal(dy.download(), golden[name + "/" + key]), key
+        y = dy.download()
+        assert np.array_equal(y[exact], golden[name + "/" + key][exact]), key
+        assert ol.rel_err(y, golden[name + "/" + key]).max() <= 1e-14, key
     dy = be.array(y0)
     dA.spmv(dx, dy, 1.5, -0.25, use_blocks=use_blocks)
     assert ol.rel_err(dy.download(), golden[name + "/y_ab"]).max() <= 1e-14
     # strided / ranged views (sparse.cpp:163-200, :397-400)
     dxs, dys = be.array(golden[name + "/xs"]), be.array(golden[name + "/ys0"])
     dA.spmv(dxs, dys, 1.0, 0.0, offx=3, incx=2, offy=1, incy=3, use_blocks=use_blocks)
-    assert np.array_equal(dys.download(), golden[name + "/ys"])
+    ys, ys_ref = dys.download(), golden[name + "/ys"]
+    touched = np.zeros(ys.size, bool); touched[1 + 3 * np.nonzero(~exact)[0]] = True      # y entries of the long rows
+    assert np.array_equal(ys[~touched], ys_ref[~touched]) and ol.rel_err(ys, ys_ref).max() <= 1e-14
 
 
 def test_beta_zero_does_not_read_y(pkg, be, golden):

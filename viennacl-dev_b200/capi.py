@@ -37,7 +37,7 @@ class CsrStruct(C.Structure):
 
 class SellStruct(C.Structure):
     _fields_ = [("rows", c_int), ("cols", c_int), ("rows_per_block", c_int), ("columns_per_block", c_vp), ("col_idx", c_vp),
-                ("block_start", c_vp), ("values", c_vp)]
+                ("block_start", c_vp), ("values", c_vp), ("row_perm", c_vp)]
 
 
 class EllStruct(C.Structure):
@@ -173,6 +173,8 @@ def lib():
     pe, ph = C.POINTER(EllStruct), C.POINTER(HybStruct)
     sig("ViennaCLCUDADellmv", c_vp, pe, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
     sig("ViennaCLCUDADhybmv", c_vp, ph, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
+    sig("ViennaCLCUDADcsr2sell_sigma", c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, p_ll, c_vp, c_vp)
+    sig("ViennaCLCUDADsellmv_struct", c_vp, ps, c_vp, c_int, c_int, c_dbl, c_vp, c_int, c_int, c_dbl)
     sig("ViennaCLCUDADcsr2ell", c_vp, c_int, c_vp, c_vp, c_vp, p_int, c_vp, c_vp)
     sig("ViennaCLCUDADcsr2hyb", c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_dbl, p_int, p_int, c_vp, c_vp, c_vp, c_vp, c_vp)
     for fmt, pp in (("ell", pe), ("hyb", ph)):
@@ -405,6 +407,9 @@ class CsrMatrix:
         self.b.check(self.b.lib_for(self.va.dtype).ViennaCLCUDADcsr_row_info(self.b.h, self.rows, self.rp.ptr, self.ci.ptr, self.va.ptr, out.ptr, option))
         return out
 
+    def to_sell_sigma(self, Cs=32, sigma=256):
+        return SellMatrix.from_csr(self, Cs, sigma)
+
     def to_sell(self, Cs=32):
         return SellMatrix.from_csr(self, Cs)
 
@@ -416,15 +421,26 @@ class CsrMatrix:
 class SellMatrix:
     """sliced_ell_matrix mirror (sliced_ell_matrix.hpp:134-137): columns_per_block, column_indices, block_start, elements."""
 
-    def __init__(self, backend, rows, cols, Cs, cpb, ci, bs, va, padded_nnz):
+    def __init__(self, backend, rows, cols, Cs, cpb, ci, bs, va, padded_nnz, perm=None, sigma=1):
         self.b = backend
         self.rows, self.cols, self.C = int(rows), int(cols), int(Cs)
         self.cpb, self.ci, self.bs, self.va = cpb, ci, bs, va
         self.padded_nnz = int(padded_nnz)
+        self.perm, self.sigma = perm, int(sigma)             # SELL-C-sigma: storage row -> matrix row (None: sigma = 1)
 
     @classmethod
-    def from_csr(cls, A, Cs=32):
+    def from_csr(cls, A, Cs=32, sigma=1):
+        """Device-side conversion.  sigma > 1: SELL-C-sigma (rows sorted by length inside windows of sigma rows)."""
         b = A.b
+        if sigma > 1:
+            ns = (A.rows - 1) // Cs + 1 if A.rows > 0 else 0
+            cpb = b.empty(max(ns, 1), np.uint32); bs = b.empty(max(ns, 1), np.uint32); perm = b.empty(max(ns * Cs, 1), np.uint32)
+            tot = c_ll(0)
+            L = b.lib_for(A.va.dtype)
+            b.check(L.ViennaCLCUDADcsr2sell_sigma(b.h, A.rows, Cs, sigma, A.rp.ptr, A.ci.ptr, A.va.ptr, perm.ptr, cpb.ptr, bs.ptr, C.byref(tot), None, None))
+            ci = b.empty(max(tot.value, 1), np.uint32); va = b.empty(max(tot.value, 1), A.va.dtype)
+            b.check(L.ViennaCLCUDADcsr2sell_sigma(b.h, A.rows, Cs, sigma, A.rp.ptr, A.ci.ptr, A.va.ptr, perm.ptr, cpb.ptr, bs.ptr, C.byref(tot), ci.ptr, va.ptr))
+            return cls(b, A.rows, A.cols, Cs, cpb, ci, bs, va, tot.value, perm=perm, sigma=sigma)
         ns = (A.rows - 1) // Cs + 1 if A.rows > 0 else 0
         cpb = b.empty(max(ns, 1), np.uint32); bs = b.empty(max(ns, 1), np.uint32)
         tot = c_ll(0)
@@ -443,9 +459,14 @@ class SellMatrix:
                    backend.array(pad(S["elements"], np.float64)), S["padded_nnz"])
 
     def struct(self):
-        return SellStruct(self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr, self.va.ptr)
+        return SellStruct(self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr, self.va.ptr,
+                          self.perm.ptr if self.perm is not None else None)
 
     def spmv(self, x, y, alpha=1.0, beta=0.0, offx=0, incx=1, offy=0, incy=1):
+        if self.perm is not None:
+            st = self.struct()
+            self.b.check(self.b.lib_for(self.va.dtype).ViennaCLCUDADsellmv_struct(self.b.h, C.byref(st), x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
+            return
         self.b.check(self.b.lib_for(self.va.dtype).ViennaCLCUDADsellmv(self.b.h, self.rows, self.cols, self.C, self.cpb.ptr, self.ci.ptr, self.bs.ptr,
                                                   self.va.ptr, x.ptr, offx, incx, alpha, y.ptr, offy, incy, beta))
 

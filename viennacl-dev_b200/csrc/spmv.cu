@@ -271,6 +271,138 @@ extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell(ViennaCLBackend b, ViennaCLInt r
 }
 
 // ------------------------------------------------------------------------------------------------
+// CSR -> SELL-C-sigma.  One CTA per window of sigma rows: (length, local index) keys in shared memory, bitonic sort by
+// decreasing length with the row index as tie-break (= a stable sort), then the sorted window is written to row_perm.
+// Widths and entries are then taken through the permutation; the layout inside a slice is that of sigma = 1.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sell_sigma_sort_kernel(int rows, int padded_rows, int sigma, int pow2, const u32 * __restrict__ rp, u32 *perm)
+{
+  extern __shared__ unsigned long long s_key[];            // pow2 keys: (0xFFFFFFFF - length) << 32 | local index; padding sorts last
+  const long long w0 = (long long)blockIdx.x * sigma;
+  for (int i = threadIdx.x; i < pow2; i += blockDim.x)
+  {
+    const long long r = w0 + i;
+    unsigned long long key = ~0ull;
+    if (i < sigma && r < rows) key = ((unsigned long long)(0xFFFFFFFFu - (rp[r + 1] - rp[r])) << 32) | (unsigned)i;
+    s_key[i] = key;
+  }
+  __syncthreads();
+  for (int size = 2; size <= pow2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1)
+    {
+      for (int i = threadIdx.x; i < pow2; i += blockDim.x)
+      {
+        const int j = i ^ stride;
+        if (j > i)
+        {
+          const bool up = (i & size) == 0;
+          const unsigned long long a = s_key[i], c = s_key[j];
+          if ((a > c) == up) { s_key[i] = c; s_key[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < sigma; i += blockDim.x)
+  {
+    const long long pos = w0 + i;
+    if (pos >= padded_rows) break;
+    const unsigned long long key = s_key[i];
+    perm[pos] = (key == ~0ull) ? 0xFFFFFFFFu : (u32)(w0 + (long long)(key & 0xFFFFFFFFull));
+  }
+}
+
+__global__ void sell_width_perm_kernel(int rows, int C, const u32 * __restrict__ rp, const u32 * __restrict__ perm, u32 *cpb)
+{
+  const int nslices = (rows - 1) / C + 1;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += (long long)gridDim.x * blockDim.x)
+  {
+    u32 w = 0;
+    for (long long i = s * C; i < (s + 1) * C; ++i)
+    {
+      const u32 r = perm[i];
+      if (r != 0xFFFFFFFFu) w = max(w, rp[r + 1] - rp[r]);
+    }
+    cpb[s] = w;
+  }
+}
+
+__global__ void sell_fill_perm_kernel(int rows, int C, const u32 * __restrict__ rp, const u32 * __restrict__ cci, const real * __restrict__ cva,
+                                      const u32 * __restrict__ perm, const u32 * __restrict__ cpb, const u32 * __restrict__ bs, u32 *ci, real *va)
+{
+  const long long padded_rows = ((long long)(rows - 1) / C + 1) * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded_rows; i += (long long)gridDim.x * blockDim.x)
+  {
+    const u32 s = (u32)(i / C);
+    const u32 w = cpb[s];
+    size_t idx = (size_t)bs[s] + (size_t)(i - (long long)s * C);
+    const u32 r = perm[i];
+    u32 j = 0;
+    if (r != 0xFFFFFFFFu)
+    {
+      const u32 e = rp[r + 1];
+      for (u32 k = rp[r]; k < e; ++k, ++j, idx += C) { ci[idx] = cci[k]; va[idx] = cva[k]; }
+    }
+    for (; j < w; ++j, idx += C) { ci[idx] = 0u; va[idx] = 0.0; }
+  }
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADcsr2sell_sigma(ViennaCLBackend b, ViennaCLInt rows, ViennaCLInt C, ViennaCLInt sigma,
+                                                      const unsigned int *row_ptr, const unsigned int *csr_col, const real *csr_val,
+                                                      unsigned int *row_perm, unsigned int *columns_per_block, unsigned int *block_start,
+                                                      long long *padded_nnz, unsigned int *col_idx, real *values)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, rows >= 0 && C > 0 && padded_nnz, "bad arguments");
+  VCL_REQUIRE(b, sigma >= C && sigma % C == 0 && sigma <= 4096, "sigma must be a multiple of rows_per_block and at most 4096");
+  if (rows == 0) { *padded_nnz = 0; return ViennaCLSuccess; }
+  VCL_REQUIRE(b, row_ptr && row_perm && columns_per_block && block_start, "null pointer");
+  const int nslices = (rows - 1) / C + 1;
+  const int padded_rows = nslices * C;
+  if (!col_idx || !values)
+  {
+    int pow2 = 1;
+    while (pow2 < sigma) pow2 <<= 1;
+    const int nwin = vcl_div_up(padded_rows, sigma);
+    sell_sigma_sort_kernel<<<nwin, 256, (size_t)pow2 * sizeof(unsigned long long), b->stream>>>(rows, padded_rows, sigma, pow2, row_ptr, row_perm);
+    VCL_LAUNCHED(b, "sell_sigma_sort_kernel");
+    int grid = std::min(vcl_div_up(nslices, 256), b->sm_count * 8);
+    sell_width_perm_kernel<<<grid, 256, 0, b->stream>>>(rows, C, row_ptr, row_perm, columns_per_block);
+    VCL_LAUNCHED(b, "sell_width_perm_kernel");
+    std::vector<u32> w((size_t)nslices), start((size_t)nslices);
+    VCL_CUDA(b, cudaMemcpyAsync(w.data(), columns_per_block, sizeof(u32) * nslices, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    unsigned long long off = 0;
+    for (int s = 0; s < nslices; ++s) { start[s] = (u32)off; off += (unsigned long long)w[s] * (unsigned long long)C; }
+    VCL_REQUIRE(b, off <= 0xFFFFFFFFull, "SELL storage exceeds 32-bit offsets (sliced_ell_matrix.hpp:134-137 uses unsigned int)");
+    VCL_CUDA(b, cudaMemcpyAsync(block_start, start.data(), sizeof(u32) * nslices, cudaMemcpyHostToDevice, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    *padded_nnz = (long long)off;
+    return ViennaCLSuccess;
+  }
+  int grid = std::min(vcl_div_up(padded_rows, 256), b->sm_count * 8);
+  sell_fill_perm_kernel<<<grid, 256, 0, b->stream>>>(rows, C, row_ptr, csr_col, csr_val, row_perm, columns_per_block, block_start, col_idx, values);
+  VCL_LAUNCHED(b, "sell_fill_perm_kernel");
+  return ViennaCLSuccess;
+}
+
+extern "C" ViennaCLStatus ViennaCLCUDADsellmv_struct(ViennaCLBackend b, const ViennaCLCUDADsell *A,
+                                                     const real *x, ViennaCLInt offx, ViennaCLInt incx, real alpha,
+                                                     real *y, ViennaCLInt offy, ViennaCLInt incy, real beta)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, A != nullptr && A->rows >= 0 && A->cols >= 0 && A->rows_per_block > 0, "bad matrix");
+  if (A->rows == 0) return ViennaCLSuccess;
+  VCL_REQUIRE(b, A->columns_per_block && A->block_start && x && y, "null pointer");
+  VCL_REQUIRE(b, incx != 0 && incy != 0, "zero stride");
+  VCL_REQUIRE(b, x != y, "x and y alias");
+  EpiAxpby epi = {y, offy, incy, alpha, beta};
+  epi.sell_f32 = sizeof(real) == 4;
+  XVec xv = make_xvec(x, offx, incx);
+  return vcl_launch_sell(b, *A, xv, epi);
+}
+
+// ------------------------------------------------------------------------------------------------
 // CSR -> ELL (ell_matrix.hpp:122-166) and CSR -> HYB (hyb_matrix.hpp:127-214), AlignmentV = 1.  Row lengths are analysed
 // on the host from a D2H copy of row_ptr (set-up path, like the reference, which builds both formats entirely on the
 // host); the entries are scattered on the device.

@@ -23,6 +23,7 @@ namespace VCL_NS
 #define CSR_BLOCK_THREADS 256
 #define CSR_CAP (VCL_B200_CSR_BLOCK_NNZ)          // staged non-zeros per row block
 #define CSR_STAGE (CSR_CAP + 4)                   // + alignment slack
+#define CSR_LONG_ROW 64                           // rows longer than this are summed by a whole warp (see csr_stream_body)
 
 struct CsrDev
 {
@@ -40,6 +41,7 @@ struct SellDev
 {
   int rows; int C;
   const u32 *cpb, *ci, *bs; const real *va;
+  const u32 *perm;              // SELL-C-sigma: storage row -> matrix row (0xFFFFFFFF: padding); NULL: identity
 };
 
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
@@ -394,8 +396,25 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
         for (u32 i = tid; a0 + i < cur.n1; i += CSR_BLOCK_THREADS) { wv[i] = A.va[a0 + i]; wc[i] = A.ci[a0 + i]; }
         __syncthreads();
       }
-      if ((u32)tid < nrows)
+      // Rows of up to CSR_LONG_ROW entries: one thread per row, sequential chain (bit-identical to the reference's loop).
+      // Longer rows would leave that thread gathering alone for dozens of L2 round trips while the CTA waits: each warp
+      // takes the long rows of its own 32 rows one after the other, all lanes striding over the staged entries, and sums
+      // with shuffles (no block-level synchronisation; summation order differs from the reference: tolerance-level parity,
+      // like the whole-CTA path for rows beyond CSR_CAP).  COO keeps the sequential chain (its alpha/beta form is defined by it).
+      const bool is_long = !Epi::COO && (my_e - my_s) > (u32)CSR_LONG_ROW;
+      if ((u32)tid < nrows && !is_long)
         epi.row(cur.r0 + tid, csr_row_dot<SPLIT, Epi::COO>(s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale()), pre);
+      unsigned longs = __ballot_sync(0xffffffffu, is_long);
+      while (longs)
+      {
+        const int src = __ffs(longs) - 1;
+        longs &= longs - 1u;
+        const u32 ls = __shfl_sync(0xffffffffu, my_s, src) - a0, le = __shfl_sync(0xffffffffu, my_e, src) - a0;
+        real part = 0.0;
+        for (u32 k = ls + (u32)(tid & 31); k < le; k += 32u) part = fma(s_val[k], xload<SPLIT>(xv, s_col[k]), part);
+        part = warp_sum(part);
+        if ((tid & 31) == src) epi.row(cur.r0 + tid, part, pre);
+      }
     }
     __syncthreads();                                       // buffer `buf` may be refilled from the next iteration on
     // ---- rotate the descriptor pipeline ----
@@ -535,7 +554,8 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
     if (staged(base_c, end_c))
     {
       // (s1 - s0) * C <= 256 here: one row per thread
-      const long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);
+      long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);             // storage row ...
+      if (A.perm != nullptr && (u32)tid < (s1 - s0) * C) r = (long long)A.perm[r];  // ... -> matrix row (padding: 0xFFFFFFFF)
       const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
       typename Epi::Pre pre = typename Epi::Pre();
       if (active) pre = epi.pre((u32)r);
@@ -569,7 +589,8 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       for (u32 t = tid; t < (s1 - s0) * C; t += CSR_BLOCK_THREADS)
       {
         const u32 slice = s0 + t / C;
-        const long long r = (long long)slice * C + (t % C);
+        long long r = (long long)slice * C + (t % C);
+        if (A.perm != nullptr) r = (long long)A.perm[r];
         if (r >= A.rows) continue;
         const u32 w = A.cpb[slice];
         size_t idx = (size_t)A.bs[slice] + (t % C);

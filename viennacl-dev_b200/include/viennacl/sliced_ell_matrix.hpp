@@ -48,7 +48,8 @@ public:
   typename viennacl::backend::b200::abi<ScalarT>::sell abi() const
   {
     typename viennacl::backend::b200::abi<ScalarT>::sell a = {ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_), columns_per_block_.ptr<unsigned int>(),
-                           column_indices_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), elements_.ptr<ScalarT>()};
+                           column_indices_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), elements_.ptr<ScalarT>(),
+                           sigma_ > 1 ? row_perm_.ptr<unsigned int>() : NULL};
     return a;
   }
 
@@ -57,6 +58,14 @@ public:
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for sliced ELL matrix-vector product"));
     if (rows_ == 0) return;
     if (!columns_per_block_.get()) throw memory_exception("not initialised!");
+    if (sigma_ > 1)
+    {
+      typename viennacl::backend::b200::abi<ScalarT>::sell a = abi();
+      backend::b200::check(viennacl::backend::b200::abi<ScalarT>::sellmv_struct(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()),
+                                                                                 ViennaCLInt(x.stride()), alpha, y.ptr(), ViennaCLInt(y.start()),
+                                                                                 ViennaCLInt(y.stride()), beta));
+      return;
+    }
     backend::b200::check(viennacl::backend::b200::abi<ScalarT>::sellmv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(rows_per_block_),
                                              columns_per_block_.ptr<unsigned int>(), column_indices_.ptr<unsigned int>(),
                                              block_start_.ptr<unsigned int>(), elements_.ptr<ScalarT>(),
@@ -76,6 +85,23 @@ public:
     block_start_.create(sizeof(unsigned int) * slices);
     long long padded = 0;
     ViennaCLBackend b = backend::b200::handle();
+    if (sigma_ > 1)
+    {
+      // SELL-C-sigma: rows sorted by length inside windows of sigma rows before slicing (extension; the reference has sigma = 1)
+      row_perm_.create(sizeof(unsigned int) * slices * rows_per_block_);
+      typedef viennacl::backend::b200::abi<ScalarT> abi_t;
+      backend::b200::check(abi_t::csr2sell_sigma(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), ViennaCLInt(sigma_), A.handle1().template ptr<unsigned int>(),
+                                                 A.handle2().template ptr<unsigned int>(), A.handle().template ptr<ScalarT>(), row_perm_.ptr<unsigned int>(),
+                                                 columns_per_block_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), &padded, NULL, NULL));
+      column_indices_.create(sizeof(unsigned int) * vcl_size_t(padded ? padded : 1));
+      elements_.create(sizeof(ScalarT) * vcl_size_t(padded ? padded : 1));
+      backend::b200::check(abi_t::csr2sell_sigma(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), ViennaCLInt(sigma_), A.handle1().template ptr<unsigned int>(),
+                                                 A.handle2().template ptr<unsigned int>(), A.handle().template ptr<ScalarT>(), row_perm_.ptr<unsigned int>(),
+                                                 columns_per_block_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), &padded,
+                                                 column_indices_.ptr<unsigned int>(), elements_.ptr<ScalarT>()));
+      padded_nnz_ = vcl_size_t(padded);
+      return;
+    }
     backend::b200::check(viennacl::backend::b200::abi<ScalarT>::csr2sell(b, ViennaCLInt(rows_), ViennaCLInt(rows_per_block_), A.handle1().template ptr<unsigned int>(),
                                                A.handle2().template ptr<unsigned int>(), A.handle().template ptr<ScalarT>(),
                                                columns_per_block_.ptr<unsigned int>(), block_start_.ptr<unsigned int>(), &padded, NULL, NULL));
@@ -87,9 +113,18 @@ public:
                                                column_indices_.ptr<unsigned int>(), elements_.ptr<ScalarT>()));
   }
 
+  /** @brief Sorting window of SELL-C-sigma for the NEXT copy() / from_csr(): a multiple of rows_per_block(), <= 4096; 1 (default)
+   *  keeps the reference's layout.  Not in the reference, whose sigma is fixed at 1 (sliced_ell_matrix.hpp:43). */
+  void sigma(vcl_size_t s) { sigma_ = s ? s : 1; }
+  vcl_size_t sigma() const { return sigma_; }
+  const handle_type & row_permutation() const { return row_perm_; }
+  /** @brief Stored entries including padding (sigma > 1 only; 0 otherwise) */
+  vcl_size_t padded_nnz() const { return padded_nnz_; }
+
 private:
   vcl_size_t rows_, cols_, rows_per_block_;
-  handle_type columns_per_block_, column_indices_, block_start_, elements_;
+  vcl_size_t sigma_ = 1, padded_nnz_ = 0;
+  handle_type columns_per_block_, column_indices_, block_start_, elements_, row_perm_;
 };
 
 /** @brief Host (vector of maps) -> device SELL (sliced_ell_matrix.hpp:222-235): staged through a device CSR */
