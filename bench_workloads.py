@@ -123,6 +123,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
                    "partition": "none" if world == 1 else "1-D row slabs, NVLink halo of one 256x256 plane per neighbour"},
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "frac_of_nominal_8TBps": per_gpu / 8000.0, "peak_source": peak_src, "kernel": kernel,
+                     "note": "the measured peak is a device copy (half reads, half writes); this kernel reads 13x more than it writes and can exceed it",
                      "algorithmic_bytes_per_launch": nbytes, "traffic": _traffic_from_profiles("csr_spmv_256")},
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "checksum": checksum,
