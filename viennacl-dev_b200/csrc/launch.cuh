@@ -69,7 +69,8 @@ template<class Epi>
 static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
 {
   SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm};
-  const int occ = vcl_occupancy(sell_kernel<Epi>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+  const int occ = A.row_perm ? vcl_occupancy(sell_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES)
+                             : vcl_occupancy(sell_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int C = A.rows_per_block;
   const int nslices = (A.rows - 1) / C + 1;
   const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
@@ -77,7 +78,8 @@ static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell
   // SELL-C-sigma puts the widest slices at the start of every sorting window, i.e. at a fixed period of the block index: an odd
   // grid is coprime with that power-of-two period, so the wide blocks are dealt evenly to the persistent CTAs
   if (A.row_perm != nullptr && grid > 1 && (grid & 1) == 0) grid -= 1;
-  sell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  if (A.row_perm) sell_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  else            sell_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "sell_kernel");
   return ViennaCLSuccess;
 }

@@ -479,7 +479,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // C not a multiple of 4 / larger than the CTA, take the direct path.
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
-template<class Epi>
+template<class Epi, bool PERM>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
@@ -555,7 +555,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
     {
       // (s1 - s0) * C <= 256 here: one row per thread
       long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);             // storage row ...
-      if (A.perm != nullptr && (u32)tid < (s1 - s0) * C) r = (long long)A.perm[r];  // ... -> matrix row (padding: 0xFFFFFFFF)
+      if (PERM && (u32)tid < (s1 - s0) * C) r = (long long)A.perm[r];  // ... -> matrix row (padding: 0xFFFFFFFF)
       const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
       typename Epi::Pre pre = typename Epi::Pre();
       if (active) pre = epi.pre((u32)r);
@@ -590,7 +590,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       {
         const u32 slice = s0 + t / C;
         long long r = (long long)slice * C + (t % C);
-        if (A.perm != nullptr) r = (long long)A.perm[r];
+        if (PERM) r = (long long)A.perm[r];
         if (r >= A.rows) continue;
         const u32 w = A.cpb[slice];
         size_t idx = (size_t)A.bs[slice] + (t % C);
