@@ -239,6 +239,9 @@ def test_sell_c_sigma_layout_and_product(pkg, be, dtype, Cs, sigma):
     ref2 = o.sell_spmv(o.sell_build(A, Cs), x, y0.copy(), 1.5, -0.25)
     dx = be.array(x)
     dy = be.array(np.full(rows, np.nan, dtype))
+    S1.spmv(dx, dy)                                      # sigma = 1 and sigma > 1 kernels in ONE process: they share a function-pointer
+    assert np.array_equal(dy.download(), ref1)           # type, and each needs its own opt-in to > 48 KB of dynamic shared memory
+    dy = be.array(np.full(rows, np.nan, dtype))
     S.spmv(dx, dy)
     assert np.array_equal(dy.download(), ref1)
     dy = be.array(y0)

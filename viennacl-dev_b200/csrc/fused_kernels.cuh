@@ -159,14 +159,10 @@ __device__ __forceinline__ void st2(real *p, long long i, real2 v) { *reinterpre
 // ------------------------------------------------------------------------------------------------
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
-                                               SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges &pr)
+// the entries of this thread: returns its share of <r,r>.  Shared by the stand-alone kernel and the persistent one.
+__device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p, real *r, const real *Ap, real alpha, real beta, const PushRanges &pr)
 {
-  __shared__ real s_red[32];
-  if (st != nullptr && st->done != VCL_RUNNING) return;
-  const real alpha = st ? st->alpha : alpha_v;
-  const real beta  = st ? st->beta  : beta_v;
-  real acc[1] = {0.0};
+  real acc = 0.0;
   const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
@@ -175,7 +171,7 @@ __device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, re
     vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
     vr.x = fma(-alpha, va.x, vr.x);      vr.y = fma(-alpha, va.y, vr.y);
     vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
-    acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
+    acc = fma(vr.x, vr.x, acc);          acc = fma(vr.y, vr.y, acc);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
     if (pr.n) { push_entry(pr, k, vp.x); push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
   }
@@ -185,10 +181,21 @@ __device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, re
     x[k] = fma(alpha, vp, x[k]);
     vr = fma(-alpha, Ap[k], vr);
     vp = fma(beta, vp, vr);
-    acc[0] = fma(vr, vr, acc[0]);
+    acc = fma(vr, vr, acc);
     p[k] = vp; r[k] = vr;
     if (pr.n) push_entry(pr, k, vp);
   }
+  return acc;
+}
+
+__device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
+                                               SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges &pr)
+{
+  __shared__ real s_red[32];
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  const real alpha = st ? st->alpha : alpha_v;
+  const real beta  = st ? st->beta  : beta_v;
+  real acc[1] = {cg_update_entries(n, x, p, r, Ap, alpha, beta, pr)};
   if (pr.n) __threadfence_system();                 // this thread's remote stores are performed before its CTA takes a ticket
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
   {
@@ -209,14 +216,10 @@ cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real al
 // Jacobi-PCG update: p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s; u = r ./ diag; <r,u>
 // (one pass: 7 reads + 5 writes per entry; the reference's generic PCG makes ~10 passes and 2 blocking reductions)
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(VEC_THREADS)
-pcg_update_kernel(long long n, real *x, real *r, real *u, const real *w, real *p, real *s, const real *diag,
-                  SolverState *st, real *partials, unsigned int *ticket, real *out_gamma)
+__device__ __forceinline__ real pcg_update_entries(long long n, real *x, real *r, real *u, const real *w, real *p, real *s, const real *diag,
+                                                   real alpha, real beta)
 {
-  __shared__ real s_red[32];
-  if (st->done != VCL_RUNNING) return;
-  const real alpha = st->alpha, beta = st->beta;
-  real acc[1] = {0.0};
+  real acc = 0.0;
   const long long npairs = aligned16(x, r, u, w, p, s, diag) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
@@ -228,7 +231,7 @@ pcg_update_kernel(long long n, real *x, real *r, real *u, const real *w, real *p
     vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
     vr.x = fma(-alpha, vs.x, vr.x);      vr.y = fma(-alpha, vs.y, vr.y);
     vu.x = vr.x / vd.x;                  vu.y = vr.y / vd.y;
-    acc[0] = fma(vr.x, vu.x, acc[0]);    acc[0] = fma(vr.y, vu.y, acc[0]);
+    acc = fma(vr.x, vu.x, acc);          acc = fma(vr.y, vu.y, acc);
     st2(p, k, vp); st2(s, k, vs); st2(x, k, vx); st2(r, k, vr); st2(u, k, vu);
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
@@ -237,9 +240,19 @@ pcg_update_kernel(long long n, real *x, real *r, real *u, const real *w, real *p
     x[k] = fma(alpha, vp, x[k]);
     const real vr = fma(-alpha, vs, r[k]);
     const real vu = vr / diag[k];
-    acc[0] = fma(vr, vu, acc[0]);
+    acc = fma(vr, vu, acc);
     p[k] = vp; s[k] = vs; r[k] = vr; u[k] = vu;
   }
+  return acc;
+}
+
+static __global__ void __launch_bounds__(VEC_THREADS)
+pcg_update_kernel(long long n, real *x, real *r, real *u, const real *w, real *p, real *s, const real *diag,
+                  SolverState *st, real *partials, unsigned int *ticket, real *out_gamma)
+{
+  __shared__ real s_red[32];
+  if (st->done != VCL_RUNNING) return;
+  real acc[1] = {pcg_update_entries(n, x, r, u, w, p, s, diag, st->alpha, st->beta)};
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_gamma = acc[0];
 }
 
@@ -262,15 +275,9 @@ pcg_init_kernel(long long n, const real *r, real *u, const real *diag, real *par
 // BiCGStab: s = r - alpha Ap with alpha = <r,r0*>/<Ap,r0*> taken from device memory; <s,s>
 // (host_based/iterative_operations.hpp:518-563; cuda K9 :733-788 recomputes alpha in every CTA, here it is two loads)
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(VEC_THREADS)
-bicgstab_update_s_kernel(long long n, real *s, const real *r, const real *Ap,
-                         const real *in_r_r0, const real *in_Ap_r0,
-                         SolverState *st, real *partials, unsigned int *ticket, real *out_ss)
+__device__ __forceinline__ real bicgstab_s_entries(long long n, real *s, const real *r, const real *Ap, real alpha)
 {
-  __shared__ real s_red[32];
-  if (st != nullptr && st->done != VCL_RUNNING) return;
-  const real alpha = (*in_r_r0) / (*in_Ap_r0);
-  real acc[1] = {0.0};
+  real acc = 0.0;
   const long long npairs = aligned16(s, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
@@ -278,19 +285,58 @@ bicgstab_update_s_kernel(long long n, real *s, const real *r, const real *Ap,
     const real2 vr = ld2(r, k), va = ld2(Ap, k);
     real2 vs;
     vs.x = fma(-alpha, va.x, vr.x); vs.y = fma(-alpha, va.y, vr.y);
-    acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
+    acc = fma(vs.x, vs.x, acc); acc = fma(vs.y, vs.y, acc);
     st2(s, k, vs);
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
     const real vs = fma(-alpha, Ap[k], r[k]);
-    acc[0] = fma(vs, vs, acc[0]);
+    acc = fma(vs, vs, acc);
     s[k] = vs;
   }
+  return acc;
+}
+
+static __global__ void __launch_bounds__(VEC_THREADS)
+bicgstab_update_s_kernel(long long n, real *s, const real *r, const real *Ap,
+                         const real *in_r_r0, const real *in_Ap_r0,
+                         SolverState *st, real *partials, unsigned int *ticket, real *out_ss)
+{
+  __shared__ real s_red[32];
+  if (st != nullptr && st->done != VCL_RUNNING) return;
+  real acc[1] = {bicgstab_s_entries(n, s, r, Ap, (*in_r_r0) / (*in_Ap_r0))};
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0) *out_ss = acc[0];
 }
 
 // x += alpha p + omega s;  r = s - omega As;  p = r + beta (p - omega Ap);  <r,r0*>     (host_based/iterative_operations.hpp:572-621)
+__device__ __forceinline__ real bicgstab_update_entries(long long n, real *x, real *p, const real *s, real *r, const real *As, const real *Ap,
+                                                        const real *r0, real alpha, real beta, real omega)
+{
+  real acc = 0.0;
+  const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
+  {
+    const long long k = i * 2;
+    real2 vx = ld2(x, k), vp = ld2(p, k); const real2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
+    real2 vr;
+    vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
+    vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
+    vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
+    acc = fma(vr.x, v0.x, acc);                      acc = fma(vr.y, v0.y, acc);
+    st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
+  }
+  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+  {
+    real vp = p[k]; const real vs = s[k];
+    x[k] += alpha * vp + omega * vs;
+    const real vr = fma(-omega, As[k], vs);
+    vp = fma(beta, fma(-omega, Ap[k], vp), vr);
+    acc = fma(vr, r0[k], acc);
+    r[k] = vr; p[k] = vp;
+  }
+  return acc;
+}
+
 static __global__ void __launch_bounds__(VEC_THREADS)
 bicgstab_update_kernel(long long n, real *x, real alpha_v, real *p, real omega_v, const real *s,
                        real *r, const real *As, real beta_v, const real *Ap, const real *r0,
@@ -301,28 +347,7 @@ bicgstab_update_kernel(long long n, real *x, real alpha_v, real *p, real omega_v
   const real alpha = st ? st->alpha : alpha_v;
   const real beta  = st ? st->beta  : beta_v;
   const real omega = st ? st->omega : omega_v;
-  real acc[1] = {0.0};
-  const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
-  {
-    const long long k = i * 2;
-    real2 vx = ld2(x, k), vp = ld2(p, k); const real2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
-    real2 vr;
-    vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
-    vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
-    vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
-    acc[0] = fma(vr.x, v0.x, acc[0]);                acc[0] = fma(vr.y, v0.y, acc[0]);
-    st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
-  }
-  for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-  {
-    real vp = p[k]; const real vs = s[k];
-    x[k] += alpha * vp + omega * vs;
-    const real vr = fma(-omega, As[k], vs);
-    vp = fma(beta, fma(-omega, Ap[k], vp), vr);
-    acc[0] = fma(vr, r0[k], acc[0]);
-    r[k] = vr; p[k] = vp;
-  }
+  real acc[1] = {bicgstab_update_entries(n, x, p, s, r, As, Ap, r0, alpha, beta, omega)};
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red) && threadIdx.x == 0)
   {
     *out_r_r0 = acc[0];

@@ -2,24 +2,31 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include "spmv_kernels.cuh"
 
 namespace VCL_NS
 {
 
-// Resident CTAs per SM for a kernel, queried once per instantiation (all B200s of a box are identical).
+// Resident CTAs per SM for a kernel, queried once per KERNEL (all B200s of a box are identical).  The cache is keyed by the
+// function address, not by its type: kernels that differ only in a non-type template argument (csr_stream_kernel<Epi, SPLIT>,
+// sell_kernel<Epi, PERM>) share one function-pointer type, and each of them needs its own opt-in to > 48 KB of dynamic
+// shared memory.
 template<class K>
 static int vcl_occupancy(K kernel, int threads, int dyn_smem = 0)
 {
-  static int cached = 0;
-  if (cached == 0)
-  {
-    int n = 0;
-    if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess || n <= 0) n = 1;
-    cached = n;
-  }
-  return cached;
+  static std::mutex mtx;
+  static std::unordered_map<const void*, int> cache;
+  std::lock_guard<std::mutex> lock(mtx);
+  const void *key = reinterpret_cast<const void*>(kernel);
+  std::unordered_map<const void*, int>::const_iterator it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess || n <= 0) n = 1;
+  cache[key] = n;
+  return n;
 }
 
 static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -78,30 +78,9 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
     // it is written before the first barrier of an iteration but read after the second one: a CTA that is already in
     // the next iteration's update must not overwrite what a slower CTA is still summing.
     real *part_rr = partials + (2 + (it & 1)) * VCL_MAX_BLOCKS;
-    // ---- vector update with this CTA's share of the entries (cg_update_kernel's arithmetic) ----
+    // ---- vector update with this CTA's share of the entries (the loop of cg_update_kernel) ----
     {
-      const real alpha = s_st.alpha, beta = s_st.beta;
-      real acc[1] = {0.0};
-      const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
-      {
-        const long long k = i * 2;
-        real2 vx = ld2(x, k), vp = ld2(p, k), vr = ld2(r, k); const real2 va = ld2(Ap, k);
-        vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
-        vr.x = fma(-alpha, va.x, vr.x);      vr.y = fma(-alpha, va.y, vr.y);
-        vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
-        acc[0] = fma(vr.x, vr.x, acc[0]);    acc[0] = fma(vr.y, vr.y, acc[0]);
-        st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
-      }
-      for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-      {
-        real vp = p[k], vr = r[k];
-        x[k] = fma(alpha, vp, x[k]);
-        vr = fma(-alpha, Ap[k], vr);
-        vp = fma(beta, vp, vr);
-        acc[0] = fma(vr, vr, acc[0]);
-        p[k] = vp; r[k] = vr;
-      }
+      real acc[1] = {cg_update_entries(n, x, p, r, Ap, s_st.alpha, s_st.beta, PushRanges())};
       block_sum<1>(acc, s_sum);
       if (threadIdx.x == 0) part_rr[blockIdx.x] = acc[0];
     }
@@ -147,31 +126,7 @@ pcg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *r, real *u,
     if (s_st.done != VCL_RUNNING) break;
     real *part_gamma = partials + (2 + (it & 1)) * VCL_MAX_BLOCKS;     // double-buffered like <r,r> in cg_persistent_kernel
     {
-      const real alpha = s_st.alpha, beta = s_st.beta;
-      real acc[1] = {0.0};
-      const long long npairs = aligned16(x, r, u, w, p, s, diag) ? (n >> 1) : 0;
-      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
-      {
-        const long long k = i * 2;
-        real2 vx = ld2(x, k), vr = ld2(r, k), vu = ld2(u, k), vp = ld2(p, k), vs = ld2(s, k);
-        const real2 vw = ld2(w, k), vd = ld2(diag, k);
-        vp.x = fma(beta, vp.x, vu.x);        vp.y = fma(beta, vp.y, vu.y);
-        vs.x = fma(beta, vs.x, vw.x);        vs.y = fma(beta, vs.y, vw.y);
-        vx.x = fma(alpha, vp.x, vx.x);       vx.y = fma(alpha, vp.y, vx.y);
-        vr.x = fma(-alpha, vs.x, vr.x);      vr.y = fma(-alpha, vs.y, vr.y);
-        vu.x = vr.x / vd.x;                  vu.y = vr.y / vd.y;
-        acc[0] = fma(vr.x, vu.x, acc[0]);    acc[0] = fma(vr.y, vu.y, acc[0]);
-        st2(p, k, vp); st2(s, k, vs); st2(x, k, vx); st2(r, k, vr); st2(u, k, vu);
-      }
-      for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
-      {
-        const real vp = fma(beta, p[k], u[k]), vs = fma(beta, s[k], w[k]);
-        x[k] = fma(alpha, vp, x[k]);
-        const real vr = fma(-alpha, vs, r[k]);
-        const real vu = vr / diag[k];
-        acc[0] = fma(vr, vu, acc[0]);
-        p[k] = vp; s[k] = vs; r[k] = vr; u[k] = vu;
-      }
+      real acc[1] = {pcg_update_entries(n, x, r, u, w, p, s, diag, s_st.alpha, s_st.beta)};
       block_sum<1>(acc, s_sum);
       if (threadIdx.x == 0) part_gamma[blockIdx.x] = acc[0];
     }
@@ -246,7 +201,6 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
   CsrCarry carry = {0u, 0};
   real *part_ss = partials + 3 * VCL_MAX_BLOCKS, *part_rr0 = partials + 4 * VCL_MAX_BLOCKS;
   const XVec xv_p = {p, (u32)sizeof(real), nullptr, 0u}, xv_s = {s, (u32)sizeof(real), nullptr, 0u};
-  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
 
   for (int it = 0; it < iterations; ++it)
   {
@@ -265,24 +219,7 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
     }
     // ---- s = r - alpha Ap, <s,s> ----
     {
-      const real alpha = s_st.sums[0] / s_st.sums[3];
-      real acc[1] = {0.0};
-      const long long npairs = aligned16(s, r, Ap) ? (n >> 1) : 0;
-      for (long long i = tid0; i < npairs; i += nthr)
-      {
-        const long long k = i * 2;
-        const real2 vr = ld2(r, k), va = ld2(Ap, k);
-        real2 vs;
-        vs.x = fma(-alpha, va.x, vr.x); vs.y = fma(-alpha, va.y, vr.y);
-        acc[0] = fma(vs.x, vs.x, acc[0]); acc[0] = fma(vs.y, vs.y, acc[0]);
-        st2(s, k, vs);
-      }
-      for (long long k = 2 * npairs + tid0; k < n; k += nthr)
-      {
-        const real vs = fma(-alpha, Ap[k], r[k]);
-        acc[0] = fma(vs, vs, acc[0]);
-        s[k] = vs;
-      }
+      real acc[1] = {bicgstab_s_entries(n, s, r, Ap, s_st.sums[0] / s_st.sums[3])};
       block_sum<1>(acc, s_sum);
       if (threadIdx.x == 0) part_ss[blockIdx.x] = acc[0];
     }
@@ -307,29 +244,7 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
     if (s_st.done != VCL_RUNNING) break;                                           // converged: the iterate before this update is returned
     // ---- x += alpha p + omega s; r = s - omega As; p = r + beta (p - omega Ap); <r,r0*> ----
     {
-      const real alpha = s_st.alpha, beta = s_st.beta, omega = s_st.omega;
-      real acc[1] = {0.0};
-      const long long npairs = aligned16(x, p, s, r, As, Ap, r0) ? (n >> 1) : 0;
-      for (long long i = tid0; i < npairs; i += nthr)
-      {
-        const long long k = i * 2;
-        real2 vx = ld2(x, k), vp = ld2(p, k); const real2 vs = ld2(s, k), vAs = ld2(As, k), vAp = ld2(Ap, k), v0 = ld2(r0, k);
-        real2 vr;
-        vx.x += alpha * vp.x + omega * vs.x;             vx.y += alpha * vp.y + omega * vs.y;
-        vr.x = fma(-omega, vAs.x, vs.x);                 vr.y = fma(-omega, vAs.y, vs.y);
-        vp.x = fma(beta, fma(-omega, vAp.x, vp.x), vr.x); vp.y = fma(beta, fma(-omega, vAp.y, vp.y), vr.y);
-        acc[0] = fma(vr.x, v0.x, acc[0]);                acc[0] = fma(vr.y, v0.y, acc[0]);
-        st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
-      }
-      for (long long k = 2 * npairs + tid0; k < n; k += nthr)
-      {
-        real vp = p[k]; const real vs = s[k];
-        x[k] += alpha * vp + omega * vs;
-        const real vr = fma(-omega, As[k], vs);
-        vp = fma(beta, fma(-omega, Ap[k], vp), vr);
-        acc[0] = fma(vr, r0[k], acc[0]);
-        r[k] = vr; p[k] = vp;
-      }
+      real acc[1] = {bicgstab_update_entries(n, x, p, s, r, As, Ap, r0, s_st.alpha, s_st.beta, s_st.omega)};
       block_sum<1>(acc, s_sum);
       if (threadIdx.x == 0) part_rr0[blockIdx.x] = acc[0];
     }
