@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FACADE = os.path.join(ROOT, "viennacl-dev_b200", "lib", "facade")
-PROGS = ["sparse_prod", "iterative", "wrap_cuda_buffer", "matrix_free", "matrix_market", "sparse_prod_float", "iterative_float"]
+PROGS = ["sparse_prod", "iterative", "wrap_cuda_buffer", "matrix_free", "matrix_market", "api_surface", "sparse_prod_float", "iterative_float"]
 
 
 def _build():

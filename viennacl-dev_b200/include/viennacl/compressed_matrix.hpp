@@ -8,6 +8,7 @@
 #include <map>
 #include "viennacl/forwards.h"
 #include "viennacl/vector.hpp"
+#include "viennacl/tools/adapter.hpp"
 
 namespace viennacl
 {
@@ -91,6 +92,85 @@ public:
   handle_type & handle() { return elements_; }
 
   viennacl::memory_types memory_context() const { return CUDA_MEMORY; }
+  /** @brief compressed_matrix.hpp:1120-1141; this build has one memory domain, anything else is refused loudly */
+  void switch_memory_context(viennacl::context new_ctx) { check_ctx(new_ctx); }
+
+  /** @brief Read access to entry (i, j); 0 if it is not stored (compressed_matrix.hpp:1013-1040).  One small D2H per call. */
+  NumericT operator()(vcl_size_t i, vcl_size_t j) const
+  {
+    assert(i < rows_ && j < cols_ && bool("index out of bounds"));
+    unsigned int rp[2];
+    backend::memory_read(row_buffer_, sizeof(unsigned int) * i, sizeof(unsigned int) * 2, rp);
+    const vcl_size_t len = rp[1] - rp[0];
+    if (len == 0) return NumericT(0);
+    std::vector<unsigned int> ci(len);
+    backend::memory_read(col_buffer_, sizeof(unsigned int) * rp[0], sizeof(unsigned int) * len, &ci[0]);
+    for (vcl_size_t k = 0; k < len; ++k)
+      if (ci[k] == j)
+      {
+        NumericT v;
+        backend::memory_read(elements_, sizeof(NumericT) * (rp[0] + k), sizeof(NumericT), &v);
+        return v;
+      }
+    return NumericT(0);
+  }
+
+  /** @brief Writes entry (i, j), inserting it if it is not stored yet (the entry_proxy assignment of compressed_matrix.hpp:
+   *  1013-1100; an insertion rebuilds the arrays, exactly as costly as in the reference). */
+  void set_entry(vcl_size_t i, vcl_size_t j, NumericT value)
+  {
+    assert(i < rows_ && j < cols_ && bool("index out of bounds"));
+    std::vector<unsigned int> rp(rows_ + 1), ci(nonzeros_ ? nonzeros_ : 1);
+    std::vector<NumericT> va(nonzeros_ ? nonzeros_ : 1);
+    backend::memory_read(row_buffer_, 0, sizeof(unsigned int) * rp.size(), &rp[0]);
+    if (nonzeros_ > 0)
+    {
+      backend::memory_read(col_buffer_, 0, sizeof(unsigned int) * nonzeros_, &ci[0]);
+      backend::memory_read(elements_, 0, sizeof(NumericT) * nonzeros_, &va[0]);
+    }
+    unsigned int k = rp[i];
+    while (k < rp[i + 1] && ci[k] < j) ++k;
+    if (k < rp[i + 1] && ci[k] == j)
+    {
+      backend::memory_write(elements_, sizeof(NumericT) * k, sizeof(NumericT), &value);
+      return;
+    }
+    ci.resize(nonzeros_); va.resize(nonzeros_);
+    ci.insert(ci.begin() + k, static_cast<unsigned int>(j));
+    va.insert(va.begin() + k, value);
+    for (vcl_size_t r = i + 1; r <= rows_; ++r) rp[r] += 1;
+    set(&rp[0], &ci[0], &va[0], rows_, cols_, nonzeros_ + 1);
+  }
+
+  /** @brief Resizes the matrix (compressed_matrix.hpp:946-1010): entries outside the new shape are dropped when `preserve`,
+   *  otherwise the matrix is emptied. */
+  void resize(vcl_size_t new_size1, vcl_size_t new_size2, bool preserve = true)
+  {
+    assert(new_size1 > 0 && new_size2 > 0 && bool("Cannot resize to zero size!"));
+    std::vector<unsigned int> rp(rows_ + 1, 0u), ci(nonzeros_ ? nonzeros_ : 1);
+    std::vector<NumericT> va(nonzeros_ ? nonzeros_ : 1);
+    if (preserve && rows_ > 0)
+    {
+      backend::memory_read(row_buffer_, 0, sizeof(unsigned int) * rp.size(), &rp[0]);
+      if (nonzeros_ > 0)
+      {
+        backend::memory_read(col_buffer_, 0, sizeof(unsigned int) * nonzeros_, &ci[0]);
+        backend::memory_read(elements_, 0, sizeof(NumericT) * nonzeros_, &va[0]);
+      }
+    }
+    std::vector<unsigned int> nrp(new_size1 + 1, 0u), nci;
+    std::vector<NumericT> nva;
+    for (vcl_size_t r = 0; r < new_size1; ++r)
+    {
+      if (preserve && r < rows_)
+        for (unsigned int k = rp[r]; k < rp[r + 1]; ++k)
+          if (ci[k] < new_size2) { nci.push_back(ci[k]); nva.push_back(va[k]); }
+      nrp[r + 1] = static_cast<unsigned int>(nci.size());
+    }
+    const vcl_size_t nnz = nci.size();
+    if (nci.empty()) { nci.push_back(0u); nva.push_back(NumericT(0)); }
+    set(&nrp[0], &nci[0], &nva[0], new_size1, new_size2, nnz);
+  }
 
   /** @brief The raw-array view the C-ABI takes */
   typename viennacl::backend::b200::abi<NumericT>::csr abi() const
@@ -119,6 +199,22 @@ private:
   vcl_size_t rows_, cols_, nonzeros_, row_block_num_;
   handle_type row_buffer_, row_blocks_, col_buffer_, elements_;
 };
+
+template<typename IndexT, typename NumericT, unsigned int AlignmentV>
+void copy(std::vector< std::map<IndexT, NumericT> > const & cpu_matrix, compressed_matrix<NumericT, AlignmentV> & gpu_matrix);
+
+/** @brief tools::(const_)sparse_matrix_adapter -> device CSR (the generic CPUMatrixT overload of compressed_matrix.hpp:49-105
+ *  for the adapter of tools/adapter.hpp); the adapter's dimensions are kept */
+template<typename NumericT, typename SizeT, unsigned int AlignmentV>
+void copy(tools::const_sparse_matrix_adapter<NumericT, SizeT> const & cpu_matrix, compressed_matrix<NumericT, AlignmentV> & gpu_matrix)
+{
+  viennacl::copy(cpu_matrix.get(), gpu_matrix);
+  if (gpu_matrix.size1() != cpu_matrix.size1() || gpu_matrix.size2() != cpu_matrix.size2())
+    gpu_matrix.resize(cpu_matrix.size1(), cpu_matrix.size2(), true);
+}
+template<typename NumericT, typename SizeT, unsigned int AlignmentV>
+void copy(tools::sparse_matrix_adapter<NumericT, SizeT> const & cpu_matrix, compressed_matrix<NumericT, AlignmentV> & gpu_matrix)
+{ viennacl::copy(static_cast<tools::const_sparse_matrix_adapter<NumericT, SizeT> const &>(cpu_matrix), gpu_matrix); }
 
 /** @brief Host (vector of maps) -> device CSR (compressed_matrix.hpp:190-218); cols = max column + 1 unless the matrix was sized */
 template<typename IndexT, typename NumericT, unsigned int AlignmentV>

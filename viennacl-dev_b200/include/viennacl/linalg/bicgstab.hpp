@@ -201,4 +201,5 @@ private:
 
 }
 }
+#include "viennacl/linalg/stl_solve.hpp"
 #endif

@@ -191,4 +191,5 @@ private:
 
 }
 }
+#include "viennacl/linalg/stl_solve.hpp"
 #endif

@@ -239,4 +239,5 @@ private:
 
 }
 }
+#include "viennacl/linalg/stl_solve.hpp"
 #endif

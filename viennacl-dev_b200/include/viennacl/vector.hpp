@@ -56,6 +56,21 @@ private:
   vcl_size_t size_; NumericT value_; viennacl::context ctx_;
 };
 
+/** @brief Unit vector e_index of the given size (detail/vector_def.hpp:60-74) */
+template<typename NumericT>
+class unit_vector
+{
+public:
+  unit_vector(vcl_size_t s, vcl_size_t ind, viennacl::context ctx = viennacl::context()) : size_(s), index_(ind), ctx_(ctx)
+  { assert(ind < s && bool("Provided index out of range!")); }
+  vcl_size_t size() const { return size_; }
+  vcl_size_t index() const { return index_; }
+  viennacl::context context() const { return ctx_; }
+private:
+  vcl_size_t size_, index_;
+  viennacl::context ctx_;
+};
+
 template<typename NumericT>
 class zero_vector : public scalar_vector<NumericT>
 {
@@ -254,6 +269,15 @@ public:
     return *this;
   }
 
+  vector_base & operator=(unit_vector<NumericT> const & v)
+  {
+    ensure_size(v.size());
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::assign(backend::b200::handle(), int(size_), ptr(), int(start_), int(stride_), NumericT(0)));
+    const NumericT one = NumericT(1);
+    backend::memory_write(elements_, sizeof(NumericT) * (start_ + v.index() * stride_), sizeof(NumericT), &one);
+    return *this;
+  }
+
   // ---- queries ----
   size_type size() const { return size_; }
   size_type internal_size() const { return internal_size_; }
@@ -382,6 +406,7 @@ public:
   vector(detail::lincomb<NumericT> const & e) : base_type() { base_type::operator=(e); }
   vector(scalar_vector<NumericT> const & v) : base_type(v.size(), v.context()) { if (v.value() != NumericT(0)) base_type::operator=(v); }
   vector(zero_vector<NumericT> const & v) : base_type(v.size(), v.context()) {}
+  vector(unit_vector<NumericT> const & v) : base_type(v.size(), v.context()) { base_type::operator=(v); }
   template<typename MatrixT> vector(detail::matvec_expr<MatrixT, NumericT> const & e) : base_type() { base_type::operator=(e); }
   template<typename MatrixT> vector(detail::vec_matvec_expr<MatrixT, NumericT> const & e) : base_type() { base_type::operator=(e); }
 
@@ -526,6 +551,29 @@ template<typename NumericT, typename CPUVectorT>
 void copy(CPUVectorT const & cpu_vec, vector_base<NumericT> & gpu_vec) { viennacl::copy(cpu_vec.begin(), cpu_vec.end(), gpu_vec.begin()); }
 template<typename NumericT, typename CPUVectorT>
 void copy(vector_base<NumericT> const & gpu_vec, CPUVectorT & cpu_vec) { viennacl::copy(gpu_vec.begin(), gpu_vec.end(), cpu_vec.begin()); }
+
+/** @brief async_copy (vector.hpp:1276-1312, :1400-1440): the transfer is enqueued on the backend's stream and NOT waited for; the
+ *  host range must stay valid (and, device -> host, unread) until backend::finish().  Contiguous ranges only. */
+template<typename NumericT, typename CPUIt>
+void async_copy(CPUIt const & cpu_begin, CPUIt const & cpu_end, vector_iterator<NumericT> gpu_begin)
+{
+  vcl_size_t n = vcl_size_t(cpu_end - cpu_begin);
+  if (n == 0) return;
+  assert(gpu_begin.stride() == 1 && bool("async_copy needs a contiguous device range"));
+  backend::memory_write(const_cast<backend::mem_handle &>(gpu_begin.handle()), sizeof(NumericT) * gpu_begin.offset(), sizeof(NumericT) * n, &(*cpu_begin), true);
+}
+template<typename NumericT, typename CPUIt>
+void async_copy(vector_iterator<NumericT> const & gpu_begin, vector_iterator<NumericT> const & gpu_end, CPUIt cpu_begin)
+{
+  vcl_size_t n = vcl_size_t(gpu_end - gpu_begin);
+  if (n == 0) return;
+  assert(gpu_begin.stride() == 1 && bool("async_copy needs a contiguous device range"));
+  backend::memory_read(gpu_begin.handle(), sizeof(NumericT) * gpu_begin.offset(), sizeof(NumericT) * n, &(*cpu_begin), true);
+}
+template<typename NumericT, typename CPUVectorT>
+void async_copy(CPUVectorT const & cpu_vec, vector_base<NumericT> & gpu_vec) { viennacl::async_copy(cpu_vec.begin(), cpu_vec.end(), gpu_vec.begin()); }
+template<typename NumericT, typename CPUVectorT>
+void async_copy(vector_base<NumericT> const & gpu_vec, CPUVectorT & cpu_vec) { viennacl::async_copy(gpu_vec.begin(), gpu_vec.end(), cpu_vec.begin()); }
 
 namespace traits
 {
