@@ -47,6 +47,29 @@ def test_facade_program_passes_on_gpu(prog):
     assert "COMPLETED SUCCESSFULLY" in r.stdout
 
 
+@pytest.mark.gpu
+def test_plain_c_example_passes_on_gpu():
+    """examples/c_api_cg.c: the C-ABI used from C99 (gcc -std=c99 -pedantic), double and float entry points."""
+    exe = os.path.join(FACADE, "c_api_cg")
+    if not os.access(exe, os.X_OK):
+        _build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:]); print(r.stderr[-2000:])
+    assert r.returncode == 0 and "C EXAMPLE COMPLETED SUCCESSFULLY" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_plain_c_example_builds_and_refuses_without_device(pkg):
+    import torch
+    if not pkg.library_available():
+        pkg.build_library()
+    _build()
+    exe = os.path.join(FACADE, "c_api_cg")
+    assert os.access(exe, os.X_OK)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
 def test_matrix_market_host_parsing(pkg):
     """viennacl/io/matrix_market.hpp is host code: general / symmetric / pattern headers, index bases, malformed input."""
     if not pkg.library_available():
