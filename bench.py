@@ -26,6 +26,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from bench_workloads import WORKLOAD_SPMV, WORKLOAD_CG512, spmv_config      # noqa: E402  (shared by both arms)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -81,9 +82,31 @@ def dist_env():
 
 
 # --------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """Host threads this process may use.  NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def ref_solve_c1(r, o, kind):
+    """BASELINE configs[0] end to end on the host: solve(A, b, cg_tag(1e-8)) with host b in, host x out (examples/benchmarks/solver.cpp:106-120)."""
+    A = o.stencil2d(1024, 1024)
+    b = np.ones(A.rows)
+    if kind == "reference":
+        r.solve("cg", A, b, tol=1e-8, maxit=20)
+        res = r.solve("cg", A, b, tol=1e-8, maxit=5000)
+        sec = res["seconds"]
+    else:
+        t0 = time.perf_counter(); res = o.cg(A, b, tol=1e-8, maxit=5000); sec = time.perf_counter() - t0
+    return {"workload": "solve(cg_tag(1e-8)) lap2d 1024^2, host b -> host x", "solve_ms": sec * 1e3, "iterations": int(res["iters"]),
+            "iterations_per_sec": res["iters"] / sec, "error": float(res["error"])}
+
+
 def run_reference(args):
     """--impl reference: the reference's own OpenMP host backend (oracle/_ref, compiled from /root/reference) timed on the
-    host cores on the SAME workload/metric; rank 0 only."""
+    host cores on the SAME workload / metric / config as the GPU arm, all host threads; rank 0 only."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -92,11 +115,13 @@ def run_reference(args):
     o = ol.oracle()
     kind = "reference" if ol.have_ref() else "port"
     r = ol.ref() if kind == "reference" else o
-    cores = r.max_threads()
-    r.set_threads(cores); o.set_threads(cores)
+    cores = host_cores()
+    o.set_threads(cores); r.set_threads(cores)
     n1 = 256
+    ngpu = max(1, args.gpus)
     if args.workload == "spmv":
-        A = o.stencil3d(n1, n1, n1)
+        # weak scaling: the GPU arm's matrix at N GPUs is the 256 x 256 x (256 N) grid -- the CPU arm runs the same matrix
+        A = o.stencil3d(n1, n1, n1 * ngpu)
         x = o.uniform(A.cols, 1, 1.0, 2.0)
         steps, warm = max(1, args.steps), max(1, args.warmup)
         if kind == "reference":
@@ -112,30 +137,34 @@ def run_reference(args):
             sec = time.perf_counter() - t0
         nbytes = 12 * A.nnz + 20 * A.rows
         val = nbytes * steps / sec / 1e9
+        cfg = spmv_config(n1, ngpu)
+        assert cfg["rows"] == A.rows and cfg["nnz"] == A.nnz
+        cfg["note"] = "reference OpenMP host backend (viennacl/linalg/host_based), %d host threads, the whole %dx%dx%d matrix of the GPU arm" % (cores, n1, n1, n1 * ngpu)
         line = {"metric": "spmv_effective_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": sec / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "impl": "reference",
-                "config": {"workload": "csr_spmv_lap3d_7pt_256^3", "rows": A.rows, "nnz": A.nnz, "format": "CSR", "index": "u32",
-                           "note": "reference OpenMP host backend (viennacl/linalg/host_based), all host threads, same matrix/vector as the GPU arm (per-GPU slab; the CPU arm does not grow with N)"},
-                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind, "sample": "%d SpMV passes over the full 256^3 matrix" % steps},
+                "data": "synthetic", "impl": "reference", "config": cfg,
+                "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind,
+                                 "sample": "%d SpMV passes over the full %dx%dx%d matrix" % (steps, n1, n1, n1 * ngpu)},
                 "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if ngpu == 1 and not args.no_extras:
+            line["e2e_solve"] = ref_solve_c1(r, o, kind)
     else:
-        # CG on 512^3 needs ~12 GB of host CSR and minutes per iteration budget: bounded sample = 256^3, fixed iterations
-        A = o.stencil3d(n1, n1, n1)
+        # BASELINE configs[4] for real: pipelined CG on the 512^3 Laplacian (11.3 GB of host CSR), a bounded number of iterations
+        A = o.stencil3d(512, 512, 512)
         b = np.ones(A.rows)
         its = max(2, min(args.steps, 20))
-        res = r.solve("cg", A, b, tol=0.0, maxit=its) if kind == "reference" else None
-        if res is None:
-            t0 = time.perf_counter(); o.cg(A, b, tol=0.0, maxit=its); sec = time.perf_counter() - t0
+        if kind == "reference":
+            res = r.solve("cg", A, b, tol=0.0, maxit=its)
+            sec, done = res["seconds"], res["iters"]
         else:
-            sec = res["seconds"]
-        # scale to the 512^3 problem by bytes per iteration (8x rows/nnz): iterations/s on the full workload
-        val = its / sec / 8.0
-        line = {"metric": "cg_iterations_per_sec", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": its, "warmup": 0,
+            t0 = time.perf_counter(); res = o.cg(A, b, tol=0.0, maxit=its); sec = time.perf_counter() - t0; done = res["iters"]
+        val = done / sec
+        line = {"metric": "cg_iterations_per_sec", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": done, "warmup": 0,
                 "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "reference",
-                "config": {"workload": "cg_lap3d_7pt_512^3", "note": "bounded sample: %d CG iterations on the 256^3 Laplacian, scaled by the 8x byte ratio to 512^3" % its},
-                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": kind, "sample": "%d iterations on 256^3, x1/8" % its},
+                "config": {"workload": WORKLOAD_CG512, "rows": A.rows, "nnz": A.nnz,
+                           "note": "reference pipelined CG (cg.hpp:128-187, OpenMP host backend, %d threads) on the full 512^3 system, %d iterations incl. set-up" % (cores, done)},
+                "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": kind, "sample": "%d CG iterations on the full 512^3 system" % done},
                 "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -147,7 +176,7 @@ def cpu_baseline_spmv(n1, reps=10):
     import oracle_lib as ol
     o = ol.oracle()
     kind = "reference" if ol.have_ref() else "port"
-    cores = o.max_threads()
+    cores = host_cores()
     o.set_threads(cores)
     A = o.stencil3d(n1, n1, n1)
     x = o.uniform(A.cols, 1, 1.0, 2.0)
@@ -174,7 +203,7 @@ def cpu_baseline_cg(n1=1024, iters=200):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     o = ol.oracle()
-    cores = o.max_threads()
+    cores = host_cores()
     o.set_threads(cores)
     A = o.stencil2d(n1, n1)
     b = np.ones(A.rows)
@@ -190,6 +219,45 @@ def cpu_baseline_cg(n1=1024, iters=200):
         sec, its, kind = time.perf_counter() - t0, res["iters"], "port"
     return {"iterations_per_sec": its / sec, "iterations": its, "cores": cores, "kind": kind,
             "sample": "%d pipelined CG iterations on the %dx%d Laplacian (reference cg.hpp, OpenMP host backend)" % (its, n1, n1)}
+
+
+def legacy_cuda_baseline(n1=256):
+    """SECOND baseline (rank 0, N = 1): the reference's OWN CUDA backend (viennacl/linalg/cuda/*, unmodified, compiled for sm_100
+    by oracle/Makefile -> oracle/_ref/libvcl_ref_cuda.so) on the same GPU and the same matrices.  Every result is first checked
+    against the reference host backend / the oracle (check K1's output before trusting it as a baseline)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    rc = ol.ref_cuda()
+    if rc is None:
+        return {"unavailable": "oracle/_ref/libvcl_ref_cuda.so not built or no GPU visible to it"}
+    o = ol.oracle()
+    o.set_threads(host_cores())
+    out = {"what": "unmodified viennacl CUDA backend (cuda/sparse_matrix_operations.hpp, cuda/iterative_operations.hpp), nvcc -arch=sm_100, same GPU"}
+    A = o.stencil3d(n1, n1, n1)
+    x = o.uniform(A.cols, 1, 1.0, 2.0)
+    y_ref = o.csr_spmv(A, x)
+    nbytes = 12 * A.nnz + 20 * A.rows
+    for fmt in ("csr", "sell"):
+        try:
+            reps = 20
+            y, sec = rc.spmv(A, x, reps=reps, fmt=fmt)
+            err = float(ol.rel_err(y, y_ref).max())
+            out[fmt + "_spmv_256"] = {"ms_per_step": sec / reps * 1e3, "effective_GBps": nbytes * reps / sec / 1e9, "max_rel_err_vs_oracle": err,
+                                      "correct": bool(err <= 1e-12)}
+        except Exception as e:                                  # a crash of the legacy kernels must not take the bench line down
+            out[fmt + "_spmv_256"] = {"failed": str(e)[:200]}
+    del A, x, y_ref
+    try:
+        A = o.stencil2d(1024, 1024)
+        b = np.ones(A.rows)
+        rc.solve("cg", A, b, tol=1e-8, maxit=50)
+        res = rc.solve("cg", A, b, tol=1e-8, maxit=5000)
+        true = float(np.linalg.norm(b - o.csr_spmv(A, res["x"])) / np.linalg.norm(b))
+        out["cg_lap2d_1024"] = {"iterations": res["iters"], "solve_ms": res["seconds"] * 1e3, "iterations_per_sec": res["iters"] / res["seconds"],
+                                "error": res["error"], "true_residual": true, "correct": bool(true < 1e-7)}
+    except Exception as e:
+        out["cg_lap2d_1024"] = {"failed": str(e)[:200]}
+    return out
 
 
 def main():
@@ -257,6 +325,11 @@ def main():
             line["cpu_baseline"] = cpu_baseline_spmv(n1)
             if not args.no_extras and line.get("cg") and "lap2d_1024" in line["cg"]:
                 line["cg"]["lap2d_1024"]["cpu_baseline"] = cpu_baseline_cg()
+            if not args.no_extras:
+                line["legacy_cuda_baseline"] = legacy_cuda_baseline(n1)
+                lc = line["legacy_cuda_baseline"].get("csr_spmv_256", {})
+                if lc.get("effective_GBps"):
+                    line["legacy_cuda_baseline"]["ratio_csr_spmv"] = line["value"] / lc["effective_GBps"]
     else:
         import bench_workloads as bw
         line = bw.cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler, peak, peak_src)

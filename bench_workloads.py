@@ -9,6 +9,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
+WORKLOAD_SPMV = "csr_spmv_lap3d_7pt_256^3_per_gpu"
+WORKLOAD_CG512 = "cg_lap3d_7pt_512^3"
+
+
+def spmv_config(n1, world):
+    """The part of `config` both arms share (same workload, same matrix: the 7-point Laplacian on the n1 x n1 x (n1*world) grid)."""
+    nx, ny, nz = n1, n1, n1 * world
+    rows = nx * ny * nz
+    return {"workload": WORKLOAD_SPMV, "grid": [nx, ny, nz], "rows": rows, "nnz": 7 * rows - 2 * (nx * ny + ny * nz + nx * nz),
+            "rows_per_gpu": rows // world, "format": "CSR (u32 indices)"}
+
+
 def _traffic_from_profiles(kernel_key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/ncu_traffic.json)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -44,6 +56,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
         D = None
         step = lambda: A.spmv(x, y)
     nbytes = 12 * A.nnz + 20 * n                      # SURVEY 8d, per rank (halo planes not counted)
+    parity = spmv_parity(pkg, be, A, D, x, y, rb, global_rows, world)
 
     sampler.start()
     for _ in range(args.warmup):
@@ -112,19 +125,23 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
 
     if rank != 0:
         return None
-    kernel = "csr_stream_kernel<EpiAxpby>"
+    kernel = "csr_stream_kernel<EpiAxpby, SPLIT=%s>" % ("false" if world == 1 else "true")
+    cfg = spmv_config(n1, world)
+    cfg.update({"nnz_rank0": A.nnz, "row_blocks": "<=256 rows / <=2048 nnz", "bytes_per_step_per_gpu": nbytes,
+                "l2_policy": "inputs (1.74 GB per step) are larger than the 126 MB L2; no flush needed",
+                "partition": "none" if world == 1 else "1-D row slabs, NVLink halo of one 256x256 plane per neighbour, pushed by the product kernel itself",
+                "transport": "single GPU" if D is None else D.info()["transport"]})
     return {
         "metric": "spmv_effective_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "csr_spmv_lap3d_7pt_256^3_per_gpu", "grid": [n1, n1, n1 * world], "rows_per_gpu": n, "nnz_per_gpu": A.nnz,
-                   "format": "CSR (u32 indices) row blocks <=256 rows/<=2048 nnz", "bytes_per_step_per_gpu": nbytes,
-                   "l2_policy": "inputs (1.74 GB per step) are larger than the 126 MB L2; no flush needed",
-                   "partition": "none" if world == 1 else "1-D row slabs, NVLink halo of one 256x256 plane per neighbour"},
+        "config": cfg,
+        "parity": parity,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "frac_of_nominal_8TBps": per_gpu / 8000.0, "peak_source": peak_src, "kernel": kernel,
                      "note": "the measured peak is a device copy (half reads, half writes); this kernel reads 13x more than it writes and can exceed it",
-                     "algorithmic_bytes_per_launch": nbytes, "traffic": _traffic_from_profiles("csr_spmv_256")},
+                     "algorithmic_bytes_per_launch": nbytes,
+                     "traffic": _traffic_from_profiles("csr_spmv_256" if world == 1 else "csr_spmv_256_split")},
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "checksum": checksum,
                 "note": "every step: pinned host x -> device, y = prod(A, x) through the C-ABI, y -> pinned host; the matrix stays resident "
@@ -133,6 +150,42 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
         "gpu_launches": int(l1 - l0),
         "clocks": sampler.summary(),
     }
+
+
+def spmv_parity(pkg, be, A, D, x, y, rb, global_rows, world):
+    """Correctness evidence inside the bench line.
+    N > 1: every rank recomputes ITS slab with the plain single-GPU product on a full-length x (slab rows x global columns; x is
+    regenerated in full from the same seed) and compares bit for bit with the row-partitioned product -- halo exchange, column
+    renumbering and the interior/boundary split must not change a single bit.  all ranks must agree (MIN over ranks).
+    N = 1: the product is compared bit for bit with the reference's host backend on a 1M-row window is left to the tests;
+    here the checksum of y is recorded."""
+    import torch
+    n = A.rows
+    out = {}
+    if world > 1:
+        import torch.distributed as dist
+        D.spmv(x, y)
+        xf, yr = be.empty(global_rows), be.zeros(n)
+        be.check(be.L.ViennaCLCUDADfill_uniform(be.h, global_rows, xf.ptr, 1, 0, 1.0, 2.0))
+        A.spmv(xf, yr)                                  # plain csrmv: global column indices, no halo, no renumbering
+        a, b_ = y.download(), yr.download()
+        same = bool(np.array_equal(a, b_))
+        t = torch.tensor([1.0 if same else 0.0, float(np.abs(a - b_).max())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t[0:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(t[1:2], op=dist.ReduceOp.MAX)
+        out["spmv_bitexact"] = bool(t[0].item() == 1.0)
+        out["spmv_max_abs_diff"] = float(t[1].item())
+        out["spmv_check"] = "row-partitioned product == single-GPU csrmv of the slab on the full x, bit for bit, on every rank"
+        xf.free(); yr.free()
+    else:
+        A.spmv(x, y)
+        # the same product through the plan-free kernel (one thread per row, sequential order = the reference's loop)
+        y2 = be.zeros(n)
+        A.spmv(x, y2, use_blocks=False)
+        out["spmv_bitexact"] = bool(np.array_equal(y.download(), y2.download()))
+        out["spmv_check"] = "row-block TMA kernel == plan-free sequential kernel, bit for bit (vs the reference host backend: tests/test_gpu_parity.py)"
+        y2.free()
+    return out
 
 
 def sell_side(pkg, be, args, n1, peak):
@@ -178,10 +231,40 @@ def cg_side(pkg, be, args, rank, world, barrier, max_over_ranks):
         out["lap2d_1024"] = {"iterations_per_sec": its / (ms * 1e-3), "iterations": its, "ms": ms,
                              "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb,
                              "note": "includes solver set-up (3 reductions, state upload); 32 iterations per launch of the persistent cooperative kernel (cg_persistent_kernel); working set ~100 MB"}
+        out["lap2d_1024"]["e2e_solve"] = solve_e2e_c1(pkg, be, A)
         del A, b, x
         out["config3_bicgstab_jacobi_cd3d_256"] = bicgstab_side(pkg, be)
         out["config4_gmres30_cd2d_4096"] = gmres_side(pkg, be)
     out["lap3d_512"] = cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters=100, warm=10)
+    return out
+
+
+def solve_e2e_c1(pkg, be, A):
+    """BASELINE configs[0] end to end through the C-ABI, the way a user of solve() sees it: b in (pinned) HOST memory -> device,
+    CG to 1e-8 (converged, not a fixed budget), x -> host memory; wall clock around the whole thing, synchronised on both sides.
+    The reference arm (`bench.py --impl reference`) reports the same call on the host cores as `e2e_solve`."""
+    n = A.rows
+    hb, hx = C.c_void_p(), C.c_void_p()
+    be.check(be.L.ViennaCLHostAllocPinned(be.h, C.byref(hb), 8 * n))
+    be.check(be.L.ViennaCLHostAllocPinned(be.h, C.byref(hx), 8 * n))
+    np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_double)), shape=(n,))[:] = 1.0
+    db, dx = be.empty(n), be.empty(n)
+    best, tag = None, None
+    for rep in range(3):
+        be.sync()
+        t0 = time.perf_counter()
+        be.check(be.L.ViennaCLCUDAMemWrite(be.h, db.ptr, 0, hb, 8 * n, 1))
+        tag = pkg.SolverTag(tol=1e-8, max_iterations=5000).solve("cg", A, db, dx)
+        be.check(be.L.ViennaCLCUDAMemRead(be.h, dx.ptr, 0, hx, 8 * n, 0))
+        be.sync()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    xs = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(n,))
+    out = {"workload": "solve(cg_tag(1e-8)) lap2d 1024^2, host b -> host x", "solve_ms": best, "iterations": tag.iters,
+           "iterations_per_sec": tag.iters / (best * 1e-3), "error": tag.error, "h2d_bytes": 8 * n, "d2h_bytes": 8 * n,
+           "x_checksum": float(xs[::1024].sum())}
+    be.check(be.L.ViennaCLHostFreePinned(be.h, hb)); be.check(be.L.ViennaCLHostFreePinned(be.h, hx))
+    db.free(); dx.free()
     return out
 
 
@@ -223,6 +306,20 @@ def gmres_side(pkg, be):
             "bytes_per_restart_cycle": per_cycle, "effective_GBps": per_cycle * cycles / (ms * 1e-3) / 1e9}
 
 
+def _global_norm2(be, x, world):
+    """||x|| over all ranks' slabs (device nrm2 per rank, sum of squares over ranks)."""
+    v = C.c_double(0)
+    be.check(be.L.ViennaCLCUDADnrm2(be.h, x.n, C.byref(v), x.ptr, 0, 1))
+    sq = v.value * v.value
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([sq], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        sq = float(t.item())
+    return float(np.sqrt(sq))
+
+
 def cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters, warm):
     n1 = 512
     rows = n1 ** 3
@@ -235,15 +332,33 @@ def cg512_measure(pkg, be, rank, world, barrier, max_over_ranks, iters, warm):
         D = pkg.DistCsr(be, rows, rb, re_, A)
         solve = lambda t: D.cg(b, x, t)
     else:
+        D = None
         solve = lambda t: t.solve("cg", A, b, x)
     _cg_run(pkg, be, solve, warm)
     barrier()
     ms, its = _cg_run(pkg, be, solve, iters)
     barrier()
     ms = max_over_ranks(ms)
+    # ---- parity: (i) the estimate and ||x|| after the fixed budget must not depend on the number of GPUs (compare the lines of the
+    # 1 / 2 / 4 / 8-GPU runs: ~1e-10 relative), (ii) 20 iterations against the UNMODIFIED reference on the full 512^3 system
+    # (tests/golden/baseline_configs.json, case c5_cg_lap3d_512_budget, 1 host thread) ----
+    tag = pkg.SolverTag(tol=0.0, max_iterations=iters)
+    solve(tag)
+    parity = {"iterations": tag.iters, "error_after_budget": tag.error, "x_norm_after_budget": _global_norm2(be, x, world)}
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_configs.json")))["c5_cg_lap3d_512_budget"]
+        tag20 = pkg.SolverTag(tol=g["tol"], max_iterations=g["maxit"])
+        solve(tag20)
+        xn = _global_norm2(be, x, world)
+        parity.update({"ref20_error": g["error"], "error_20it": tag20.error, "error_20it_rel_diff": abs(tag20.error - g["error"]) / g["error"],
+                       "ref20_x_norm": g["x_norm"], "x_norm_20it": xn, "x_norm_20it_rel_diff": abs(xn - g["x_norm"]) / g["x_norm"],
+                       "matches_reference_20it": bool(abs(tag20.error - g["error"]) <= 1e-9 * g["error"] and abs(xn - g["x_norm"]) <= 1e-9 * g["x_norm"])})
+    except (OSError, KeyError):
+        pass
     nb = 12 * (7 * rows - 6 * n1 * n1) + 76 * rows
     return {"iterations_per_sec": its / (ms * 1e-3), "iterations": its, "ms": ms, "n_gpus": world,
-            "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb,
+            "effective_GBps": nb * its / (ms * 1e-3) / 1e9, "bytes_per_iteration": nb, "parity": parity,
+            "transport": "single GPU" if D is None else D.info()["transport"],
             "note": "pipelined CG, fixed %d-iteration budget, b = 1, includes solver set-up" % iters}
 
 
@@ -259,7 +374,7 @@ def cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler,
     return {"metric": "cg_iterations_per_sec", "value": r["iterations_per_sec"], "unit": "it/s", "n_gpus": world, "steps": r["iterations"],
             "warmup": args.warmup, "ms_per_step": r["ms"] / max(r["iterations"], 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cg_lap3d_7pt_512^3", "rows": 512 ** 3, "nnz": 7 * 512 ** 3 - 6 * 512 * 512,
+            "config": {"workload": WORKLOAD_CG512, "rows": 512 ** 3, "nnz": 7 * 512 ** 3 - 6 * 512 * 512,
                        "partition": "none" if world == 1 else "1-D row slabs, halo + 3-scalar allreduce per iteration",
                        "l2_policy": "21.5 GB per iteration, larger than L2"},
             "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,

@@ -56,6 +56,13 @@ ViennaCLStatus ViennaCLBackendTimerBegin(ViennaCLBackend backend);
 ViennaCLStatus ViennaCLBackendTimerEnd(ViennaCLBackend backend, double *milliseconds);
 /* Writes a scratch buffer larger than L2 so that the next timed call starts cold. */
 ViennaCLStatus ViennaCLBackendFlushL2(ViennaCLBackend backend);
+/* Per-handle tuning knobs (all have working defaults):
+ *   "persistent_rows"  largest system (rows) solved by the persistent cooperative kernels (whole CG / BiCGStab iterations and
+ *                      GMRES cycles inside one launch); larger systems take the multi-kernel drivers.  -1: built-in default
+ *                      (10M rows; env VCL_B200_PERSISTENT_ROWS at handle creation), 0: always multi-kernel.
+ *   "l2_resident"      persistent kernels keep a matrix that fits L2 resident there (evict-last) instead of streaming it
+ *                      (evict-first): -1 auto by working-set size, 0 never, 1 always. */
+ViennaCLStatus ViennaCLBackendSetOption(ViennaCLBackend backend, const char *name, long long value);
 /* Counts kernels launched by this library on this handle since creation (bench.py's gpu_launches). */
 ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend backend, long long *launches);
 

@@ -1,0 +1,41 @@
+"""Generates tests/golden/bicgstab_spread.json: how far the UNMODIFIED reference's own BiCGStab iteration counts move when only
+the ORDER of its inner-product summation changes (OpenMP thread count 1 / 2 / 4 / 8 -> different partial-sum grouping,
+host_based/vector_operations.hpp:463-472), on BASELINE config 3 (3-D upwind convection-diffusion 256^3, b = 1, tol 1e-8).
+BiCGStab is not backward stable with respect to such perturbations; this file is the measured yardstick the
+GPU tests use for the pipelined variant instead of a fixed +-2.
+
+    python tests/golden/make_golden_spread.py        (build container only; ~15 minutes)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib as ol  # noqa: E402
+
+
+def main():
+    o = ol.oracle(); r = ol.ref()
+    out = {}
+    for grid, c in (((256, 256, 256), (0.5, 0.25, 0.125)), ((128, 128, 128), (0.5, 0.25, 0.125))):
+        o.set_threads(8)
+        A = o.stencil3d(*grid, *c); b = np.ones(A.rows)
+        for pre in ("none", "jacobi"):
+            key = "cd3d_%d_%s" % (grid[0], "pipelined" if pre == "none" else "jacobi")
+            out[key] = {}
+            for t in (1, 2, 4, 8):
+                r.set_threads(t)
+                res = r.solve("bicgstab", A, b, precond=pre, tol=1e-8, maxit=2000, hist_cap=2000)
+                o.set_threads(8)
+                true = float(np.linalg.norm(b - o.csr_spmv(A, res["x"])) / np.linalg.norm(b))
+                out[key][str(t)] = dict(iters=int(res["iters"]), error=float(res["error"]), true_residual=true,
+                                        history_every_25=[float(v) for v in res["history"][::25]])
+                print(key, t, out[key][str(t)]["iters"], res["error"], true, flush=True)
+                json.dump(out, open(os.path.join(HERE, "bicgstab_spread.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -413,7 +413,52 @@ class _Ref:
         return self.lib.vclref_time_csr_spmv(A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, x, y, reps)
 
 
+class _RefCuda:
+    """The reference's OWN CUDA backend compiled for sm_100 (oracle/ref_cuda_shim.cu): bench.py's `legacy_cuda_baseline`."""
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "_ref", "libvcl_ref_cuda.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = lib = C.CDLL(path)
+        ip, dp = C.POINTER(c_int), C.POINTER(c_dbl)
+        lib.vclrefcuda_available.restype = c_int
+        lib.vclrefcuda_spmv.argtypes = [c_int, c_int, c_int, c_int, u32p, u32p, f64p, f64p, f64p, c_int, dp]
+        lib.vclrefcuda_solve.argtypes = [c_int, c_int, c_int, c_int, u32p, u32p, f64p, f64p, f64p, c_dbl, c_int, c_int, ip, dp, dp]
+
+    def available(self):
+        return bool(self.lib.vclrefcuda_available())
+
+    def spmv(self, A, x, reps=10, fmt="csr"):
+        y = np.zeros(A.rows)
+        sec = c_dbl(0)
+        rc = self.lib.vclrefcuda_spmv(0 if fmt == "csr" else 1, A.rows, A.cols, A.nnz, A.rp, A.ci, A.v, np.ascontiguousarray(x), y, reps, C.byref(sec))
+        if rc != 0:
+            raise RuntimeError("vclrefcuda_spmv rc=%d" % rc)
+        return y, sec.value
+
+    def solve(self, solver, A, b, precond="none", tol=1e-8, maxit=300, krylov=20):
+        x = np.zeros(A.rows)
+        it, err, sec = c_int(0), c_dbl(0), c_dbl(0)
+        rc = self.lib.vclrefcuda_solve(_Ref.SOLVERS[solver], 1 if precond == "jacobi" else 0, A.rows, A.nnz, A.rp, A.ci, A.v,
+                                       np.ascontiguousarray(b), x, tol, maxit, krylov, C.byref(it), C.byref(err), C.byref(sec))
+        if rc != 0:
+            raise RuntimeError("vclrefcuda_solve rc=%d" % rc)
+        return dict(x=x, iters=it.value, error=err.value, seconds=sec.value)
+
+
 _cache = {}
+
+
+def ref_cuda():
+    """None when the shim is not built or no GPU is visible."""
+    if "rc" not in _cache:
+        try:
+            r = _RefCuda()
+            _cache["rc"] = r if r.available() else None
+        except (FileNotFoundError, OSError):
+            _cache["rc"] = None
+    return _cache["rc"]
 
 
 def oracle(dtype=np.float64):

@@ -1,0 +1,198 @@
+"""Parity AT SIZE on the BASELINE.json configurations (run with -m gpu on a B200).
+
+Golden values: tests/golden/baseline_configs.json, produced by tests/golden/make_golden_configs.py from the UNMODIFIED reference
+(OpenMP host backend, one thread) -- iteration counts, error estimates, true residuals and a strided sample of x for
+  C1  CG, 2-D Laplacian 1024^2                                         (cg.hpp:128-187)
+  C2  CG, 3-D Laplacian 256^3, fixed budget of 20 iterations
+  C3  BiCGStab + Jacobi and pipelined BiCGStab, convection-diffusion 256^3   (bicgstab.hpp:398-489 / :97-215)
+  C4  GMRES(30), convection-diffusion 512^2 (the reduced grid SURVEY 8d prescribes) and 4096^2 with a 60-iteration budget
+  C5  CG, 3-D Laplacian 512^3, fixed budget of 20 iterations; 128^3 to convergence
+Every solver test runs twice: through the persistent cooperative kernels (the default for systems of that size) and with
+option "persistent_rows" = 0, i.e. through the multi-kernel CSR drivers that bench.py times at 256^3 / 512^3 / 4096^2.
+Measured deltas are appended to gpurun_out/parity_deltas.jsonl (copied to profiles/ for the record).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_configs.json")))
+SPREAD = json.load(open(os.path.join(ROOT, "tests", "golden", "bicgstab_spread.json")))
+DRIVERS = ["persistent", "multikernel"]
+
+
+def note(**kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_deltas.jsonl"), "a") as f:
+        f.write(json.dumps(kw) + "\n")
+
+
+@pytest.fixture
+def driver(request, be):
+    be.set_option("persistent_rows", -1 if request.param == "persistent" else 0)
+    yield request.param
+    be.set_option("persistent_rows", -1)
+
+
+def sample(dx, g):
+    """The entries of x the golden file keeps (stride g['x_sample_stride'], 1024 of them)."""
+    n, s = g["rows"], g["x_sample_stride"]
+    idx = np.arange(1024, dtype=np.int64) * s + s // 2
+    return dx.download()[idx]
+
+
+def true_residual(be, A, db, dx):
+    """||b - A x|| / ||b|| on the device through the C-ABI (csrmv, avbv, nrm2)."""
+    n = A.rows
+    dr = be.empty(n)
+    A.spmv(dx, dr)
+    be.check(be.L.ViennaCLCUDADavbv(be.h, n, dr.ptr, 0, 1, db.ptr, 0, 1, 1.0, dr.ptr, 0, 1, -1.0))
+    nr, nb = C.c_double(0), C.c_double(0)
+    be.check(be.L.ViennaCLCUDADnrm2(be.h, n, C.byref(nr), dr.ptr, 0, 1))
+    be.check(be.L.ViennaCLCUDADnrm2(be.h, n, C.byref(nb), db.ptr, 0, 1))
+    dr.free()
+    return nr.value / nb.value
+
+
+def solve_case(pkg, be, key, solver, **tagkw):
+    g = GOLD[key]
+    nx, ny, nz = g["grid"]
+    A = pkg.CsrMatrix.stencil(be, nx, ny, nz, *g["c"])
+    assert A.rows == g["rows"] and A.nnz == g["nnz"]
+    db, dx = be.array(np.ones(A.rows)), be.zeros(A.rows)
+    tag = pkg.SolverTag(tol=g["tol"], max_iterations=g["maxit"], **tagkw).solve(solver, A, db, dx)
+    return g, A, db, dx, tag
+
+
+def rel_sample_diff(x, xr):
+    xr = np.asarray(xr)
+    return float(np.linalg.norm(x - xr) / np.linalg.norm(xr))
+
+
+# ------------------------------------------------------------------------------------------------------------------ C1
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+def test_c1_cg_lap2d_1024(pkg, be, driver):
+    g, A, db, dx, tag = solve_case(pkg, be, "c1_cg_lap2d_1024", "cg")
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    tr = true_residual(be, A, db, dx)
+    note(case="c1", driver=driver, iters=tag.iters, ref_iters=g["iters"], error=tag.error, ref_error=g["error"], x_sample_rel=d, true_residual=tr)
+    assert abs(tag.iters - g["iters"]) <= 2
+    assert tag.error < g["tol"] and tr <= g["true_residual"] * (1 + 1e-6) + g["tol"]
+    assert d <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------ C2 / C5 budget
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+@pytest.mark.parametrize("key", ["c2_cg_lap3d_256_budget", "c5_cg_lap3d_512_budget"])
+def test_cg_fixed_budget_at_size(pkg, be, key, driver):
+    """20 CG iterations on 256^3 / 512^3: estimate and iterate agree with the reference to 1e-9 relative."""
+    if key.startswith("c5") and driver == "persistent":
+        pytest.skip("512^3 is above the persistent-kernel row limit: the multi-kernel driver is the only path")
+    g, A, db, dx, tag = solve_case(pkg, be, key, "cg")
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    note(case=key, driver=driver, iters=tag.iters, error=tag.error, ref_error=g["error"], x_sample_rel=d)
+    assert tag.iters == g["iters"] == 20
+    assert abs(tag.error - g["error"]) <= 1e-9 * g["error"]
+    assert d <= 1e-9
+
+
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+def test_c5_cg_lap3d_128_converged(pkg, be, driver):
+    g, A, db, dx, tag = solve_case(pkg, be, "c5_cg_lap3d_128", "cg")
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    tr = true_residual(be, A, db, dx)
+    note(case="c5_128", driver=driver, iters=tag.iters, ref_iters=g["iters"], error=tag.error, x_sample_rel=d, true_residual=tr)
+    assert abs(tag.iters - g["iters"]) <= 2
+    assert tag.error < g["tol"] and tr <= g["true_residual"] * (1 + 1e-6) + g["tol"]
+    assert d <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------ C3
+def test_c3_bicgstab_jacobi_cd3d_256(pkg, be):
+    """BiCGStab + Jacobi at 256^3 (five fused kernels per iteration; there is no persistent form of this driver)."""
+    g, A, db, dx, tag = solve_case(pkg, be, "c3_bicgstab_jacobi_cd3d_256", "bicgstab", precond=1)
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    tr = true_residual(be, A, db, dx)
+    spread = [v["iters"] for v in SPREAD["cd3d_256_jacobi"].values()]
+    note(case="c3_jacobi", iters=tag.iters, ref_iters=g["iters"], ref_spread=spread, error=tag.error, ref_error=g["error"], x_sample_rel=d,
+         true_residual=tr, ref_true_residual=g["true_residual"])
+    assert tag.error < g["tol"]
+    assert tr <= 5 * g["true_residual"]               # the reference's own true residual is 5x its estimate here (recurrence drift)
+    assert d <= 1e-6
+    lo, hi = min(spread + [g["iters"]]), max(spread + [g["iters"]])
+    assert lo - 2 <= tag.iters <= hi + 2, (tag.iters, g["iters"], spread)
+
+
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+def test_c3_bicgstab_pipelined_cd3d_256(pkg, be, driver):
+    """Pipelined BiCGStab at 256^3.  The count of this method depends on the ORDER of the inner-product sums: the reference itself
+    moves by tens of iterations when only its OpenMP thread count changes (tests/golden/bicgstab_spread.json); the bar is
+    therefore the reference's own range (+-2), the same tolerance reached, and the same solution."""
+    g, A, db, dx, tag = solve_case(pkg, be, "c3_bicgstab_pipelined_cd3d_256", "bicgstab")
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    tr = true_residual(be, A, db, dx)
+    spread = [v["iters"] for v in SPREAD["cd3d_256_pipelined"].values()]
+    note(case="c3_pipelined", driver=driver, iters=tag.iters, ref_iters=g["iters"], ref_spread=spread, error=tag.error, ref_error=g["error"],
+         x_sample_rel=d, true_residual=tr, ref_true_residual=g["true_residual"])
+    assert tag.error < g["tol"]
+    assert tr <= 5 * g["true_residual"]
+    assert d <= 1e-6
+    lo, hi = min(spread + [g["iters"]]), max(spread + [g["iters"]])
+    assert lo - 2 <= tag.iters <= hi + 2, (tag.iters, g["iters"], spread)
+
+
+# ------------------------------------------------------------------------------------------------------------------ C4
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+def test_c4_gmres30_cd2d_512(pkg, be, driver):
+    """GMRES(30) on the 512^2 grid: the count equals the fixed reference pipelined path (1110) = ceil(Householder 1085 / 30) * 30."""
+    g, A, db, dx, tag = solve_case(pkg, be, "c4_gmres30_cd2d_512", "gmres", krylov_dim=30)
+    p = g["pipelined_gmresfix"]
+    d = rel_sample_diff(sample(dx, g), p["x_sample"])
+    tr = true_residual(be, A, db, dx)
+    note(case="c4_512", driver=driver, iters=tag.iters, ref_iters_householder=g["iters"], ref_iters_pipelined=p["iters"], error=tag.error,
+         ref_error=p["error"], x_sample_rel=d, true_residual=tr)
+    assert tag.iters == -(-g["iters"] // 30) * 30
+    assert abs(tag.iters - p["iters"]) <= 2
+    assert tag.error < g["tol"] and tr < 2 * g["tol"]
+    assert d <= 1e-6
+
+
+def test_c4_gmres30_cd2d_4096_budget(pkg, be):
+    """Two restart cycles (60 inner iterations) of the multi-kernel GMRES driver on the full 4096^2 grid vs the fixed reference."""
+    g, A, db, dx, tag = solve_case(pkg, be, "c4_gmres30_cd2d_4096_budget", "gmres", krylov_dim=30)
+    d = rel_sample_diff(sample(dx, g), g["x_sample"])
+    note(case="c4_4096_budget", iters=tag.iters, error=tag.error, ref_error=g["error"], x_sample_rel=d)
+    assert tag.iters == g["iters"] == 60
+    assert abs(tag.error - g["error"]) <= 1e-9 * g["error"]
+    assert d <= 1e-8
+
+
+# ------------------------------------------------------------------------------------------------------------------ small goldens, both drivers
+@pytest.mark.parametrize("driver", DRIVERS, indirect=True)
+@pytest.mark.parametrize("name", ["lap2d_63x65", "cd2d_48x50", "cd3d_11x10x9"])
+def test_small_goldens_both_drivers(pkg, be, orc, golden, name, driver):
+    """The golden solver runs of test_gpu_parity.py through BOTH CSR driver forms; deltas recorded per case."""
+    import oracle_lib as ol
+    A = orc.stencil2d(63, 65) if name == "lap2d_63x65" else (orc.stencil2d(48, 50, 0.5, 0.0) if name == "cd2d_48x50"
+                                                             else orc.stencil3d(11, 10, 9, 0.5, 0.25, 0.125))
+    b = np.ones(A.rows)
+    dA = pkg.CsrMatrix.from_host(be, A.rows, A.cols, A.rp, A.ci, A.v)
+    db = be.array(b)
+    runs = [("bicgstab", "bicgstab_none", {}), ("bicgstab", "bicgstab_jacobi", {"precond": 1}), ("gmres", "gmres_pipelined_fixed", {"krylov_dim": 30})]
+    if name.startswith("lap"):
+        runs.insert(0, ("cg", "cg_none", {}))
+    for solver, key, kw in runs:
+        dx = be.array(np.full(A.rows, 123.0))
+        tag = pkg.SolverTag(tol=1e-8, max_iterations=1000, **kw).solve(solver, dA, db, dx)
+        it = int(golden["solve/%s/%s/iters" % (name, key)][0])
+        xr = golden["solve/%s/%s/x" % (name, key)]
+        x = dx.download()
+        note(case="small/%s/%s" % (name, key), driver=driver, iters=tag.iters, ref_iters=it, x_rel=float(np.linalg.norm(x - xr) / np.linalg.norm(xr)))
+        assert abs(tag.iters - it) <= 2, (key, tag.iters, it)
+        assert np.linalg.norm(x - xr) <= 1e-5 * np.linalg.norm(xr)
+        assert tag.error < 1e-8

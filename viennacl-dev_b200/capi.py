@@ -128,6 +128,7 @@ def lib():
     sig("ViennaCLBackendTimerEnd", c_vp, p_dbl)
     sig("ViennaCLBackendFlushL2", c_vp)
     sig("ViennaCLBackendLaunchCount", c_vp, p_ll)
+    sig("ViennaCLBackendSetOption", c_vp, C.c_char_p, c_ll)
     sig("ViennaCLBackendCommGetUniqueId", c_vp, c_vp)
     sig("ViennaCLBackendCommInit", c_vp, c_vp, c_int, c_int)
     sig("ViennaCLBackendCommDestroy", c_vp)
@@ -257,6 +258,10 @@ class Backend:
         n = c_ll(0)
         self.check(self.L.ViennaCLBackendLaunchCount(self.h, C.byref(n)))
         return n.value
+
+    def set_option(self, name, value):
+        """Per-handle knobs of include/vcl_b200.h: "persistent_rows" (0: multi-kernel drivers only), "l2_resident"."""
+        self.check(self.L.ViennaCLBackendSetOption(self.h, name.encode(), int(value)))
 
     def device_info(self):
         d, s = c_int(0), c_int(0)

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "prec.cuh"
 #include "solver_state.cuh"
+#include <cstdlib>
 using vcl_f64::SolverState;       // the double-precision state is the larger one: both builds fit
 
 ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, const char *file, int line)
@@ -55,6 +56,8 @@ static ViennaCLStatus backend_init(ViennaCLBackend b, int device, void *stream)
   b->device = device;
   b->sm_count = prop.multiProcessorCount;
   b->l2_bytes = (size_t)prop.l2CacheSize;
+  { int v = 0; b->coop_launch = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, device) == cudaSuccess && v) ? 1 : 0; }
+  { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); if (e) b->persistent_rows = atoll(e); }
   if (stream) { b->stream = (cudaStream_t)stream; b->owns_stream = false; }
   else { VCL_CUDA(b, cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)); b->owns_stream = true; }
   {
@@ -69,9 +72,9 @@ static ViennaCLStatus backend_init(ViennaCLBackend b, int device, void *stream)
   VCL_CUDA(b, cudaMalloc(&b->partials, sizeof(double) * VCL_MAX_QUANT * VCL_MAX_BLOCKS));
   VCL_CUDA(b, cudaMalloc(&b->tickets, sizeof(unsigned int) * 16));
   VCL_CUDA(b, cudaMemset(b->tickets, 0, sizeof(unsigned int) * 16));
-  VCL_CUDA(b, cudaMalloc(&b->dscal, sizeof(double) * 64));
-  VCL_CUDA(b, cudaMemset(b->dscal, 0, sizeof(double) * 64));
-  VCL_CUDA(b, cudaMallocHost(&b->hscal, sizeof(double) * 64));
+  VCL_CUDA(b, cudaMalloc(&b->dscal, sizeof(double) * VCL_DSCAL_COUNT));
+  VCL_CUDA(b, cudaMemset(b->dscal, 0, sizeof(double) * VCL_DSCAL_COUNT));
+  VCL_CUDA(b, cudaMallocHost(&b->hscal, sizeof(double) * VCL_DSCAL_COUNT));
   VCL_CUDA(b, cudaMalloc(&b->dstate, sizeof(SolverState)));
   VCL_CUDA(b, cudaMemset(b->dstate, 0, sizeof(SolverState)));
   VCL_CUDA(b, cudaMallocHost(&b->hstate, sizeof(SolverState)));
@@ -175,6 +178,15 @@ ViennaCLStatus ViennaCLBackendFlushL2(ViennaCLBackend b)
   }
   VCL_CUDA(b, cudaMemsetAsync(b->flush_buf, 0, b->flush_bytes, b->stream));
   return ViennaCLSuccess;
+}
+
+ViennaCLStatus ViennaCLBackendSetOption(ViennaCLBackend b, const char *name, long long value)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, name != nullptr, "null option name");
+  if (!strcmp(name, "persistent_rows")) { b->persistent_rows = value; return ViennaCLSuccess; }
+  if (!strcmp(name, "l2_resident")) { b->l2_resident = (int)value; return ViennaCLSuccess; }
+  return vcl_fail(b, ViennaCLB200InvalidArgument, "unknown option", __FILE__, __LINE__);
 }
 
 ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend b, long long *launches)

@@ -31,7 +31,7 @@ struct ViennaCLBackend_impl
   // reduction scratch shared by all kernels launched through this handle (kernels on one stream never overlap)
   double *partials = nullptr;                  // [VCL_MAX_QUANT][VCL_MAX_BLOCKS]
   unsigned int *tickets = nullptr;             // [16], zero between kernels
-  double *dscal = nullptr;                     // 64 device doubles: results of stand-alone reductions etc.
+  double *dscal = nullptr;                     // VCL_DSCAL_COUNT device doubles: results of stand-alone reductions etc. (layout below)
   double *hscal = nullptr;                     // pinned mirror of dscal
   void *dstate = nullptr;                      // device solver state (SolverState of the build that runs, solver_state.cuh)
   void *hstate = nullptr;                      // pinned mirror
@@ -43,7 +43,18 @@ struct ViennaCLBackend_impl
   // NCCL (dlopen'ed lazily, dist.cu)
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+
+  // per-handle options (ViennaCLBackendSetOption) and device facts
+  long long persistent_rows = -1;              // row limit of the persistent cooperative solver kernels; -1: built-in default, 0: never
+  int l2_resident = -1;                        // keep small matrices resident in L2 inside the persistent kernels: -1 auto, 0 never, 1 always
+  int coop_launch = 0;                         // device supports cooperative launches
 };
+
+// Layout of dscal (slots of 8 bytes, whichever precision runs): [0, 16) solver set-up reductions, [16, 32) per-op API chunk sums,
+// [32, 40) row-partitioned CG rank-local sums, [40, 44) coo2csr flag, [44, 48) row-block scratch, [64, 64 + VCL_GMRES_MAX_KRYLOV)
+// folded <v_i, v_k> of the per-op Gram-Schmidt stage 2.
+#define VCL_DSCAL_COUNT 192
+#define VCL_DSCAL_GS_FOLD 64
 
 #define VCL_MAX_BLOCKS 16384    // upper bound on the grid of any reducing kernel (partials: 64 x 16384 doubles = 8 MB)
 #define VCL_MAX_QUANT  64       // quantities reduced at once (GMRES stage 1 reduces up to VCL_GMRES_MAX_KRYLOV dots)
@@ -52,7 +63,9 @@ ViennaCLStatus vcl_fail(ViennaCLBackend b, ViennaCLStatus st, const char *what, 
 ViennaCLStatus vcl_cuda_fail(ViennaCLBackend b, cudaError_t e, const char *what, const char *file, int line);
 ViennaCLStatus vcl_ws_reserve(ViennaCLBackend b, size_t bytes);   // ensures b->ws holds >= bytes
 
-#define VCL_CHECK_BACKEND(b) do { if (!(b)) return ViennaCLB200NotInitialized; } while (0)
+// every entry point: a handle is bound to ONE device; make it current for the calling thread (several handles on several
+// devices may live in one process, include/viennacl/backend/mem_handle.hpp)
+#define VCL_CHECK_BACKEND(b) do { if (!(b)) return ViennaCLB200NotInitialized; (void)cudaSetDevice((b)->device); } while (0)
 #define VCL_REQUIRE(b, cond, msg) do { if (!(cond)) return vcl_fail((b), ViennaCLB200InvalidArgument, msg, __FILE__, __LINE__); } while (0)
 #define VCL_CUDA(b, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return vcl_cuda_fail((b), e__, #expr, __FILE__, __LINE__); } while (0)
 #define VCL_TRY(expr) do { ViennaCLStatus s__ = (expr); if (s__ != ViennaCLSuccess) return s__; } while (0)

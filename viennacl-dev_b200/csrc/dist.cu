@@ -48,7 +48,7 @@ struct ViennaCLB200DistCsr_impl
   void *win_mem = nullptr; size_t win_bytes = 0;
   void *peer_base[VCL_MAX_PEERS] = {nullptr};
   PeerWindow hwin; PeerWindow *d_win = nullptr;
-  HaloPush push;
+  HaloPush push; HaloPush *d_push = nullptr;     // d_push: device copy read by the product kernel's push phase
   bool fused_push = false;           // every destination's send list is one contiguous range: cg_update_kernel pushes
   long long push_lo[VCL_MAX_PUSH_RANGES] = {0}, push_hi[VCL_MAX_PUSH_RANGES] = {0};
   unsigned int wait_mask = 0;
@@ -190,18 +190,20 @@ ViennaCLStatus p2p_push(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *
 }
 
 // all row blocks in one launch: interior first, boundary blocks (which wait for halo sequence number `seq`) last
-CsrDev p2p_all_blocks(ViennaCLB200DistCsr A, u64 seq)
+// with_push: the kernel itself sends x's boundary entries before it starts on the row blocks (b->tickets + 8 counts the CTAs)
+CsrDev p2p_all_blocks(ViennaCLBackend b, ViennaCLB200DistCsr A, u64 seq, bool with_push)
 {
   const int par = (int)(seq & 1ULL);
   CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->ord_start, A->ord_end, A->n_interior + A->n_boundary,
-              A->n_interior, A->wait_mask, A->hwin.halo_flag[A->hwin.me] + par * A->hwin.W, seq, A->d_err};
+              A->n_interior, A->wait_mask, A->hwin.halo_flag[A->hwin.me] + par * A->hwin.W, seq, A->d_err,
+              (with_push && A->push.ndst > 0) ? A->d_push : nullptr, A->send_idx, b->tickets + 8};
   return d;
 }
 
 template<class Epi>
 ViennaCLStatus p2p_launch_csr(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi epi)
 {
-  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+  const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int grid = std::max(1, std::min(d.nblk, std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
   csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "csr_stream_kernel(peer)");
@@ -251,9 +253,15 @@ ViennaCLStatus dist_plain_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const d
   EpiAxpby epi = {y, 0, 1, 1.0, 0.0};
   if (A->p2p)
   {
+    // ONE launch: the product kernel pushes x's boundary entries from its own head, computes the interior row blocks while
+    // the neighbours' entries travel, and waits for their flags only before the boundary blocks
     const u64 seq = ++A->halo_seq;
-    VCL_TRY(p2p_push(b, A, x, seq, nullptr));
-    return p2p_launch_csr(b, p2p_all_blocks(A, seq), p2p_xvec(A, x, seq), epi);
+    if (getenv("VCL_B200_SEPARATE_PUSH"))                 // experiment knob: the round-1 form (push kernel + product kernel)
+    {
+      VCL_TRY(p2p_push(b, A, x, seq, nullptr));
+      return p2p_launch_csr(b, p2p_all_blocks(b, A, seq, false), p2p_xvec(A, x, seq), epi);
+    }
+    return p2p_launch_csr(b, p2p_all_blocks(b, A, seq, true), p2p_xvec(A, x, seq), epi);
   }
   XVec xv = make_xvec(x, 0, 1, A->halo_buf, (u32)A->n);
   VCL_TRY(start_halo(b, A, x));
@@ -366,6 +374,8 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
   }
   // send segments are contiguous and ordered by destination rank; ranks without entries contribute empty segments
   hp.begin[hp.ndst] = A->total_send;
+  VCL_CUDA(b, cudaMalloc(&A->d_push, sizeof(HaloPush)));
+  VCL_CUDA(b, cudaMemcpy(A->d_push, &hp, sizeof(HaloPush), cudaMemcpyHostToDevice));
   // contiguous send ranges?  (slab partitions of banded matrices: yes) -> the producing kernel can push by itself
   A->fused_push = false;
   if (hp.ndst > 0 && hp.ndst <= VCL_MAX_PUSH_RANGES && !(getenv("VCL_B200_NO_FUSED_PUSH")))
@@ -570,7 +580,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
       cudaStreamSynchronize(b->stream);
     }
     for (int q = 0; q < b->world; ++q) if (q != b->rank && A->peer_base[q]) cudaIpcCloseMemHandle(A->peer_base[q]);
-    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err);
+    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err); cudaFree(A->d_push);
   }
   if (A->ev_x) cudaEventDestroy(A->ev_x);
   if (A->ev_halo) cudaEventDestroy(A->ev_halo);
@@ -674,10 +684,10 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         }
         cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr, pr);
         VCL_LAUNCHED(b, "cg_update_kernel");
-        if (!A->fused_push) VCL_TRY(p2p_push(b, A, p, hseq, st));
+        // scattered send lists: the product kernel pushes from its own head (after its st->done test) -- no push kernel either way
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr};
-        CsrDev dd = p2p_all_blocks(A, hseq);
+        CsrDev dd = p2p_all_blocks(b, A, hseq, !A->fused_push);
 #ifdef VCL_PEER_DEBUG
         dd.dbg = A->hwin.dbg; dd.dbg_seq = rseq;
 #endif

@@ -3,30 +3,43 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
-#include <unordered_map>
+#include <map>
+#include <utility>
 #include "spmv_kernels.cuh"
 
 namespace VCL_NS
 {
 
-// Resident CTAs per SM for a kernel, queried once per KERNEL (all B200s of a box are identical).  The cache is keyed by the
-// function address, not by its type: kernels that differ only in a non-type template argument (csr_stream_kernel<Epi, SPLIT>,
-// sell_kernel<Epi, PERM>) share one function-pointer type, and each of them needs its own opt-in to > 48 KB of dynamic
-// shared memory.
+// Resident CTAs per SM for a kernel on the handle's device, queried once per (DEVICE, KERNEL).  The opt-in to > 48 KB of
+// dynamic shared memory (cudaFuncAttributeMaxDynamicSharedMemorySize) is a per-device attribute of the function, so a second
+// handle on another device of the same process needs its own call.  The key uses the function ADDRESS, not its type:
+// kernels that differ only in a non-type template argument (csr_stream_kernel<Epi, SPLIT>, sell_kernel<Epi, PERM>) share one
+// function-pointer type.  The caller has made b->device current (VCL_CHECK_BACKEND).
 template<class K>
-static int vcl_occupancy(K kernel, int threads, int dyn_smem = 0)
+static int vcl_occupancy(ViennaCLBackend b, K kernel, int threads, int dyn_smem = 0)
 {
   static std::mutex mtx;
-  static std::unordered_map<const void*, int> cache;
+  static std::map<std::pair<int, const void*>, int> cache;
   std::lock_guard<std::mutex> lock(mtx);
-  const void *key = reinterpret_cast<const void*>(kernel);
-  std::unordered_map<const void*, int>::const_iterator it = cache.find(key);
+  const std::pair<int, const void*> key(b->device, reinterpret_cast<const void*>(kernel));
+  std::map<std::pair<int, const void*>, int>::const_iterator it = cache.find(key);
   if (it != cache.end()) return it->second;
   int n = 0;
   if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess || n <= 0) n = 1;
   cache[key] = n;
   return n;
+}
+
+// L2 policy for the streams of a CSR matrix of `nnz` entries and `rows` rows (CsrDev::l2_mode): keep it resident (evict-last) when
+// the arrays plus four work vectors fit in 85 % of L2 -- the matrix is then re-read from L2 by every solver iteration or
+// repeated product; otherwise stream it evict-first so that it does not push the gathered x entries out.
+// Option "l2_resident" of the handle overrides: 0 never, 1 always, 2 normal policy.
+static inline int vcl_l2_mode(ViennaCLBackend b, long long nnz, long long rows)
+{
+  if (b->l2_resident >= 0) return b->l2_resident;
+  const double bytes = (double)(sizeof(real) + 4) * (double)nnz + 4.0 * (double)rows + 4.0 * (double)sizeof(real) * (double)rows;
+  return (b->l2_bytes > 0 && bytes <= 0.85 * (double)b->l2_bytes) ? 1 : 0;
 }
 
 static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -37,16 +50,17 @@ template<class Epi>
 static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &A, XVec xv, Epi epi)
 {
   CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.row_blocks ? A.row_blocks + 1 : nullptr, A.num_blocks};
+  d.l2_mode = vcl_l2_mode(b, A.nnz, A.rows);
   if (A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx))
   {
-    const int occ = vcl_occupancy(csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     int grid = std::min(A.num_blocks, std::min(b->sm_count * occ, VCL_MAX_BLOCKS));
     csr_stream_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
     VCL_LAUNCHED(b, "csr_stream_kernel");
   }
   else
   {
-    const int occ = vcl_occupancy(csr_scalar_kernel<Epi>, 256);
+    const int occ = vcl_occupancy(b, csr_scalar_kernel<Epi>, 256);
     int grid = std::max(1, std::min(vcl_div_up(A.rows, 256), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
     csr_scalar_kernel<Epi><<<grid, 256, 0, b->stream>>>(d, xv, epi);
     VCL_LAUNCHED(b, "csr_scalar_kernel");
@@ -61,7 +75,7 @@ static ViennaCLStatus vcl_launch_csr_split(ViennaCLBackend b, const CsrDev &d, X
   if (d.nblk <= 0) return ViennaCLSuccess;
   // Persistent by default.  VCL_B200_SPLIT_CHUNK=k (experiment knob) makes CTAs retire after ~k row blocks so that
   // communication kernels on the high-priority stream find SM slots while the interior blocks run.
-  const int occ = vcl_occupancy(csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+  const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int resident = b->sm_count * occ;
   static int chunk = -1;
   if (chunk < 0) { const char *e = getenv("VCL_B200_SPLIT_CHUNK"); chunk = e ? atoi(e) : 0; }
@@ -72,30 +86,36 @@ static ViennaCLStatus vcl_launch_csr_split(ViennaCLBackend b, const CsrDev &d, X
   return ViennaCLSuccess;
 }
 
-template<class Epi>
-static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
+template<class Epi, bool PERM, int CT>
+static ViennaCLStatus vcl_launch_sell_as(ViennaCLBackend b, const SellDev &d, XVec xv, Epi epi)
 {
-  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm};
-  const int occ = A.row_perm ? vcl_occupancy(sell_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES)
-                             : vcl_occupancy(sell_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
-  const int C = A.rows_per_block;
-  const int nslices = (A.rows - 1) / C + 1;
+  const int occ = vcl_occupancy(b, sell_kernel<Epi, PERM, CT>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+  const int C = d.C;
+  const int nslices = (d.rows - 1) / C + 1;
   const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
   int grid = std::max(1, std::min(vcl_div_up(nslices, spb), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
   // SELL-C-sigma puts the widest slices at the start of every sorting window, i.e. at a fixed period of the block index: an odd
   // grid is coprime with that power-of-two period, so the wide blocks are dealt evenly to the persistent CTAs
-  if (A.row_perm != nullptr && grid > 1 && (grid & 1) == 0) grid -= 1;
-  if (A.row_perm) sell_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
-  else            sell_kernel<Epi, false><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  if (PERM && grid > 1 && (grid & 1) == 0) grid -= 1;
+  sell_kernel<Epi, PERM, CT><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "sell_kernel");
   return ViennaCLSuccess;
+}
+
+template<class Epi>
+static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
+{
+  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm};
+  // the slice height of the reference's default layout gets its own instantiation (sliced_ell_matrix.hpp:146-147: C = 32)
+  if (A.row_perm) return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, true, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, true, 0>(b, d, xv, epi);
+  return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, false, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, false, 0>(b, d, xv, epi);
 }
 
 template<class Epi>
 static ViennaCLStatus vcl_launch_ell(ViennaCLBackend b, const ViennaCLCUDADhyb &A, XVec xv, Epi epi)
 {
   EllDev d = {A.ell.rows, A.ell.internal_rows, A.ell.maxnnz, A.ell.coords, A.ell.elements, A.csr_rows, A.csr_cols, A.csr_elements};
-  const int occ = vcl_occupancy(ell_kernel<Epi>, CSR_BLOCK_THREADS);
+  const int occ = vcl_occupancy(b, ell_kernel<Epi>, CSR_BLOCK_THREADS);
   int grid = std::max(1, std::min(vcl_div_up(A.ell.rows, CSR_BLOCK_THREADS), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
   ell_kernel<Epi><<<grid, CSR_BLOCK_THREADS, 0, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "ell_kernel");

@@ -91,6 +91,37 @@ __device__ __forceinline__ void push_entry(const PushRanges &pr, long long k, do
     if (d < pr.n && k >= pr.lo[d] && k < pr.hi[d]) pr.dst[d][k - pr.lo[d]] = v;
 }
 
+// Halo push from the head of the kernel that consumes the halo (the row-partitioned product is ONE launch): the first K CTAs
+// of the grid -- the ones the hardware schedules first -- send x[idx[i]] to the destinations' receive buffers, ~4 entries
+// per thread; every thread fences its own remote stores and the CTA that takes the last of the K tickets publishes the
+// sequence number to every destination with a release store.  Nothing waits here, and the other CTAs go straight to
+// their row blocks.
+template<class T>    // T = double; a template only because the single-precision build also compiles (never runs) the row-partitioned branch
+__device__ __forceinline__ void halo_push_share(const HaloPush &hp, const unsigned int *idx, const T *x, u64 seq, unsigned int *ticket)
+{
+  __shared__ bool s_push_last;
+  const int ndst = hp.ndst, total = hp.begin[ndst];
+  const unsigned int K = min(gridDim.x, (unsigned int)max(1, (total + 1023) / 1024));
+  if (blockIdx.x >= K) return;                              // uniform over the CTA
+  const int par = (int)(seq & 1ULL);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += K * blockDim.x)
+  {
+    int d = 0;
+    while (i >= hp.begin[d + 1]) ++d;
+    hp.dst[d][(size_t)par * hp.stride[d] + (size_t)(i - hp.begin[d])] = x[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_push_last = (atomicAdd(ticket, 1u) == K - 1);
+  __syncthreads();
+  if (s_push_last)
+  {
+    __threadfence_system();
+    if ((int)threadIdx.x < ndst) st_release_sys(hp.flag[threadIdx.x] + par * hp.W + hp.me, seq);
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
 // All-reduce (sum) of N <= 4 doubles across the ranks, executed by ONE CTA per rank (>= W threads).
 // vals: shared memory, N inputs (valid before the call, written by thread 0) -> N global sums (valid for thread 0 after).
 // gather: shared memory, >= W*4 doubles.

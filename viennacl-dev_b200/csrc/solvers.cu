@@ -104,15 +104,12 @@ static inline int diag_precond_option(int precond)
 const int kBatch = 32;   // iterations enqueued between two looks at the device state
 
 // Use the persistent cooperative kernel?  CSR with a row-block plan and 16-byte aligned arrays (the TMA path), a device that
-// supports cooperative launches, and a system small enough that fixed latencies matter (VCL_B200_PERSISTENT_ROWS, default
-// 10M rows -- measured: ahead up to 200^3, level at 256^3; 0 disables).
+// supports cooperative launches, and a system small enough that fixed latencies matter (option "persistent_rows" of the
+// handle, default 10M rows -- measured: ahead up to 200^3, level at 256^3; 0 disables).
 static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n, int row_limit_divisor = 1)
 {
-  static long long max_rows = -1;
-  static int coop = -1;
-  if (max_rows < 0) { const char *e = getenv("VCL_B200_PERSISTENT_ROWS"); max_rows = e ? atoll(e) : 10000000LL; }
-  if (coop < 0) { int v = 0; coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, b->device) == cudaSuccess && v) ? 1 : 0; }
-  return coop == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
+  const long long max_rows = b->persistent_rows >= 0 ? b->persistent_rows : 10000000LL;
+  return b->coop_launch == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +152,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
   int coop_grid = 0;                                       // persistent form for small / medium systems, see cg_solve
   if (persistent_cg_wanted(b, A.csr, n, 3))                // 7 streamed vectors per update: level with two kernels from ~2M rows (128^3), behind at 256^3
   {
-    const int occ = vcl_occupancy(pcg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = vcl_occupancy(b, pcg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
   }
   int launched = 0;
@@ -165,6 +162,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      d.l2_mode = vcl_l2_mode(b, A.csr.nnz, A.csr.rows);
       XVec xv = make_xvec(u, 0, 1);
       long long nn = n; int iters_arg = nb;
       real *partials = VCL_PARTIALS(b);
@@ -243,7 +241,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
   int coop_grid = 0;
   if (A.fmt == 0 && persistent_cg_wanted(b, A.csr, n))
   {
-    const int occ = vcl_occupancy(cg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = vcl_occupancy(b, cg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
   }
   int launched = 0;
@@ -253,6 +251,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      d.l2_mode = vcl_l2_mode(b, A.csr.nnz, A.csr.rows);
       XVec xv = make_xvec(p, 0, 1);
       long long nn = n; int iters_arg = nb;
       real *partials = VCL_PARTIALS(b);
@@ -322,7 +321,7 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real 
   int coop_grid = 0;                                       // persistent form for small / medium CSR systems, see cg_solve
   if (A.fmt == 0 && !tag->monitor && persistent_cg_wanted(b, A.csr, n))
   {
-    const int occ = vcl_occupancy(bicgstab_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = vcl_occupancy(b, bicgstab_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
   }
   while (launched < tag->max_iterations && !stopped)
@@ -331,6 +330,7 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real 
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      d.l2_mode = vcl_l2_mode(b, A.csr.nnz, A.csr.rows);
       long long nn = n; int iters_arg = nb;
       real *partials = VCL_PARTIALS(b);
       const real *cr0 = r0;
@@ -535,7 +535,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
   int coop_grid = 0;
   if (A.fmt == 0 && m <= GMRES_PERSISTENT_MAX_KRYLOV && persistent_cg_wanted(b, A.csr, n, 16))      // ahead up to 512^2, behind from 1024^2 (measured)
   {
-    const int occ = vcl_occupancy(gmres_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = vcl_occupancy(b, gmres_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
   }
   for (unsigned restart = 0; restart <= max_restarts; ++restart)
@@ -564,6 +564,7 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
     {
       // small / medium CSR systems: the whole cycle in one cooperative kernel (persistent.cuh)
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
+      d.l2_mode = vcl_l2_mode(b, A.csr.nnz, A.csr.rows);
       long long nn = n, iszz = isz; int mm = m;
       real *partials = VCL_PARTIALS(b);
       const real *cres = res, *cdiag = diag;
@@ -647,18 +648,30 @@ __global__ void chunk_sum_kernel(const real *in, int chunk, real *out)
   if (threadIdx.x == 0) out[0] = acc[0];
 }
 
+// Per-op API: a producer writes the FULLY REDUCED value into element 0 of its chunk of the caller's inner_prod_buffer; the
+// consumers (and the reference's drivers, cg.hpp:168-172) sum whole chunks.  The rest of the chunk is zeroed here so that a
+// buffer that still holds stale values -- e.g. reference-style per-block partials -- cannot leak into alpha, ||v_k||^2 or h_j.
+ViennaCLStatus zero_chunk_tail(ViennaCLBackend b, real *chunk_begin, long long chunk)
+{
+  if (chunk > 1) VCL_CUDA(b, cudaMemsetAsync(chunk_begin + 1, 0, sizeof(real) * (size_t)(chunk - 1), b->stream));
+  return ViennaCLSuccess;
+}
+
 MatOp from_csr(const ViennaCLCUDADcsr *A) { MatOp m; m.fmt = 0; m.csr = *A; m.sell = ViennaCLCUDADsell(); m.hyb = ViennaCLCUDADhyb(); return m; }
 MatOp from_sell(const ViennaCLCUDADsell *A) { MatOp m; m.fmt = 1; m.sell = *A; m.csr = ViennaCLCUDADcsr(); m.hyb = ViennaCLCUDADhyb(); return m; }
 MatOp from_hyb(const ViennaCLCUDADhyb *A) { MatOp m; m.fmt = 2; m.hyb = *A; m.csr = ViennaCLCUDADcsr(); m.sell = ViennaCLCUDADsell(); return m; }
 MatOp from_ell(const ViennaCLCUDADell *A) { ViennaCLCUDADhyb h = ViennaCLCUDADhyb(); h.ell = *A; return from_hyb(&h); }
 
 ViennaCLStatus fused_prod_api(ViennaCLBackend b, const MatOp &A, const real *p, real *Ap, const real *r0,
-                              real *out_ApAp, real *out_pAp, real *out_Apr0)
+                              real *out_ApAp, real *out_pAp, real *out_Apr0, long long chunk)
 {
   VCL_CHECK_BACKEND(b);
   VCL_TRY(check_matrix(b, A));
   if (A.rows() == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, p && Ap && p != Ap, "bad vectors");
+  VCL_TRY(zero_chunk_tail(b, out_ApAp, chunk));
+  VCL_TRY(zero_chunk_tail(b, out_pAp, chunk));
+  if (r0 && out_Apr0 && out_Apr0 != out_ApAp && out_Apr0 != out_pAp) VCL_TRY(zero_chunk_tail(b, out_Apr0, chunk));
   if (r0)
   {
     EpiFused<STEP_NONE, true, false> e = {Ap, p, r0, nullptr, VCL_PARTIALS(b), b->tickets, nullptr, out_ApAp, out_pAp, out_Apr0, {0.0, 0.0, 0.0}, nullptr};
@@ -717,18 +730,18 @@ ViennaCLStatus ViennaCLCUDADhybmv(ViennaCLBackend b, const ViennaCLCUDADhyb *A, 
 
 ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
-  return fused_prod_api(b, from_ell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
+  return fused_prod_api(b, from_ell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr, chunk); }
 ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments"); const int chunk = buf_size / 3;
-  return fused_prod_api(b, from_hyb(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr); }
+  return fused_prod_api(b, from_hyb(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr, chunk); }
 ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap,
                                                         const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
-  return fused_prod_api(b, from_ell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
+  return fused_prod_api(b, from_ell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset, chunk); }
 ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap,
                                                         const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 { VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
-  return fused_prod_api(b, from_hyb(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset); }
+  return fused_prod_api(b, from_hyb(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset, chunk); }
 ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_ell(ViennaCLBackend b, const ViennaCLCUDADell *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
 { return ViennaCLCUDADpipelined_cg_prod_ell(b, A, p, Ap, buf, buf_size); }
 ViennaCLStatus ViennaCLCUDADpipelined_gmres_prod_hyb(ViennaCLBackend b, const ViennaCLCUDADhyb *A, const real *p, real *Ap, real *buf, ViennaCLInt buf_size)
@@ -742,6 +755,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_cg_vector_update(ViennaCLBackend b, Vienna
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && buf && buf_size >= 3, "bad arguments");
   if (n == 0) return ViennaCLSuccess;
+  VCL_TRY(zero_chunk_tail(b, buf, buf_size / 3));
   cg_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, p, r, Ap, alpha, beta, nullptr, VCL_PARTIALS(b), b->tickets, buf);
   VCL_LAUNCHED(b, "cg_update_kernel");
   return ViennaCLSuccess;
@@ -752,7 +766,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_csr(ViennaCLBackend b, const Vienn
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
   const int chunk = buf_size / 3;
-  return fused_prod_api(b, from_csr(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
+  return fused_prod_api(b, from_csr(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr, chunk);
 }
 
 ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *p, real *Ap,
@@ -760,7 +774,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_cg_prod_sell(ViennaCLBackend b, const Vien
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && buf_size >= 3, "bad arguments");
   const int chunk = buf_size / 3;
-  return fused_prod_api(b, from_sell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr);
+  return fused_prod_api(b, from_sell(A), p, Ap, nullptr, buf + chunk, buf + 2 * chunk, nullptr, chunk);
 }
 
 ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_update_s(ViennaCLBackend b, ViennaCLInt n, real *s, const real *r, const real *Ap,
@@ -773,6 +787,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_update_s(ViennaCLBackend b, Vienn
   VCL_LAUNCHED(b, "chunk_sum_kernel");
   chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + 3 * (size_t)chunk, chunk, VCL_DSCAL(b) + 17);
   VCL_LAUNCHED(b, "chunk_sum_kernel");
+  VCL_TRY(zero_chunk_tail(b, buf + chunk_offset, chunk));
   bicgstab_update_s_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, VCL_DSCAL(b) + 16, VCL_DSCAL(b) + 17, nullptr,
                                                                         VCL_PARTIALS(b), b->tickets, buf + chunk_offset);
   VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
@@ -786,8 +801,8 @@ ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_vector_update(ViennaCLBackend b, 
 {
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && buf, "bad arguments");
-  (void)chunk;
   if (n == 0) return ViennaCLSuccess;
+  VCL_TRY(zero_chunk_tail(b, buf, chunk));
   bicgstab_update_kernel<<<vec_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, result, alpha, p, omega, s, residual, As, beta, Ap, r0star,
                                                                       nullptr, VCL_PARTIALS(b), b->tickets, buf);
   VCL_LAUNCHED(b, "bicgstab_update_kernel");
@@ -798,14 +813,14 @@ ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_csr(ViennaCLBackend b, const
                                                         const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
-  return fused_prod_api(b, from_csr(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
+  return fused_prod_api(b, from_csr(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset, chunk);
 }
 
 ViennaCLStatus ViennaCLCUDADpipelined_bicgstab_prod_sell(ViennaCLBackend b, const ViennaCLCUDADsell *A, const real *p, real *Ap,
                                                          const real *r0star, real *buf, ViennaCLInt chunk, ViennaCLInt chunk_offset)
 {
   VCL_CHECK_BACKEND(b); VCL_REQUIRE(b, A && buf && r0star && chunk >= 1, "bad arguments");
-  return fused_prod_api(b, from_sell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset);
+  return fused_prod_api(b, from_sell(A), p, Ap, r0star, buf + chunk, buf + 2 * (size_t)chunk, buf + chunk_offset, chunk);
 }
 
 ViennaCLStatus ViennaCLCUDADpipelined_gmres_normalize_vk(ViennaCLBackend b, ViennaCLInt n, real *v_k, const real *residual,
@@ -817,6 +832,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_normalize_vk(ViennaCLBackend b, Vien
   if (n == 0) return ViennaCLSuccess;
   chunk_sum_kernel<<<1, 256, 0, b->stream>>>(buf + chunk, chunk, VCL_DSCAL(b) + 16);      // ||v_k||^2 lives in chunk 1
   VCL_LAUNCHED(b, "chunk_sum_kernel");
+  VCL_TRY(zero_chunk_tail(b, r_dot_vk + chunk_offset, chunk));
   gmres_normalize_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(n, v_k, residual, R, offset_in_R, VCL_DSCAL(b) + 16,
                                                                          r_dot_vk + chunk_offset, VCL_PARTIALS(b), b->tickets);
   VCL_LAUNCHED(b, "gmres_normalize_kernel");
@@ -829,6 +845,7 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage1(ViennaCLBackend 
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, n >= 0 && basis && vi_in_vk && k >= 0 && k < VCL_GMRES_MAX_KRYLOV && chunk >= 1, "bad arguments");
   if (n == 0 || k == 0) return ViennaCLSuccess;
+  if (chunk > 1) VCL_CUDA(b, cudaMemsetAsync(vi_in_vk, 0, sizeof(real) * (size_t)k * (size_t)chunk, b->stream));
   return launch_gs1(b, scalar_grid(b, n), basis, n, internal_n, k, vi_in_vk, chunk);
 }
 
@@ -842,11 +859,12 @@ ViennaCLStatus ViennaCLCUDADpipelined_gmres_gram_schmidt_stage2(ViennaCLBackend 
   // second reduction stage of <v_i, v_k>: fold each chunk into its first element (no-op for our own stage 1)
   for (int j = 0; j < k; ++j)
   {
-    chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, VCL_DSCAL(b) + 16 + j);
+    chunk_sum_kernel<<<1, 256, 0, b->stream>>>(vi_in_vk + (size_t)j * chunk, chunk, VCL_DSCAL(b) + VCL_DSCAL_GS_FOLD + j);
     VCL_LAUNCHED(b, "chunk_sum_kernel");
   }
   VCL_REQUIRE(b, (internal_n & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u, "Krylov basis must be 16-byte aligned with an even internal size");
-  gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, VCL_DSCAL(b) + 16, 1, R, krylov_dim,
+  VCL_TRY(zero_chunk_tail(b, buf + chunk, chunk));
+  gmres_gs2_kernel<<<scalar_grid(b, n), VEC_THREADS, 0, b->stream>>>(basis, n, internal_n, k, VCL_DSCAL(b) + VCL_DSCAL_GS_FOLD, 1, R, krylov_dim,
                                                                    buf + chunk, VCL_PARTIALS(b), b->tickets);
   VCL_LAUNCHED(b, "gmres_gs2_kernel");
   return ViennaCLSuccess;

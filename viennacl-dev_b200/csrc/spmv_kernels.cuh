@@ -34,6 +34,11 @@ struct CsrDev
   // peer-memory halo (row-partitioned path, peer.cuh): list positions >= wait_from read halo columns and must first see
   // wait_flags[q] >= wait_seq for every source rank q in wait_mask.  wait_mask == 0: nothing to wait for.
   int wait_from; unsigned int wait_mask; const unsigned long long *wait_flags; unsigned long long wait_seq; int *err;
+  // halo push fused into the head of the product launch (plain row-partitioned products): every CTA first sends its share of
+  // this rank's boundary entries of x to the neighbours (push != NULL; sequence number = wait_seq), then joins the row-block loop
+  const HaloPush *push; const u32 *push_idx; unsigned int *push_ticket;
+  int l2_mode;                                  // L2 policy of the matrix streams: 0 evict-first (streamed once), 1 evict-last (a matrix that
+                                                // fits L2 and is re-read every solver iteration), 2 normal
   unsigned long long *dbg; unsigned long long dbg_seq;     // VCL_PEER_DEBUG builds only
 };
 
@@ -97,6 +102,16 @@ __device__ __forceinline__ unsigned long long l2_evict_first_policy()
 {
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+// A matrix that fits L2 together with the solver's vectors is re-read every iteration (BASELINE config 1: 67 MB of CSR arrays,
+// 34 MB of vectors, 126 MB of L2): streaming it evict-first would throw it away each time.  mode: see CsrDev::l2_mode.
+__device__ __forceinline__ unsigned long long l2_policy(int mode)
+{
+  unsigned long long pol;
+  if (mode == 1)      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  else if (mode == 2) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(pol));
+  else                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
   return pol;
 }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, unsigned long long pol)
@@ -163,6 +178,9 @@ struct EpiCoo
 //   class 0  normal block: 16-byte aligned enclosing range, <= CSR_CAP entries           -> TMA
 //   class 1  one row longer than CSR_CAP: the whole CTA strides over it straight from global memory
 //   class 2  range whose 16-byte padded end would pass the end of the arrays (last block) -> guarded synchronous staging
+//   class 3  a block of a FOREIGN plan that breaks this library's limits (more than 256 rows, or several rows with more
+//            than CSR_CAP entries -- e.g. the reference's own handle3() blocks, compressed_matrix.hpp:1152-1188: <= 1024
+//            entries but any number of rows) -> threads stride over the rows and read them straight from global memory
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -191,7 +209,8 @@ struct CsrBlockDesc { u32 r0, r1, n0, n1; };
 
 __device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
 {
-  if (d.n1 - d.n0 > CSR_CAP) return 1;
+  if (d.r1 - d.r0 > (u32)CSR_BLOCK_THREADS) return 3;
+  if (d.n1 - d.n0 > CSR_CAP) return (d.r1 - d.r0 == 1u) ? 1 : 3;
   const u32 a0 = d.n0 & ~3u;
   const u32 cnt4 = (d.n1 - a0 + 3u) & ~3u;
   return (cnt4 == 0u || a0 + cnt4 > nnz) ? 2 : 0;
@@ -249,7 +268,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
   if (epi.skip()) return;
   const int tid = threadIdx.x;
   const int step = (int)gridDim.x;
-  const unsigned long long pol = l2_evict_first_policy();
+  const unsigned long long pol = l2_policy(A.l2_mode);
 #ifdef VCL_PEER_DEBUG
   if (SPLIT && A.dbg && blockIdx.x == 0 && tid == 0) A.dbg[(A.dbg_seq % 1024) * 4 + 2] = global_ns();
 #endif
@@ -336,6 +355,12 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
   }
   int buf = 0;                                             // buffer of the current block
 
+  if (SPLIT && A.push != nullptr)
+  {
+    // the copy of this CTA's first row block is already in flight; now send x's boundary entries (remote stores over NVLink)
+    halo_push_share(*A.push, A.push_idx, xv.x, A.wait_seq, A.push_ticket);
+  }
+
   for (; bi < A.nblk; bi += step)
   {
     // ---- keep the pipeline full: copy of block j+S-1, row pointers of j+1, nnz range of j+S, row range of j+S+1 ----
@@ -363,7 +388,21 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
     const CsrBlockDesc cur = D[0];
     const u32 nrows = cur.r1 - cur.r0;
     const int cls = csr_block_class(cur, A.nnz);
-    if (cls == 1)
+    if (cls == 3)
+    {
+      // block outside this library's plan limits: correct for any partition of the rows into blocks, at scalar-kernel speed
+      for (u32 r = cur.r0 + (u32)tid; r < cur.r1; r += CSR_BLOCK_THREADS)
+      {
+        const typename Epi::Pre pre = epi.pre(r);
+        const u32 rs = A.rp[r], re = A.rp[r + 1];
+        real dot = Epi::COO ? epi.init(pre) : 0.0;
+        const u32 ff = first_fused(rs, re, xv);
+        for (u32 k = rs; k < re; ++k)
+          dot = Epi::COO ? fma(rmul(epi.term_scale(), A.va[k]), xload<SPLIT>(xv, A.ci[k]), dot) : madd_at(A.va[k], xload<SPLIT>(xv, A.ci[k]), dot, k, ff);
+        epi.row(r, dot, pre);
+      }
+    }
+    else if (cls == 1)
     {
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       real part[1] = {0.0};
@@ -479,7 +518,11 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // C not a multiple of 4 / larger than the CTA, take the direct path.
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
-template<class Epi, bool PERM>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
+// CT: slice height known at compile time (32, the reference's default, sliced_ell_matrix.hpp:146-147) or 0 = read A.C.  With a
+// constant C the in-slice strides fold into the immediate offsets of the shared-memory loads and tid / C, tid % C become a
+// shift and a mask; the generic form spent 31 % of its issue slots on IMAD address arithmetic and two 32-bit divisions per
+// pass (ncu source page, profiles/ncu_summary_r2.md) and ran 8 % behind the CSR kernel although it moves 3.5 % fewer bytes.
+template<class Epi, bool PERM, int CT>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
@@ -497,8 +540,9 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   const int tid = threadIdx.x;
   const int step = (int)gridDim.x;
   const unsigned long long pol = l2_evict_first_policy();
-  const u32 C = (u32)A.C;
-  const u32 nslices = (u32)((A.rows - 1) / A.C + 1);
+  const u32 C = CT ? (u32)CT : (u32)A.C;
+  const u32 nslices = ((u32)A.rows - 1u) / C + 1u;
+  const u32 t_slice = (u32)tid / C, t_lane = (u32)tid % C;                 // this thread's slice within a pass and row within the slice
   const u32 spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1u;      // slices per CTA pass
   const int nblocks = (int)((nslices + spb - 1) / spb);
   const bool can_stage = (C % 4u) == 0u && C <= CSR_BLOCK_THREADS &&
@@ -530,9 +574,9 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   // this thread's row of pass b: slice width and offset of its first entry
   auto my_row = [&](int b, u32 &w, u32 &first)
   {
-    const u32 slice = (u32)b * spb + (u32)tid / C;
+    const u32 slice = (u32)b * spb + t_slice;
     w = 0; first = 0;
-    if ((u32)tid < spb * C && slice < nslices) { w = A.cpb[slice]; first = A.bs[slice] + (u32)tid % C; }
+    if ((u32)tid < spb * C && slice < nslices) { w = A.cpb[slice]; first = A.bs[slice] + t_lane; }
   };
 
   int b = blockIdx.x;
@@ -554,7 +598,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
     if (staged(base_c, end_c))
     {
       // (s1 - s0) * C <= 256 here: one row per thread
-      long long r = (long long)(s0 + (u32)tid / C) * C + ((u32)tid % C);             // storage row ...
+      long long r = (long long)(s0 + t_slice) * C + t_lane;                          // storage row ...
       if (PERM && (u32)tid < (s1 - s0) * C) r = (long long)A.perm[r];  // ... -> matrix row (padding: 0xFFFFFFFF)
       const bool active = (u32)tid < (s1 - s0) * C && r < A.rows;
       typename Epi::Pre pre = typename Epi::Pre();

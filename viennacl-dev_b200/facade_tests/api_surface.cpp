@@ -47,6 +47,45 @@ int main()
     viennacl::backend::finish();
     expect(back == h, "async_copy host -> device -> host (ordered on the backend's stream, finished by backend::finish())");
   }
+  // ---- vector expressions whose operands alias the destination (the reference evaluates them through temporaries) ----
+  {
+    const std::size_t n = 1000;
+    std::vector<T> ha(n), hb(n), hx(n), got(n);
+    for (std::size_t i = 0; i < n; ++i) { ha[i] = T(i) * 0.25 + 1.0; hb[i] = 3.0 - T(i) * 0.125; hx[i] = T(i % 7) - 2.0; }
+    viennacl::vector<T> a(n), b(n), x(n);
+    viennacl::copy(ha, a); viennacl::copy(hb, b);
+    bool ok = true;
+    viennacl::copy(hx, x);
+    x = a + b + x;                                       // third operand is the destination
+    viennacl::copy(x, got);
+    for (std::size_t i = 0; i < n; ++i) ok = ok && std::fabs(got[i] - (ha[i] + hb[i] + hx[i])) <= 1e-13 * (1.0 + std::fabs(got[i]));
+    expect(ok, "x = a + b + x");
+    ok = true; viennacl::copy(hx, x);
+    x = x + 2.0 * a - x;                                 // first and third operand alias
+    viennacl::copy(x, got);
+    for (std::size_t i = 0; i < n; ++i) ok = ok && std::fabs(got[i] - 2.0 * ha[i]) <= 1e-13 * (1.0 + std::fabs(got[i]));
+    expect(ok, "x = x + 2 a - x");
+    ok = true; viennacl::copy(hx, x);
+    x = x + x + x;                                       // all three alias: temporary
+    viennacl::copy(x, got);
+    for (std::size_t i = 0; i < n; ++i) ok = ok && std::fabs(got[i] - 3.0 * hx[i]) <= 1e-13 * (1.0 + std::fabs(got[i]));
+    expect(ok, "x = x + x + x");
+    ok = true; viennacl::copy(hx, x);
+    x += a + b - x;                                      // accumulate form: x + a + b - x
+    viennacl::copy(x, got);
+    for (std::size_t i = 0; i < n; ++i) ok = ok && std::fabs(got[i] - (ha[i] + hb[i])) <= 1e-12 * (1.0 + std::fabs(got[i]));
+    expect(ok, "x += a + b - x");
+    ok = true; viennacl::copy(hx, x);
+    {
+      // overlapping views of one buffer: lo = x[0, 600), hi = x[400, 1000):  lo = hi + lo
+      viennacl::vector_range<viennacl::vector<T> > lo(x, viennacl::range(0, 600)), hi(x, viennacl::range(400, 1000));
+      lo = hi + lo;
+    }
+    viennacl::copy(x, got);
+    for (std::size_t i = 0; i < 600; ++i) ok = ok && std::fabs(got[i] - (hx[i + 400] + hx[i])) <= 1e-13 * (1.0 + std::fabs(got[i]));
+    for (std::size_t i = 600; i < n; ++i) ok = ok && got[i] == hx[i];
+    expect(ok, "lo = hi + lo on overlapping ranges of one vector");
+  }
   // ---- result_of ----
   expect(same_type<viennacl::result_of::cpu_value_type< viennacl::vector<float> >::type, float>::value &&
          same_type<viennacl::result_of::cpu_value_type< viennacl::compressed_matrix<double> >::type, double>::value &&

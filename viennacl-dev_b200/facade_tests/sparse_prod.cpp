@@ -153,6 +153,17 @@ static int product_tests(const char *name, NumericT epsilon, StlMatrix const & s
   // constructor from expression
   viennacl::vector<NumericT> vcl_fresh = viennacl::linalg::prod(vcl_matrix, vcl_rhs);
   CHECK("vector constructed from prod(A, x)", result, vcl_fresh);
+
+  // products after clear() (tests/src/sparse.cpp:988-1060): the cleared matrix holds no entries, A x = 0, y += A x leaves y alone
+  vcl_matrix.clear();
+  result = std::vector<NumericT>(result.size(), NumericT(0));
+  vcl_result = vcl_rhs;                                           // stale content must be overwritten
+  vcl_result = viennacl::linalg::prod(vcl_matrix, vcl_rhs);
+  CHECK("matrix-vector product after clear()", result, vcl_result);
+  result = rhs;
+  vcl_result = vcl_rhs;
+  vcl_result += viennacl::linalg::prod(vcl_matrix, vcl_rhs);
+  CHECK("matrix-vector product (+=) after clear()", result, vcl_result);
   return EXIT_SUCCESS;
 }
 

@@ -65,6 +65,7 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for coordinate matrix-vector product"));
     if (rows_ == 0) return;
+    if (nonzeros_ == 0 || !idx_rows_.get()) { detail::scale_by_beta(y, beta); return; }   // no entries (clear()): A x = 0
     backend::b200::check(viennacl::backend::b200::abi<NumericT>::coomv(backend::b200::handle(), ViennaCLInt(rows_), ViennaCLInt(cols_), ViennaCLInt(nonzeros_),
                                             idx_rows_.ptr<unsigned int>(), idx_cols_.ptr<unsigned int>(), elements_.ptr<NumericT>(),
                                             idx_blocks_.ptr<unsigned int>(), ViennaCLInt(row_block_num_),

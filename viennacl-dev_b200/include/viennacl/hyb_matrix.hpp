@@ -62,6 +62,7 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for HYB matrix-vector product"));
     if (rows_ == 0) return;
+    if (!ell_elements_.get() && !csr_rows_.get()) { detail::scale_by_beta(y, beta); return; }   // no entries (clear()): A x = 0
     typename viennacl::backend::b200::abi<NumericT>::hyb a = abi();
     backend::b200::check(viennacl::backend::b200::abi<NumericT>::hybmv(backend::b200::handle(), &a, x.ptr(), ViennaCLInt(x.start()), ViennaCLInt(x.stride()), alpha,
                                             y.ptr(), ViennaCLInt(y.start()), ViennaCLInt(y.stride()), beta));

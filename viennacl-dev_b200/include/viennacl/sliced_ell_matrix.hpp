@@ -57,7 +57,7 @@ public:
   {
     assert(size1() == y.size() && size2() == x.size() && bool("Size check failed for sliced ELL matrix-vector product"));
     if (rows_ == 0) return;
-    if (!columns_per_block_.get()) throw memory_exception("not initialised!");
+    if (!columns_per_block_.get()) { detail::scale_by_beta(y, beta); return; }      // no entries (clear(), or never filled): A x = 0
     if (sigma_ > 1)
     {
       typename viennacl::backend::b200::abi<ScalarT>::sell a = abi();

@@ -6,6 +6,7 @@
 
 #include <vector>
 #include <cassert>
+#include <algorithm>
 #include <cmath>
 #include <ostream>
 #include "viennacl/forwards.h"
@@ -360,10 +361,40 @@ protected:
     else
       detail::vec_mul_dispatch(*e.A, *e.x, alpha, *this, beta, 0);
   }
-  void eval(detail::lincomb<NumericT> const & e, bool accumulate)
+  // Does operand o share memory with this vector?  0: no; 1: the very same view (element i of o IS element i of *this: in-place
+  // element-wise evaluation is safe); 2: another view of the same buffer (overlap possible: evaluate through a temporary)
+  int alias_kind(vector_base const * o) const
   {
-    if (e.terms == 0) return;
-    assert(e.size() == size_ && bool("Incompatible vector sizes!"));
+    if (!(o->handle() == elements_)) return 0;
+    return (o->start() == start_ && o->stride() == stride_) ? 1 : 2;
+  }
+  void eval(detail::lincomb<NumericT> const & e_in, bool accumulate)
+  {
+    if (e_in.terms == 0) return;
+    assert(e_in.size() == size_ && bool("Incompatible vector sizes!"));
+    detail::lincomb<NumericT> e = e_in;
+    // Aliasing (the reference evaluates such expressions through temporaries, vector.hpp op_executor specialisations): a
+    // three-term expression takes two passes, and the operand of the SECOND pass must not be the destination itself --
+    // x = a + b + x would otherwise add the already overwritten x.  Reorder so that aliasing operands are read by the first
+    // pass (in place, element by element); different views of the destination's buffer, or three aliasing operands, go
+    // through a temporary.
+    {
+      int kinds[3] = {0, 0, 0}, n_alias = 0; bool other_view = false;
+      for (int k = 0; k < e.terms; ++k) { kinds[k] = alias_kind(e.v[k]); n_alias += kinds[k] != 0; other_view |= kinds[k] == 2; }
+      if (other_view || (e.terms == 3 && n_alias == 3))
+      {
+        vector_base temp(size_);
+        temp.eval(e, false);
+        detail::lincomb<NumericT> l; l.push(&temp, NumericT(1));
+        eval(l, accumulate);
+        return;
+      }
+      if (e.terms == 3 && kinds[2] != 0)
+      {
+        const int swap_with = kinds[0] == 0 ? 0 : 1;          // a non-aliasing operand of the first pass
+        std::swap(e.v[2], e.v[swap_with]); std::swap(e.c[2], e.c[swap_with]);
+      }
+    }
     ViennaCLBackend b = backend::b200::handle();
     const vector_base *a = e.v[0], *c = e.terms > 1 ? e.v[1] : e.v[0];
     const NumericT ca = e.c[0], cc = e.terms > 1 ? e.c[1] : NumericT(0);
@@ -415,6 +446,20 @@ public:
 
   void swap(vector & other) { base_type::swap(other); }
 };
+
+// y = beta * y (beta == 0: y = 0 without reading it): the product with a matrix that holds no entries, e.g. after clear()
+// (tests/src/sparse.cpp:988-1060 "products after clear()")
+namespace detail
+{
+  template<typename NumericT>
+  void scale_by_beta(vector_base<NumericT> & y, NumericT beta)
+  {
+    if (y.size() == 0 || beta == NumericT(1)) return;
+    if (beta == NumericT(0)) { y.clear(); return; }
+    backend::b200::check(viennacl::backend::b200::abi<NumericT>::av(backend::b200::handle(), int(y.size()), y.ptr(), int(y.start()), int(y.stride()),
+                                                                  y.ptr(), int(y.start()), int(y.stride()), beta));
+  }
+}
 
 // ---------------------------------------------------------------------------------------------- views
 template<typename VectorType>
