@@ -222,6 +222,20 @@ def cpu_baseline_cg(n1=1024, iters=200):
 
 
 def legacy_cuda_baseline(n1=256):
+    """Runs _legacy_cuda_child in a SEPARATE process (python bench.py --legacy-cuda-child): the legacy kernels live in their own
+    CUDA context and a crash inside them (they are unmodified 2016 code on a 2025 GPU) cannot take the bench line down."""
+    try:
+        p = subprocess.run([sys.executable, "-X", "faulthandler", os.path.abspath(__file__), "--legacy-cuda-child", str(n1)],
+                           capture_output=True, text=True, timeout=600)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "legacy CUDA baseline timed out after 600 s"}
+    for ln in reversed(p.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return {"unavailable": "legacy CUDA baseline process died (rc %d): %s" % (p.returncode, p.stderr.strip()[-300:])}
+
+
+def _legacy_cuda_child(n1=256):
     """SECOND baseline (rank 0, N = 1): the reference's OWN CUDA backend (viennacl/linalg/cuda/*, unmodified, compiled for sm_100
     by oracle/Makefile -> oracle/_ref/libvcl_ref_cuda.so) on the same GPU and the same matrices.  Every result is first checked
     against the reference host backend / the oracle (check K1's output before trusting it as a baseline)."""
@@ -269,7 +283,11 @@ def main():
     ap.add_argument("--workload", default="spmv", choices=["spmv", "cg512"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the SELL / CG side measurements")
+    ap.add_argument("--legacy-cuda-child", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.legacy_cuda_child:
+        print(json.dumps(_legacy_cuda_child(args.legacy_cuda_child)), flush=True)
+        return
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":

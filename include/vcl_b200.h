@@ -61,7 +61,9 @@ ViennaCLStatus ViennaCLBackendFlushL2(ViennaCLBackend backend);
  *                      GMRES cycles inside one launch); larger systems take the multi-kernel drivers.  -1: built-in default
  *                      (10M rows; env VCL_B200_PERSISTENT_ROWS at handle creation), 0: always multi-kernel.
  *   "l2_resident"      persistent kernels keep a matrix that fits L2 resident there (evict-last) instead of streaming it
- *                      (evict-first): -1 auto by working-set size, 0 never, 1 always. */
+ *                      (evict-first): 0 never (default: measured slower on B200), 1 evict-last, 2 normal policy.
+ *   "persistent_cg_form"  1 (default): one-pass persistent CG -- one grid barrier per iteration, the product recomputes the
+ *                      updated search direction on the fly; 2: the two-phase form (update, barrier, product, barrier). */
 ViennaCLStatus ViennaCLBackendSetOption(ViennaCLBackend backend, const char *name, long long value);
 /* Counts kernels launched by this library on this handle since creation (bench.py's gpu_launches). */
 ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend backend, long long *launches);

@@ -32,7 +32,9 @@ SAMPLE = 1024            # entries of x kept (evenly strided over the vector)
 
 
 def sample_idx(n):
-    return (np.arange(SAMPLE, dtype=np.int64) * (n // SAMPLE)) + (n // SAMPLE) // 2
+    """1024 entries spread over the whole vector by a multiplicative hash: a fixed stride would sit on one grid plane (a stride of
+    16384 on the 256^3 grid only ever visits x = 0)."""
+    return (np.arange(1, SAMPLE + 1, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(n)).astype(np.int64)
 
 
 def true_residual(o, A, x, b):
@@ -43,7 +45,7 @@ def record(name, A, b, res, o, extra):
     idx = sample_idx(A.rows)
     rec = dict(name=name, rows=A.rows, nnz=A.nnz, iters=int(res["iters"]), error=float(res["error"]),
                true_residual=true_residual(o, A, res["x"], b), x_norm=float(np.linalg.norm(res["x"])),
-               x_sample_stride=int(A.rows // SAMPLE), x_sample=[float(v) for v in res["x"][idx]], seconds=float(res["seconds"]), threads=1)
+               x_sample_rule="idx_k = (k * 2654435761) mod rows, k = 1..1024", x_sample=[float(v) for v in res["x"][idx]], seconds=float(res["seconds"]), threads=1)
     rec.update(extra)
     return rec
 

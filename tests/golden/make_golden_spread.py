@@ -17,9 +17,31 @@ sys.path.insert(0, os.path.dirname(HERE))
 import oracle_lib as ol  # noqa: E402
 
 
+def small(out):
+    """The small solver goldens of make_golden.py (BiCGStab, no preconditioner / Jacobi) at 1 / 2 / 3 / 4 / 8 threads."""
+    o = ol.oracle(); r = ol.ref()
+    for name, A in (("lap2d_63x65", o.stencil2d(63, 65)), ("cd2d_48x50", o.stencil2d(48, 50, 0.5, 0.0)), ("cd3d_11x10x9", o.stencil3d(11, 10, 9, 0.5, 0.25, 0.125))):
+        b = np.ones(A.rows)
+        for pre in ("none", "jacobi"):
+            key = "small/%s/bicgstab_%s" % (name, pre)
+            out[key] = {}
+            for t in (1, 2, 3, 4, 8):
+                r.set_threads(t)
+                res = r.solve("bicgstab", A, b, precond=pre, tol=1e-8, maxit=1000)
+                out[key][str(t)] = dict(iters=int(res["iters"]), error=float(res["error"]))
+            print(key, {t: v["iters"] for t, v in out[key].items()}, flush=True)
+
+
 def main():
     o = ol.oracle(); r = ol.ref()
+    path = os.path.join(HERE, "bicgstab_spread.json")
+    if "--small" in sys.argv:                   # add / refresh only the small cases (seconds)
+        out = json.load(open(path))
+        small(out)
+        json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+        return
     out = {}
+    small(out)
     for grid, c in (((256, 256, 256), (0.5, 0.25, 0.125)), ((128, 128, 128), (0.5, 0.25, 0.125))):
         o.set_threads(8)
         A = o.stencil3d(*grid, *c); b = np.ones(A.rows)

@@ -186,6 +186,7 @@ ViennaCLStatus ViennaCLBackendSetOption(ViennaCLBackend b, const char *name, lon
   VCL_REQUIRE(b, name != nullptr, "null option name");
   if (!strcmp(name, "persistent_rows")) { b->persistent_rows = value; return ViennaCLSuccess; }
   if (!strcmp(name, "l2_resident")) { b->l2_resident = (int)value; return ViennaCLSuccess; }
+  if (!strcmp(name, "persistent_cg_form")) { b->persistent_cg_form = (int)value; return ViennaCLSuccess; }
   return vcl_fail(b, ViennaCLB200InvalidArgument, "unknown option", __FILE__, __LINE__);
 }
 

@@ -69,6 +69,7 @@ __device__ __forceinline__ void bicgstab_advance(SolverState *st)
 // Fused SpMV epilogue:  Ap[r] = dot (optionally / diag[r]);  <Ap,Ap>, <p,Ap>, <Ap,r0*>
 // host_based/iterative_operations.hpp:58-103.  STEP selects what the last CTA does after the reduction.
 // ------------------------------------------------------------------------------------------------
+enum { DIST_CG = 1, DIST_BICG_P = 2, DIST_BICG_S = 3, DIST_PCG = 4 };
 enum { STEP_NONE = 0, STEP_CG = 1, STEP_BICGSTAB = 2, STEP_PBICG_ALPHA = 3, STEP_PBICG_OMEGA = 4, STEP_PCG = 5 };
 
 template<int STEP, bool USE_R0, bool JACOBI>
@@ -80,9 +81,14 @@ struct EpiFused
   real *out0, *out1, *out2;      // totals: <Ap,Ap>, <p,Ap>, <Ap,r0*>
   real acc[3];
   const real *add_from;          // optional: 3 totals of an earlier launch over a disjoint row subset (interior + boundary split)
-  // row-partitioned CG over peer memory (peer.cuh): the last CTA all-reduces {*loc_rr, <Ap,Ap>, <p,Ap>} across the ranks
-  // and then advances the CG scalars -- identical on every rank.  win == NULL: single-domain behaviour.
-  const PeerWindow *win; unsigned long long red_seq; const real *loc_rr;
+  // row-partitioned solvers over peer memory (peer.cuh): the last CTA all-reduces this launch's rank-local totals together
+  // with ONE rank-local total of the preceding vector kernel (*loc_extra) across the ranks and then advances the solver's
+  // scalars -- identical on every rank.  win == NULL: single-domain behaviour.  dist_mode (what is reduced -> where it goes):
+  //   DIST_CG       {*loc <r,r>, <Ap,Ap>, <p,Ap>}                  -> sums[0..2], cg_advance
+  //   DIST_BICG_P   {*loc <r,r0*>, <Ap,r0*>}                        -> sums[0], sums[3]                 (Ap = A p)
+  //   DIST_BICG_S   {*loc <s,s>, <As,As>, <As,s>, <As,r0*>}         -> sums[5], sums[1], sums[2], sums[4], bicgstab_advance
+  //   DIST_PCG      {*loc gamma = <r,u>, delta = <w,u>}             -> sums[0], pcg_advance(delta)
+  const PeerWindow *win; unsigned long long red_seq; const real *loc_extra; int dist_mode;
   static constexpr int NQ = 3;
   static constexpr bool COO = false;
   // the epilogue's own per-row operands, all requested BEFORE the row's gather chain so that their latency overlaps with it
@@ -116,12 +122,21 @@ struct EpiFused
 #ifdef VCL_PEER_DEBUG
       const u64 t_a = global_ns();
 #endif
-      if (threadIdx.x == 0) { smem[0] = *loc_rr; smem[1] = acc[0]; smem[2] = acc[1]; }
-      peer_allreduce<3>(win, red_seq, smem, smem + 32);
       if (threadIdx.x == 0)
       {
-        st->sums[0] = smem[0]; st->sums[1] = smem[1]; st->sums[2] = smem[2];
-        cg_advance(st);
+        smem[0] = *loc_extra; smem[1] = 0.0; smem[2] = 0.0; smem[3] = 0.0;
+        if (dist_mode == DIST_CG)          { smem[1] = acc[0]; smem[2] = acc[1]; }
+        else if (dist_mode == DIST_BICG_P) { smem[1] = acc[2]; }
+        else if (dist_mode == DIST_BICG_S) { smem[1] = acc[0]; smem[2] = acc[1]; smem[3] = acc[2]; }
+        else                               { smem[1] = acc[1]; }
+      }
+      peer_allreduce<4>(win, red_seq, smem, smem + 32);
+      if (threadIdx.x == 0)
+      {
+        if (dist_mode == DIST_CG)          { st->sums[0] = smem[0]; st->sums[1] = smem[1]; st->sums[2] = smem[2]; cg_advance(st); }
+        else if (dist_mode == DIST_BICG_P) { st->sums[0] = smem[0]; st->sums[3] = smem[1]; }
+        else if (dist_mode == DIST_BICG_S) { st->sums[5] = smem[0]; st->sums[1] = smem[1]; st->sums[2] = smem[2]; st->sums[4] = smem[3]; bicgstab_advance(st); }
+        else                               { st->sums[0] = smem[0]; pcg_advance(st, smem[1]); }
 #ifdef VCL_PEER_DEBUG
         if (win->dbg) { u64 *d = win->dbg + (red_seq % 1024) * 4; d[0] = t_a; d[1] = global_ns(); }
 #endif

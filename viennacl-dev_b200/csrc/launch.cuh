@@ -31,15 +31,14 @@ static int vcl_occupancy(ViennaCLBackend b, K kernel, int threads, int dyn_smem 
   return n;
 }
 
-// L2 policy for the streams of a CSR matrix of `nnz` entries and `rows` rows (CsrDev::l2_mode): keep it resident (evict-last) when
-// the arrays plus four work vectors fit in 85 % of L2 -- the matrix is then re-read from L2 by every solver iteration or
-// repeated product; otherwise stream it evict-first so that it does not push the gathered x entries out.
-// Option "l2_resident" of the handle overrides: 0 never, 1 always, 2 normal policy.
-static inline int vcl_l2_mode(ViennaCLBackend b, long long nnz, long long rows)
+// L2 policy for the streams of a CSR matrix (CsrDev::l2_mode).  Default: evict-first -- the matrix is streamed and must not push
+// the gathered x entries out of L2.  Keeping a matrix that fits L2 resident (evict-last / normal) was MEASURED SLOWER on B200
+// for BASELINE config 1 (1024^2 CG: 25.9 us per iteration evict-first, 27.8 evict-last, 28.5 normal; profiles/cg1024_l2_r2a.log):
+// with evict-first the matrix streams from HBM while the vectors are served by L2, two sources in parallel.  Option
+// "l2_resident" of the handle selects 1 (evict-last) or 2 (normal) for experiments.
+static inline int vcl_l2_mode(ViennaCLBackend b, long long, long long)
 {
-  if (b->l2_resident >= 0) return b->l2_resident;
-  const double bytes = (double)(sizeof(real) + 4) * (double)nnz + 4.0 * (double)rows + 4.0 * (double)sizeof(real) * (double)rows;
-  return (b->l2_bytes > 0 && bytes <= 0.85 * (double)b->l2_bytes) ? 1 : 0;
+  return b->l2_resident > 0 ? b->l2_resident : 0;
 }
 
 static inline bool vcl_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

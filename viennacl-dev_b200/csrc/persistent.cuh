@@ -64,6 +64,19 @@ __device__ __forceinline__ void sum_partials(const real *partials, real (&tot)[N
   block_sum<NQ>(tot, smem);
 }
 
+// the same for NQ arrays given by pointer (arrays that are double-buffered separately), ONE block-level reduction for all of them
+template<int NQ>
+__device__ __forceinline__ void sum_partials_of(const real * const (&arr)[NQ], real (&tot)[NQ], real *smem)
+{
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+  {
+    tot[q] = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) tot[q] += __ldcg(arr[q] + i);
+  }
+  block_sum<NQ>(tot, smem);
+}
+
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, real *Ap,
                      SolverState *st, real *partials, int iterations)
@@ -93,12 +106,12 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
     EpiCgPartial epi = {Ap, p, partials, {0.0, 0.0}};
     csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry);
     grid.sync();                                           // Ap and all partials visible
-    real tot[2], rr[1];
-    sum_partials<2>(partials, tot, s_sum);                 // <Ap,Ap>, <p,Ap>
-    sum_partials<1>(part_rr, rr, s_sum);                   // <r,r>
+    real tot[3];
+    const real * const arrs[3] = {part_rr, partials, partials + VCL_MAX_BLOCKS};
+    sum_partials_of<3>(arrs, tot, s_sum);                  // <r,r>, <Ap,Ap>, <p,Ap>: one block-level reduction for the three
     if (threadIdx.x == 0)
     {
-      s_st.sums[0] = rr[0]; s_st.sums[1] = tot[0]; s_st.sums[2] = tot[1];
+      s_st.sums[0] = tot[0]; s_st.sums[1] = tot[1]; s_st.sums[2] = tot[2];
       cg_advance(&s_st);                                   // cg.hpp:170-180
     }
     __syncthreads();
@@ -108,6 +121,100 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
     csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry, true);        // wait for the copy issued ahead, if any
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *st = s_st;
+}
+// ------------------------------------------------------------------------------------------------
+// One-pass persistent CG: ONE phase and ONE grid barrier per iteration.
+//
+// The two-phase kernel above is bound by fixed latencies on BASELINE config 1 (1024^2: 25.9 us per iteration of which ~11 us do
+// not depend on the size): update phase, barrier, product phase, barrier.  The barrier between update and product exists
+// only because the product gathers p_new at OTHER rows.  Here the product recomputes those entries on the fly,
+//     p_new[c] = fma(beta, p[c], fma(-alpha, Ap[c], r[c]))      -- bit-identical to what the update phase would have stored,
+// from the PREVIOUS iteration's r / p / Ap (three gathers per entry instead of one; they hit L1 / L2), and the row's own update
+// (x += alpha p; r_new; p_new) moves into the product's epilogue.  r, p and Ap are double-buffered: every CTA reads set A
+// anywhere and writes set B at its own rows, so one barrier per iteration orders everything; x is only touched at own rows.
+// After the barrier every CTA sums the per-CTA partials of <r,r>, <Ap,Ap>, <p,Ap> (double-buffered by iteration parity) in the
+// same fixed order and advances its own copy of the scalars (cg_advance, cg.hpp:170-180).  Per-entry arithmetic and the
+// stopping rule are those of the two-kernel driver; only the grouping of the partial sums differs.
+// ------------------------------------------------------------------------------------------------
+// CTAS = resident CTAs per SM the kernel is compiled for: 2 (<= 128 registers: 24 gathers in flight per thread, 8 entries x 3 vectors,
+// without spills) or 3 (<= 85 registers).
+struct EpiCgOnePass
+{
+  const real *r0, *p0, *Ap0;     // previous iteration (read at any row)
+  real *r1, *p1, *Ap1, *x;       // this iteration (written at own rows)
+  real alpha, beta;
+  real *partials;                // [3][VCL_MAX_BLOCKS]: <r,r>, <Ap,Ap>, <p,Ap>
+  real acc[3];
+  static constexpr int NQ = 3;
+  static constexpr bool COO = false;
+  static constexpr bool XFUSED = true;
+  struct Pre { real r, p, Ap, x; };
+  __device__ __forceinline__ real init(const Pre &) const { return 0.0; }
+  __device__ __forceinline__ real term_scale() const { return 1.0; }
+  __device__ __forceinline__ bool skip() const { return false; }
+  __device__ __forceinline__ real xg(u32 c) const { return fma(beta, p0[c], fma(-alpha, Ap0[c], r0[c])); }
+  __device__ __forceinline__ Pre pre(u32 i) const { Pre q; q.r = r0[i]; q.p = p0[i]; q.Ap = Ap0[i]; q.x = x[i]; return q; }
+  __device__ __forceinline__ void row(u32 i, real dot, const Pre &q)
+  {
+    const real rn = fma(-alpha, q.Ap, q.r);                // the operations of cg_update_entries, in the same order
+    const real pn = fma(beta, q.p, rn);
+    x[i] = fma(alpha, q.p, q.x);
+    r1[i] = rn; p1[i] = pn; Ap1[i] = dot;
+    acc[0] = fma(rn, rn, acc[0]);
+    acc[1] = fma(dot, dot, acc[1]);
+    acc[2] = fma(pn, dot, acc[2]);
+  }
+  __device__ __forceinline__ void finish(real *smem)
+  {
+    block_sum<3>(acc, smem);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) partials[q * VCL_MAX_BLOCKS + blockIdx.x] = acc[q];
+    }
+  }
+};
+
+// bufs: r, p, Ap of set A followed by set B; st->pad0 tells which set is current (0: A) and is updated on exit
+template<int CTAS>
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CTAS)
+cg_onepass_kernel(CsrDev A, real *x, real *rA, real *pA, real *ApA, real *rB, real *pB, real *ApB,
+                  SolverState *st, real *partials, int iterations)
+{
+  cgrp::grid_group grid = cgrp::this_grid();
+  __shared__ SolverState s_st;
+  __shared__ real s_sum[3 * 32];
+  if (threadIdx.x == 0) s_st = *st;
+  __syncthreads();
+  CsrCarry carry = {0u, 0};
+  const XVec xv = {x, (u32)sizeof(real), nullptr, 0u};    // unit stride (the float build's fuse pattern looks at it); entries come from xg()
+  int cur = s_st.pad0;
+
+  for (int it = 0; it < iterations; ++it)
+  {
+    if (s_st.done != VCL_RUNNING) break;                   // identical in every CTA
+    real *part = partials + (size_t)(it & 1) * 3 * VCL_MAX_BLOCKS;    // a CTA already in iteration it+1 must not overwrite what a slower one still sums
+    {
+      EpiCgOnePass epi = {cur ? rB : rA, cur ? pB : pA, cur ? ApB : ApA, cur ? rA : rB, cur ? pA : pB, cur ? ApA : ApB, x,
+                          s_st.alpha, s_st.beta, part, {0.0, 0.0, 0.0}};
+      csr_stream_body<EpiCgOnePass, false, true>(A, xv, epi, &carry);
+    }
+    grid.sync();                                           // the new r / p / Ap and all partials are visible
+    real tot[3];
+    sum_partials<3>(part, tot, s_sum);
+    if (threadIdx.x == 0)
+    {
+      s_st.sums[0] = tot[0]; s_st.sums[1] = tot[1]; s_st.sums[2] = tot[2];
+      cg_advance(&s_st);                                   // cg.hpp:170-180
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  {
+    EpiCgOnePass epi = {rA, pA, ApA, rB, pB, ApB, x, 0.0, 0.0, partials, {0.0, 0.0, 0.0}};
+    csr_stream_body<EpiCgOnePass, false, true>(A, xv, epi, &carry, true);        // wait for the copy issued ahead, if any
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { s_st.pad0 = cur; *st = s_st; }
 }
 // ------------------------------------------------------------------------------------------------
 // Jacobi / row-scaling preconditioned CG (single-reduction form, see pcg_update_kernel) in the same persistent form:
@@ -138,13 +245,13 @@ pcg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *r, real *u,
     EpiCgPartial epi = {w, u, partials, {0.0, 0.0}};       // partial arrays [0]: <w,w> (unused), [1]: <u,w>
     csr_stream_body<EpiCgPartial, false, true>(A, xv, epi, &carry);
     grid.sync();
-    real delta[1], gamma[1];
-    sum_partials<1>(partials + VCL_MAX_BLOCKS, delta, s_sum);
-    sum_partials<1>(part_gamma, gamma, s_sum);
+    real dg[2];
+    const real * const arrs[2] = {partials + VCL_MAX_BLOCKS, part_gamma};
+    sum_partials_of<2>(arrs, dg, s_sum);                   // delta = <w,u>, gamma = <r,u>
     if (threadIdx.x == 0)
     {
-      s_st.sums[0] = gamma[0];
-      pcg_advance(&s_st, delta[0]);
+      s_st.sums[0] = dg[1];
+      pcg_advance(&s_st, dg[0]);
     }
     __syncthreads();
   }
@@ -199,7 +306,7 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
 {
   cgrp::grid_group grid = cgrp::this_grid();
   __shared__ SolverState s_st;
-  __shared__ real s_sum[3 * 32];
+  __shared__ real s_sum[4 * 32];
   if (threadIdx.x == 0) s_st = *st;
   __syncthreads();
   CsrCarry carry = {0u, 0};
@@ -235,12 +342,12 @@ bicgstab_persistent_kernel(CsrDev A, long long n, real *x, real *r, real *p, con
     }
     grid.sync();
     {
-      real t[3], ss[1];
-      sum_partials<3>(partials, t, s_sum);
-      sum_partials<1>(part_ss, ss, s_sum);
+      real t[4];
+      const real * const arrs[4] = {partials, partials + VCL_MAX_BLOCKS, partials + 2 * VCL_MAX_BLOCKS, part_ss};
+      sum_partials_of<4>(arrs, t, s_sum);
       if (threadIdx.x == 0)
       {
-        s_st.sums[1] = t[0]; s_st.sums[2] = t[1]; s_st.sums[4] = t[2]; s_st.sums[5] = ss[0];
+        s_st.sums[1] = t[0]; s_st.sums[2] = t[1]; s_st.sums[4] = t[2]; s_st.sums[5] = t[3];
         bicgstab_advance(&s_st);                                                   // bicgstab.hpp:184-199
       }
       __syncthreads();

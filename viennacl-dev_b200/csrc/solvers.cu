@@ -206,9 +206,13 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
   VCL_CUDA(b, cudaSetDevice(b->device));
   if (diag_precond_option(tag->precond) >= 0) return pcg_jacobi(b, A, rhs, x, tag);
   VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: unknown preconditioner id");
-  VCL_TRY(vcl_ws_reserve(b, 3 * Carver::need(n)));
+  // Small and medium CSR systems: whole iterations inside one cooperative kernel (persistent.cuh).  The one-pass form keeps a
+  // second set of r / p / Ap (double buffering), hence six work vectors instead of three.
+  const bool want_coop = A.fmt == 0 && persistent_cg_wanted(b, A.csr, n);
+  VCL_TRY(vcl_ws_reserve(b, (want_coop ? 6 : 3) * Carver::need(n)));
   Carver cv(b->ws);
   real *r = cv.take(n), *p = cv.take(n), *Ap = cv.take(n);
+  real *r2 = want_coop ? cv.take(n) : nullptr, *p2 = want_coop ? cv.take(n) : nullptr, *Ap2 = want_coop ? cv.take(n) : nullptr;
 
   VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(real) * n, b->stream));
   VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(real) * n, cudaMemcpyDeviceToDevice, b->stream));
@@ -235,14 +239,19 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
 
   const int grid = vec_grid(b, n);
   const int batch = tag->monitor ? 1 : kBatch;
-  // Small and medium CSR systems: whole iterations inside one cooperative kernel (persistent.cuh) -- the per-iteration cost
-  // of two launches, two ramps and two reduction tails (~16 us) shrinks to two grid barriers (~8.7 us in all).  Large
-  // systems are bound by HBM and keep the two-kernel form.
+  // Persistent forms (persistent.cuh): "onepass" (default) = one phase and one grid barrier per iteration, the product recomputes
+  // the updated p on the fly; "twophase" = update phase, barrier, product phase, barrier (option "persistent_cg_form" = 2).
+  // Large systems are bound by HBM and keep the two-kernel form.
   int coop_grid = 0;
-  if (A.fmt == 0 && persistent_cg_wanted(b, A.csr, n))
+  const bool onepass = b->persistent_cg_form != 2;
+  const void *onepass_fn = b->persistent_cg_form == 3 ? (const void*)cg_onepass_kernel<3> : (const void*)cg_onepass_kernel<2>;
+  if (want_coop)
   {
-    const int occ = vcl_occupancy(b, cg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int occ = !onepass ? vcl_occupancy(b, cg_persistent_kernel, CSR_BLOCK_THREADS, CSR_SMEM_BYTES)
+                             : (b->persistent_cg_form == 3 ? vcl_occupancy(b, cg_onepass_kernel<3>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES)
+                                                           : vcl_occupancy(b, cg_onepass_kernel<2>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES));
     coop_grid = std::max(1, std::min(b->sm_count * occ, std::max(A.csr.num_blocks, vcl_div_up(n, 2 * CSR_BLOCK_THREADS))));
+    if (onepass) coop_grid = std::max(1, std::min(b->sm_count * occ, A.csr.num_blocks));
   }
   int launched = 0;
   while (launched < tag->max_iterations)
@@ -255,18 +264,22 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
       XVec xv = make_xvec(p, 0, 1);
       long long nn = n; int iters_arg = nb;
       real *partials = VCL_PARTIALS(b);
-      void *args[] = {&d, &xv, &nn, &x, &p, &r, &Ap, &st, &partials, &iters_arg};
-      const cudaError_t ce = cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args,
-                                                         (size_t)CSR_SMEM_BYTES, b->stream);
+      void *args2[] = {&d, &xv, &nn, &x, &p, &r, &Ap, &st, &partials, &iters_arg};
+      void *args1[] = {&d, &x, &r, &p, &Ap, &r2, &p2, &Ap2, &st, &partials, &iters_arg};
+      const cudaError_t ce = onepass ? cudaLaunchCooperativeKernel(onepass_fn, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args1,
+                                                                   (size_t)CSR_SMEM_BYTES, b->stream)
+                                     : cudaLaunchCooperativeKernel((const void*)cg_persistent_kernel, dim3(coop_grid), dim3(CSR_BLOCK_THREADS), args2,
+                                                                   (size_t)CSR_SMEM_BYTES, b->stream);
       if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources)
       {
         (void)cudaGetLastError();                          // the SMs are shared with another client (MPS, a second stream): two-kernel form
         coop_grid = 0;
+        if (h->pad0) { std::swap(r, r2); std::swap(p, p2); std::swap(Ap, Ap2); }      // the current r / p / Ap are in the second set
       }
       else
       {
         VCL_CUDA(b, ce);
-        VCL_LAUNCHED(b, "cg_persistent_kernel");
+        VCL_LAUNCHED(b, onepass ? "cg_onepass_kernel" : "cg_persistent_kernel");
       }
     }
     if (coop_grid == 0)

@@ -12,6 +12,7 @@
 // results agree bit-for-bit with it (see madd()).  x is gathered through L1/L2 (adjacent rows of a stencil matrix
 // gather adjacent x entries, so the gathers of a warp coalesce).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "prec.cuh"
 #include "solver_state.cuh"
@@ -71,6 +72,19 @@ __device__ __forceinline__ real xload(const XVec &xv, u32 c)
     return base[c];
   }
   return *reinterpret_cast<const real*>(reinterpret_cast<const char*>(xv.x) + (unsigned long long)c * xv.inc8);
+}
+
+// Where an entry of the operand vector comes from.  Normally x itself (xload); an epilogue that declares XFUSED = true supplies
+// the entry through its own xg(col) instead -- the one-pass persistent CG (persistent.cuh) RECOMPUTES p_new[col] =
+// r[col] - alpha Ap[col] + beta p[col] on the fly, which removes the separate vector-update phase and one of the two grid
+// barriers of an iteration.
+template<class Epi, class = void> struct epi_xfused { static constexpr bool value = false; };
+template<class Epi> struct epi_xfused<Epi, typename std::enable_if<Epi::XFUSED>::type> { static constexpr bool value = true; };
+template<bool SPLIT, class Epi>
+__device__ __forceinline__ real xget(const Epi &epi, const XVec &xv, u32 c)
+{
+  if constexpr (epi_xfused<Epi>::value) return epi.xg(c);
+  else return xload<SPLIT>(xv, c);
 }
 
 // In-row CSR accumulation step.  The reference host backend (host_based/sparse_matrix_operations.hpp:167-184), built with
@@ -220,8 +234,8 @@ __device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
 // entries are issued before the first multiply-add (predicated, so a 7-point row costs ONE round trip to L2, not three).
 // COO == true: coordinate_matrix semantics (host_based/sparse_matrix_operations.hpp:1233-1246): the chain starts at beta*y
 // and every term is fma(alpha*a, x, .) -- what the reference build does for that format.
-template<bool SPLIT, bool COO>
-__device__ __forceinline__ real csr_row_dot(const real *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv,
+template<bool SPLIT, bool COO, class Epi>
+__device__ __forceinline__ real csr_row_dot(const Epi &epi, const real *s_val, const u32 *s_col, u32 j, u32 e, const XVec &xv,
                                               real init = 0.0, real alpha = 1.0)
 {
   real dot = COO ? init : 0.0;
@@ -233,7 +247,7 @@ __device__ __forceinline__ real csr_row_dot(const real *s_val, const u32 *s_col,
     for (int k = 0; k < 8; ++k)
     {
       const bool ok = j + k < e;
-      xx[k] = ok ? xload<SPLIT>(xv, s_col[j + k]) : 0.0;
+      xx[k] = ok ? xget<SPLIT>(epi, xv, s_col[j + k]) : 0.0;
       v[k] = ok ? s_val[j + k] : 0.0;
     }
     // empty slots hold v = x = +0.0: adding +0.0 never changes the bits of `dot` (a round-to-nearest sum that starts at
@@ -398,7 +412,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
         real dot = Epi::COO ? epi.init(pre) : 0.0;
         const u32 ff = first_fused(rs, re, xv);
         for (u32 k = rs; k < re; ++k)
-          dot = Epi::COO ? fma(rmul(epi.term_scale(), A.va[k]), xload<SPLIT>(xv, A.ci[k]), dot) : madd_at(A.va[k], xload<SPLIT>(xv, A.ci[k]), dot, k, ff);
+          dot = Epi::COO ? fma(rmul(epi.term_scale(), A.va[k]), xget<SPLIT>(epi, xv, A.ci[k]), dot) : madd_at(A.va[k], xget<SPLIT>(epi, xv, A.ci[k]), dot, k, ff);
         epi.row(r, dot, pre);
       }
     }
@@ -407,7 +421,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       real part[1] = {0.0};
       for (u32 k = cur.n0 + tid; k < cur.n1; k += CSR_BLOCK_THREADS)
-        part[0] = fma(A.va[k], xload<SPLIT>(xv, A.ci[k]), part[0]);
+        part[0] = fma(A.va[k], xget<SPLIT>(epi, xv, A.ci[k]), part[0]);
       __shared__ real s_long[32];
       block_sum<1>(part, s_long);
       if (tid == 0)
@@ -442,7 +456,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
       // like the whole-CTA path for rows beyond CSR_CAP).  COO keeps the sequential chain (its alpha/beta form is defined by it).
       const bool is_long = !Epi::COO && (my_e - my_s) > (u32)CSR_LONG_ROW;
       if ((u32)tid < nrows && !is_long)
-        epi.row(cur.r0 + tid, csr_row_dot<SPLIT, Epi::COO>(s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale()), pre);
+        epi.row(cur.r0 + tid, csr_row_dot<SPLIT, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale()), pre);
       unsigned longs = __ballot_sync(0xffffffffu, is_long);
       while (longs)
       {
@@ -450,7 +464,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
         longs &= longs - 1u;
         const u32 ls = __shfl_sync(0xffffffffu, my_s, src) - a0, le = __shfl_sync(0xffffffffu, my_e, src) - a0;
         real part = 0.0;
-        for (u32 k = ls + (u32)(tid & 31); k < le; k += 32u) part = fma(s_val[k], xload<SPLIT>(xv, s_col[k]), part);
+        for (u32 k = ls + (u32)(tid & 31); k < le; k += 32u) part = fma(s_val[k], xget<SPLIT>(epi, xv, s_col[k]), part);
         part = warp_sum(part);
         if ((tid & 31) == src) epi.row(cur.r0 + tid, part, pre);
       }
