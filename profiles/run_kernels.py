@@ -46,7 +46,9 @@ elif what == "spmv":
         A.spmv(x, y)
         S.spmv(x, y)
 elif what in ("cg", "cg1024"):
-    pkg.SolverTag(tol=0.0, max_iterations=4).solve("cg", A, b, y)
+    if len(sys.argv) > 2:
+        be.set_option("persistent_cg_form", int(sys.argv[2]))
+    pkg.SolverTag(tol=0.0, max_iterations=32 if what == "cg1024" else 4).solve("cg", A, b, y)
 elif what == "cg_sell":
     pkg.SolverTag(tol=0.0, max_iterations=4).solve("cg", A.to_sell(32), b, y)
 elif what == "bicgstab":

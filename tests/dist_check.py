@@ -39,6 +39,30 @@ def random_spd(n, seed):
     return ol.CSR(n, n, S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data)
 
 
+def big_case(pkg, be, rank, world):
+    """CG on the 128^3 Laplacian to 1e-8 on every partitioning against the UNMODIFIED reference's single-domain run
+    (tests/golden/baseline_configs.json, case c5_cg_lap3d_128: count +-2, same estimate, same x at the sampled entries)."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_configs.json")))["c5_cg_lap3d_128"]
+    nx, ny, nz = g["grid"]
+    n = nx * ny * nz
+    rb, re_ = n * rank // world, n * (rank + 1) // world
+    dA = pkg.CsrMatrix.stencil(be, nx, ny, nz, row_begin=rb, row_end=re_)
+    D = pkg.DistCsr(be, n, rb, re_, dA)
+    db, dx = be.array(np.ones(re_ - rb)), be.zeros(re_ - rb)
+    tag = D.cg(db, dx, pkg.SolverTag(tol=g["tol"], max_iterations=g["maxit"]))
+    idx = (np.arange(1, 1025, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(n)).astype(np.int64)
+    mine = (idx >= rb) & (idx < re_)
+    x = dx.download()
+    xs, xr = x[idx[mine] - rb], np.asarray(g["x_sample"])[mine]
+    d = float(np.abs(xs - xr).max() / np.abs(np.asarray(g["x_sample"])).max()) if mine.any() else 0.0
+    good = abs(tag.iters - g["iters"]) <= 2 and tag.error < g["tol"] and d <= 1e-6
+    print("[rank %d/%d] lap3d_128^3 (reference golden): cg iters %d (reference %d) err %.3e (reference %.3e) max sample diff %.2e  %s [%s]"
+          % (rank, world, tag.iters, g["iters"], tag.error, g["error"], d, "OK" if good else "FAIL", D.info()["transport"]), flush=True)
+    D.close()
+    return good
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -97,6 +121,8 @@ def main():
         if not good:
             print("[rank %d] %s maxit case FAIL iters=%d" % (rank, name, tag.iters), flush=True)
         D.close()
+    if "--big" in sys.argv:
+        ok &= big_case(pkg, be, rank, world)
     if world > 1:
         t = torch.tensor([1.0 if ok else 0.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)

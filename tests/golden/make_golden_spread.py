@@ -30,6 +30,53 @@ def small(out):
                 res = r.solve("bicgstab", A, b, precond=pre, tol=1e-8, maxit=1000)
                 out[key][str(t)] = dict(iters=int(res["iters"]), error=float(res["error"]))
             print(key, {t: v["iters"] for t, v in out[key].items()}, flush=True)
+            if pre == "jacobi":
+                out[key + "/summation_orders"] = generic_bicgstab_orders(A, pre)
+                print(key + "/summation_orders", {t: v["iters"] for t, v in out[key + "/summation_orders"].items()}, flush=True)
+
+
+def generic_bicgstab_orders(A, precond):
+    """The reference's generic (preconditioned) BiCGStab, bicgstab.hpp:398-489, restated in numpy with the inner products summed in
+    different ORDERS -- sequential (the reference at one thread), exactly rounded (math.fsum), pairwise (np.sum), BLAS (np.dot) and
+    k interleaved partial sums.  Everything else is identical.  Shows how far the iteration count moves under admissible
+    summation orders: the yardstick for a device whose reductions are necessarily grouped differently."""
+    import math
+    S = A.to_scipy(); n = A.rows
+    b = np.ones(n); diag = S.diagonal() if precond == "jacobi" else np.ones(n)
+
+    def seq(a, c):
+        t = 0.0
+        for v in (a * c):
+            t += v
+        return t
+
+    orders = {"sequential": seq, "exact_fsum": lambda a, c: math.fsum(a * c), "pairwise_np_sum": lambda a, c: float(np.sum(a * c)), "blas_np_dot": lambda a, c: float(np.dot(a, c))}
+    for k in (2, 3, 7, 32, 256):
+        orders["interleaved_%d" % k] = (lambda k: lambda a, c: float(sum(np.sum((a * c)[j::k]) for j in range(k))))(k)
+    out = {}
+    for name, dot in orders.items():
+        x = np.zeros(n); r = (b - S @ x) / diag; p = r.copy(); r0 = r.copy()
+        nb = math.sqrt(dot(b, b)); ip = math.sqrt(dot(r, r)); ip *= ip
+        its = -1
+        for i in range(1000):
+            t0 = (S @ p) / diag
+            alpha = ip / dot(t0, r0)
+            s = r - alpha * t0
+            t1 = (S @ s) / diag
+            nt = math.sqrt(dot(t1, t1))
+            omega = dot(t1, s) / (nt * nt)
+            x += alpha * p + omega * s
+            r = s - omega * t1
+            if math.sqrt(dot(r, r)) / nb < 1e-8:
+                its = i + 1
+                break
+            new = dot(r, r0)
+            beta = new / ip * alpha / omega
+            ip = new
+            p -= omega * t0
+            p = r + beta * p
+        out[name] = dict(iters=its)
+    return out
 
 
 def main():

@@ -600,3 +600,65 @@ def test_cg_persistent_kernel_on_ragged_spd_system(pkg, be, orc):
     assert rel[:5].max() < 1e-12, rel
     few = pkg.SolverTag(tol=1e-30, max_iterations=37).solve("cg", dA, db, dx)          # budget not a multiple of the batch
     assert few.iters == 37
+
+
+def test_foreign_row_block_plans(pkg, be, orc):
+    """Row-block plans NOT made by ViennaCLCUDAcsr_row_blocks: the reference's own handle3() blocks
+    (compressed_matrix.hpp:1152-1188: <= 1024 entries per block, any number of rows), one block holding the whole matrix, and a
+    malformed plan.  The library checks a foreign plan once (vcl_plan_ok) and sends the product to the plan-free kernel when the
+    plan breaks the limits of the TMA kernel -- the result must be the reference's in every case, and rewriting the plan's
+    memory through the C-ABI must drop the cached verdict."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    # rows of 0..3 entries: a reference-style block collects ~680 rows (> 256)
+    cnt = rng.integers(0, 4, n)
+    rp = np.zeros(n + 1, np.uint32); rp[1:] = np.cumsum(cnt)
+    ci = np.concatenate([np.sort(rng.choice(n, c, replace=False)) for c in cnt]).astype(np.uint32)
+    va = rng.uniform(-1, 1, int(rp[-1]))
+    x = rng.uniform(1, 2, n)
+    import scipy.sparse as sp
+    y_ref = sp.csr_matrix((va, ci.astype(np.int64), rp.astype(np.int64)), shape=(n, n)) @ x
+    dA = pkg.CsrMatrix.from_host(be, n, n, rp, ci, va)
+    dx = be.array(x)
+
+    def ref_blocks():                                 # the reference's generate_row_block_information (compressed_matrix.hpp:1152-1188), restated
+        blk, acc, i = [0], 0, 0
+        while i < n:
+            acc += int(rp[i + 1] - rp[i])
+            if acc > 1024:
+                if i - blk[-1] > 0:
+                    blk.append(i); i -= 1             # the current row opens the next batch
+                else:
+                    blk.append(i + 1)                 # a row longer than the buffer
+                acc = 0
+            i += 1
+        if acc > 0:
+            blk.append(n)
+        return np.array(blk, np.uint32)
+
+    plans = {"own": None, "reference": ref_blocks(), "one_block": np.array([0, n], np.uint32), "pairs": np.arange(0, n + 1, 2, dtype=np.uint32)}
+    assert np.diff(plans["reference"].astype(np.int64)).max() > 256
+    for name, blk in plans.items():
+        dy = be.array(np.full(n, 7.0))
+        if blk is not None:
+            dA.blocks = be.array(blk); dA.nblocks = len(blk) - 1
+        l0 = be.launches()
+        dA.spmv(dx, dy)
+        dA.spmv(dx, dy)
+        assert be.launches() - l0 == (2 if name == "own" else 3), name          # foreign plan: one check launch, once
+        assert ol_rel(dy.download(), y_ref) <= 1e-13, name
+    # same buffer, new contents written through the C-ABI: the verdict must not survive
+    good = plans["pairs"]
+    dA.blocks = be.array(good); dA.nblocks = len(good) - 1
+    dy = be.zeros(n)
+    dA.spmv(dx, dy)
+    bad = good.copy(); bad[1:-1] = 0; bad[-2] = n          # same length: [0, 0, ..., 0, n, n] = one huge block in the middle
+    dA.blocks.upload(bad)
+    dy2 = be.zeros(n)
+    dA.spmv(dx, dy2)
+    assert ol_rel(dy2.download(), y_ref) <= 1e-13
+
+
+def ol_rel(a, b):
+    import oracle_lib as ol
+    return float(ol.rel_err(a, b).max())

@@ -197,6 +197,59 @@ ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend b, long long *launches
   return ViennaCLSuccess;
 }
 
+// ---------------------------------------------------------------- row-block plans ----------------------------------------------------------------
+} // extern "C"
+
+__global__ void plan_check_kernel(const u32 *rp, int rows, const u32 *blk, int nb, int *bad)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= nb; i += gridDim.x * blockDim.x)
+  {
+    const u32 r0 = blk[i];
+    bool wrong = r0 > (u32)rows || (i == 0 && r0 != 0u) || (i == nb && r0 != (u32)rows);
+    if (!wrong && i < nb)
+    {
+      const u32 r1 = blk[i + 1];
+      wrong = r1 < r0 || r1 > (u32)rows;
+      if (!wrong && r1 - r0 > 1u)
+        wrong = r1 - r0 > (u32)VCL_B200_CSR_BLOCK_ROWS || rp[r1] - rp[r0] > (u32)VCL_B200_CSR_BLOCK_NNZ;
+    }
+    if (wrong) *bad = 1;
+  }
+}
+
+bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks)
+{
+  if (!row_blocks || num_blocks <= 0) return false;
+  std::map<const void*, ViennaCLBackend_impl::PlanRec>::const_iterator it = b->plans.find(row_blocks);
+  if (it != b->plans.end() && it->second.row_ptr == row_ptr && it->second.rows == rows && it->second.num_blocks == num_blocks) return it->second.ok;
+  int *flag = reinterpret_cast<int*>(b->dscal + 48);
+  int bad = 1;
+  if (cudaMemsetAsync(flag, 0, sizeof(int), b->stream) == cudaSuccess)
+  {
+    plan_check_kernel<<<std::max(1, std::min((num_blocks + 256) / 256, b->sm_count * 4)), 256, 0, b->stream>>>(row_ptr, rows, row_blocks, num_blocks, flag);
+    b->launches++;
+    if (cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess)
+    { (void)cudaGetLastError(); bad = 1; }
+  }
+  const ViennaCLBackend_impl::PlanRec rec = {row_ptr, rows, num_blocks, bad == 0};
+  b->plans[row_blocks] = rec;
+  return rec.ok;
+}
+
+void vcl_plan_register(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks)
+{
+  const ViennaCLBackend_impl::PlanRec rec = {row_ptr, rows, num_blocks, true};
+  b->plans[row_blocks] = rec;
+}
+
+void vcl_plan_forget(ViennaCLBackend b, const void *dst, size_t bytes)
+{
+  if (b->plans.empty() || !dst) return;
+  std::map<const void*, ViennaCLBackend_impl::PlanRec>::iterator lo = b->plans.lower_bound(dst);
+  while (lo != b->plans.end() && (const char*)lo->first < (const char*)dst + (bytes ? bytes : 1)) lo = b->plans.erase(lo);
+}
+
+extern "C" {
 // ---------------------------------------------------------------- memory ----------------------------------------------------------------
 ViennaCLStatus ViennaCLCUDAMemAlloc(ViennaCLBackend b, void **ptr, size_t bytes)
 {
@@ -213,6 +266,7 @@ ViennaCLStatus ViennaCLCUDAMemFree(ViennaCLBackend b, void *ptr)
 {
   VCL_CHECK_BACKEND(b);
   if (!ptr) return ViennaCLSuccess;
+  vcl_plan_forget(b, ptr, 0);
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   VCL_CUDA(b, cudaFree(ptr));
   return ViennaCLSuccess;
@@ -223,6 +277,7 @@ ViennaCLStatus ViennaCLCUDAMemWrite(ViennaCLBackend b, void *dst, size_t off, co
   VCL_CHECK_BACKEND(b);
   if (bytes == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, dst && src, "null pointer");
+  vcl_plan_forget(b, (char*)dst + off, bytes);
   VCL_CUDA(b, cudaMemcpyAsync((char*)dst + off, src, bytes, cudaMemcpyHostToDevice, b->stream));
   if (!async) VCL_CUDA(b, cudaStreamSynchronize(b->stream));
   return ViennaCLSuccess;
@@ -243,6 +298,7 @@ ViennaCLStatus ViennaCLCUDAMemCopy(ViennaCLBackend b, const void *src, size_t so
   VCL_CHECK_BACKEND(b);
   if (bytes == 0) return ViennaCLSuccess;
   VCL_REQUIRE(b, dst && src, "null pointer");
+  vcl_plan_forget(b, (char*)dst + doff, bytes);
   VCL_CUDA(b, cudaMemcpyAsync((char*)dst + doff, (const char*)src + soff, bytes, cudaMemcpyDeviceToDevice, b->stream));
   return ViennaCLSuccess;
 }
@@ -251,6 +307,7 @@ ViennaCLStatus ViennaCLCUDAMemSet(ViennaCLBackend b, void *dst, ViennaCLInt valu
 {
   VCL_CHECK_BACKEND(b);
   if (bytes == 0) return ViennaCLSuccess;
+  vcl_plan_forget(b, dst, bytes);
   VCL_CUDA(b, cudaMemsetAsync(dst, value, bytes, b->stream));
   return ViennaCLSuccess;
 }

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 #include "vcl_b200.h"
@@ -49,10 +50,24 @@ struct ViennaCLBackend_impl
   int l2_resident = -1;                        // keep small matrices resident in L2 inside the persistent kernels: -1 auto, 0 never, 1 always
   int persistent_cg_form = 1;                  // 1: one-pass persistent CG (one grid barrier per iteration), 2: the two-phase form
   int coop_launch = 0;                         // device supports cooperative launches
+
+  // CSR row-block plans this handle has seen (key: device address of the plan), see vcl_plan_ok
+  struct PlanRec { const void *row_ptr; int rows, num_blocks; bool ok; };
+  std::map<const void*, PlanRec> plans;
 };
 
+// Is (row_blocks, num_blocks) a plan the TMA row-block kernels may use for this matrix -- every block <= VCL_B200_CSR_BLOCK_ROWS rows
+// and <= VCL_B200_CSR_BLOCK_NNZ entries, or one longer row?  Plans made by ViennaCLCUDAcsr_row_blocks are registered as such; any
+// other plan (e.g. the reference's own handle3() blocks, compressed_matrix.hpp:1152-1188: <= 1024 entries but any number of
+// rows) is checked ONCE on the device (one small kernel + one 4-byte read) and the verdict is cached per plan address; a plan
+// that breaks the limits sends the product to the plan-free kernel instead of giving wrong rows.  Writing to / freeing the
+// plan's memory through the C-ABI drops the cached verdict (vcl_plan_forget).
+bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks);
+void vcl_plan_register(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks);
+void vcl_plan_forget(ViennaCLBackend b, const void *dst, size_t bytes);
+
 // Layout of dscal (slots of 8 bytes, whichever precision runs): [0, 16) solver set-up reductions, [16, 32) per-op API chunk sums,
-// [32, 40) row-partitioned CG rank-local sums, [40, 44) coo2csr flag, [44, 48) row-block scratch, [64, 64 + VCL_GMRES_MAX_KRYLOV)
+// [32, 40) row-partitioned CG rank-local sums, [40, 44) coo2csr flag, [44, 48) row-block scratch, [48, 49) plan check, [64, 64 + VCL_GMRES_MAX_KRYLOV)
 // folded <v_i, v_k> of the per-op Gram-Schmidt stage 2.
 #define VCL_DSCAL_COUNT 192
 #define VCL_DSCAL_GS_FOLD 64

@@ -686,7 +686,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         VCL_LAUNCHED(b, "cg_update_kernel");
         // scattered send lists: the product kernel pushes from its own head (after its st->done test) -- no push kernel either way
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
-                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr};
+                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr, DIST_CG};
         CsrDev dd = p2p_all_blocks(b, A, hseq, !A->fused_push);
 #ifdef VCL_PEER_DEBUG
         dd.dbg = A->hwin.dbg; dd.dbg_seq = rseq;

@@ -109,7 +109,8 @@ const int kBatch = 32;   // iterations enqueued between two looks at the device 
 static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, long long n, int row_limit_divisor = 1)
 {
   const long long max_rows = b->persistent_rows >= 0 ? b->persistent_rows : 10000000LL;
-  return b->coop_launch == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx);
+  return b->coop_launch == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx) &&
+         vcl_plan_ok(b, A.row_ptr, A.rows, A.row_blocks, A.num_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -102,6 +102,7 @@ extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCL
       VCL_REQUIRE(b, *num_blocks >= nb, "row_blocks buffer too small");
       uniform_blocks_kernel<<<std::max(1, std::min(vcl_div_up(nb + 1, 256), b->sm_count * 4)), 256, 0, b->stream>>>(rows, G, nb, row_blocks);
       VCL_LAUNCHED(b, "uniform_blocks_kernel");
+      vcl_plan_register(b, row_ptr, rows, row_blocks, nb);
     }
     *num_blocks = nb;
     return ViennaCLSuccess;
@@ -116,6 +117,7 @@ extern "C" ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend b, ViennaCL
     VCL_REQUIRE(b, *num_blocks >= nb, "row_blocks buffer too small");
     VCL_CUDA(b, cudaMemcpyAsync(row_blocks, blk.data(), sizeof(u32) * blk.size(), cudaMemcpyHostToDevice, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    vcl_plan_register(b, row_ptr, rows, row_blocks, nb);
   }
   *num_blocks = nb;
   return ViennaCLSuccess;

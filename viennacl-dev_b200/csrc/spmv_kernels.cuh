@@ -192,9 +192,10 @@ struct EpiCoo
 //   class 0  normal block: 16-byte aligned enclosing range, <= CSR_CAP entries           -> TMA
 //   class 1  one row longer than CSR_CAP: the whole CTA strides over it straight from global memory
 //   class 2  range whose 16-byte padded end would pass the end of the arrays (last block) -> guarded synchronous staging
-//   class 3  a block of a FOREIGN plan that breaks this library's limits (more than 256 rows, or several rows with more
-//            than CSR_CAP entries -- e.g. the reference's own handle3() blocks, compressed_matrix.hpp:1152-1188: <= 1024
-//            entries but any number of rows) -> threads stride over the rows and read them straight from global memory
+// Plans that break these limits (more than 256 rows in a block, or several rows with more than CSR_CAP entries -- e.g. the
+// reference's own handle3() blocks, compressed_matrix.hpp:1152-1188: <= 1024 entries but any number of rows) never reach this
+// kernel: the host checks every foreign plan once (vcl_plan_ok, common.cuh) and sends such products to csr_scalar_kernel.
+// (Handling them HERE as a fourth block class cost the 256^3 product 8 %: 0.272 ms against 0.2515, profiles/ab_spmv_r2c.log.)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
@@ -223,8 +224,7 @@ struct CsrBlockDesc { u32 r0, r1, n0, n1; };
 
 __device__ __forceinline__ int csr_block_class(const CsrBlockDesc &d, u32 nnz)
 {
-  if (d.r1 - d.r0 > (u32)CSR_BLOCK_THREADS) return 3;
-  if (d.n1 - d.n0 > CSR_CAP) return (d.r1 - d.r0 == 1u) ? 1 : 3;
+  if (d.n1 - d.n0 > CSR_CAP) return 1;
   const u32 a0 = d.n0 & ~3u;
   const u32 cnt4 = (d.n1 - a0 + 3u) & ~3u;
   return (cnt4 == 0u || a0 + cnt4 > nnz) ? 2 : 0;
@@ -402,21 +402,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
     const CsrBlockDesc cur = D[0];
     const u32 nrows = cur.r1 - cur.r0;
     const int cls = csr_block_class(cur, A.nnz);
-    if (cls == 3)
-    {
-      // block outside this library's plan limits: correct for any partition of the rows into blocks, at scalar-kernel speed
-      for (u32 r = cur.r0 + (u32)tid; r < cur.r1; r += CSR_BLOCK_THREADS)
-      {
-        const typename Epi::Pre pre = epi.pre(r);
-        const u32 rs = A.rp[r], re = A.rp[r + 1];
-        real dot = Epi::COO ? epi.init(pre) : 0.0;
-        const u32 ff = first_fused(rs, re, xv);
-        for (u32 k = rs; k < re; ++k)
-          dot = Epi::COO ? fma(rmul(epi.term_scale(), A.va[k]), xget<SPLIT>(epi, xv, A.ci[k]), dot) : madd_at(A.va[k], xget<SPLIT>(epi, xv, A.ci[k]), dot, k, ff);
-        epi.row(r, dot, pre);
-      }
-    }
-    else if (cls == 1)
+    if (cls == 1)
     {
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       real part[1] = {0.0};
