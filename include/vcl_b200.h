@@ -74,6 +74,8 @@ ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend backend, long long *la
 ViennaCLStatus ViennaCLBackendCommGetUniqueId(ViennaCLBackend backend, void *id_bytes /* VCL_B200_COMM_ID_BYTES */);
 ViennaCLStatus ViennaCLBackendCommInit(ViennaCLBackend backend, const void *id_bytes, ViennaCLInt rank, ViennaCLInt world_size);
 ViennaCLStatus ViennaCLBackendCommDestroy(ViennaCLBackend backend);
+/* Polls the communicator for asynchronous errors (ncclCommGetAsyncError); the NCCL transport does so itself once per solver batch. */
+ViennaCLStatus ViennaCLBackendCommCheck(ViennaCLBackend backend);
 
 /* ---------------------------------------------------------------- memory ----------------------------------------------------------------- */
 /* backend/cuda.hpp:103-200 (memory_create / memory_copy / memory_write / memory_read) */
@@ -118,7 +120,10 @@ ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend backend, ViennaCLInt r
 
 /* y[offy + i*incy] = alpha * (A x)_i + (beta != 0 ? beta * y[...] : 0);  x read at offx + col*incx.
  * linalg/sparse_matrix_operations.hpp:90-121 -> cuda/sparse_matrix_operations.hpp:262-396 (kernels :137-249).
- * row_blocks may be NULL (then a plan-free subwarp-per-row kernel is used). */
+ * row_blocks: a plan from ViennaCLCUDAcsr_row_blocks, or ANY partition of the rows into consecutive blocks (e.g. the reference's own
+ * handle3() plan) -- a plan this library did not make is checked once per plan address (cached; rewriting or freeing the plan's
+ * memory through this API drops the verdict) and, when a block breaks the limits above, the product runs through the plan-free
+ * kernel (one thread per row, no staging) -- as it does for row_blocks == NULL or arrays that are not 16-byte aligned. */
 ViennaCLStatus ViennaCLCUDADcsrmv(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
                                   const unsigned int *row_ptr, const unsigned int *col_idx, const double *values,
                                   const unsigned int *row_blocks, ViennaCLInt num_blocks,
@@ -352,7 +357,7 @@ ViennaCLStatus ViennaCLCUDAconvert_StoD(ViennaCLBackend backend, long long n, co
 ViennaCLStatus ViennaCLCUDADcsr_mixed_precision_cg(ViennaCLBackend backend, const ViennaCLCUDADcsr *A, const float *values_float,
                                                    const double *b, double *x, float inner_tolerance, ViennaCLB200SolverTag *tag);
 
-/* ---------------------------------------------------------------- row-partitioned (multi-GPU) CG ------------------------------------------ */
+/* ---------------------------------------------------------------- row-partitioned (multi-GPU) solvers ------------------------------------- */
 /* New (no reference counterpart).  Rank g owns a contiguous block of rows of a square matrix; `A_local` holds those rows with
  * GLOBAL column indices.  DistCreate analyses the halo (columns outside the owned range, assumed to belong to the two
  * neighbouring ranks only... general owners are supported through an all-to-all send list), remaps the columns to
@@ -368,8 +373,14 @@ ViennaCLStatus ViennaCLCUDADdist_csrmv(ViennaCLBackend backend, ViennaCLB200Dist
  * by the solver's own kernels), 0 = NCCL send/recv + allreduce.  Also returns the halo size and the interior/boundary split. */
 ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend backend, ViennaCLB200DistCsr A, ViennaCLInt *peer_memory,
                                           ViennaCLInt *halo_entries, ViennaCLInt *interior_blocks, ViennaCLInt *boundary_blocks);
+/* cg.hpp:128-187 over slabs; tag->precond: none, Jacobi or row scaling (diagonal preconditioners, single-reduction PCG as in the
+ * single-GPU library). */
 ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *b_local, double *x_local,
                                         ViennaCLB200SolverTag *tag);
+/* bicgstab.hpp:97-215 (pipelined, no preconditioner) over slabs: two halo exchanges and two all-reduces per iteration, both inside
+ * the product kernels on the peer-memory transport. */
+ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *b_local, double *x_local,
+                                              ViennaCLB200SolverTag *tag);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,10 @@ ViennaCLStatus ViennaCLCUDASnrm2(ViennaCLBackend backend, ViennaCLInt n, float *
 
 /* y[offy + i*incy] = alpha * (A x)_i + (beta != 0 ? beta * y[...] : 0);  x read at offx + col*incx.
  * linalg/sparse_matrix_operations.hpp:90-121 -> cuda/sparse_matrix_operations.hpp:262-396 (kernels :137-249).
- * row_blocks may be NULL (then a plan-free subwarp-per-row kernel is used). */
+ * row_blocks: a plan from ViennaCLCUDAcsr_row_blocks, or ANY partition of the rows into consecutive blocks (e.g. the reference's own
+ * handle3() plan) -- a plan this library did not make is checked once per plan address (cached; rewriting or freeing the plan's
+ * memory through this API drops the verdict) and, when a block breaks the limits above, the product runs through the plan-free
+ * kernel (one thread per row, no staging) -- as it does for row_blocks == NULL or arrays that are not 16-byte aligned. */
 ViennaCLStatus ViennaCLCUDAScsrmv(ViennaCLBackend backend, ViennaCLInt rows, ViennaCLInt cols, ViennaCLInt nnz,
                                   const unsigned int *row_ptr, const unsigned int *col_idx, const float *values,
                                   const unsigned int *row_blocks, ViennaCLInt num_blocks,

@@ -636,7 +636,8 @@ def test_foreign_row_block_plans(pkg, be, orc):
             blk.append(n)
         return np.array(blk, np.uint32)
 
-    plans = {"own": None, "reference": ref_blocks(), "one_block": np.array([0, n], np.uint32), "pairs": np.arange(0, n + 1, 2, dtype=np.uint32)}
+    own = dA.blocks.download()[:dA.nblocks + 1]
+    plans = {"own": None, "own_copy": own.copy(), "reference": ref_blocks(), "one_block": np.array([0, n], np.uint32), "pairs": np.arange(0, n + 1, 2, dtype=np.uint32)}
     assert np.diff(plans["reference"].astype(np.int64)).max() > 256
     for name, blk in plans.items():
         dy = be.array(np.full(n, 7.0))

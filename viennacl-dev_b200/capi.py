@@ -132,6 +132,7 @@ def lib():
     sig("ViennaCLBackendCommGetUniqueId", c_vp, c_vp)
     sig("ViennaCLBackendCommInit", c_vp, c_vp, c_int, c_int)
     sig("ViennaCLBackendCommDestroy", c_vp)
+    sig("ViennaCLBackendCommCheck", c_vp)
     sig("ViennaCLCUDAMemAlloc", c_vp, p_vp, c_sz)
     sig("ViennaCLCUDAMemFree", c_vp, c_vp)
     sig("ViennaCLCUDAMemWrite", c_vp, c_vp, c_sz, c_vp, c_sz, c_int)
@@ -195,6 +196,7 @@ def lib():
     sig("ViennaCLCUDADdist_csrmv", c_vp, c_vp, c_vp, c_vp)
     sig("ViennaCLCUDADdist_csr_info", c_vp, c_vp, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int))
     sig("ViennaCLCUDADdist_csr_cg", c_vp, c_vp, c_vp, c_vp, pt)
+    sig("ViennaCLCUDADdist_csr_bicgstab", c_vp, c_vp, c_vp, c_vp, pt)
     _lib = L
     return L
 
@@ -648,6 +650,10 @@ class DistCsr:
 
     def cg(self, b, x, tag):
         self.b.check(self.b.L.ViennaCLCUDADdist_csr_cg(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))
+        return tag
+
+    def bicgstab(self, b, x, tag):
+        self.b.check(self.b.L.ViennaCLCUDADdist_csr_bicgstab(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))
         return tag
 
     def close(self):

@@ -217,7 +217,7 @@ __global__ void plan_check_kernel(const u32 *rp, int rows, const u32 *blk, int n
   }
 }
 
-bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks)
+bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, long long nnz, const unsigned int *row_blocks, int num_blocks)
 {
   if (!row_blocks || num_blocks <= 0) return false;
   std::map<const void*, ViennaCLBackend_impl::PlanRec>::const_iterator it = b->plans.find(row_blocks);
@@ -231,6 +231,7 @@ bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const
     if (cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess || cudaStreamSynchronize(b->stream) != cudaSuccess)
     { (void)cudaGetLastError(); bad = 1; }
   }
+  if (nnz / num_blocks < 1200) bad = 1;                   // small blocks: the plan-free kernel is the faster one (common.cuh)
   const ViennaCLBackend_impl::PlanRec rec = {row_ptr, rows, num_blocks, bad == 0};
   b->plans[row_blocks] = rec;
   return rec.ok;

@@ -48,7 +48,27 @@ const NcclApi *vcl_nccl(const char **why)
   return g_ok ? &g_api : nullptr;
 }
 
+// Poll the communicator for asynchronous errors (ncclCommGetAsyncError): called by the NCCL transport once per solver batch, after
+// the stream synchronisation, and by ViennaCLBackendCommCheck.
+ViennaCLStatus vcl_comm_check(ViennaCLBackend b)
+{
+  if (!b->nccl_comm) return ViennaCLSuccess;
+  const NcclApi *api = vcl_nccl(nullptr);
+  if (!api) return ViennaCLSuccess;
+  ncclResult_t async = ncclSuccess;
+  const ncclResult_t r = api->CommGetAsyncError((ncclComm_t)b->nccl_comm, &async);
+  if (r != ncclSuccess) return vcl_fail(b, ViennaCLB200CommError, api->GetErrorString(r), __FILE__, __LINE__);
+  if (async != ncclSuccess && async != ncclInProgress) return vcl_fail(b, ViennaCLB200CommError, api->GetErrorString(async), __FILE__, __LINE__);
+  return ViennaCLSuccess;
+}
+
 extern "C" {
+
+ViennaCLStatus ViennaCLBackendCommCheck(ViennaCLBackend b)
+{
+  VCL_CHECK_BACKEND(b);
+  return vcl_comm_check(b);
+}
 
 ViennaCLStatus ViennaCLBackendCommGetUniqueId(ViennaCLBackend b, void *id_bytes)
 {

@@ -60,9 +60,11 @@ struct ViennaCLBackend_impl
 // and <= VCL_B200_CSR_BLOCK_NNZ entries, or one longer row?  Plans made by ViennaCLCUDAcsr_row_blocks are registered as such; any
 // other plan (e.g. the reference's own handle3() blocks, compressed_matrix.hpp:1152-1188: <= 1024 entries but any number of
 // rows) is checked ONCE on the device (one small kernel + one 4-byte read) and the verdict is cached per plan address; a plan
-// that breaks the limits sends the product to the plan-free kernel instead of giving wrong rows.  Writing to / freeing the
-// plan's memory through the C-ABI drops the cached verdict (vcl_plan_forget).
-bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks);
+// that breaks the limits sends the product to the plan-free kernel instead of giving wrong rows -- and so does a valid foreign
+// plan whose blocks are small (fewer than 1200 entries on average: the staging buffers stay half empty; measured at 256^3 with
+// the reference's 1024-entry blocks: 0.329 ms through the TMA kernel, 0.286 ms plan-free, profiles/ab_plans_r2.log).  Writing to /
+// freeing the plan's memory through the C-ABI drops the cached verdict (vcl_plan_forget).
+bool vcl_plan_ok(ViennaCLBackend b, const unsigned int *row_ptr, int rows, long long nnz, const unsigned int *row_blocks, int num_blocks);
 void vcl_plan_register(ViennaCLBackend b, const unsigned int *row_ptr, int rows, const unsigned int *row_blocks, int num_blocks);
 void vcl_plan_forget(ViennaCLBackend b, const void *dst, size_t bytes);
 

@@ -18,6 +18,7 @@
 // reduction per iteration, cg.hpp:116-118).
 #include "fused_kernels.cuh"
 #include "launch.cuh"
+#include "nvtx.cuh"
 #include "blas1.cuh"
 #include "nccl_dyn.cuh"
 #include <cmath>
@@ -268,6 +269,152 @@ ViennaCLStatus dist_plain_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const d
   VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, epi, b->stream));
   VCL_TRY(wait_halo(b, A));
   VCL_TRY(vcl_launch_csr_split(b, subset(A, true), xv, epi, b->stream));
+  return ViennaCLSuccess;
+}
+
+__global__ void bicgstab_advance_kernel(SolverState *st)
+{
+  if (st->done == VCL_RUNNING) bicgstab_advance(st);
+}
+
+__global__ void bicgstab_maxit_kernel(SolverState *st)
+{
+  if (st->done == VCL_RUNNING && st->iters >= st->maxit) st->done = VCL_MAXIT;
+}
+
+__global__ void pcg_advance_kernel(SolverState *st, const double *delta)
+{
+  if (st->done == VCL_RUNNING) pcg_advance(st, *delta);
+}
+
+// NCCL transport (also the single-rank form): global sums of `count` rank-local totals, out of place so that re-issuing the
+// collective after convergence (kernels skipped, `loc` unchanged) reproduces the same global sums
+ViennaCLStatus nccl_sums(ViennaCLBackend b, const double *loc, double *glob, int count)
+{
+  if (b->world == 1)
+  {
+    VCL_CUDA(b, cudaMemcpyAsync(glob, loc, sizeof(double) * count, cudaMemcpyDeviceToDevice, b->stream));
+    return ViennaCLSuccess;
+  }
+  const NcclApi *api = vcl_nccl(nullptr);
+  VCL_NCCL(b, api, api->AllReduce(loc, glob, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)b->nccl_comm, b->stream));
+  return ViennaCLSuccess;
+}
+
+// NCCL transport: y = A x [./ diag] as interior launch + halo wait + boundary launch; the rank-local totals <y,y>, <x,y>, <y,r0*>
+// land in *o0, *o1, *o2 (any of them may be NULL)
+template<bool USE_R0, bool JACOBI>
+ViennaCLStatus nccl_fused_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *x, double *y, const double *r0, const double *diag,
+                               SolverState *st, double *o0, double *o1, double *o2)
+{
+  XVec xv = make_xvec(x, 0, 1, A->halo_buf, (u32)A->n);
+  VCL_TRY(start_halo(b, A, x));
+  const bool both = A->n_interior > 0 && A->n_boundary > 0;
+  if (A->n_interior > 0)
+  {
+    EpiFused<STEP_NONE, USE_R0, JACOBI> ei = {y, x, r0, diag, b->partials, b->tickets, st, both ? A->tmp_sums + 0 : o0, both ? A->tmp_sums + 1 : o1,
+                                              both ? A->tmp_sums + 2 : o2, {0.0, 0.0, 0.0}, nullptr};
+    VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, ei, b->stream));
+  }
+  VCL_TRY(wait_halo(b, A));
+  if (A->n_boundary > 0)
+  {
+    EpiFused<STEP_NONE, USE_R0, JACOBI> eb = {y, x, r0, diag, b->partials, b->tickets, st, o0, o1, o2, {0.0, 0.0, 0.0}, both ? A->tmp_sums : nullptr};
+    VCL_TRY(vcl_launch_csr_split(b, subset(A, true), xv, eb, b->stream));
+  }
+  return ViennaCLSuccess;
+}
+
+ViennaCLStatus dist_pull_state(ViennaCLBackend b, ViennaCLB200DistCsr A)
+{
+  VCL_CUDA(b, cudaMemcpyAsync(VCL_HSTATE(b), VCL_DSTATE(b), sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  if (A->p2p) return p2p_check(b, A);
+  return vcl_comm_check(b);                                // asynchronous NCCL errors (a peer died, a transport failed) surface here
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-partitioned CG with a diagonal preconditioner (Jacobi / row scaling): the single-reduction PCG of solvers.cu (pcg_jacobi)
+// over slabs -- per iteration one vector kernel, one halo exchange, one fused product whose last CTA all-reduces
+// {gamma = <r,u>, delta = <w,u>} across the ranks and advances alpha / beta (peer-memory transport).
+// ------------------------------------------------------------------------------------------------
+ViennaCLStatus dist_pcg(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *rhs, double *x, ViennaCLB200SolverTag *tag, int info_option)
+{
+  const long long n = A->n;
+  const size_t need = ((size_t)std::max<long long>(n, 1) * sizeof(double) + 255) / 256 * 256;
+  VCL_TRY(vcl_ws_reserve(b, 6 * need));
+  char *w0 = (char*)b->ws;
+  double *r = (double*)w0, *u = (double*)(w0 + need), *w = (double*)(w0 + 2 * need), *p = (double*)(w0 + 3 * need), *s = (double*)(w0 + 4 * need),
+         *diag = (double*)(w0 + 5 * need);
+  const int grid = (int)std::max(1LL, std::min((n / 2 + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+  double *loc = b->dscal + 32;                             // [0] gamma, [1] delta (rank-local)
+
+  // the diagonal entry of local row i is the entry with LOCAL column i (owned columns are renumbered to [0, n))
+  if (n > 0) VCL_TRY(ViennaCLCUDADcsr_row_info(b, (int)n, A->rp, A->ci_local, A->va, diag, info_option));
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(p, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(s, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(b->dscal, 0, 2 * sizeof(double), b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(loc, 0, 2 * sizeof(double), b->stream));
+  if (n > 0)
+  {
+    pcg_init_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, r, u, diag, b->partials, b->tickets, b->dscal + 0);
+    VCL_LAUNCHED(b, "pcg_init_kernel");
+  }
+  VCL_TRY(dist_plain_prod(b, A, u, w));
+  if (n > 0) VCL_TRY(vcl_dot_async(b, n, w, 0, 1, u, 0, 1, b->dscal + 1));
+  VCL_TRY(allreduce_sum(b, A, b->dscal, 2));
+  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  const double gamma0 = b->hscal[0], delta0 = b->hscal[1];
+  if (std::fabs(gamma0) <= tag->abs_tolerance * tag->abs_tolerance) return ViennaCLSuccess;
+
+  SolverState *h = VCL_HSTATE(b);
+  std::memset(h, 0, sizeof(SolverState));
+  h->alpha = gamma0 / delta0; h->beta = 0.0; h->ip_rr0 = gamma0; h->norm_rhs_sq = gamma0; h->norm_rhs = std::sqrt(std::fabs(gamma0));
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations; h->sums[0] = gamma0;
+  VCL_CUDA(b, cudaMemcpyAsync(b->dstate, h, sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  SolverState *st = VCL_DSTATE(b);
+
+  const int kBatch = 32;
+  int launched = 0;
+  const u64 halo_base = A->halo_seq, red_base = A->red_seq;
+  while (launched < tag->max_iterations)
+  {
+    const int nb = std::min(kBatch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
+    for (int k = 0; k < nb; ++k)
+    {
+      if (n > 0)
+      {
+        pcg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, r, u, w, p, s, diag, st, b->partials, b->tickets, loc + 0);
+        VCL_LAUNCHED(b, "pcg_update_kernel");
+      }
+      if (A->p2p)
+      {
+        const u64 hseq = halo_base + (u64)(launched + k + 1), rseq = red_base + (u64)(launched + k + 1);
+        EpiFused<STEP_NONE, false, false> e = {w, u, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
+                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc + 0, DIST_PCG};
+        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, hseq, true), p2p_xvec(A, u, hseq), e));
+      }
+      else
+      {
+        VCL_TRY((nccl_fused_prod<false, false>(b, A, u, w, nullptr, nullptr, st, nullptr, loc + 1, nullptr)));
+        VCL_TRY(nccl_sums(b, loc, b->dscal + 36, 2));
+        VCL_CUDA(b, cudaMemcpyAsync(&st->sums[0], b->dscal + 36, sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+        pcg_advance_kernel<<<1, 1, 0, b->stream>>>(st, b->dscal + 37);
+        VCL_LAUNCHED(b, "pcg_advance_kernel");
+      }
+    }
+    launched += nb;
+    VCL_TRY(dist_pull_state(b, A));
+    if (h->done != VCL_RUNNING) break;
+  }
+  if (A->p2p) { A->halo_seq = halo_base + (u64)h->iters; A->red_seq = red_base + (u64)h->iters; }
+  tag->iters = h->iters;
+  tag->error = std::sqrt(std::fabs(h->sums[0] / gamma0));
   return ViennaCLSuccess;
 }
 
@@ -603,6 +750,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend b, ViennaCLB200DistCsr
 
 ViennaCLStatus ViennaCLCUDADdist_csrmv(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *x_local, double *y_local)
 {
+  VCL_RANGE("vcl:dist_csrmv");
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, A && (A->n == 0 || (x_local && y_local)) && x_local != y_local, "bad arguments");
   if (A->n == 0 && b->world == 1) return ViennaCLSuccess;
@@ -612,14 +760,28 @@ ViennaCLStatus ViennaCLCUDADdist_csrmv(ViennaCLBackend b, ViennaCLB200DistCsr A,
 // cg.hpp:128-187 over row-partitioned data: local fused kernels + halo exchange + one allreduce per iteration.
 ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:dist_cg");
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, A && tag, "bad arguments");
-  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: only the unpreconditioned pipelined path is provided");
   VCL_REQUIRE(b, tag->monitor == nullptr, "monitor callbacks are not supported on the row-partitioned path");
   const long long n = A->n;
   tag->iters = 0; tag->error = 0.0;
   VCL_REQUIRE(b, n == 0 || (rhs && x), "null vector");
   VCL_CUDA(b, cudaSetDevice(b->device));
+  {
+    // diagonal preconditioners (jacobi_precond.hpp:103-130, row_scaling.hpp): row_info option 3 / 0 / 1 / 2
+    int opt = -1;
+    switch (tag->precond)
+    {
+    case ViennaCLB200PrecondJacobi: opt = 3; break;
+    case ViennaCLB200PrecondRowScalingInf: opt = 0; break;
+    case ViennaCLB200PrecondRowScaling1: opt = 1; break;
+    case ViennaCLB200PrecondRowScaling2: opt = 2; break;
+    default: break;
+    }
+    if (opt >= 0) return dist_pcg(b, A, rhs, x, tag, opt);
+  }
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "CG: unknown preconditioner id");
   const size_t need = ((size_t)std::max<long long>(n, 1) * sizeof(double) + 255) / 256 * 256;
   VCL_TRY(vcl_ws_reserve(b, 3 * need));
   double *r = (double*)b->ws, *p = (double*)((char*)b->ws + need), *Ap = (double*)((char*)b->ws + 2 * need);
@@ -665,6 +827,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
     while (launched < tag->max_iterations)
     {
       const int nb = std::min(kBatch, tag->max_iterations - launched);
+      VCL_RANGE("vcl:batch");
       for (int k = 0; k < nb; ++k)
       {
         // iteration i = launched + k + 1 uses exchange numbers base + i; once st->done is set every later kernel returns
@@ -730,6 +893,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(kBatch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
     for (int k = 0; k < nb; ++k)
     {
       // NB: the kernels below are skipped on the device once st->done is set, but the collectives are still issued --
@@ -762,10 +926,116 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
     launched += nb;
     VCL_CUDA(b, cudaMemcpyAsync(h, st, sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    VCL_TRY(vcl_comm_check(b));                            // asynchronous NCCL errors (a peer died, a transport failed) surface here
     if (h->done != VCL_RUNNING) break;
   }
   tag->iters = h->iters;
   tag->error = std::sqrt(std::fabs(h->sums[0]) / norm_rhs_squared);
+  return ViennaCLSuccess;
+}
+
+// bicgstab.hpp:97-215 (pipelined BiCGStab, no preconditioner) over row-partitioned data.  Per iteration: two fused products, each
+// with its own halo exchange and its own all-reduce in the product kernel's tail ({<r,r0*>, <Ap,r0*>} after Ap = A p;
+// {<s,s>, <As,As>, <As,s>, <As,r0*>} after As = A s, followed by the scalar recurrences), and two vector kernels.
+ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_RANGE("vcl:dist_bicgstab");
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, A && tag, "bad arguments");
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "row-partitioned BiCGStab: only the unpreconditioned pipelined path is provided");
+  VCL_REQUIRE(b, tag->monitor == nullptr, "monitor callbacks are not supported on the row-partitioned path");
+  const long long n = A->n;
+  tag->iters = 0; tag->error = 0.0;
+  VCL_REQUIRE(b, n == 0 || (rhs && x), "null vector");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+  const size_t need = ((size_t)std::max<long long>(n, 1) * sizeof(double) + 255) / 256 * 256;
+  VCL_TRY(vcl_ws_reserve(b, 6 * need));
+  char *w0 = (char*)b->ws;
+  double *r = (double*)w0, *p = (double*)(w0 + need), *r0 = (double*)(w0 + 2 * need), *Ap = (double*)(w0 + 3 * need), *s = (double*)(w0 + 4 * need),
+         *As = (double*)(w0 + 5 * need);
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(p, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(r0, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  // rank-local totals, laid out like SolverState::sums: [0] <r,r0*>, [1] <As,As>, [2] <As,s>, [3] <Ap,r0*>, [4] <As,r0*>, [5] <s,s>
+  double *loc = b->dscal + 32;
+  VCL_CUDA(b, cudaMemsetAsync(loc, 0, 8 * sizeof(double), b->stream));
+  if (n > 0) VCL_TRY(vcl_dot_async(b, n, r, 0, 1, r, 0, 1, loc + 0));
+  VCL_CUDA(b, cudaMemcpyAsync(b->dscal, loc, sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  VCL_TRY(allreduce_sum(b, A, b->dscal, 1));
+  VCL_CUDA(b, cudaMemcpyAsync(b->hscal, b->dscal, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  const double norm_rhs = std::sqrt(b->hscal[0]);
+  if (norm_rhs <= tag->abs_tolerance) return ViennaCLSuccess;                       // bicgstab.hpp:140-141
+
+  SolverState *h = VCL_HSTATE(b);
+  std::memset(h, 0, sizeof(SolverState));
+  h->norm_rhs = norm_rhs; h->norm_rhs_sq = norm_rhs * norm_rhs; h->residual_norm = norm_rhs;
+  h->tol = tag->tolerance; h->abs_tol = tag->abs_tolerance; h->maxit = tag->max_iterations;
+  h->sums[0] = norm_rhs * norm_rhs;                                                 // bicgstab.hpp:131
+  VCL_CUDA(b, cudaMemcpyAsync(b->dstate, h, sizeof(SolverState), cudaMemcpyHostToDevice, b->stream));
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  SolverState *st = VCL_DSTATE(b);
+
+  const int grid = (int)std::max(1LL, std::min((n / 2 + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
+  const int kBatch = 32;
+  int launched = 0;
+  const u64 halo_base = A->halo_seq, red_base = A->red_seq;
+  while (launched < tag->max_iterations)
+  {
+    const int nb = std::min(kBatch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
+    for (int k = 0; k < nb; ++k)
+    {
+      const u64 it = (u64)(launched + k);                  // iteration it + 1 uses exchanges 2 it + 1 and 2 it + 2
+      if (A->p2p)
+      {
+        EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
+                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, red_base + 2 * it + 1, loc + 0, DIST_BICG_P};
+        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, halo_base + 2 * it + 1, true), p2p_xvec(A, p, halo_base + 2 * it + 1), e1));
+      }
+      else
+      {
+        VCL_TRY((nccl_fused_prod<true, false>(b, A, p, Ap, r0, nullptr, st, nullptr, nullptr, loc + 3)));
+        VCL_TRY(nccl_sums(b, loc, &st->sums[0], 4));      // <r,r0*> and <Ap,r0*> are needed now (alpha); [1], [2] are rewritten below
+      }
+      if (n > 0)
+      {
+        bicgstab_update_s_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, s, r, Ap, &st->sums[0], &st->sums[3], st, b->partials, b->tickets, loc + 5);
+        VCL_LAUNCHED(b, "bicgstab_update_s_kernel");
+      }
+      if (A->p2p)
+      {
+        EpiFused<STEP_NONE, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
+                                               {0.0, 0.0, 0.0}, nullptr, A->d_win, red_base + 2 * it + 2, loc + 5, DIST_BICG_S};
+        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, halo_base + 2 * it + 2, true), p2p_xvec(A, s, halo_base + 2 * it + 2), e2));
+      }
+      else
+      {
+        VCL_TRY((nccl_fused_prod<true, false>(b, A, s, As, r0, nullptr, st, loc + 1, loc + 2, loc + 4)));
+        VCL_TRY(nccl_sums(b, loc, &st->sums[0], 6));
+        bicgstab_advance_kernel<<<1, 1, 0, b->stream>>>(st);
+        VCL_LAUNCHED(b, "bicgstab_advance_kernel");
+      }
+      if (n > 0)
+      {
+        bicgstab_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, 0.0, p, 0.0, s, r, As, 0.0, Ap, r0, st, b->partials, b->tickets, loc + 0);
+        VCL_LAUNCHED(b, "bicgstab_update_kernel");
+      }
+      else
+      {
+        // a rank without rows still has to raise MAXIT like the others (bicgstab_update_kernel does it for them)
+        bicgstab_maxit_kernel<<<1, 1, 0, b->stream>>>(st);
+        VCL_LAUNCHED(b, "bicgstab_maxit_kernel");
+      }
+    }
+    launched += nb;
+    VCL_TRY(dist_pull_state(b, A));
+    if (h->done != VCL_RUNNING) break;
+  }
+  if (A->p2p) { A->halo_seq = halo_base + 2 * (u64)h->iters; A->red_seq = red_base + 2 * (u64)h->iters; }
+  tag->iters = h->iters;
+  tag->error = h->residual_norm / norm_rhs;                                          // bicgstab.hpp:212
   return ViennaCLSuccess;
 }
 

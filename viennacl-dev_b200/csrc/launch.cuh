@@ -51,7 +51,7 @@ static ViennaCLStatus vcl_launch_csr(ViennaCLBackend b, const ViennaCLCUDADcsr &
   CsrDev d = {A.rows, (u32)A.nnz, A.row_ptr, A.col_idx, A.values, A.row_blocks, A.row_blocks ? A.row_blocks + 1 : nullptr, A.num_blocks};
   d.l2_mode = vcl_l2_mode(b, A.nnz, A.rows);
   if (A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx) &&
-      vcl_plan_ok(b, A.row_ptr, A.rows, A.row_blocks, A.num_blocks))
+      vcl_plan_ok(b, A.row_ptr, A.rows, A.nnz, A.row_blocks, A.num_blocks))
   {
     const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, false>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
     int grid = std::min(A.num_blocks, std::min(b->sm_count * occ, VCL_MAX_BLOCKS));

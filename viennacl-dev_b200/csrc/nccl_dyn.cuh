@@ -3,10 +3,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
+#include "common.cuh"
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2, ncclInternalError = 3, ncclInvalidArgument = 4,
+               ncclInvalidUsage = 5, ncclRemoteError = 6, ncclInProgress = 7 } ncclResult_t;
 typedef enum { ncclInt8 = 0, ncclChar = 0, ncclUint8 = 1, ncclInt32 = 2, ncclInt = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5,
                ncclFloat16 = 6, ncclHalf = 6, ncclFloat32 = 7, ncclFloat = 7, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
@@ -28,3 +30,6 @@ struct NcclApi
 
 // NULL when no libnccl could be loaded; *why receives a description.
 const NcclApi *vcl_nccl(const char **why);
+
+// polls ncclCommGetAsyncError on the handle's communicator (comm.cu); ViennaCLSuccess without a communicator
+ViennaCLStatus vcl_comm_check(ViennaCLBackend b);

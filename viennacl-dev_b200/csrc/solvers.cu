@@ -4,6 +4,7 @@
 // at the state once per batch (with a monitor callback installed: once per iteration, as the reference's contract demands).
 #include "fused_kernels.cuh"
 #include "launch.cuh"
+#include "nvtx.cuh"
 #include "persistent.cuh"
 #include "blas1.cuh"
 #include <cmath>
@@ -110,7 +111,7 @@ static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, l
 {
   const long long max_rows = b->persistent_rows >= 0 ? b->persistent_rows : 10000000LL;
   return b->coop_launch == 1 && n <= max_rows / row_limit_divisor && A.row_blocks && A.num_blocks > 0 && vcl_aligned16(A.values) && vcl_aligned16(A.col_idx) &&
-         vcl_plan_ok(b, A.row_ptr, A.rows, A.row_blocks, A.num_blocks);
+         vcl_plan_ok(b, A.row_ptr, A.rows, A.nnz, A.row_blocks, A.num_blocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -121,6 +122,7 @@ static bool persistent_cg_wanted(ViennaCLBackend b, const ViennaCLCUDADcsr &A, l
 // ------------------------------------------------------------------------------------------------
 ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:pcg_jacobi");
   VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
@@ -160,6 +162,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
@@ -197,6 +200,7 @@ ViennaCLStatus pcg_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, re
 // ------------------------------------------------------------------------------------------------
 ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:cg");
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
   VCL_TRY(check_matrix(b, A));
@@ -258,6 +262,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
   while (launched < tag->max_iterations)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
@@ -306,6 +311,7 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
 // ------------------------------------------------------------------------------------------------
 ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:bicgstab_pipelined");
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 6 * Carver::need(n)));
   Carver cv(b->ws);
@@ -341,6 +347,7 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real 
   while (launched < tag->max_iterations && !stopped)
   {
     const int nb = std::min(batch, tag->max_iterations - launched);
+    VCL_RANGE("vcl:batch");
     if (coop_grid > 0)
     {
       CsrDev d = {A.csr.rows, (u32)A.csr.nnz, A.csr.row_ptr, A.csr.col_idx, A.csr.values, A.csr.row_blocks, A.csr.row_blocks + 1, A.csr.num_blocks};
@@ -389,6 +396,7 @@ ViennaCLStatus bicgstab_pipelined(ViennaCLBackend b, const MatOp &A, const real 
 // ------------------------------------------------------------------------------------------------
 ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:bicgstab_jacobi");
   VCL_REQUIRE(b, A.fmt == 0, "Jacobi needs the CSR matrix (row_info, linalg/sparse_matrix_operations.hpp:48-74)");
   const long long n = A.rows();
   VCL_TRY(vcl_ws_reserve(b, 7 * Carver::need(n)));
@@ -425,6 +433,7 @@ ViennaCLStatus bicgstab_jacobi(ViennaCLBackend b, const MatOp &A, const real *rh
     const int remaining = tag->max_iterations - h->iters;
     if (remaining <= 0) break;
     const int nb = std::min(batch, remaining);
+    VCL_RANGE("vcl:batch");
     for (int k = 0; k < nb; ++k)
     {
       EpiFused<STEP_PBICG_ALPHA, true, true> e1 = {t0, p, r0, diag, VCL_PARTIALS(b), b->tickets, st, nullptr, nullptr, nullptr, {0.0, 0.0, 0.0}, nullptr};
@@ -496,6 +505,7 @@ int scalar_grid(ViennaCLBackend b, long long n)
 
 ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
+  VCL_RANGE("vcl:gmres");
   VCL_CHECK_BACKEND(b);
   VCL_REQUIRE(b, tag != nullptr, "null tag");
   VCL_TRY(check_matrix(b, A));
