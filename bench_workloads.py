@@ -78,7 +78,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
     # device->host copy of step i overlaps the host->device copy of step i+1 (PCIe is full duplex); every step still moves
     # its own x in and its own y out.  Row-partitioned runs use the one handle the communicator is bound to.
     lanes = []
-    n_lanes = 2 if world == 1 else 1
+    n_lanes = int(os.environ.get("VCL_BENCH_LANES", "2")) if world == 1 else 1
     for li in range(n_lanes):
         b_l = be if li == 0 else pkg.Backend(be.device_info()[0])
         x_l, y_l = (x, y) if li == 0 else (b_l.empty(n), b_l.zeros(n))
@@ -88,7 +88,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
         be.check(be.L.ViennaCLCUDAMemRead(be.h, x.ptr, 0, hx, 8 * n, 0))
         lanes.append((b_l, x_l, y_l, hx, hy))
     e2e_steps = max(4, min(args.steps, 10))
-    e2e_steps += e2e_steps % n_lanes
+    e2e_steps = (e2e_steps + n_lanes - 1) // n_lanes * n_lanes
 
     def e2e_step(i):
         b_l, x_l, y_l, hx, hy = lanes[i % n_lanes]
@@ -145,8 +145,8 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "checksum": checksum,
                 "note": "every step: pinned host x -> device, y = prod(A, x) through the C-ABI, y -> pinned host; the matrix stays resident "
-                        "like a viennacl::compressed_matrix; " + ("2 backend handles (streams) alternate so D2H of step i overlaps H2D of step i+1"
-                                                                  if n_lanes == 2 else "one handle (communicator-bound)")},
+                        "like a viennacl::compressed_matrix; " + ("%d backend handles (streams) take the steps in turn so D2H of step i overlaps H2D of step i+1" % n_lanes
+                                                                  if n_lanes > 1 else "one handle (communicator-bound)")},
         "gpu_launches": int(l1 - l0),
         "clocks": sampler.summary(),
     }

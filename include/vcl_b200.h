@@ -62,8 +62,9 @@ ViennaCLStatus ViennaCLBackendFlushL2(ViennaCLBackend backend);
  *                      (10M rows; env VCL_B200_PERSISTENT_ROWS at handle creation), 0: always multi-kernel.
  *   "l2_resident"      persistent kernels keep a matrix that fits L2 resident there (evict-last) instead of streaming it
  *                      (evict-first): 0 never (default: measured slower on B200), 1 evict-last, 2 normal policy.
- *   "persistent_cg_form"  1 (default): one-pass persistent CG -- one grid barrier per iteration, the product recomputes the
- *                      updated search direction on the fly; 2: the two-phase form (update, barrier, product, barrier). */
+ *   "persistent_cg_form"  0 (default): chosen by size; 1: one-pass persistent CG -- one grid barrier per iteration, the product
+ *                      recomputes the updated search direction on the fly (best up to ~600k rows); 2: the two-phase form (update,
+ *                      barrier, product, barrier); 3: one-pass compiled for 3 CTAs per SM. */
 ViennaCLStatus ViennaCLBackendSetOption(ViennaCLBackend backend, const char *name, long long value);
 /* Counts kernels launched by this library on this handle since creation (bench.py's gpu_launches). */
 ViennaCLStatus ViennaCLBackendLaunchCount(ViennaCLBackend backend, long long *launches);
@@ -114,7 +115,9 @@ ViennaCLStatus ViennaCLCUDADnrm2(ViennaCLBackend backend, ViennaCLInt n, double 
  * Each block holds whole rows: at most VCL_B200_CSR_BLOCK_ROWS rows and VCL_B200_CSR_BLOCK_NNZ non-zeros, or one longer row.
  * Two-call protocol: row_blocks == NULL returns the count in *num_blocks; then pass a device buffer of (*num_blocks + 1) u32. */
 #define VCL_B200_CSR_BLOCK_ROWS 256
+#ifndef VCL_B200_CSR_BLOCK_NNZ
 #define VCL_B200_CSR_BLOCK_NNZ  2048
+#endif
 ViennaCLStatus ViennaCLCUDAcsr_row_blocks(ViennaCLBackend backend, ViennaCLInt rows, const unsigned int *row_ptr,
                                           unsigned int *row_blocks, ViennaCLInt *num_blocks);
 

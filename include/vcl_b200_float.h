@@ -36,6 +36,10 @@ ViennaCLStatus ViennaCLCUDASnrm2(ViennaCLBackend backend, ViennaCLInt n, float *
 /* CSR row blocks: compressed_matrix.hpp:1152-1188 (generate_row_block_information) -> handle3()/blocks1().
  * Each block holds whole rows: at most VCL_B200_CSR_BLOCK_ROWS rows and VCL_B200_CSR_BLOCK_NNZ non-zeros, or one longer row.
  * Two-call protocol: row_blocks == NULL returns the count in *num_blocks; then pass a device buffer of (*num_blocks + 1) u32. */
+#define VCL_B200_CSR_BLOCK_ROWS 256
+#ifndef VCL_B200_CSR_BLOCK_NNZ
+#define VCL_B200_CSR_BLOCK_NNZ  2048
+#endif
 
 /* y[offy + i*incy] = alpha * (A x)_i + (beta != 0 ? beta * y[...] : 0);  x read at offx + col*incx.
  * linalg/sparse_matrix_operations.hpp:90-121 -> cuda/sparse_matrix_operations.hpp:262-396 (kernels :137-249).

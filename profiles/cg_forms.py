@@ -22,4 +22,4 @@ for n1 in sizes:
             best = ms if best is None else min(best, ms)
         print("cg %d^2 %-13s: %d iters err %.6e  %.2f ms -> %.0f it/s (%.2f us/iter)"
               % (n1, name, t.iters, t.error, best, t.iters / best * 1e3, best * 1e3 / max(t.iters, 1)), flush=True)
-    be.set_option("persistent_rows", -1); be.set_option("persistent_cg_form", 1)
+    be.set_option("persistent_rows", -1); be.set_option("persistent_cg_form", 0)

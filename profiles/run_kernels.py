@@ -3,7 +3,7 @@
     ncu --set full --clock-control none --import-source on -k regex:<name> -s 1 -c 2 -o gpurun_out/prof_<name> \
         python profiles/run_kernels.py <what>
 
-what: spmv (CSR + SELL, 256^3) | cg (3 iterations at 256^3, CSR) | cg_sell | bicgstab | bicgstab_jacobi | gmres | gmres_jacobi |
+what: spmv (CSR + SELL, 256^3) | spmv_split (the SPLIT instantiation, world 1) | cg (3 iterations at 256^3, CSR) | cg_sell | bicgstab | bicgstab_jacobi | gmres | gmres_jacobi |
       cg1024 (persistent cooperative kernel) | spmv_f32 (float CSR / SELL / ELL, 256^3)
 """
 import os
@@ -40,6 +40,11 @@ if what == "spmv_f32":
         Af.spmv(xf, yf); Sf.spmv(xf, yf); Ef.spmv(xf, yf)
 elif what == "gmres_jacobi":
     pkg.SolverTag(tol=0.0, max_iterations=30, krylov_dim=30, precond=1).solve("gmres", A, b, y)
+elif what == "spmv_split":
+    # the row-partitioned instantiation csr_stream_kernel<EpiAxpby, SPLIT=true> on one rank (no halo: all row blocks are interior)
+    D = pkg.DistCsr(be, n, 0, n, A)
+    for _ in range(3):
+        D.spmv(x, y)
 elif what == "spmv":
     S = A.to_sell(32)
     for _ in range(3):

@@ -23,7 +23,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "baseline_configs.json")))
 SPREAD = json.load(open(os.path.join(ROOT, "tests", "golden", "bicgstab_spread.json")))
-DRIVERS = ["persistent", "persistent_twophase", "multikernel"]
+DRIVERS = ["persistent", "persistent_onepass", "persistent_twophase", "multikernel"]
 
 
 def note(**kw):
@@ -35,10 +35,10 @@ def note(**kw):
 @pytest.fixture
 def driver(request, be):
     be.set_option("persistent_rows", 0 if request.param == "multikernel" else -1)
-    be.set_option("persistent_cg_form", 2 if request.param == "persistent_twophase" else 1)
+    be.set_option("persistent_cg_form", {"persistent_twophase": 2, "persistent_onepass": 1}.get(request.param, 0))
     yield request.param
     be.set_option("persistent_rows", -1)
-    be.set_option("persistent_cg_form", 1)
+    be.set_option("persistent_cg_form", 0)
 
 
 def sample(dx, g):

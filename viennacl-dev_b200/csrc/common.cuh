@@ -48,7 +48,7 @@ struct ViennaCLBackend_impl
   // per-handle options (ViennaCLBackendSetOption) and device facts
   long long persistent_rows = -1;              // row limit of the persistent cooperative solver kernels; -1: built-in default, 0: never
   int l2_resident = -1;                        // keep small matrices resident in L2 inside the persistent kernels: -1 auto, 0 never, 1 always
-  int persistent_cg_form = 1;                  // 1: one-pass persistent CG (one grid barrier per iteration), 2: the two-phase form
+  int persistent_cg_form = 0;                  // 0: by size, 1 / 3: one-pass persistent CG (one grid barrier per iteration; 2 / 3 CTAs per SM), 2: the two-phase form
   int coop_launch = 0;                         // device supports cooperative launches
 
   // CSR row-block plans this handle has seen (key: device address of the plan), see vcl_plan_ok

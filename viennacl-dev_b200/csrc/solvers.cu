@@ -248,7 +248,10 @@ ViennaCLStatus cg_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real
   // the updated p on the fly; "twophase" = update phase, barrier, product phase, barrier (option "persistent_cg_form" = 2).
   // Large systems are bound by HBM and keep the two-kernel form.
   int coop_grid = 0;
-  const bool onepass = b->persistent_cg_form != 2;
+  // form 0 (default) = by size: the one-pass form wins while fixed latencies dominate (512^2: 10.5 against 13.5 us per iteration),
+  // is level at 1M rows and loses once the three gathers per entry cost more L2 traffic than the saved barrier (2048^2: 117
+  // against 104 us; profiles/cg_forms_r2b.log)
+  const bool onepass = b->persistent_cg_form == 0 ? n <= 600000 : b->persistent_cg_form != 2;
   const void *onepass_fn = b->persistent_cg_form == 3 ? (const void*)cg_onepass_kernel<3> : (const void*)cg_onepass_kernel<2>;
   if (want_coop)
   {

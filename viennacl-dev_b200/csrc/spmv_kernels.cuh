@@ -218,7 +218,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #define CSR_NSTAGE 2                                                               // shared-memory ring depth (blocks)
 #endif
 #define CSR_SMEM_BYTES (CSR_NSTAGE * CSR_STAGE * (int)(sizeof(real) + sizeof(u32)))  // dynamic shared memory
+#ifndef CSR_MIN_CTAS
 #define CSR_MIN_CTAS (CSR_NSTAGE <= 2 ? 4 : (CSR_NSTAGE == 3 ? 3 : 2))
+#endif
 
 struct CsrBlockDesc { u32 r0, r1, n0, n1; };
 
@@ -526,13 +528,13 @@ template<class Epi, bool PERM, int CT>      // PERM: SELL-C-sigma (storage row -
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
-  constexpr int S = CSR_NSTAGE;
+  constexpr int S = 2;                                     // this kernel is written for a two-stage ring (it uses the first two CSR stages)
   extern __shared__ __align__(128) unsigned char csr_smem[];
   __shared__ __align__(8) unsigned long long s_bar[S];
   __shared__ real s_red[(Epi::NQ > 0 ? Epi::NQ : 1) * 32];
   real *s_val0 = reinterpret_cast<real*>(csr_smem);
   u32 *s_col0 = reinterpret_cast<u32*>(csr_smem + S * CSR_STAGE * sizeof(real));
-  static_assert(CSR_NSTAGE == 2, "sell_kernel is written for a two-stage ring");
+  static_assert(CSR_NSTAGE >= 2, "sell_kernel needs two stages of the CSR ring");
 
   if (epi.skip()) return;
   const real * __restrict__ va = A.va;
