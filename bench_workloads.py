@@ -78,7 +78,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
     # device->host copy of step i overlaps the host->device copy of step i+1 (PCIe is full duplex); every step still moves
     # its own x in and its own y out.  Row-partitioned runs use the one handle the communicator is bound to.
     lanes = []
-    n_lanes = int(os.environ.get("VCL_BENCH_LANES", "2")) if world == 1 else 1
+    n_lanes = int(os.environ.get("VCL_BENCH_LANES", "4")) if world == 1 else 1
     for li in range(n_lanes):
         b_l = be if li == 0 else pkg.Backend(be.device_info()[0])
         x_l, y_l = (x, y) if li == 0 else (b_l.empty(n), b_l.zeros(n))

@@ -66,6 +66,8 @@ traffic = {}
 for d in rows_out:
     if d["capture"].endswith("spmv") and "csr_stream_kernel<EpiAxpby" in d["kernel"]:
         traffic["csr_spmv_256"] = d["dram_total"]
+    if d["capture"].endswith("spmv_split") and "csr_stream_kernel<EpiAxpby" in d["kernel"]:
+        traffic["csr_spmv_256_split"] = d["dram_total"]      # the SPLIT instantiation of the row-partitioned runs, captured at world 1
     if d["capture"].endswith("spmv") and "sell_kernel<EpiAxpby" in d["kernel"]:
         traffic["sell_spmv_256"] = d["dram_total"]
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
