@@ -339,15 +339,28 @@ def main():
             cg = bw.cg_side(pkg, be, args, rank, world, barrier, max_over_ranks)
             if rank == 0:
                 line["cg"] = cg
+        # clocks / throttle reasons were sampled (every 0.1 s) from the first warm-up step to here: the timed SpMV region, the e2e
+        # region and the side measurements -- all of it GPU load of this process
+        sampler.stop_flag.set()
+        if rank == 0:
+            line["clocks"] = sampler.summary()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_spmv(n1)
             if not args.no_extras and line.get("cg") and "lap2d_1024" in line["cg"]:
                 line["cg"]["lap2d_1024"]["cpu_baseline"] = cpu_baseline_cg()
             if not args.no_extras:
                 line["legacy_cuda_baseline"] = legacy_cuda_baseline(n1)
-                lc = line["legacy_cuda_baseline"].get("csr_spmv_256", {})
-                if lc.get("effective_GBps"):
-                    line["legacy_cuda_baseline"]["ratio_csr_spmv"] = line["value"] / lc["effective_GBps"]
+                lg = line["legacy_cuda_baseline"]
+                if lg.get("csr_spmv_256", {}).get("effective_GBps"):
+                    lg["ratio_csr_spmv"] = line["value"] / lg["csr_spmv_256"]["effective_GBps"]
+                if lg.get("sell_spmv_256", {}).get("effective_GBps") and line.get("sell"):
+                    lg["ratio_sell_spmv"] = line["sell"]["value"] / lg["sell_spmv_256"]["effective_GBps"]
+                if lg.get("cg_lap2d_1024", {}).get("iterations_per_sec") and line.get("cg"):
+                    lg["ratio_cg_lap2d_1024"] = line["cg"]["lap2d_1024"]["iterations_per_sec"] / lg["cg_lap2d_1024"]["iterations_per_sec"]
+                if lg.get("csr_spmv_256", {}).get("correct") is False:
+                    lg["note"] = ("the legacy CSR kernel K1 (cuda/sparse_matrix_operations.hpp:137-178) returns WRONG rows on sm_100: its warp-synchronous "
+                                  "shared-memory reduction has no __syncwarp (:168-173, SURVEY 0); its time is still reported, the SELL kernel and the CG "
+                                  "(adaptive CSR kernel K7) are correct")
     else:
         import bench_workloads as bw
         line = bw.cg512_workload(pkg, be, args, rank, world, barrier, max_over_ranks, sampler, peak, peak_src)

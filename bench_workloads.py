@@ -113,7 +113,6 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
     e2e_sync()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
-    sampler.stop_flag.set()
     e2e_ms = max_over_ranks(e2e_ms)
     e2e_val = nbytes * world * e2e_steps / (e2e_ms * 1e-3) / 1e9
     checksum = float(sum(np.ctypeslib.as_array(C.cast(ln[4], C.POINTER(C.c_double)), shape=(n,))[:1024].sum() for ln in lanes) / n_lanes)
@@ -148,7 +147,6 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
                         "like a viennacl::compressed_matrix; " + ("%d backend handles (streams) take the steps in turn so D2H of step i overlaps H2D of step i+1" % n_lanes
                                                                   if n_lanes > 1 else "one handle (communicator-bound)")},
         "gpu_launches": int(l1 - l0),
-        "clocks": sampler.summary(),
     }
 
 

@@ -384,6 +384,10 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend backend, ViennaCLB200Dis
  * the product kernels on the peer-memory transport. */
 ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *b_local, double *x_local,
                                               ViennaCLB200SolverTag *tag);
+/* gmres.hpp:181-367 (pipelined GMRES(m), no preconditioner) over slabs: the basis is partitioned like the vectors; the k Gram-Schmidt
+ * dots of an inner iteration are all-reduced together. */
+ViennaCLStatus ViennaCLCUDADdist_csr_gmres(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *b_local, double *x_local,
+                                           ViennaCLB200SolverTag *tag);
 
 #ifdef __cplusplus
 }

@@ -197,6 +197,7 @@ def lib():
     sig("ViennaCLCUDADdist_csr_info", c_vp, c_vp, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int))
     sig("ViennaCLCUDADdist_csr_cg", c_vp, c_vp, c_vp, c_vp, pt)
     sig("ViennaCLCUDADdist_csr_bicgstab", c_vp, c_vp, c_vp, c_vp, pt)
+    sig("ViennaCLCUDADdist_csr_gmres", c_vp, c_vp, c_vp, c_vp, pt)
     _lib = L
     return L
 
@@ -654,6 +655,10 @@ class DistCsr:
 
     def bicgstab(self, b, x, tag):
         self.b.check(self.b.L.ViennaCLCUDADdist_csr_bicgstab(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))
+        return tag
+
+    def gmres(self, b, x, tag):
+        self.b.check(self.b.L.ViennaCLCUDADdist_csr_gmres(self.b.h, self.h, b.ptr, x.ptr, C.byref(tag.t)))
         return tag
 
     def close(self):

@@ -19,6 +19,8 @@
 #include "fused_kernels.cuh"
 #include "launch.cuh"
 #include "nvtx.cuh"
+#include "gmres_host.cuh"
+#include "gmres_launch.cuh"
 #include "blas1.cuh"
 #include "nccl_dyn.cuh"
 #include <cmath>
@@ -222,7 +224,14 @@ ViennaCLStatus p2p_check(ViennaCLBackend b, ViennaCLB200DistCsr A)      // after
 {
   int err = 0;
   VCL_CUDA(b, cudaMemcpy(&err, A->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) return vcl_fail(b, ViennaCLB200CommError, "peer-memory exchange timed out (a partner rank did not arrive)", __FILE__, __LINE__);
+  if (err)
+  {
+    char msg[192];
+    std::snprintf(msg, sizeof msg, "peer-memory %s exchange timed out on rank %d: sequence number ...%u (of this object's chain), waiting for rank %u; "
+                  "results from that launch on are undefined", ((unsigned)err >> 28) == 2u ? "reduction" : "halo", b->rank, (unsigned)err & 0xfffffu,
+                  ((unsigned)err >> 20) & 0xffu);
+    return vcl_fail(b, ViennaCLB200CommError, msg, __FILE__, __LINE__);
+  }
   return ViennaCLSuccess;
 }
 
@@ -236,8 +245,8 @@ CsrDev subset(ViennaCLB200DistCsr A, bool boundary)
 
 ViennaCLStatus allreduce_sum(ViennaCLBackend b, ViennaCLB200DistCsr A, double *buf, int count)
 {
-  if (b->world == 1) return ViennaCLSuccess;
-  if (A->p2p)
+  if (b->world == 1 || count <= 0) return ViennaCLSuccess;
+  if (A->p2p && count <= 4)                              // longer vectors (GMRES: up to krylov_dim dots at once) go through NCCL
   {
     peer_allreduce_kernel<<<1, 32, 0, b->stream>>>(A->d_win, ++A->red_seq, buf, count);
     VCL_LAUNCHED(b, "peer_allreduce_kernel");
@@ -1036,6 +1045,117 @@ ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend b, ViennaCLB200Dis
   if (A->p2p) { A->halo_seq = halo_base + 2 * (u64)h->iters; A->red_seq = red_base + 2 * (u64)h->iters; }
   tag->iters = h->iters;
   tag->error = h->residual_norm / norm_rhs;                                          // bicgstab.hpp:212
+  return ViennaCLSuccess;
+}
+
+// gmres.hpp:181-367 (pipelined GMRES(m), classical Gram-Schmidt, no preconditioner) over row-partitioned data.  The basis lives
+// in slabs; per inner iteration: one row-partitioned product (halo exchange inside the launch on the peer-memory transport),
+// Gram-Schmidt stage 1 on the slab -> all-reduce of the k dots -> stage 2 -> all-reduce of ||v_k||^2 -> normalise; the
+// <r, v_k> of a cycle are all-reduced once, at its end.  R and xi are then global, so the host half of the cycle
+// (vcl_gmres_cycle_host) takes identical decisions on every rank.
+ViennaCLStatus ViennaCLCUDADdist_csr_gmres(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *rhs, double *x, ViennaCLB200SolverTag *tag)
+{
+  VCL_RANGE("vcl:dist_gmres");
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, A && tag, "bad arguments");
+  VCL_REQUIRE(b, tag->precond == ViennaCLB200PrecondNone, "row-partitioned GMRES: only the unpreconditioned pipelined path is provided");
+  VCL_REQUIRE(b, tag->monitor == nullptr, "monitor callbacks are not supported on the row-partitioned path");
+  VCL_REQUIRE(b, tag->krylov_dim >= 1 && tag->krylov_dim <= VCL_GMRES_MAX_KRYLOV, "krylov_dim must be in [1, 64]");
+  const long long n = A->n;
+  tag->iters = 0; tag->error = 0.0;
+  VCL_REQUIRE(b, n == 0 || (rhs && x), "null vector");
+  VCL_CUDA(b, cudaSetDevice(b->device));
+  const int m = tag->krylov_dim;
+  const long long isz = (std::max<long long>(n, 1) + 127) / 128 * 128;
+  auto need = [](size_t cnt) { return (cnt * sizeof(double) + 255) / 256 * 256; };
+  VCL_TRY(vcl_ws_reserve(b, need((size_t)std::max<long long>(n, 1)) + need((size_t)isz * m) + need((size_t)m * m) + 3 * need(m)));
+  char *w0 = (char*)b->ws;
+  double *res = (double*)w0;               w0 += need((size_t)std::max<long long>(n, 1));
+  double *V = (double*)w0;                 w0 += need((size_t)isz * m);
+  double *R = (double*)w0;                 w0 += need((size_t)m * m);
+  double *d_xi = (double*)w0;              w0 += need(m);
+  double *d_h = (double*)w0;               w0 += need(m);
+  double *d_coef = (double*)w0;
+  double *d_nsq = b->dscal + 8, *d_ss = b->dscal + 9;
+  std::vector<double> hR((size_t)m * m), xi(m), eta(m), coef(m, 0.0);
+
+  VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
+  VCL_CUDA(b, cudaMemcpyAsync(res, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(R, 0, sizeof(double) * m * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_xi, 0, sizeof(double) * m, b->stream));
+  VCL_CUDA(b, cudaMemsetAsync(d_coef, 0, sizeof(double) * m, b->stream));
+  // global <v, v> of a slab vector, on the host
+  auto global_ss = [&](const double *v, double *out) -> ViennaCLStatus
+  {
+    VCL_CUDA(b, cudaMemsetAsync(d_ss, 0, sizeof(double), b->stream));
+    if (n > 0) VCL_TRY(vcl_dot_async(b, n, v, 0, 1, v, 0, 1, d_ss));
+    VCL_TRY(allreduce_sum(b, A, d_ss, 1));
+    VCL_CUDA(b, cudaMemcpyAsync(b->hscal, d_ss, sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    *out = b->hscal[0];
+    return ViennaCLSuccess;
+  };
+  double ss = 0.0;
+  VCL_TRY(global_ss(res, &ss));
+  const double norm_rhs = std::sqrt(ss);
+  double rho_0 = norm_rhs, rho = 1.0;
+
+  unsigned max_restarts = (unsigned)tag->max_iterations / (unsigned)m;         // gmres.hpp:74-80
+  if (max_restarts > 0 && max_restarts * (unsigned)m == (unsigned)tag->max_iterations) max_restarts -= 1;
+  const int grid = scalar_grid(b, std::max<long long>(n, 1));
+
+  for (unsigned restart = 0; restart <= max_restarts; ++restart)
+  {
+    VCL_RANGE("vcl:gmres_cycle");
+    if (restart > 0)
+    {
+      VCL_TRY(dist_plain_prod(b, A, x, res));
+      if (n > 0) { residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rhs); VCL_LAUNCHED(b, "residual_kernel"); }
+      VCL_TRY(global_ss(res, &ss));
+      rho_0 = std::sqrt(ss);
+    }
+    if (rho_0 <= tag->abs_tolerance) break;                                     // gmres.hpp:227-228
+    if (n > 0) { scale_residual_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, res, rho_0); VCL_LAUNCHED(b, "scale_residual_kernel"); }
+    rho = 1.0;
+    if (rho_0 / norm_rhs < tag->tolerance || rho_0 < tag->abs_tolerance) break;  // gmres.hpp:234-235
+
+    for (int k = 0; k < m; ++k)
+    {
+      double *vk = V + (size_t)k * isz;
+      const double *src = (k == 0) ? res : V + (size_t)(k - 1) * isz;
+      VCL_TRY(dist_plain_prod(b, A, src, vk));
+      VCL_CUDA(b, cudaMemsetAsync(d_nsq, 0, sizeof(double), b->stream));
+      if (k > 0)
+      {
+        VCL_CUDA(b, cudaMemsetAsync(d_h, 0, sizeof(double) * k, b->stream));
+        if (n > 0) VCL_TRY(launch_gs1(b, grid, V, n, isz, k, d_h, 1));
+        VCL_TRY(allreduce_sum(b, A, d_h, k));
+        if (n > 0)
+        {
+          gmres_gs2_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(V, n, isz, k, d_h, 1, R, m, d_nsq, b->partials, b->tickets);
+          VCL_LAUNCHED(b, "gmres_gs2_kernel");
+        }
+        else                                                 // a rank without rows still keeps its copy of R (the host half reads it)
+          VCL_CUDA(b, cudaMemcpy2DAsync(R + (size_t)k * m, sizeof(double), d_h, sizeof(double), sizeof(double), k, cudaMemcpyDeviceToDevice, b->stream));
+      }
+      else if (n > 0) VCL_TRY(vcl_dot_async(b, n, vk, 0, 1, vk, 0, 1, d_nsq));
+      VCL_TRY(allreduce_sum(b, A, d_nsq, 1));
+      gmres_normalize_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, vk, res, R, k * m + k, d_nsq, d_xi + k, b->partials, b->tickets);
+      VCL_LAUNCHED(b, "gmres_normalize_kernel");
+    }
+    VCL_TRY(allreduce_sum(b, A, d_xi, m));
+    VCL_CUDA(b, cudaMemcpyAsync(xi.data(), d_xi, sizeof(double) * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaMemcpyAsync(hR.data(), R, sizeof(double) * m * m, cudaMemcpyDeviceToHost, b->stream));
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+    if (A->p2p) VCL_TRY(p2p_check(b, A)); else VCL_TRY(vcl_comm_check(b));
+
+    bool converged = false;
+    const size_t kk = vcl_gmres_cycle_host<double>(tag, m, hR, xi, eta, coef, rho, rho_0, norm_rhs, false, &converged);
+    VCL_CUDA(b, cudaMemcpyAsync(d_coef, coef.data(), sizeof(double) * m, cudaMemcpyHostToDevice, b->stream));
+    if (n > 0) { gmres_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, res, V, isz, d_coef, (int)kk); VCL_LAUNCHED(b, "gmres_update_kernel"); }
+    VCL_CUDA(b, cudaStreamSynchronize(b->stream));                               // coef (pageable) must outlive the copy
+    tag->error = std::fabs(rho * rho_0 / norm_rhs);                              // gmres.hpp:360
+  }
   return ViennaCLSuccess;
 }
 

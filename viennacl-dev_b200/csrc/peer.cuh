@@ -71,8 +71,14 @@ __device__ __forceinline__ u64 global_ns()
   return t;
 }
 
+// Error word raised on a time-out: kind (1: halo flag, 2: reduction flag) in bits 28.., the partner rank in bits 20..27 and the
+// low 20 bits of the sequence number of the exchange that did not complete; the first time-out wins.  The results of the launch
+// that timed out (and of everything enqueued after it) are undefined; the host reports the decoded word at the next batch
+// boundary (dist.cu: p2p_check) -- "which exchange, waiting for whom".
+#define VCL_PEER_ERR(kind, partner, seq) ((int)(((unsigned)(kind) << 28) | (((unsigned)(partner) & 0xffu) << 20) | ((unsigned)(seq) & 0xfffffu)))
+
 // Spins until *flag >= seq (acquire).  Returns false on time-out after raising *err.
-__device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err)
+__device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err, int kind = 1, int partner = 0)
 {
   if (ld_acquire_sys(flag) >= seq) return true;
   const u64 t0 = global_ns();
@@ -80,7 +86,7 @@ __device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err)
   {
     __nanosleep(40);
     if (ld_acquire_sys(flag) >= seq) return true;
-    if (global_ns() - t0 > VCL_PEER_TIMEOUT_NS) { if (err) atomicExch(err, 1); return false; }
+    if (global_ns() - t0 > VCL_PEER_TIMEOUT_NS) { if (err) atomicCAS(err, 0, VCL_PEER_ERR(kind, partner, seq)); return false; }
   }
 }
 
@@ -138,7 +144,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerWindow *win, u64 seq, d
     __threadfence_system();
     st_release_sys(win->red_flag[tid] + par * W + me, seq);
     // every rank's contribution lands in my own window
-    peer_wait(win->red_flag[me] + par * W + tid, seq, win->err);
+    peer_wait(win->red_flag[me] + par * W + tid, seq, win->err, 2, tid);
     const double *mine = win->red[me] + (size_t)(par * W + tid) * 4;
 #pragma unroll
     for (int j = 0; j < N; ++j) gather[tid * 4 + j] = __ldcg(mine + j);

@@ -5,6 +5,8 @@
 #include "fused_kernels.cuh"
 #include "launch.cuh"
 #include "nvtx.cuh"
+#include "gmres_host.cuh"
+#include "gmres_launch.cuh"
 #include "persistent.cuh"
 #include "blas1.cuh"
 #include <cmath>
@@ -475,37 +477,6 @@ ViennaCLStatus bicgstab_solve(ViennaCLBackend b, const MatOp &A, const real *rhs
 // ------------------------------------------------------------------------------------------------
 // GMRES(m), pipelined simpler-GMRES with classical Gram-Schmidt  (gmres.hpp:181-367)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VEC_THREADS)
-scale_residual_kernel(long long n, real *res, real rho0)
-{
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    res[i] = res[i] / rho0;
-}
-
-__global__ void __launch_bounds__(VEC_THREADS)
-residual_kernel(long long n, real *res, const real *rhs)     // res = rhs - res
-{
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    res[i] = rhs[i] - res[i];
-}
-
-ViennaCLStatus launch_gs1(ViennaCLBackend b, int grid, const real *basis, long long n, long long isz, int k, real *out_h, int stride)
-{
-  VCL_REQUIRE(b, (isz & 1) == 0 && (reinterpret_cast<uintptr_t>(basis) & 15u) == 0u,
-              "Krylov basis must be 16-byte aligned with an even internal size (the reference pads vectors to 128 entries, forwards.h:385)");
-  (void)grid;
-  const int gy = (k + GS1_COLS - 1) / GS1_COLS;                      // column groups
-  const int gx = std::max(1, std::min(vcl_div_up(n / 2, VEC_THREADS), std::min(std::max(b->sm_count * 8 / gy, b->sm_count), VCL_MAX_BLOCKS)));
-  gmres_gs1_kernel<<<dim3(gx, gy), VEC_THREADS, 0, b->stream>>>(basis, n, isz, k, out_h, stride, VCL_PARTIALS(b), b->tickets);
-  VCL_LAUNCHED(b, "gmres_gs1_kernel");
-  return ViennaCLSuccess;
-}
-
-int scalar_grid(ViennaCLBackend b, long long n)
-{
-  return (int)std::max(1LL, std::min((n + VEC_THREADS - 1) / VEC_THREADS, (long long)std::min(b->sm_count * 8, VCL_MAX_BLOCKS)));
-}
-
 ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, real *x, ViennaCLB200SolverTag *tag)
 {
   VCL_RANGE("vcl:gmres");
@@ -630,28 +601,8 @@ ViennaCLStatus gmres_solve(ViennaCLBackend b, const MatOp &A, const real *rhs, r
     VCL_CUDA(b, cudaMemcpyAsync(hR.data(), R, sizeof(real) * m * m, cudaMemcpyDeviceToHost, b->stream));
     VCL_CUDA(b, cudaStreamSynchronize(b->stream));
 
-    size_t kk = (size_t)k;
-    const size_t full = kk;                                                      // gmres.hpp:306-314
-    for (size_t i = 0; i < kk; ++i)
-      if (std::fabs(hR[i + i * kk]) < tag->tolerance * hR[0]) { kk = i; break; }
-
     bool converged = false;
-    for (size_t i = 0; i < kk; ++i)                                              // gmres.hpp:318-331
-    {
-      tag->iters += 1;
-      if (xi[i] >= rho || xi[i] <= -rho) { kk = i; break; }
-      rho *= std::sin(std::acos(xi[i] / rho));
-      if (jac && std::fabs(rho * rho_0 / norm_rhs) < tag->tolerance) { kk = i + 1; converged = true; break; }   // gmres.hpp:579-584
-    }
-
-    eta = xi;                                                                    // gmres.hpp:336-345
-    for (long i2 = (long)kk - 1; i2 > -1; --i2)
-    {
-      const size_t i = (size_t)i2;
-      for (size_t j = i + 1; j < kk; ++j) eta[i] -= hR[i + j * full] * eta[j];
-      eta[i] /= hR[i + i * full];
-    }
-    for (size_t i = 0; i < kk; ++i) coef[i] = rho_0 * eta[i];                    // gmres.hpp:351-352
+    const size_t kk = vcl_gmres_cycle_host<real>(tag, k, hR, xi, eta, coef, rho, rho_0, norm_rhs, jac, &converged);
 
     VCL_CUDA(b, cudaMemcpyAsync(d_coef, coef.data(), sizeof(real) * m, cudaMemcpyHostToDevice, b->stream));
     gmres_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, res, V, isz, d_coef, (int)kk);

@@ -393,7 +393,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
 #ifdef VCL_PEER_DEBUG
       const u64 t_w = global_ns();
 #endif
-      if (tid < VCL_MAX_PEERS && ((A.wait_mask >> tid) & 1u)) peer_wait(A.wait_flags + tid, A.wait_seq, A.err);
+      if (tid < VCL_MAX_PEERS && ((A.wait_mask >> tid) & 1u)) peer_wait(A.wait_flags + tid, A.wait_seq, A.err, 1, tid);
       __syncthreads();
 #ifdef VCL_PEER_DEBUG
       if (A.dbg && tid == 0) atomicMax(A.dbg + (A.dbg_seq % 1024) * 4 + 3, global_ns() - t_w);
