@@ -105,7 +105,7 @@ static ViennaCLStatus vcl_launch_sell_as(ViennaCLBackend b, const SellDev &d, XV
 template<class Epi>
 static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
 {
-  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm, A.cols};
+  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm};
   // the slice height of the reference's default layout gets its own instantiation (sliced_ell_matrix.hpp:146-147: C = 32)
   if (A.row_perm) return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, true, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, true, 0>(b, d, xv, epi);
   return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, false, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, false, 0>(b, d, xv, epi);

@@ -48,7 +48,6 @@ struct SellDev
   int rows; int C;
   const u32 *cpb, *ci, *bs; const real *va;
   const u32 *perm;              // SELL-C-sigma: storage row -> matrix row (0xFFFFFFFF: padding); NULL: identity
-  int cols;
 };
 
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
@@ -517,7 +516,8 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // by the same two-stage TMA pipeline as a CSR row block (block j+1 is in flight while block j is computed), then one
 // thread per row walks its slice-column-major entries (stride C in shared memory: consecutive rows hit consecutive banks)
 // with one fma chain, all gathers of up to 8 entries issued before the first fma.  Zero-valued (padding) slots never
-// touch x (cuda/sparse_matrix_operations.hpp:2231, host :1833).  Passes whose range does not fit the staging buffer, or
+// touch x (cuda/sparse_matrix_operations.hpp:2231, host :1833; gathering first and masking afterwards -- so that the x load does
+// not wait for the value -- was measured: 0.2667 -> 0.2685 ms at 256^3, no gain, profiles/ab_sell_r2j.log).  Passes whose range does not fit the staging buffer, or
 // C not a multiple of 4 / larger than the CTA, take the direct path.
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
@@ -546,9 +546,6 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   const u32 C = CT ? (u32)CT : (u32)A.C;
   const u32 nslices = ((u32)A.rows - 1u) / C + 1u;
   const u32 t_slice = (u32)tid / C, t_lane = (u32)tid % C;                 // this thread's slice within a pass and row within the slice
-#ifdef VCL_AB_SELL_UNCOND
-  const u32 cmax = A.cols > 0 ? (u32)A.cols - 1u : 0u;
-#endif
   const u32 spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1u;      // slices per CTA pass
   const int nblocks = (int)((nslices + spb - 1) / spb);
   const bool can_stage = (C % 4u) == 0u && C <= CSR_BLOCK_THREADS &&
@@ -621,26 +618,11 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         {
           real v[8], xx[8];
 #pragma unroll
-#ifdef VCL_AB_SELL_UNCOND
-          // gather first, look at the value afterwards: the x load no longer waits for the shared-memory load of the value.
-          // A padding slot gathers the column its index names (0 in the reference's layout; clamped for foreign arrays) and
-          // is then masked, so a NaN / Inf in that x entry still cannot reach the row (cuda/sparse_matrix_operations.hpp:2231)
-          for (int k = 0; k < 8; ++k)
-          {
-            const bool in = j + k < w_c;
-            const u32 c = in ? min(s_col[idx + k * C], cmax) : 0u;
-            xx[k] = xload<false>(xv, c);
-            v[k] = in ? s_val[idx + k * C] : 0.0;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) xx[k] = nonzero(v[k]) ? xx[k] : 0.0;
-#else
           for (int k = 0; k < 8; ++k)
           {
             v[k] = (j + k < w_c) ? s_val[idx + k * C] : 0.0;
             xx[k] = nonzero(v[k]) ? xload<false>(xv, s_col[idx + k * C]) : 0.0;
           }
-#endif
           // zero (padding / empty) slots have v = x = +0.0 and leave the bits of `acc` unchanged: no predicates needed
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc = fma(xx[k], v[k], acc);
