@@ -4,6 +4,8 @@
 // Prints one line per check; tests/test_ref_binding.py compares the counts with the reference's host-backend goldens.
 #include <cmath>
 #include <cstdio>
+#include <ctime>
+#include <string>
 #include <map>
 #include <vector>
 #include "viennacl/vector.hpp"
@@ -89,18 +91,46 @@ static void run(const char *name, const char *fmt, HostMatrix const & H, bool sp
   }
 }
 
-int main()
+// `bench`: BASELINE configs[0] (CG, 2-D Laplacian 1024^2, tol 1e-8) through the reference's own driver, timed like
+// examples/benchmarks/solver.cpp:106-120 (finish() on both sides).  Built twice: with the binding (new kernels under the reference's
+// driver, which still reads its 768 partial sums back every iteration, cg.hpp:168) and without (the reference's own CUDA kernels).
+static void bench()
+{
+  const HostMatrix H = stencil2d(1024, 1024, 0.0, 0.0);
+  viennacl::compressed_matrix<double> A;
+  viennacl::copy(H, A);
+  viennacl::vector<double> b = viennacl::scalar_vector<double>(H.size(), 1.0);
+  for (int rep = 0; rep < 3; ++rep)
+  {
+    viennacl::linalg::cg_tag tag(1e-8, 5000);
+    viennacl::backend::finish();
+    const double t0 = (double)clock() / CLOCKS_PER_SEC;
+    struct timespec a, c; clock_gettime(CLOCK_MONOTONIC, &a);
+    viennacl::vector<double> sol = viennacl::linalg::solve(A, b, tag);
+    viennacl::backend::finish();
+    clock_gettime(CLOCK_MONOTONIC, &c);
+    const double sec = (c.tv_sec - a.tv_sec) + 1e-9 * (c.tv_nsec - a.tv_nsec);
+    (void)t0;
+    std::printf("REFBIND bench cg_lap2d_1024 rep %d iters %u error %.6e seconds %.6f iterations_per_sec %.1f\n", rep, (unsigned)tag.iters(), tag.error(), sec,
+                tag.iters() / sec);
+  }
+}
+
+int main(int argc, char **argv)
 {
   try
   {
+    if (argc > 1 && std::string(argv[1]) == "bench") { bench(); std::printf("REFBIND DONE\n"); return 0; }
     const HostMatrix L = stencil2d(63, 65, 0.0, 0.0), C = stencil2d(48, 50, 0.5, 0.0);
     run<viennacl::compressed_matrix<double> >("lap2d_63x65", "csr", L, true);
     run<viennacl::compressed_matrix<double> >("cd2d_48x50", "csr", C, false);
     run<viennacl::sliced_ell_matrix<double> >("lap2d_63x65", "sell", L, true);
     run<viennacl::sliced_ell_matrix<double> >("cd2d_48x50", "sell", C, false);
+#ifdef VCL_REF_BINDING
     long long launches = 0;
     ViennaCLBackendLaunchCount(viennacl::linalg::b200::backend(), &launches);
     std::printf("REFBIND launches_of_libvcl_b200 %lld\n", launches);
+#endif
     std::printf("REFBIND DONE\n");
   }
   catch (std::exception const & e)
