@@ -221,6 +221,17 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #ifndef CSR_MIN_CTAS
 #define CSR_MIN_CTAS (CSR_NSTAGE <= 2 ? 4 : (CSR_NSTAGE == 3 ? 3 : 2))
 #endif
+// Resident CTAs per SM the stand-alone product kernels are compiled for.  The float build stages 8 instead of 12 bytes per entry
+// (32.8 KB per CTA), so more CTAs fit one SM, and its kernels are bound by the latency of the gather chain, not by HBM: measured at
+// 256^3 (profiles/ab_float_ctas_r2n.log) CSR 0.1967 / 0.1898 / 0.2112 ms and SELL-32 0.1969 / 0.1754 / 0.1680 ms with 4 / 5 / 6 CTAs
+// (48 / 40 registers, no spills).  The persistent cooperative kernels keep CSR_MIN_CTAS (they spill below 64 registers).
+#if defined(VCL_F32) && CSR_NSTAGE <= 2
+#define CSR_STREAM_MIN_CTAS 5
+#define SELL_MIN_CTAS(NQ, CT) (((NQ) == 0 && (CT) == 32) ? 6 : 5)      // 6 (40 registers) only where it does not spill: the plain product, C = 32
+#else
+#define CSR_STREAM_MIN_CTAS CSR_MIN_CTAS
+#define SELL_MIN_CTAS(NQ, CT) CSR_MIN_CTAS
+#endif
 
 struct CsrBlockDesc { u32 r0, r1, n0, n1; };
 
@@ -482,7 +493,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
 }
 
 template<class Epi, bool SPLIT>
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_STREAM_MIN_CTAS)
 csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 {
   csr_stream_body<Epi, SPLIT, false>(A, xv, epi);
@@ -526,7 +537,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // shift and a mask; the generic form spent 31 % of its issue slots on IMAD address arithmetic and two 32-bit divisions per
 // pass (ncu source page, profiles/ncu_summary_r2.md) and ran 8 % behind the CSR kernel although it moves 3.5 % fewer bytes.
 template<class Epi, bool PERM, int CT>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
-__global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_MIN_CTAS)
+__global__ void __launch_bounds__(CSR_BLOCK_THREADS, SELL_MIN_CTAS(Epi::NQ, CT))
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
   constexpr int S = 2;                                     // this kernel is written for a two-stage ring (it uses the first two CSR stages)
