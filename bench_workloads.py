@@ -73,6 +73,25 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
     value = nbytes * world * args.steps / (ms * 1e-3) / 1e9
     per_gpu = value / world
 
+    # BASELINE configs[1] asks for CSR vs sliced ELL: the same row-partitioned product with the slabs stored as SELL-32 (N > 1)
+    sell_part = None
+    if world > 1 and not args.no_extras:
+        D.set_format("sell", 32)
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        be.timer_begin()
+        for _ in range(args.steps):
+            step()
+        ms_s = max_over_ranks(be.timer_end())
+        barrier()
+        ys = y.download()
+        D.set_format("csr")
+        step()
+        yc = y.download()
+        sell_part = {"metric": "sell32_spmv_effective_GBps (row-partitioned, bytes counted as for CSR)", "value": nbytes * world * args.steps / (ms_s * 1e-3) / 1e9,
+                     "ms_per_step": ms_s / args.steps, "max_rel_diff_vs_csr_rank0": float(np.max(np.abs(ys - yc) / np.maximum(np.abs(yc), 1e-300)))}
+
     # ---- end to end through the public call with HOST vectors: x host->device, y = A*x, y device->host, every step ----
     # Single GPU: two backend handles (= two streams, the unit of concurrency of the C-ABI) alternate, so that the
     # device->host copy of step i overlaps the host->device copy of step i+1 (PCIe is full duplex); every step still moves
@@ -147,6 +166,7 @@ def spmv_workload(pkg, be, args, rank, world, n1, barrier, max_over_ranks, sampl
                         "like a viennacl::compressed_matrix; " + ("%d backend handles (streams) take the steps in turn so D2H of step i overlaps H2D of step i+1" % n_lanes
                                                                   if n_lanes > 1 else "one handle (communicator-bound)")},
         "gpu_launches": int(l1 - l0),
+        "sell_partitioned": sell_part,
     }
 
 

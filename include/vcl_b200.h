@@ -372,6 +372,10 @@ ViennaCLStatus ViennaCLCUDADdist_csr_create(ViennaCLBackend backend, long long g
                                             const double *values, ViennaCLB200DistCsr *out);
 ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend backend, ViennaCLB200DistCsr *A);
 ViennaCLStatus ViennaCLCUDADdist_csrmv(ViennaCLBackend backend, ViennaCLB200DistCsr A, const double *x_local, double *y_local);
+/* Storage format of the slab used by the products and solver steps: 0 = CSR (default), 1 = SELL-C with sigma = 1 (the layout of
+ * sliced_ell_matrix.hpp:134-214, built on the device; rows_per_block <= 0: 32).  With SELL the per-row arithmetic is the reference's
+ * SELL arithmetic: results equal the single-domain SELL product bit for bit. */
+ViennaCLStatus ViennaCLCUDADdist_csr_set_format(ViennaCLBackend backend, ViennaCLB200DistCsr A, ViennaCLInt format, ViennaCLInt rows_per_block);
 /* Which transport the object uses: 1 = peer memory (CUDA IPC windows over NVLink; halo pushes and the reduction are done
  * by the solver's own kernels), 0 = NCCL send/recv + allreduce.  Also returns the halo size and the interior/boundary split. */
 ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend backend, ViennaCLB200DistCsr A, ViennaCLInt *peer_memory,

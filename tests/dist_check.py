@@ -141,6 +141,26 @@ def main():
             ok &= good
             print("[rank %d/%d] %-22s %-8s iters %d (single-domain %d%s) err %.2e rel-x-diff %.2e  %s"
                   % (rank, world, name, solver, t2.iters, t1.iters, "" if o_it is None else ", oracle %d" % o_it, t2.error, err2, "OK" if good else "FAIL"), flush=True)
+        # ---- the slab stored as SELL-32 (set_format): product bit-identical to the single-domain SELL product, same CG ----
+        D.set_format("sell", 32)
+        S_full = full.to_sell(32)
+        dyf = be.zeros(n)
+        S_full.spmv(be.array(x), dyf)
+        for _ in range(2):
+            D.spmv(dx, dy)
+        same_s = np.array_equal(dy.download(), dyf.download()[rb:re_])
+        dxf = be.zeros(n)
+        t1 = pkg.SolverTag(tol=1e-9, max_iterations=2000).solve("cg", S_full, dbf, dxf)
+        dsol3 = be.zeros(re_ - rb)
+        t2 = D.cg(db, dsol3, pkg.SolverTag(tol=1e-9, max_iterations=2000))
+        xs, xf = dsol3.download(), dxf.download()[rb:re_]
+        err3 = np.linalg.norm(xs - xf) / max(np.linalg.norm(xf), 1e-300)
+        t3 = D.bicgstab(db, dsol3, pkg.SolverTag(tol=1e-9, max_iterations=2000))
+        good = same_s and abs(t2.iters - t1.iters) <= 2 and err3 < 1e-6 and t3.error < 1e-9
+        ok &= good
+        print("[rank %d/%d] %-22s SELL-32 slab: spmv bit-exact=%s  cg iters %d (single-domain SELL %d) rel-x-diff %.2e  bicgstab iters %d  %s"
+              % (rank, world, name, same_s, t2.iters, t1.iters, err3, t3.iters, "OK" if good else "FAIL"), flush=True)
+        D.set_format("csr")
         # budget exhaustion must report the same iterate on every partitioning
         tag = D.cg(db, dsol, pkg.SolverTag(tol=1e-30, max_iterations=9))
         ref9 = o.cg(A, b, tol=1e-30, maxit=9)

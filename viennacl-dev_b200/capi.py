@@ -198,6 +198,7 @@ def lib():
     sig("ViennaCLCUDADdist_csr_cg", c_vp, c_vp, c_vp, c_vp, pt)
     sig("ViennaCLCUDADdist_csr_bicgstab", c_vp, c_vp, c_vp, c_vp, pt)
     sig("ViennaCLCUDADdist_csr_gmres", c_vp, c_vp, c_vp, c_vp, pt)
+    sig("ViennaCLCUDADdist_csr_set_format", c_vp, c_vp, c_int, c_int)
     _lib = L
     return L
 
@@ -639,6 +640,11 @@ class DistCsr:
         self.h = c_vp()
         backend.check(backend.L.ViennaCLCUDADdist_csr_create(backend.h, global_rows, row_begin, row_end, A_local.nnz,
                                                              A_local.rp.ptr, A_local.ci.ptr, A_local.va.ptr, C.byref(self.h)))
+
+    def set_format(self, fmt="csr", rows_per_block=32):
+        """Storage of the slab for products / solver steps: "csr" (default) or "sell" (SELL-C, sigma = 1)."""
+        self.b.check(self.b.L.ViennaCLCUDADdist_csr_set_format(self.b.h, self.h, 1 if fmt == "sell" else 0, rows_per_block))
+        return self
 
     def spmv(self, x, y):
         self.b.check(self.b.L.ViennaCLCUDADdist_csrmv(self.b.h, self.h, x.ptr, y.ptr))

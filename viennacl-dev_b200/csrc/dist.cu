@@ -58,6 +58,10 @@ struct ViennaCLB200DistCsr_impl
   u32 *ord_start = nullptr, *ord_end = nullptr;   // row ranges of the blocks in the order [interior | boundary]
   u64 halo_seq = 0, red_seq = 0;     // exchanges EXECUTED so far (identical on every rank)
   int *d_err = nullptr;
+  // ---- optional SELL-C copy of the slab (ViennaCLCUDADdist_csr_set_format): local column indices, sigma = 1 ----
+  int fmt = 0, sell_C = 0, sell_passes = 0;
+  u32 *s_cpb = nullptr, *s_bs = nullptr, *s_ci = nullptr; double *s_va = nullptr;
+  unsigned char *s_needs = nullptr;  // per CTA pass of sell_kernel: does it gather from the halo?
 };
 
 namespace {
@@ -220,6 +224,44 @@ XVec p2p_xvec(ViennaCLB200DistCsr A, const double *x, u64 seq)
   return xv;
 }
 
+// one CTA per pass of sell_kernel (256 / C slices): does any stored non-zero gather from the halo (local column >= n_local)?
+__global__ void sell_pass_needs_halo_kernel(int passes, int spb, int nslices, int C, const u32 * __restrict__ cpb, const u32 * __restrict__ bs,
+                                            const u32 * __restrict__ ci, const double * __restrict__ va, u32 n_local, unsigned char *needs)
+{
+  for (int p = blockIdx.x; p < passes; p += gridDim.x)
+  {
+    const int s0 = p * spb, s1 = min(s0 + spb, nslices);
+    const u32 k0 = bs[s0], k1 = bs[s1 - 1] + cpb[s1 - 1] * (u32)C;
+    int found = 0;
+    for (u32 k = k0 + threadIdx.x; k < k1; k += blockDim.x) found |= (va[k] != 0.0 && ci[k] >= n_local);
+    found = __syncthreads_or(found);
+    if (threadIdx.x == 0) needs[p] = found ? 1 : 0;
+  }
+}
+
+// the slab as a SELL matrix for sell_kernel<..., SPLIT = true>; in_kernel: halo pushes / flag waits inside the launch (peer-memory
+// transport), otherwise the halo has arrived by stream order (NCCL transport, world 1) and the kernel neither pushes nor waits
+SellDev dist_sell_dev(ViennaCLBackend b, ViennaCLB200DistCsr A, u64 seq, bool in_kernel, bool with_push)
+{
+  SellDev d = {A->n, A->sell_C, A->s_cpb, A->s_ci, A->s_bs, A->s_va, nullptr, A->s_needs, 0u, nullptr, seq, A->d_err, nullptr, nullptr, nullptr};
+  if (in_kernel)
+  {
+    const int par = (int)(seq & 1ULL);
+    d.wait_mask = A->wait_mask;
+    d.wait_flags = A->hwin.halo_flag[A->hwin.me] + par * A->hwin.W;
+    if (with_push && A->push.ndst > 0) { d.push = A->d_push; d.push_idx = A->send_idx; d.push_ticket = b->tickets + 8; }
+  }
+  return d;
+}
+
+// peer-memory transport: the row-partitioned product as ONE launch in the slab's format
+template<class Epi>
+ViennaCLStatus p2p_launch(ViennaCLBackend b, ViennaCLB200DistCsr A, u64 seq, const double *x, Epi epi, bool with_push)
+{
+  if (A->fmt == 1) return vcl_launch_sell_split(b, dist_sell_dev(b, A, seq, true, with_push), p2p_xvec(A, x, seq), epi);
+  return p2p_launch_csr(b, p2p_all_blocks(b, A, seq, with_push), p2p_xvec(A, x, seq), epi);
+}
+
 ViennaCLStatus p2p_check(ViennaCLBackend b, ViennaCLB200DistCsr A)      // after a stream synchronisation
 {
   int err = 0;
@@ -271,10 +313,15 @@ ViennaCLStatus dist_plain_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const d
       VCL_TRY(p2p_push(b, A, x, seq, nullptr));
       return p2p_launch_csr(b, p2p_all_blocks(b, A, seq, false), p2p_xvec(A, x, seq), epi);
     }
-    return p2p_launch_csr(b, p2p_all_blocks(b, A, seq, true), p2p_xvec(A, x, seq), epi);
+    return p2p_launch(b, A, seq, x, epi, true);
   }
   XVec xv = make_xvec(x, 0, 1, A->halo_buf, (u32)A->n);
   VCL_TRY(start_halo(b, A, x));
+  if (A->fmt == 1)                                        // SELL slab on the NCCL transport / at world 1: no interior / boundary split
+  {
+    VCL_TRY(wait_halo(b, A));
+    return vcl_launch_sell_split(b, dist_sell_dev(b, A, 0, false, false), xv, epi);
+  }
   VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, epi, b->stream));
   VCL_TRY(wait_halo(b, A));
   VCL_TRY(vcl_launch_csr_split(b, subset(A, true), xv, epi, b->stream));
@@ -318,6 +365,12 @@ ViennaCLStatus nccl_fused_prod(ViennaCLBackend b, ViennaCLB200DistCsr A, const d
 {
   XVec xv = make_xvec(x, 0, 1, A->halo_buf, (u32)A->n);
   VCL_TRY(start_halo(b, A, x));
+  if (A->fmt == 1)
+  {
+    VCL_TRY(wait_halo(b, A));
+    EpiFused<STEP_NONE, USE_R0, JACOBI> e = {y, x, r0, diag, b->partials, b->tickets, st, o0, o1, o2, {0.0, 0.0, 0.0}, nullptr};
+    return vcl_launch_sell_split(b, dist_sell_dev(b, A, 0, false, false), xv, e);
+  }
   const bool both = A->n_interior > 0 && A->n_boundary > 0;
   if (A->n_interior > 0)
   {
@@ -406,7 +459,7 @@ ViennaCLStatus dist_pcg(ViennaCLBackend b, ViennaCLB200DistCsr A, const double *
         const u64 hseq = halo_base + (u64)(launched + k + 1), rseq = red_base + (u64)(launched + k + 1);
         EpiFused<STEP_NONE, false, false> e = {w, u, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc + 0, DIST_PCG};
-        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, hseq, true), p2p_xvec(A, u, hseq), e));
+        VCL_TRY(p2p_launch(b, A, hseq, u, e, true));
       }
       else
       {
@@ -726,6 +779,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
   if (A->ci_local && A->ci_local != A->ci_global) cudaFree(A->ci_local);
   cudaFree(A->send_idx); cudaFree(A->send_buf); cudaFree(A->halo_buf); cudaFree(A->blk); cudaFree(A->ord_start); cudaFree(A->ord_end);
   cudaFree(A->tmp_sums);
+  cudaFree(A->s_cpb); cudaFree(A->s_bs); cudaFree(A->s_ci); cudaFree(A->s_va); cudaFree(A->s_needs);
   if (A->p2p)
   {
     // nobody may unmap or free a window that a partner is still writing to
@@ -754,6 +808,38 @@ ViennaCLStatus ViennaCLCUDADdist_csr_info(ViennaCLBackend b, ViennaCLB200DistCsr
   if (halo_entries) *halo_entries = A->n_halo;
   if (interior_blocks) *interior_blocks = A->n_interior;
   if (boundary_blocks) *boundary_blocks = A->n_boundary;
+  return ViennaCLSuccess;
+}
+
+// Storage format of the slab for the products and solver steps: 0 = CSR (default), 1 = SELL-C (sigma = 1, the reference's layout,
+// sliced_ell_matrix.hpp:134-214) built on the device from the slab with LOCAL column indices.  Per-row arithmetic is then the
+// reference's SELL arithmetic (fused multiply-adds), i.e. results equal the single-domain SELL product bit for bit.
+ViennaCLStatus ViennaCLCUDADdist_csr_set_format(ViennaCLBackend b, ViennaCLB200DistCsr A, ViennaCLInt format, ViennaCLInt rows_per_block)
+{
+  VCL_CHECK_BACKEND(b);
+  VCL_REQUIRE(b, A && (format == 0 || format == 1), "format: 0 (CSR) or 1 (SELL)");
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  cudaFree(A->s_cpb); cudaFree(A->s_bs); cudaFree(A->s_ci); cudaFree(A->s_va); cudaFree(A->s_needs);
+  A->s_cpb = A->s_bs = A->s_ci = nullptr; A->s_va = nullptr; A->s_needs = nullptr; A->fmt = 0;
+  if (format == 0 || A->n == 0) return ViennaCLSuccess;
+  const int C = rows_per_block > 0 ? rows_per_block : 32;
+  VCL_REQUIRE(b, C <= 4096, "rows_per_block too large");
+  const int nslices = (A->n - 1) / C + 1;
+  VCL_CUDA(b, cudaMalloc(&A->s_cpb, sizeof(u32) * nslices));
+  VCL_CUDA(b, cudaMalloc(&A->s_bs, sizeof(u32) * nslices));
+  long long padded = 0;
+  VCL_TRY(ViennaCLCUDADcsr2sell(b, A->n, C, A->rp, A->ci_local, A->va, A->s_cpb, A->s_bs, &padded, nullptr, nullptr));
+  VCL_CUDA(b, cudaMalloc(&A->s_ci, sizeof(u32) * std::max<long long>(padded, 1)));
+  VCL_CUDA(b, cudaMalloc(&A->s_va, sizeof(double) * std::max<long long>(padded, 1)));
+  VCL_TRY(ViennaCLCUDADcsr2sell(b, A->n, C, A->rp, A->ci_local, A->va, A->s_cpb, A->s_bs, &padded, A->s_ci, A->s_va));
+  const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
+  A->sell_passes = (nslices + spb - 1) / spb;
+  VCL_CUDA(b, cudaMalloc(&A->s_needs, (size_t)A->sell_passes));
+  sell_pass_needs_halo_kernel<<<std::min(A->sell_passes, b->sm_count * 8), 256, 0, b->stream>>>(A->sell_passes, spb, nslices, C, A->s_cpb, A->s_bs, A->s_ci, A->s_va,
+                                                                                                 (u32)A->n, A->s_needs);
+  VCL_LAUNCHED(b, "sell_pass_needs_halo_kernel");
+  VCL_CUDA(b, cudaStreamSynchronize(b->stream));
+  A->sell_C = C; A->fmt = 1;
   return ViennaCLSuccess;
 }
 
@@ -859,11 +945,15 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         // scattered send lists: the product kernel pushes from its own head (after its st->done test) -- no push kernel either way
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr, DIST_CG};
-        CsrDev dd = p2p_all_blocks(b, A, hseq, !A->fused_push);
+        if (A->fmt == 1) VCL_TRY(p2p_launch(b, A, hseq, p, e, !A->fused_push));
+        else
+        {
+          CsrDev dd = p2p_all_blocks(b, A, hseq, !A->fused_push);
 #ifdef VCL_PEER_DEBUG
-        dd.dbg = A->hwin.dbg; dd.dbg_seq = rseq;
+          dd.dbg = A->hwin.dbg; dd.dbg_seq = rseq;
 #endif
-        VCL_TRY(p2p_launch_csr(b, dd, p2p_xvec(A, p, hseq), e));
+          VCL_TRY(p2p_launch_csr(b, dd, p2p_xvec(A, p, hseq), e));
+        }
       }
       launched += nb;
       VCL_CUDA(b, cudaMemcpyAsync(h, st, sizeof(SolverState), cudaMemcpyDeviceToHost, b->stream));
@@ -893,7 +983,6 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
     return ViennaCLSuccess;
   }
 
-  XVec xv = make_xvec(p, 0, 1, A->halo_buf, (u32)A->n);
   // rank-local sums land in `loc`, the allreduce writes the global sums into st->sums (out of place, so that re-issuing the
   // collective after convergence -- kernels skipped, `loc` unchanged -- reproduces the same global sums)
   double *loc = b->world > 1 ? b->dscal + 32 : &st->sums[0];
@@ -912,21 +1001,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc + 0);
         VCL_LAUNCHED(b, "cg_update_kernel");
       }
-      VCL_TRY(start_halo(b, A, p));
-      if (A->n_interior > 0)
-      {
-        EpiFused<STEP_NONE, false, false> ei = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st,
-                                                A->n_boundary > 0 ? A->tmp_sums + 0 : loc + 1,
-                                                A->n_boundary > 0 ? A->tmp_sums + 1 : loc + 2, nullptr, {0.0, 0.0, 0.0}, nullptr};
-        VCL_TRY(vcl_launch_csr_split(b, subset(A, false), xv, ei, b->stream));
-      }
-      VCL_TRY(wait_halo(b, A));
-      if (A->n_boundary > 0)
-      {
-        EpiFused<STEP_NONE, false, false> eb = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, loc + 1, loc + 2, nullptr,
-                                                {0.0, 0.0, 0.0}, A->n_interior > 0 ? A->tmp_sums : nullptr};
-        VCL_TRY(vcl_launch_csr_split(b, subset(A, true), xv, eb, b->stream));
-      }
+      VCL_TRY((nccl_fused_prod<false, false>(b, A, p, Ap, nullptr, nullptr, st, loc + 1, loc + 2, nullptr)));
       if (b->world > 1)
         VCL_NCCL(b, api, api->AllReduce(loc, &st->sums[0], 3, ncclDouble, ncclSum, (ncclComm_t)b->nccl_comm, b->stream));
       cg_advance_kernel<<<1, 1, 0, b->stream>>>(st);
@@ -1001,7 +1076,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend b, ViennaCLB200Dis
       {
         EpiFused<STEP_NONE, true, false> e1 = {Ap, p, r0, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, red_base + 2 * it + 1, loc + 0, DIST_BICG_P};
-        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, halo_base + 2 * it + 1, true), p2p_xvec(A, p, halo_base + 2 * it + 1), e1));
+        VCL_TRY(p2p_launch(b, A, halo_base + 2 * it + 1, p, e1, true));
       }
       else
       {
@@ -1017,7 +1092,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_bicgstab(ViennaCLBackend b, ViennaCLB200Dis
       {
         EpiFused<STEP_NONE, true, false> e2 = {As, s, r0, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, red_base + 2 * it + 2, loc + 5, DIST_BICG_S};
-        VCL_TRY(p2p_launch_csr(b, p2p_all_blocks(b, A, halo_base + 2 * it + 2, true), p2p_xvec(A, s, halo_base + 2 * it + 2), e2));
+        VCL_TRY(p2p_launch(b, A, halo_base + 2 * it + 2, s, e2, true));
       }
       else
       {

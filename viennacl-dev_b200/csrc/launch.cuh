@@ -102,10 +102,34 @@ static ViennaCLStatus vcl_launch_sell_as(ViennaCLBackend b, const SellDev &d, XV
   return ViennaCLSuccess;
 }
 
+// Row-partitioned slab in SELL (dist.cu): x = [owned | halo], halo control inside d; sigma = 1 only.
+template<class Epi>
+static ViennaCLStatus vcl_launch_sell_split(ViennaCLBackend b, const SellDev &d, XVec xv, Epi epi)
+{
+  const int C = d.C;
+  const int nslices = (d.rows - 1) / C + 1;
+  const int spb = C <= CSR_BLOCK_THREADS ? CSR_BLOCK_THREADS / C : 1;
+  if (C == 32)
+  {
+    const int occ = vcl_occupancy(b, sell_kernel<Epi, false, 32, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int grid = std::max(1, std::min(vcl_div_up(nslices, spb), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+    sell_kernel<Epi, false, 32, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  }
+  else
+  {
+    const int occ = vcl_occupancy(b, sell_kernel<Epi, false, 0, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+    const int grid = std::max(1, std::min(vcl_div_up(nslices, spb), std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
+    sell_kernel<Epi, false, 0, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  }
+  VCL_LAUNCHED(b, "sell_kernel(split)");
+  return ViennaCLSuccess;
+}
+
 template<class Epi>
 static ViennaCLStatus vcl_launch_sell(ViennaCLBackend b, const ViennaCLCUDADsell &A, XVec xv, Epi epi)
 {
-  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm};
+  SellDev d = {A.rows, A.rows_per_block, A.columns_per_block, A.col_idx, A.block_start, A.values, A.row_perm,
+               nullptr, 0u, nullptr, 0ULL, nullptr, nullptr, nullptr, nullptr};
   // the slice height of the reference's default layout gets its own instantiation (sliced_ell_matrix.hpp:146-147: C = 32)
   if (A.row_perm) return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, true, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, true, 0>(b, d, xv, epi);
   return A.rows_per_block == 32 ? vcl_launch_sell_as<Epi, false, 32>(b, d, xv, epi) : vcl_launch_sell_as<Epi, false, 0>(b, d, xv, epi);

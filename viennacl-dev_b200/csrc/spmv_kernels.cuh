@@ -48,6 +48,11 @@ struct SellDev
   int rows; int C;
   const u32 *cpb, *ci, *bs; const real *va;
   const u32 *perm;              // SELL-C-sigma: storage row -> matrix row (0xFFFFFFFF: padding); NULL: identity
+  // row-partitioned slabs (sell_kernel<..., SPLIT = true>, dist.cu): x is addressed as [owned | halo]; a CTA waits for the neighbours'
+  // halo flags before its first pass that gathers from the halo (needs[pass] != 0); push != NULL: the first CTAs send this rank's
+  // boundary entries of x from the head of the kernel (halo_push_share), as in the CSR kernel
+  const unsigned char *needs; unsigned int wait_mask; const unsigned long long *wait_flags; unsigned long long wait_seq; int *err;
+  const HaloPush *push; const u32 *push_idx; unsigned int *push_ticket;
 };
 
 // x operand.  Row-partitioned matrices address [owned | halo]: columns >= split are read from x2 (the halo receive buffer).
@@ -536,7 +541,7 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // constant C the in-slice strides fold into the immediate offsets of the shared-memory loads and tid / C, tid % C become a
 // shift and a mask; the generic form spent 31 % of its issue slots on IMAD address arithmetic and two 32-bit divisions per
 // pass (ncu source page, profiles/ncu_summary_r2.md) and ran 8 % behind the CSR kernel although it moves 3.5 % fewer bytes.
-template<class Epi, bool PERM, int CT>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
+template<class Epi, bool PERM, int CT, bool SPLIT = false>      // PERM: SELL-C-sigma (storage row -> matrix row through A.perm); false: the reference's layout
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, SELL_MIN_CTAS(Epi::NQ, CT))
 sell_kernel(SellDev A, XVec xv, Epi epi)
 {
@@ -600,9 +605,18 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   if (tid == 0 && b < nblocks && staged(base_c, end_c)) issue(base_c, end_c, 0);
   unsigned phase = 0;
   int buf = 0;
+  bool halo_ready = !(SPLIT && A.wait_mask != 0u);
+  if (SPLIT && A.push != nullptr) halo_push_share(*A.push, A.push_idx, xv.x, A.wait_seq, A.push_ticket);   // the first copy is already in flight
 
   for (; b < nblocks; b += step, buf ^= 1)
   {
+    if (SPLIT && !halo_ready && A.needs[b])
+    {
+      // first pass of this CTA that gathers from the halo: by now the neighbours' pushes have normally landed
+      if (tid < VCL_MAX_PEERS && ((A.wait_mask >> tid) & 1u)) peer_wait(A.wait_flags + tid, A.wait_seq, A.err, 1, tid);
+      __syncthreads();
+      halo_ready = true;
+    }
     if (tid == 0 && b + step < nblocks && staged(base_n, end_n)) issue(base_n, end_n, buf ^ 1);
     u32 base_2 = 0, end_2 = 0, w_n = 0, first_n = 0;
     if (b + 2 * step < nblocks) range_of(b + 2 * step, base_2, end_2);
@@ -632,7 +646,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
           for (int k = 0; k < 8; ++k)
           {
             v[k] = (j + k < w_c) ? s_val[idx + k * C] : 0.0;
-            xx[k] = nonzero(v[k]) ? xload<false>(xv, s_col[idx + k * C]) : 0.0;
+            xx[k] = nonzero(v[k]) ? xload<SPLIT>(xv, s_col[idx + k * C]) : 0.0;
           }
           // zero (padding / empty) slots have v = x = +0.0 and leave the bits of `acc` unchanged: no predicates needed
 #pragma unroll
@@ -658,10 +672,10 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         {
           const real v0 = va[idx], v1 = va[idx + C], v2 = va[idx + 2 * (size_t)C], v3 = va[idx + 3 * (size_t)C];
           const u32 c0 = ci[idx], c1 = ci[idx + C], c2 = ci[idx + 2 * (size_t)C], c3 = ci[idx + 3 * (size_t)C];
-          const real x0 = (v0 != 0.0) ? xload<false>(xv, c0) : 0.0;
-          const real x1 = (v1 != 0.0) ? xload<false>(xv, c1) : 0.0;
-          const real x2 = (v2 != 0.0) ? xload<false>(xv, c2) : 0.0;
-          const real x3 = (v3 != 0.0) ? xload<false>(xv, c3) : 0.0;
+          const real x0 = (v0 != 0.0) ? xload<SPLIT>(xv, c0) : 0.0;
+          const real x1 = (v1 != 0.0) ? xload<SPLIT>(xv, c1) : 0.0;
+          const real x2 = (v2 != 0.0) ? xload<SPLIT>(xv, c2) : 0.0;
+          const real x3 = (v3 != 0.0) ? xload<SPLIT>(xv, c3) : 0.0;
           if (v0 != 0.0) acc = fma(x0, v0, acc);
           if (v1 != 0.0) acc = fma(x1, v1, acc);
           if (v2 != 0.0) acc = fma(x2, v2, acc);
@@ -670,7 +684,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
         for (; j < w; ++j, idx += C)
         {
           const real v0 = va[idx];
-          if (v0 != 0.0) acc = fma(xload<false>(xv, ci[idx]), v0, acc);
+          if (v0 != 0.0) acc = fma(xload<SPLIT>(xv, ci[idx]), v0, acc);
         }
         epi.row((u32)r, acc, epi.pre((u32)r));
       }
