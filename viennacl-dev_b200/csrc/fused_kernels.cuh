@@ -175,9 +175,11 @@ __device__ __forceinline__ void st2(real *p, long long i, real2 v) { *reinterpre
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
 // the entries of this thread: returns its share of <r,r>.  Shared by the stand-alone kernel and the persistent one.
-__device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p, real *r, const real *Ap, real alpha, real beta, const PushRanges &pr)
+__device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p, real *r, const real *Ap, real alpha, real beta, const PushRanges &pr,
+                                                  bool *pushed = nullptr)
 {
   real acc = 0.0;
+  bool sent = false;
   const long long npairs = aligned16(x, p, r, Ap) ? (n >> 1) : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (long long)gridDim.x * blockDim.x)
   {
@@ -188,7 +190,7 @@ __device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p,
     vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
     acc = fma(vr.x, vr.x, acc);          acc = fma(vr.y, vr.y, acc);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
-    if (pr.n) { push_entry(pr, k, vp.x); push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
+    if (pr.n) { sent |= push_entry(pr, k, vp.x); sent |= push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
@@ -198,8 +200,9 @@ __device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p,
     vp = fma(beta, vp, vr);
     acc = fma(vr, vr, acc);
     p[k] = vp; r[k] = vr;
-    if (pr.n) push_entry(pr, k, vp);
+    if (pr.n) sent |= push_entry(pr, k, vp);
   }
+  if (pushed) *pushed = sent;
   return acc;
 }
 
@@ -210,8 +213,10 @@ __device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, re
   if (st != nullptr && st->done != VCL_RUNNING) return;
   const real alpha = st ? st->alpha : alpha_v;
   const real beta  = st ? st->beta  : beta_v;
-  real acc[1] = {cg_update_entries(n, x, p, r, Ap, alpha, beta, pr)};
-  if (pr.n) __threadfence_system();                 // this thread's remote stores are performed before its CTA takes a ticket
+  bool pushed = false;
+  real acc[1] = {cg_update_entries(n, x, p, r, Ap, alpha, beta, pr, &pushed)};
+  if (pushed) __threadfence_system();               // THIS thread's remote stores (3 % of the threads have any) are performed before its
+                                                    // CTA takes a ticket: grid_sum_last_block synchronises the CTA first
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
   {
     if (threadIdx.x == 0) *out_rr = acc[0];

@@ -90,11 +90,14 @@ __device__ __forceinline__ bool peer_wait(const u64 *flag, u64 seq, int *err, in
   }
 }
 
-__device__ __forceinline__ void push_entry(const PushRanges &pr, long long k, double v)
+// returns true when entry k went to at least one neighbour (the caller fences only then)
+__device__ __forceinline__ bool push_entry(const PushRanges &pr, long long k, double v)
 {
+  bool sent = false;
 #pragma unroll
   for (int d = 0; d < VCL_MAX_PUSH_RANGES; ++d)
-    if (d < pr.n && k >= pr.lo[d] && k < pr.hi[d]) pr.dst[d][k - pr.lo[d]] = v;
+    if (d < pr.n && k >= pr.lo[d] && k < pr.hi[d]) { pr.dst[d][k - pr.lo[d]] = v; sent = true; }
+  return sent;
 }
 
 // Halo push from the head of the kernel that consumes the halo (the row-partitioned product is ONE launch): the first K CTAs
