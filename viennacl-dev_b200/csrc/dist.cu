@@ -282,7 +282,8 @@ CsrDev subset(ViennaCLB200DistCsr A, bool boundary)
   const int off = boundary ? A->n_interior : 0;
   CsrDev d = {A->n, (u32)A->nnz, A->rp, A->ci_local, A->va, A->ord_start + off, A->ord_end + off,
               boundary ? A->n_boundary : A->n_interior};
-  return d;
+  d.wait_from = boundary ? 0 : d.nblk;                    // list positions >= wait_from may reference halo columns (nothing to wait for here:
+  return d;                                               // the halo has arrived by stream order); interior blocks gather with one base
 }
 
 ViennaCLStatus allreduce_sum(ViennaCLBackend b, ViennaCLB200DistCsr A, double *buf, int count)

@@ -460,7 +460,18 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
       // like the whole-CTA path for rows beyond CSR_CAP).  COO keeps the sequential chain (its alpha/beta form is defined by it).
       const bool is_long = !Epi::COO && (my_e - my_s) > (u32)CSR_LONG_ROW;
       if ((u32)tid < nrows && !is_long)
-        epi.row(cur.r0 + tid, csr_row_dot<SPLIT, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale()), pre);
+      {
+        // row-partitioned slabs: INTERIOR blocks (bi < wait_from) reference owned columns only, so they gather with the plain
+        // one-base addressing; only the boundary blocks (3 % at 256^3 per GPU) pay the base selection of the [owned | halo] form
+        // (measured: 0.2615 -> 0.2489 ms per product at world 1, 0.2546 -> 0.2507 ms on 2 GPUs).
+        // Only for the plain product (Epi::NQ == 0): with the fused solver epilogues the second copy of the row loop costs more
+        // than the selection saves (fused 512^3 CG product on 2 GPUs 284 -> 298 us, profiles/ab_interior_r2r.log).
+        constexpr bool DUAL = SPLIT && Epi::NQ == 0;
+        const real dot = (!DUAL || bi >= A.wait_from)
+                             ? csr_row_dot<SPLIT, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale())
+                             : csr_row_dot<false, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale());
+        epi.row(cur.r0 + tid, dot, pre);
+      }
       unsigned longs = __ballot_sync(0xffffffffu, is_long);
       while (longs)
       {
@@ -537,6 +548,27 @@ csr_scalar_kernel(CsrDev A, XVec xv, Epi epi)
 // C not a multiple of 4 / larger than the CTA, take the direct path.
 // The multiply-adds are fused: that is what the reference host build does for SELL (oracle/vcl_oracle.c, ARITHMETIC).
 // ------------------------------------------------------------------------------------------------
+// one SELL row from the staged slice-column-major entries: entry j of the row sits at idx + j*C; 8 gathers in flight, one fma chain
+template<bool SPLITV>
+__device__ __forceinline__ real sell_row_acc(const real *s_val, const u32 *s_col, u32 idx, u32 w, u32 C, const XVec &xv)
+{
+  real acc = 0.0;
+  for (u32 j = 0; j < w; j += 8, idx += 8 * C)
+  {
+    real v[8], xx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+      v[k] = (j + k < w) ? s_val[idx + k * C] : 0.0;
+      xx[k] = nonzero(v[k]) ? xload<SPLITV>(xv, s_col[idx + k * C]) : 0.0;
+    }
+    // zero (padding / empty) slots have v = x = +0.0 and leave the bits of `acc` unchanged: no predicates needed
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fma(xx[k], v[k], acc);
+  }
+  return acc;
+}
+
 // CT: slice height known at compile time (32, the reference's default, sliced_ell_matrix.hpp:146-147) or 0 = read A.C.  With a
 // constant C the in-slice strides fold into the immediate offsets of the shared-memory loads and tid / C, tid % C become a
 // shift and a mask; the generic form spent 31 % of its issue slots on IMAD address arithmetic and two 32-bit divisions per
@@ -613,12 +645,12 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   bool halo_ready = !(SPLIT && A.wait_mask != 0u);
   // "does pass b gather from the halo?" is fetched one pass ahead like the other descriptors (a load at the top of the pass would
   // sit on the critical path of every pass: measured +19 us per product at 256^3)
-  unsigned char need_c = (SPLIT && !halo_ready && b < nblocks) ? A.needs[phys(b)] : (unsigned char)0;
+  unsigned char need_c = (SPLIT && A.needs != nullptr && b < nblocks) ? A.needs[phys(b)] : (unsigned char)0;
   if (SPLIT && A.push != nullptr) halo_push_share(*A.push, A.push_idx, xv.x, A.wait_seq, A.push_ticket);   // the first copy is already in flight
 
   for (; b < nblocks; b += step, buf ^= 1)
   {
-    const unsigned char need_n = (SPLIT && !halo_ready && b + step < nblocks) ? A.needs[phys(b + step)] : (unsigned char)0;
+    const unsigned char need_n = (SPLIT && A.needs != nullptr && b + step < nblocks) ? A.needs[phys(b + step)] : (unsigned char)0;
     if (SPLIT && !halo_ready && need_c)
     {
       // first pass of this CTA that gathers from the halo: by now the neighbours' pushes have normally landed
@@ -646,21 +678,10 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       phase ^= 1u << buf;
       if (active)
       {
-        real acc = 0.0;
-        u32 idx = first_c - base_c;
-        for (u32 j = 0; j < w_c; j += 8, idx += 8 * C)
-        {
-          real v[8], xx[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-          {
-            v[k] = (j + k < w_c) ? s_val[idx + k * C] : 0.0;
-            xx[k] = nonzero(v[k]) ? xload<SPLIT>(xv, s_col[idx + k * C]) : 0.0;
-          }
-          // zero (padding / empty) slots have v = x = +0.0 and leave the bits of `acc` unchanged: no predicates needed
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc = fma(xx[k], v[k], acc);
-        }
+        // passes without halo columns gather with the plain one-base addressing (see csr_stream_body)
+        constexpr bool DUAL = SPLIT && Epi::NQ == 0;       // plain product only, as in csr_stream_body
+        const real acc = (SPLIT && (!DUAL || need_c)) ? sell_row_acc<true>(s_val, s_col, first_c - base_c, w_c, C, xv)
+                                                      : sell_row_acc<false>(s_val, s_col, first_c - base_c, w_c, C, xv);
         epi.row((u32)r, acc, pre);
       }
     }
