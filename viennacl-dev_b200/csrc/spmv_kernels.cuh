@@ -229,10 +229,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // Resident CTAs per SM the stand-alone product kernels are compiled for.  The float build stages 8 instead of 12 bytes per entry
 // (32.8 KB per CTA), so more CTAs fit one SM, and its kernels are bound by the latency of the gather chain, not by HBM: measured at
 // 256^3 (profiles/ab_float_ctas_r2n.log) CSR 0.1967 / 0.1898 / 0.2112 ms and SELL-32 0.1969 / 0.1754 / 0.1680 ms with 4 / 5 / 6 CTAs
-// (48 / 40 registers, no spills).  The persistent cooperative kernels keep CSR_MIN_CTAS (they spill below 64 registers).
+// (48 / 40 registers, no spills); with the raw descriptor registers of the current SELL kernel 5 CTAs are ahead of 6 (0.1747 / 0.1775 ms).
+// The persistent cooperative kernels keep CSR_MIN_CTAS (they spill below 64 registers).
 #if defined(VCL_F32) && CSR_NSTAGE <= 2
 #define CSR_STREAM_MIN_CTAS 5
-#define SELL_MIN_CTAS(NQ, CT) (((NQ) == 0 && (CT) == 32) ? 6 : 5)      // 6 (40 registers) only where it does not spill: the plain product, C = 32
+#define SELL_MIN_CTAS(NQ, CT) 5
 #else
 #define CSR_STREAM_MIN_CTAS CSR_MIN_CTAS
 #define SELL_MIN_CTAS(NQ, CT) CSR_MIN_CTAS
@@ -611,12 +612,14 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
   // entries have arrived -- instead of stalling the CTAs whose first pass lies in the first plane.  phys(): logical -> stored pass.
   const int rot = SPLIT ? nblocks / 2 : 0;
   auto phys = [&](int b) { const int q = b + rot; return q >= nblocks ? q - nblocks : q; };
-  // element range [base, end) of pass b
-  auto range_of = [&](int b, u32 &base, u32 &end)
+  // Descriptors of a pass are fetched one / two passes ahead and kept RAW in registers: any arithmetic on a freshly loaded value would
+  // stall the warp at that instruction until the load returns (in-order issue) -- the first version computed `end` and `first`
+  // right after the loads and spent 8.7 % of its stall samples there (ncu source page, profiles/ncu_summary_r2h.md).
+  // element range of pass b: base = r.x, end = r.y + r.z * C
+  auto range_raw = [&](int b, u32 &r0, u32 &r1, u32 &r2)
   {
     const u32 s0 = (u32)phys(b) * spb, s1 = min(s0 + spb, nslices);
-    base = A.bs[s0];
-    end = A.bs[s1 - 1] + A.cpb[s1 - 1] * C;
+    r0 = A.bs[s0]; r1 = A.bs[s1 - 1]; r2 = A.cpb[s1 - 1];
   };
   auto staged = [&](u32 base, u32 end) { return can_stage && end > base && end - base <= CSR_CAP; };
   auto issue = [&](u32 base, u32 end, int buf)
@@ -627,18 +630,22 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
     tma_load_1d(s_val0 + buf * CSR_STAGE, va + base, cnt * (unsigned)sizeof(real), &s_bar[buf], pol);
     tma_load_1d(s_col0 + buf * CSR_STAGE, ci + base, cnt * 4u, &s_bar[buf], pol);
   };
-  // this thread's row of pass b: slice width and offset of its first entry
-  auto my_row = [&](int b, u32 &w, u32 &first)
+  // this thread's row of pass b: slice width and (raw) start of its slice; first entry = start + t_lane
+  auto my_row_raw = [&](int b, u32 &w, u32 &start)
   {
     const u32 slice = (u32)phys(b) * spb + t_slice;
-    w = 0; first = 0;
-    if ((u32)tid < spb * C && slice < nslices) { w = A.cpb[slice]; first = A.bs[slice] + t_lane; }
+    w = 0; start = 0;
+    if ((u32)tid < spb * C && slice < nslices) { w = A.cpb[slice]; start = A.bs[slice]; }
   };
-
   int b = blockIdx.x;
   u32 base_c = 0, end_c = 0, base_n = 0, end_n = 0, w_c = 0, first_c = 0;
-  if (b < nblocks) { range_of(b, base_c, end_c); my_row(b, w_c, first_c); }
-  if (b + step < nblocks) range_of(b + step, base_n, end_n);
+  if (b < nblocks)
+  {
+    u32 q0, q1, q2, st0;
+    range_raw(b, q0, q1, q2); base_c = q0; end_c = q1 + q2 * C;
+    my_row_raw(b, w_c, st0); first_c = st0 + t_lane;
+  }
+  if (b + step < nblocks) { u32 q0, q1, q2; range_raw(b + step, q0, q1, q2); base_n = q0; end_n = q1 + q2 * C; }
   if (tid == 0 && b < nblocks && staged(base_c, end_c)) issue(base_c, end_c, 0);
   unsigned phase = 0;
   int buf = 0;
@@ -659,9 +666,9 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       halo_ready = true;
     }
     if (tid == 0 && b + step < nblocks && staged(base_n, end_n)) issue(base_n, end_n, buf ^ 1);
-    u32 base_2 = 0, end_2 = 0, w_n = 0, first_n = 0;
-    if (b + 2 * step < nblocks) range_of(b + 2 * step, base_2, end_2);
-    if (b + step < nblocks) my_row(b + step, w_n, first_n);
+    u32 raw0 = 0, raw1 = 0, raw2 = 0, w_n = 0, start_n = 0;     // consumed only at the end of this pass
+    if (b + 2 * step < nblocks) range_raw(b + 2 * step, raw0, raw1, raw2);
+    if (b + step < nblocks) my_row_raw(b + step, w_n, start_n);
 
     const u32 s0 = (u32)phys(b) * spb, s1 = min(s0 + spb, nslices);
     if (staged(base_c, end_c))
@@ -720,7 +727,7 @@ sell_kernel(SellDev A, XVec xv, Epi epi)
       }
     }
     __syncthreads();                                       // buffer `buf` may be refilled from the next iteration on
-    base_c = base_n; end_c = end_n; base_n = base_2; end_n = end_2; w_c = w_n; first_c = first_n;
+    base_c = base_n; end_c = end_n; base_n = raw0; end_n = raw1 + raw2 * C; w_c = w_n; first_c = start_n + t_lane;
     need_c = need_n;
   }
   epi.finish(s_red);
