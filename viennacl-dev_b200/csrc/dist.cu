@@ -941,7 +941,8 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
             pr.flag[d] = A->push.flag[d] + par * pr.W + pr.me;
           }
         }
-        cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr, pr);
+        if (pr.n > 0) cg_update_push_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr, pr);
+        else          cg_update_kernel<<<grid, VEC_THREADS, 0, b->stream>>>(n, x, p, r, Ap, 0.0, 0.0, st, b->partials, b->tickets, loc_rr);
         VCL_LAUNCHED(b, "cg_update_kernel");
         // scattered send lists: the product kernel pushes from its own head (after its st->done test) -- no push kernel either way
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,

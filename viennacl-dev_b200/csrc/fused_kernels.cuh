@@ -175,6 +175,7 @@ __device__ __forceinline__ void st2(real *p, long long i, real2 v) { *reinterpre
 // CG: x += alpha p; r -= alpha Ap; p = r + beta p; <r,r>        (host_based/iterative_operations.hpp:378-418)
 // ------------------------------------------------------------------------------------------------
 // the entries of this thread: returns its share of <r,r>.  Shared by the stand-alone kernel and the persistent one.
+template<bool PUSH>
 __device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p, real *r, const real *Ap, real alpha, real beta, const PushRanges &pr,
                                                   bool *pushed = nullptr)
 {
@@ -190,7 +191,7 @@ __device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p,
     vp.x = fma(beta, vp.x, vr.x);        vp.y = fma(beta, vp.y, vr.y);
     acc = fma(vr.x, vr.x, acc);          acc = fma(vr.y, vr.y, acc);
     st2(x, k, vx); st2(r, k, vr); st2(p, k, vp);
-    if (pr.n) { sent |= push_entry(pr, k, vp.x); sent |= push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
+    if (PUSH && pr.n) { sent |= push_entry(pr, k, vp.x); sent |= push_entry(pr, k + 1, vp.y); }      // new p -> the neighbours' halo buffers (NVLink)
   }
   for (long long k = 2 * npairs + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
   {
@@ -200,12 +201,13 @@ __device__ __forceinline__ real cg_update_entries(long long n, real *x, real *p,
     vp = fma(beta, vp, vr);
     acc = fma(vr, vr, acc);
     p[k] = vp; r[k] = vr;
-    if (pr.n) sent |= push_entry(pr, k, vp);
+    if (PUSH && pr.n) sent |= push_entry(pr, k, vp);
   }
   if (pushed) *pushed = sent;
   return acc;
 }
 
+template<bool PUSH>
 __device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
                                                SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges &pr)
 {
@@ -214,22 +216,32 @@ __device__ __forceinline__ void cg_update_body(long long n, real *x, real *p, re
   const real alpha = st ? st->alpha : alpha_v;
   const real beta  = st ? st->beta  : beta_v;
   bool pushed = false;
-  real acc[1] = {cg_update_entries(n, x, p, r, Ap, alpha, beta, pr, &pushed)};
+  real acc[1] = {cg_update_entries<PUSH>(n, x, p, r, Ap, alpha, beta, pr, &pushed)};
   if (pushed) __threadfence_system();               // THIS thread's remote stores (3 % of the threads have any) are performed before its
                                                     // CTA takes a ticket: grid_sum_last_block synchronises the CTA first
   if (grid_sum_last_block<1>(acc, partials, ticket, s_red))
   {
     if (threadIdx.x == 0) *out_rr = acc[0];
     // every CTA has fenced its pushes: publish the sequence number to the destinations
-    if ((int)threadIdx.x < pr.n) { __threadfence_system(); st_release_sys(pr.flag[threadIdx.x], pr.seq); }
+    if (PUSH && (int)threadIdx.x < pr.n) { __threadfence_system(); st_release_sys(pr.flag[threadIdx.x], pr.seq); }
   }
 }
 
-static __global__ void __launch_bounds__(VEC_THREADS)
+// Single-domain form.  4 resident CTAs per SM (62 registers, no spills): compiled for 5 / 6 / 8 CTAs the kernel spills (8 / 80 / 144
+// bytes of stack) and a 256^3 CG iteration goes from 416 to 414 / 452 / 485 us (profiles/ab_cgupdate_r2.log) -- not worth it.
+static __global__ void __launch_bounds__(VEC_THREADS, 4)
 cg_update_kernel(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
-                 SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges pr = PushRanges())
+                 SolverState *st, real *partials, unsigned int *ticket, real *out_rr)
 {
-  cg_update_body(n, x, p, r, Ap, alpha_v, beta_v, st, partials, ticket, out_rr, pr);
+  cg_update_body<false>(n, x, p, r, Ap, alpha_v, beta_v, st, partials, ticket, out_rr, PushRanges());
+}
+
+// Row-partitioned form: additionally writes the new p entries the neighbours need into their halo buffers (peer.cuh)
+static __global__ void __launch_bounds__(VEC_THREADS)
+cg_update_push_kernel(long long n, real *x, real *p, real *r, const real *Ap, real alpha_v, real beta_v,
+                      SolverState *st, real *partials, unsigned int *ticket, real *out_rr, const PushRanges pr)
+{
+  cg_update_body<true>(n, x, p, r, Ap, alpha_v, beta_v, st, partials, ticket, out_rr, pr);
 }
 
 // ------------------------------------------------------------------------------------------------

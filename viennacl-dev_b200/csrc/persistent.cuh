@@ -97,7 +97,7 @@ cg_persistent_kernel(CsrDev A, XVec xv, long long n, real *x, real *p, real *r, 
     real *part_rr = partials + (2 + (it & 1)) * VCL_MAX_BLOCKS;
     // ---- vector update with this CTA's share of the entries (the loop of cg_update_kernel) ----
     {
-      real acc[1] = {cg_update_entries(n, x, p, r, Ap, s_st.alpha, s_st.beta, PushRanges())};
+      real acc[1] = {cg_update_entries<false>(n, x, p, r, Ap, s_st.alpha, s_st.beta, PushRanges())};
       block_sum<1>(acc, s_sum);
       if (threadIdx.x == 0) part_rr[blockIdx.x] = acc[0];
     }
