@@ -70,5 +70,12 @@ for d in rows_out:
         traffic["csr_spmv_256_split"] = d["dram_total"]      # the SPLIT instantiation of the row-partitioned runs, captured at world 1
     if d["capture"].endswith("spmv") and "sell_kernel<EpiAxpby" in d["kernel"]:
         traffic["sell_spmv_256"] = d["dram_total"]
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+# merge: a pass that captured only some kernels must not drop the other keys
+tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+try:
+    old = json.load(open(tp))
+except Exception:
+    old = {}
+old.update(traffic)
+json.dump(old, open(tp, "w"), indent=1)
 print(open(os.path.join(ROOT, "profiles", "ncu_summary_%s.md" % tag)).read())
