@@ -600,7 +600,11 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
       A->push_hi[d] = A->push_lo[d] + (b1 - b0);
       for (int i = b0; i < b1; ++i) if (idx[i] != idx[b0] + (u32)(i - b0)) { contiguous = false; break; }
     }
-    A->fused_push = contiguous;
+    // Pushing from cg_update_kernel (the kernel that PRODUCES p) was the round-1 default; pushing from the head of the consuming
+    // product kernel measured faster (512^3 CG: 2169 -> 2197 it/s on 8 GPUs, 589.9 -> 592.4 on 2; profiles/ab_headpush_r2u.log): the
+    // update kernel runs at its single-GPU speed and the pushed entries still arrive long before the boundary blocks need them.
+    // VCL_B200_FUSED_PUSH=1 selects the old form.
+    A->fused_push = contiguous && getenv("VCL_B200_FUSED_PUSH") != nullptr;
   }
   A->p2p = true;
   return ViennaCLSuccess;
