@@ -1,4 +1,5 @@
-// dist.cu -- row-partitioned CSR SpMV and pipelined CG across the GPUs of one box, one process per GPU.
+// dist.cu -- row-partitioned SpMV (CSR or SELL slabs) and Krylov solvers (CG, CG + diagonal preconditioner, BiCGStab, GMRES) across the
+// GPUs of one box, one process per GPU.
 // No counterpart in the reference ("Partition of data is left to the user", doc/manual/multi-device.dox:9).
 //
 // Rank g owns a contiguous block of rows.  At create time the locally stored (global) column indices are analysed on the
@@ -6,11 +7,11 @@
 // hence grouped by owner), every owner learns which of its entries each peer needs (send lists), and the CSR row blocks
 // are split into INTERIOR blocks (no halo column) and BOUNDARY blocks.
 // Transport "p2p" (default; peer.cuh): every rank maps a window of every other rank's memory (CUDA IPC over NVLink).
-//   One product    = halo_push_kernel (entries -> the neighbours' receive buffers + flag)
-//                    + ONE csr_stream_kernel launch: interior row blocks first, boundary blocks wait for the flags.
-//   One CG iteration = cg_update_kernel + halo_push_kernel + the fused SpMV kernel whose last CTA all-reduces
-//                    {<r,r>, <Ap,Ap>, <p,Ap>} through the windows and advances alpha/beta/convergence -- 3 launches,
-//                    one stream, no communication kernels, no host round trip.
+//   One product    = ONE csr_stream_kernel / sell_kernel launch: its first CTAs push this rank's boundary entries to the neighbours'
+//                    receive buffers (+ flag), interior row blocks come first, boundary blocks wait for the neighbours' flags.
+//   One CG iteration = cg_update_kernel + the fused SpMV kernel whose last CTA all-reduces {<r,r>, <Ap,Ap>, <p,Ap>} through the
+//                    windows and advances alpha/beta/convergence -- 2 launches, one stream, no communication kernels, no host
+//                    round trip.  (halo_push_kernel, the round-1 stand-alone push, survives behind VCL_B200_SEPARATE_PUSH.)
 // Transport "nccl" (VCL_B200_DIST_TRANSPORT=nccl, or when IPC mapping is not possible): pack -> ncclSend/ncclRecv on the
 //   communication stream || interior blocks; boundary blocks after the halo event; ncclAllReduce of 3 doubles; a
 //   one-thread kernel advances the scalars.

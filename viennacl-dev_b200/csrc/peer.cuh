@@ -2,8 +2,10 @@
 // every other rank's device memory (CUDA IPC) and the kernels of the solver push halo entries and reduction partials
 // straight into the consumer's memory, followed by a release-store of a sequence number; consumers spin on their OWN
 // memory with acquire loads.  No communication kernel, no second stream, no host involvement inside an iteration:
-//   halo_push_kernel     x entries -> the neighbours' halo receive buffers + flag            (1 launch per product)
-//   csr_stream_kernel    interior row blocks first; boundary blocks wait for the flags        (the SpMV launch itself)
+//   halo_push_share()    called at the head of the product launch: its first CTAs send this rank's boundary x entries to the
+//                        neighbours' halo receive buffers and publish the flag                 (no launch of its own)
+//   csr_stream_kernel /  interior row blocks (passes) first; boundary blocks wait for the flags (the SpMV launch itself)
+//   sell_kernel
 //   peer_allreduce()     called by the LAST CTA of the reducing kernel: push the rank-local totals to all ranks, wait
 //                        for everyone's, sum in rank order -> bit-identical global sums on every rank
 // Buffers are double-buffered by the parity of the sequence number; every exchange pair is symmetric (a rank that sends
