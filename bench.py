@@ -265,7 +265,8 @@ def _legacy_cuda_child(n1=256):
         A = o.stencil2d(1024, 1024)
         b = np.ones(A.rows)
         rc.solve("cg", A, b, tol=1e-8, maxit=50)
-        res = rc.solve("cg", A, b, tol=1e-8, maxit=5000)
+        res = min((rc.solve("cg", A, b, tol=1e-8, maxit=5000) for _ in range(3)), key=lambda r_: r_["seconds"])    # best of 3: its per-iteration
+        # blocking read-back makes single runs jitter by 4x on a busy host
         true = float(np.linalg.norm(b - o.csr_spmv(A, res["x"])) / np.linalg.norm(b))
         out["cg_lap2d_1024"] = {"iterations": res["iters"], "solve_ms": res["seconds"] * 1e3, "iterations_per_sec": res["iters"] / res["seconds"],
                                 "error": res["error"], "true_residual": true, "correct": bool(true < 1e-7)}
