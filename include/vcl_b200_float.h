@@ -36,7 +36,9 @@ ViennaCLStatus ViennaCLCUDASnrm2(ViennaCLBackend backend, ViennaCLInt n, float *
 /* CSR row blocks: compressed_matrix.hpp:1152-1188 (generate_row_block_information) -> handle3()/blocks1().
  * Each block holds whole rows: at most VCL_B200_CSR_BLOCK_ROWS rows and VCL_B200_CSR_BLOCK_NNZ non-zeros, or one longer row.
  * Two-call protocol: row_blocks == NULL returns the count in *num_blocks; then pass a device buffer of (*num_blocks + 1) u32. */
+#ifndef VCL_B200_CSR_BLOCK_ROWS
 #define VCL_B200_CSR_BLOCK_ROWS 256
+#endif
 #ifndef VCL_B200_CSR_BLOCK_NNZ
 #define VCL_B200_CSR_BLOCK_NNZ  2048
 #endif

@@ -79,8 +79,10 @@ static ViennaCLStatus uniform_group_size(ViennaCLBackend b, int rows, const u32 
   unsigned int h[9];
   VCL_CUDA(b, cudaMemcpyAsync(h, d_max, sizeof(h), cudaMemcpyDeviceToHost, b->stream));
   VCL_CUDA(b, cudaStreamSynchronize(b->stream));
-  static_assert(VCL_B200_CSR_BLOCK_ROWS == 256, "group sizes below assume 256-row blocks");
-  for (int lg = 8; lg >= 5; --lg)
+  static_assert(VCL_B200_CSR_BLOCK_ROWS <= 256 && (VCL_B200_CSR_BLOCK_ROWS & (VCL_B200_CSR_BLOCK_ROWS - 1)) == 0, "row blocks: a power of two <= 256 rows");
+  int top = 0;
+  while ((1 << top) < VCL_B200_CSR_BLOCK_ROWS) ++top;
+  for (int lg = top; lg >= 5; --lg)
     if (h[lg] <= (unsigned int)VCL_B200_CSR_BLOCK_NNZ) { *G_out = 1 << lg; break; }
   return ViennaCLSuccess;
 }

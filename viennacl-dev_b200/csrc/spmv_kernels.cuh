@@ -21,7 +21,9 @@
 namespace VCL_NS
 {
 
+#ifndef CSR_BLOCK_THREADS
 #define CSR_BLOCK_THREADS 256
+#endif
 #define CSR_CAP (VCL_B200_CSR_BLOCK_NNZ)          // staged non-zeros per row block
 #define CSR_STAGE (CSR_CAP + 4)                   // + alignment slack
 #define CSR_LONG_ROW 64                           // rows longer than this are summed by a whole warp (see csr_stream_body)
