@@ -347,8 +347,11 @@ def test_fused_steps_vs_numpy(pkg, be, orc):
     assert abs(buf.download()[0] - r2 @ r0) <= 1e-11 * max(1.0, abs(r2 @ r0))
 
 
-def test_gmres_steps_vs_numpy(pkg, be, orc):
-    n, m, k = 5003, 12, 7
+@pytest.mark.parametrize("m,k", [(12, 7), (64, 63)])
+def test_gmres_steps_vs_numpy(pkg, be, orc, m, k):
+    """(64, 63): the largest Krylov dimension -- stage 2 folds 63 chunk sums into device scratch (that scratch overflowed
+    from k = 49 on); the state after it must still be intact, which the solves of the later tests on the same handle rely on."""
+    n = 5003
     isz = (n + 127) // 128 * 128
     rng = np.random.default_rng(2)
     V = np.zeros(isz * m)
