@@ -59,6 +59,10 @@ struct ViennaCLB200DistCsr_impl
   u32 *ord_start = nullptr, *ord_end = nullptr;   // row ranges of the blocks in the order [interior | boundary]
   u64 halo_seq = 0, red_seq = 0;     // exchanges EXECUTED so far (identical on every rank)
   int *d_err = nullptr;
+  // ---- gather vector (peer-memory transport): [owned n | halo n_halo] doubles INSIDE the window; the CG keeps its search direction
+  // p here and the neighbours push their boundary entries straight behind it, so the fused product gathers with ONE base ----
+  double *gvec = nullptr;
+  HaloPush push_g; HaloPush *d_push_g = nullptr;
   // ---- optional SELL-C copy of the slab (ViennaCLCUDADdist_csr_set_format): local column indices, sigma = 1 ----
   int fmt = 0, sell_C = 0, sell_passes = 0;
   u32 *s_cpb = nullptr, *s_bs = nullptr, *s_ci = nullptr; double *s_va = nullptr;
@@ -208,12 +212,13 @@ CsrDev p2p_all_blocks(ViennaCLBackend b, ViennaCLB200DistCsr A, u64 seq, bool wi
   return d;
 }
 
-template<class Epi>
+// XS = false: the gathered vector and its halo are one contiguous array (the gather vector inside the window)
+template<class Epi, bool XS = true>
 ViennaCLStatus p2p_launch_csr(ViennaCLBackend b, const CsrDev &d, XVec xv, Epi epi)
 {
-  const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, true>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
+  const int occ = vcl_occupancy(b, csr_stream_kernel<Epi, true, XS>, CSR_BLOCK_THREADS, CSR_SMEM_BYTES);
   const int grid = std::max(1, std::min(d.nblk, std::min(b->sm_count * occ, VCL_MAX_BLOCKS)));
-  csr_stream_kernel<Epi, true><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
+  csr_stream_kernel<Epi, true, XS><<<grid, CSR_BLOCK_THREADS, CSR_SMEM_BYTES, b->stream>>>(d, xv, epi);
   VCL_LAUNCHED(b, "csr_stream_kernel(peer)");
   return ViennaCLSuccess;
 }
@@ -488,7 +493,8 @@ static size_t win_off_rflag(int W) { return (size_t)2 * W * sizeof(u64); }
 static size_t win_off_red(int W)   { return (size_t)4 * W * sizeof(u64); }
 static size_t win_off_halo(int W)  { return ((size_t)4 * W * sizeof(u64) + (size_t)8 * W * sizeof(double) + 255) / 256 * 256; }
 
-struct PeerHello { cudaIpcMemHandle_t handle; long long n_halo; int device; int ok; };
+struct PeerHello { cudaIpcMemHandle_t handle; long long n_halo; long long n; int device; int ok; };
+static size_t win_off_gvec(int W, long long n_halo) { return (win_off_halo(W) + (size_t)2 * (size_t)std::max<long long>(n_halo, 1) * sizeof(double) + 255) / 256 * 256; }
 
 ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::vector<int> &M)
 {
@@ -499,10 +505,10 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
   int want = (W <= VCL_MAX_PEERS) && !(env && std::string(env) == "nccl");
 
   // own window (>= 2 MiB so that the allocation is not carved out of a shared driver block)
-  A->win_bytes = std::max<size_t>(win_off_halo(W) + (size_t)2 * std::max(A->n_halo, 1) * sizeof(double), (size_t)2 << 20);
+  A->win_bytes = std::max<size_t>(win_off_gvec(W, A->n_halo) + ((size_t)A->n + (size_t)std::max(A->n_halo, 1)) * sizeof(double), (size_t)2 << 20);
   PeerHello hello;
   std::memset(&hello, 0, sizeof(hello));
-  hello.n_halo = A->n_halo; hello.device = b->device; hello.ok = want;
+  hello.n_halo = A->n_halo; hello.n = A->n; hello.device = b->device; hello.ok = want;
   if (want)
   {
     if (cudaMalloc(&A->win_mem, A->win_bytes) != cudaSuccess || cudaMemsetAsync(A->win_mem, 0, A->win_bytes, b->stream) != cudaSuccess ||
@@ -587,6 +593,25 @@ ViennaCLStatus setup_p2p(ViennaCLBackend b, ViennaCLB200DistCsr A, const std::ve
   hp.begin[hp.ndst] = A->total_send;
   VCL_CUDA(b, cudaMalloc(&A->d_push, sizeof(HaloPush)));
   VCL_CUDA(b, cudaMemcpy(A->d_push, &hp, sizeof(HaloPush), cudaMemcpyHostToDevice));
+  // the same destinations for the gather-vector form: rank q's halo part starts n_q entries into its gather vector; ONE buffer
+  // (parity stride 0) -- safe inside the CG, where an all-reduce separates consecutive exchanges (see ViennaCLCUDADdist_csr_cg)
+  A->gvec = reinterpret_cast<double*>(static_cast<char*>(A->win_mem) + win_off_gvec(W, A->n_halo));
+  A->push_g = hp;
+  {
+    int d = 0;
+    for (int q = 0; q < W; ++q)
+    {
+      if (q == me || (A->send_cnt[q] == 0 && A->recv_cnt[q] == 0)) continue;
+      long long off_in_q = 0;
+      for (int p2 = 0; p2 < me; ++p2) off_in_q += M[(size_t)q * W + p2];
+      double *gq = reinterpret_cast<double*>(static_cast<char*>(A->peer_base[q]) + win_off_gvec(W, all[q].n_halo));
+      A->push_g.dst[d] = gq + all[q].n + off_in_q;
+      A->push_g.stride[d] = 0;
+      ++d;
+    }
+  }
+  VCL_CUDA(b, cudaMalloc(&A->d_push_g, sizeof(HaloPush)));
+  VCL_CUDA(b, cudaMemcpy(A->d_push_g, &A->push_g, sizeof(HaloPush), cudaMemcpyHostToDevice));
   // contiguous send ranges?  (slab partitions of banded matrices: yes) -> the producing kernel can push by itself
   A->fused_push = false;
   if (hp.ndst > 0 && hp.ndst <= VCL_MAX_PUSH_RANGES && !(getenv("VCL_B200_NO_FUSED_PUSH")))
@@ -796,7 +821,7 @@ ViennaCLStatus ViennaCLCUDADdist_csr_destroy(ViennaCLBackend b, ViennaCLB200Dist
       cudaStreamSynchronize(b->stream);
     }
     for (int q = 0; q < b->world; ++q) if (q != b->rank && A->peer_base[q]) cudaIpcCloseMemHandle(A->peer_base[q]);
-    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err); cudaFree(A->d_push);
+    cudaFree(A->win_mem); cudaFree(A->d_win); cudaFree(A->d_err); cudaFree(A->d_push); cudaFree(A->d_push_g);
   }
   if (A->ev_x) cudaEventDestroy(A->ev_x);
   if (A->ev_halo) cudaEventDestroy(A->ev_halo);
@@ -886,6 +911,14 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
   const size_t need = ((size_t)std::max<long long>(n, 1) * sizeof(double) + 255) / 256 * 256;
   VCL_TRY(vcl_ws_reserve(b, 3 * need));
   double *r = (double*)b->ws, *p = (double*)((char*)b->ws + need), *Ap = (double*)((char*)b->ws + 2 * need);
+  // Gather-vector form (peer-memory transport, CSR slabs): p lives inside the window with its halo right behind it -- the neighbours
+  // push their boundary entries of p straight to p[n ...] -- so the fused product gathers with the plain one-base addressing (the
+  // [owned | halo] base selection cost ~12 us of a 285 us product).  ONE halo buffer instead of two: inside the CG consecutive
+  // exchanges are separated by the all-reduce of the iteration between them -- a neighbour pushes exchange i+1 from the head of its
+  // product i+1, i.e. after it has the all-reduced sums of iteration i, which contain this rank's contribution, which this rank's
+  // last CTA sends only after ALL its CTAs have finished product i (and with it their reads of halo i).
+  const bool use_g = A->p2p && A->fmt == 0 && !A->fused_push && A->gvec != nullptr && !getenv("VCL_B200_NO_GVEC");
+  if (use_g) p = A->gvec;
 
   VCL_CUDA(b, cudaMemsetAsync(x, 0, sizeof(double) * n, b->stream));
   VCL_CUDA(b, cudaMemcpyAsync(r, rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, b->stream));
@@ -953,6 +986,12 @@ ViennaCLStatus ViennaCLCUDADdist_csr_cg(ViennaCLBackend b, ViennaCLB200DistCsr A
         EpiFused<STEP_NONE, false, false> e = {Ap, p, nullptr, nullptr, b->partials, b->tickets, st, nullptr, nullptr, nullptr,
                                                {0.0, 0.0, 0.0}, nullptr, A->d_win, rseq, loc_rr, DIST_CG};
         if (A->fmt == 1) VCL_TRY(p2p_launch(b, A, hseq, p, e, !A->fused_push));
+        else if (use_g)
+        {
+          CsrDev dd = p2p_all_blocks(b, A, hseq, true);
+          dd.push = A->push_g.ndst > 0 ? A->d_push_g : nullptr;
+          VCL_TRY((p2p_launch_csr<EpiFused<STEP_NONE, false, false>, false>(b, dd, make_xvec(p, 0, 1), e)));
+        }
         else
         {
           CsrDev dd = p2p_all_blocks(b, A, hseq, !A->fused_push);

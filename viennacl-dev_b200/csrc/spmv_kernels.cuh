@@ -287,7 +287,10 @@ __device__ __forceinline__ real csr_row_dot(const Epi &epi, const real *s_val, c
 // kernel does its vector update and waits at the grid barrier.
 struct CsrCarry { unsigned phase; int primed; };
 
-template<class Epi, bool SPLIT, bool REPEATED>
+// SPLIT: row-partitioned launch (halo push at the head, flag wait before the boundary blocks).  XS: x is addressed as [owned | halo] in
+// two buffers (xload<true>); XS = false with SPLIT = true is the solver form in which the gathered vector and its halo are ONE
+// contiguous array inside the peer window (dist.cu: gather vector), so every block uses the plain one-base addressing.
+template<class Epi, bool SPLIT, bool REPEATED, bool XS = SPLIT>
 __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv, Epi &epi, CsrCarry *carry = nullptr, bool drain = false)
 {
   constexpr int S = CSR_NSTAGE;
@@ -428,7 +431,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
       // one long row: the whole CTA strides over it (summation order differs from the sequential reference; tolerance-level parity)
       real part[1] = {0.0};
       for (u32 k = cur.n0 + tid; k < cur.n1; k += CSR_BLOCK_THREADS)
-        part[0] = fma(A.va[k], xget<SPLIT>(epi, xv, A.ci[k]), part[0]);
+        part[0] = fma(A.va[k], xget<XS>(epi, xv, A.ci[k]), part[0]);
       __shared__ real s_long[32];
       block_sum<1>(part, s_long);
       if (tid == 0)
@@ -469,9 +472,9 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
         // (measured: 0.2615 -> 0.2489 ms per product at world 1, 0.2546 -> 0.2507 ms on 2 GPUs).
         // Only for the plain product (Epi::NQ == 0): with the fused solver epilogues the second copy of the row loop costs more
         // than the selection saves (fused 512^3 CG product on 2 GPUs 284 -> 298 us, profiles/ab_interior_r2r.log).
-        constexpr bool DUAL = SPLIT && Epi::NQ == 0;
+        constexpr bool DUAL = XS && Epi::NQ == 0;
         const real dot = (!DUAL || bi >= A.wait_from)
-                             ? csr_row_dot<SPLIT, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale())
+                             ? csr_row_dot<XS, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale())
                              : csr_row_dot<false, Epi::COO>(epi, s_val, s_col, my_s - a0, my_e - a0, xv, epi.init(pre), epi.term_scale());
         epi.row(cur.r0 + tid, dot, pre);
       }
@@ -482,7 +485,7 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
         longs &= longs - 1u;
         const u32 ls = __shfl_sync(0xffffffffu, my_s, src) - a0, le = __shfl_sync(0xffffffffu, my_e, src) - a0;
         real part = 0.0;
-        for (u32 k = ls + (u32)(tid & 31); k < le; k += 32u) part = fma(s_val[k], xget<SPLIT>(epi, xv, s_col[k]), part);
+        for (u32 k = ls + (u32)(tid & 31); k < le; k += 32u) part = fma(s_val[k], xget<XS>(epi, xv, s_col[k]), part);
         part = warp_sum(part);
         if ((tid & 31) == src) epi.row(cur.r0 + tid, part, pre);
       }
@@ -511,11 +514,11 @@ __device__ __forceinline__ void csr_stream_body(const CsrDev &A, const XVec &xv,
   }
 }
 
-template<class Epi, bool SPLIT>
+template<class Epi, bool SPLIT, bool XS = SPLIT>
 __global__ void __launch_bounds__(CSR_BLOCK_THREADS, CSR_STREAM_MIN_CTAS)
 csr_stream_kernel(CsrDev A, XVec xv, Epi epi)
 {
-  csr_stream_body<Epi, SPLIT, false>(A, xv, epi);
+  csr_stream_body<Epi, SPLIT, false, XS>(A, xv, epi);
 }
 
 
