@@ -13,8 +13,9 @@
 // beta; all CTAs take identical decisions because they perform identical arithmetic on identical data.  CTA 0 writes the
 // state back for the host when the launch ends.  Arithmetic per entry and the stopping rule are those of the two-kernel
 // path (cg.hpp:128-187); only the grouping of the partial sums differs.
-// The file holds four kernels of this form: cg_persistent_kernel (below), pcg_persistent_kernel (Jacobi / row scaling),
-// bicgstab_persistent_kernel (pipelined BiCGStab, four phases) and gmres_persistent_kernel (one restart cycle); the drivers in
+// The file holds five kernels of this form: cg_persistent_kernel (below, two phases), cg_onepass_kernel (ONE phase and one barrier per
+// iteration: the product recomputes the updated search direction on the fly; used up to 600 k rows), pcg_persistent_kernel (Jacobi /
+// row scaling), bicgstab_persistent_kernel (pipelined BiCGStab, four phases) and gmres_persistent_kernel (one restart cycle); the drivers in
 // solvers.cu choose them by system size (persistent_cg_wanted) and fall back to the multi-kernel form when a cooperative
 // launch does not fit.
 #pragma once
